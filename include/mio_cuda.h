@@ -1,0 +1,213 @@
+/*
+ * mio_cuda.h -- C-ABI of the B200 backend for MEmilio's Graph-ODE ensemble hot path.
+ *
+ * The reference (SciCompMod/memilio @ 8851d5be) has no FFI layer; it is a header-template C++ library. The seams
+ * this ABI sits behind are (paths relative to the reference tree):
+ *   - mio::make_mobility_sim / GraphSimulation::advance      cpp/memilio/mobility/metapopulation_mobility_instant.h:656-678,
+ *                                                            cpp/memilio/mobility/graph_simulation.h:101-120
+ *   - SimulationNode::advance + Simulation::advance          cpp/memilio/mobility/metapopulation_mobility_instant.h:91-95,
+ *                                                            cpp/memilio/compartments/simulation.h:66-73,
+ *                                                            cpp/memilio/math/integrator.h:184-249
+ *   - MobilityEdge::apply_mobility                           cpp/memilio/mobility/metapopulation_mobility_instant.h:546-623
+ *   - ParameterStudy::run (create_simulation / advance /     cpp/memilio/compartments/parameter_studies.h:158-217,290-345
+ *     process_result per run)
+ *   - ensemble_percentile / ensemble_mean / sum_nodes        cpp/memilio/data/analyze_result.h:267-343
+ *
+ * The C++ facade in include/memilio_b200/ keeps the reference's names and signatures (mio::Graph, SimulationNode,
+ * MobilityEdge, make_mobility_sim, ParameterStudy) and packs into the flat descriptors below.
+ *
+ * Conventions
+ *   - plain C, no exceptions, no torch types; every function returns a mio_status (numbering of mio::StatusCode,
+ *     cpp/memilio/io/io.h:49-59) and mio_cuda_last_error_string() holds the message of the last failure.
+ *   - the caller owns every host buffer for the duration of the call only; the library copies.
+ *   - there is NO CPU fallback: if no sm_100 device is usable every compute entry point fails with MIO_UNKNOWN_ERROR.
+ *   - a handle is not thread safe; one handle per GPU.
+ *   - all floating point data is FP64. State vectors use the reference's flat layout idx = age*C + compartment
+ *     (cpp/memilio/utils/custom_index_array.h:59-95).
+ */
+#ifndef MIO_CUDA_H
+#define MIO_CUDA_H
+
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+#if defined(_WIN32)
+#define MIO_API
+#else
+#define MIO_API __attribute__((visibility("default")))
+#endif
+
+/* mio::StatusCode, cpp/memilio/io/io.h:49-59 */
+typedef enum {
+    MIO_OK            = 0,
+    MIO_UNKNOWN_ERROR = 1,
+    MIO_OUT_OF_RANGE  = 2,
+    MIO_INVALID_VALUE = 3,
+    MIO_INVALID_FILE_FORMAT = 4,
+    MIO_KEY_NOT_FOUND = 5,
+    MIO_INVALID_TYPE  = 6,
+    MIO_FILE_NOT_FOUND = 7
+} mio_status;
+
+/* model kinds */
+#define MIO_MODEL_OSECIR 0    /* cpp/models/ode_secir/model.h   : 10 compartments, 15 flows per age group */
+#define MIO_MODEL_OSECIRVVS 1 /* cpp/models/ode_secirvvs/model.h: 27 compartments, 45 flows per age group */
+
+/* integrator cores */
+#define MIO_INTEGRATOR_CK54 0  /* ControlledStepperWrapper<boost cash_karp54>, cpp/memilio/math/stepper_wrapper.h:59-202 (default) */
+#define MIO_INTEGRATOR_RKF45 1 /* mio::RKIntegratorCore, cpp/memilio/math/adapt_rk.h:145-310 */
+#define MIO_INTEGRATOR_EULER 2 /* mio::EulerIntegratorCore, cpp/memilio/math/euler.h:33-63 */
+
+/* node simulation kinds (only relevant for OSECIRVVS) */
+#define MIO_SIM_BASE 0  /* mio::Simulation<FP, Model>: plain advance, unit mobility factors, no commuter testing */
+#define MIO_SIM_MODEL 1 /* osecir::Simulation / osecirvvs::Simulation: model-specific advance + ADL mobility hooks */
+
+#define MIO_MAX_GROUPS 8
+
+/* ---- flat parameter-set layout --------------------------------------------------------------------------------
+ * A parameter set is MIO_PSET_HEADER doubles followed by num_groups age records of mio_pset_age_stride(model)
+ * doubles (age-major, so that the device lane owning age group i loads one contiguous record).
+ */
+#define MIO_PSET_HEADER 8
+/* header slots (both models) */
+#define MIO_PH_START_DAY 0            /* StartDay                       ode_secir/parameters.h:47  */
+#define MIO_PH_SEASONALITY 1          /* Seasonality                    ode_secir/parameters.h:64  */
+#define MIO_PH_TNT_MAX_RISK 2         /* TestAndTraceCapacityMaxRisk    ode_secir/parameters.h:374 */
+#define MIO_PH_COMMUTER_NONDETECTION 3 /* m_commuter_nondetection        ode_secir/parameters.h:417 */
+#define MIO_PH_START_COMMUTER_DETECTION 4
+#define MIO_PH_END_COMMUTER_DETECTION 5
+#define MIO_PH_RESERVED6 6
+#define MIO_PH_RESERVED7 7
+
+/* osecir age record (16 doubles, 14 used) -- tags of cpp/models/ode_secir/parameters.h:96-318 */
+#define MIO_OSECIR_AGE_STRIDE 16
+#define MIO_PA_TIME_EXPOSED 0
+#define MIO_PA_TIME_INS 1       /* TimeInfectedNoSymptoms */
+#define MIO_PA_TIME_ISY 2       /* TimeInfectedSymptoms */
+#define MIO_PA_TIME_ISEV 3      /* TimeInfectedSevere */
+#define MIO_PA_TIME_ICR 4       /* TimeInfectedCritical */
+#define MIO_PA_TRANS_PROB 5     /* TransmissionProbabilityOnContact */
+#define MIO_PA_REL_TRANS_NOSYMP 6 /* RelativeTransmissionNoSymptoms */
+#define MIO_PA_REC_PER_INS 7    /* RecoveredPerInfectedNoSymptoms */
+#define MIO_PA_RISK_SYMP 8      /* RiskOfInfectionFromSymptomatic */
+#define MIO_PA_MAX_RISK_SYMP 9  /* MaxRiskOfInfectionFromSymptomatic */
+#define MIO_PA_SEV_PER_ISY 10   /* SeverePerInfectedSymptoms */
+#define MIO_PA_CRIT_PER_SEV 11  /* CriticalPerSevere */
+#define MIO_PA_DEATHS_PER_SEV 12 /* DeathsPerSevere */
+#define MIO_PA_DEATHS_PER_CRIT 13 /* DeathsPerCritical */
+
+/* per-node local parameters: [ICUCapacity, TestAndTraceCapacity] (sampled per node, parameter_space.h:125-148) */
+#define MIO_NODE_LOCAL 2
+#define MIO_NL_ICU_CAPACITY 0
+#define MIO_NL_TNT_CAPACITY 1
+
+/* ---- flat contact-table layout ----------------------------------------------------------------------------------
+ * One contact table is the evaluated damping cache of a ContactMatrixGroup (cpp/memilio/epidemiology/
+ * contact_matrix.h:271-400, damping.h:571-600): for each of L contact locations the baseline B, the minimum M and the
+ * K accumulated dampings D_k active from change time t_k on (sentinels lowest()/max() are implied).
+ *   doubles[0]                    = L                       (1 <= L <= ct_max_loc)
+ *   doubles[1 .. ct_max_loc]      = K_l                     (0 <= K_l <= ct_max_pts)
+ *   then per location l, stride ct_max_pts + (2 + ct_max_pts)*G*G:
+ *        times[ct_max_pts], B[G*G], M[G*G], D[ct_max_pts][G*G]      (matrices row-major, (i,j) -> i*G + j)
+ * mio_ctable_size() returns the total number of doubles.
+ * The mobility table of a run (dampings applied to the mobility coefficients of all edges,
+ * parameter_space.h:241-248) has the same shape with L = 1 and vectors of length n = G*C in place of matrices, B
+ * and M omitted (baseline is the per-edge coefficient vector, minimum is zero):
+ *   doubles[0] = K, times[mob_max_pts], D[mob_max_pts][n]
+ */
+
+typedef struct {
+    int32_t kind;     /* MIO_INTEGRATOR_* */
+    int32_t reserved;
+    double abs_tol;   /* default 1e-10 */
+    double rel_tol;   /* default 1e-5  */
+    double dt_min;    /* default DBL_MIN */
+    double dt_max;    /* default DBL_MAX */
+} mio_integrator_desc;
+
+typedef struct {
+    int32_t model;       /* MIO_MODEL_*  */
+    int32_t sim_kind;    /* MIO_SIM_*    */
+    int32_t num_groups;  /* G, 1..MIO_MAX_GROUPS */
+    int32_t num_nodes;   /* N */
+    int32_t num_edges;   /* E (may be 0) */
+    int32_t num_psets;   /* parameter sets per run  (>=1) */
+    int32_t num_ctables; /* contact tables per run  (>=1) */
+    int32_t ct_max_loc;  /* capacity: contact locations per table */
+    int32_t ct_max_pts;  /* capacity: damping change points per location */
+    int32_t mob_max_pts; /* capacity: change points of the per-run mobility damping table; 0 = none */
+    int32_t max_runs;    /* number of run slots held on the device */
+    int32_t record_daily; /* 1: keep the state of every node at every integer day (after the edge phase) */
+    int32_t max_days;    /* capacity of the daily record (days since t0, inclusive of day 0) */
+    int32_t traj_capacity; /* >0: record every accepted integrator step of every node, up to this many points */
+    const int32_t* edge_start; /* [E] source node, reference edge order = sorted by (start,end), mobility/graph.h:233-241 */
+    const int32_t* edge_end;   /* [E] destination node */
+    const double* edge_coeff;  /* [E][n] baseline mobility coefficients (MobilityCoefficientGroup summed over its members) */
+    const int32_t* node_pset;  /* [N] parameter set used by each node   (NULL = all 0) */
+    const int32_t* node_ctable; /* [N] contact table used by each node  (NULL = all 0) */
+    mio_integrator_desc integrator;
+    double t0;
+    double dt_graph;     /* GraphSimulation m_dt; +inf for make_no_mobility_sim */
+} mio_graph_desc;
+
+typedef struct {
+    const double* psets;      /* [count][num_psets][mio_pset_size]       */
+    const double* ctables;    /* [count][num_ctables][mio_ctable_size]   */
+    const double* node_local; /* [count][N][MIO_NODE_LOCAL]              */
+    const double* y0;         /* [count][N][n]                            */
+    const double* dt0;        /* [count][N] initial integrator dt per node, NULL = 0.1 (Simulation ctor default) */
+    const double* mobtables;  /* [count][mio_mobtable_size], NULL = no mobility dampings */
+} mio_run_data;
+
+/* per (run,node) counters returned by mio_cuda_get_counters */
+#define MIO_NUM_COUNTERS 4
+#define MIO_CNT_ACCEPTED 0      /* accepted integrator steps (= time points appended by SystemIntegrator::advance) */
+#define MIO_CNT_REJECTED 1      /* failed try_step attempts */
+#define MIO_CNT_FORCED 2        /* steps forced at dt_min (integrator.h:236-239 "Adaptive step sizing failed") */
+#define MIO_CNT_UNDERFLOW 3     /* return-phase underflow fix-ups applied with this node as destination (instant.h:579-596) */
+
+typedef struct mio_handle mio_handle;
+
+MIO_API const char* mio_cuda_last_error_string(void);
+MIO_API int mio_cuda_version(void);
+MIO_API int mio_cuda_device_count(void);
+
+MIO_API int mio_num_compartments(int model);
+MIO_API int mio_pset_age_stride(int model);
+MIO_API int64_t mio_pset_size(int model, int num_groups);
+MIO_API int64_t mio_ctable_size(int num_groups, int ct_max_loc, int ct_max_pts);
+MIO_API int64_t mio_mobtable_size(int model, int num_groups, int mob_max_pts);
+
+/* make_mobility_sim: uploads the graph, allocates max_runs run slots on the current CUDA device. */
+MIO_API int mio_cuda_graph_create(const mio_graph_desc* desc, int device, mio_handle** out);
+MIO_API void mio_cuda_graph_destroy(mio_handle* h);
+
+/* (re)initialise run slots [slot0, slot0+count): parameters, initial state, t = t0 */
+MIO_API int mio_cuda_set_runs(mio_handle* h, int32_t slot0, int32_t count, const mio_run_data* data);
+/* number of slots that take part in advance() (default max_runs) */
+MIO_API int mio_cuda_set_active_runs(mio_handle* h, int32_t count);
+
+/* GraphSimulation::advance(t_max) for all active run slots */
+MIO_API int mio_cuda_advance(mio_handle* h, double t_max);
+MIO_API int mio_cuda_get_time(mio_handle* h, double* t);
+
+/* node state get_result().get_last_value(): out[count][N][n] */
+MIO_API int mio_cuda_get_state(mio_handle* h, int32_t slot0, int32_t count, double* out);
+/* SimulationBase::get_dt() per node: out[count][N] */
+MIO_API int mio_cuda_get_node_dt(mio_handle* h, int32_t slot0, int32_t count, double* out);
+/* out[count][N][MIO_NUM_COUNTERS] */
+MIO_API int mio_cuda_get_counters(mio_handle* h, int32_t slot0, int32_t count, int64_t* out);
+/* daily record (record_daily=1): out[count][N][num_days][n], num_days = days recorded so far (returned) */
+MIO_API int mio_cuda_get_daily(mio_handle* h, int32_t slot0, int32_t count, int32_t* num_days, double* out,
+                               int64_t out_capacity);
+/* recorded trajectories (traj_capacity>0): times[count][N][cap], values[count][N][cap][n], npts[count][N] */
+MIO_API int mio_cuda_get_trajectory(mio_handle* h, int32_t slot0, int32_t count, int32_t* npts, double* times,
+                                    double* values);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* MIO_CUDA_H */

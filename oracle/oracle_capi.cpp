@@ -1,0 +1,270 @@
+// oracle_capi.cpp -- C entry points of the CPU ORACLE (test infrastructure, NOT product code; see mio_oracle.hpp).
+// They take the same flat descriptors as the CUDA C-ABI (include/mio_cuda.h) so that tests feed identical bytes to
+// both sides. Loaded with ctypes by tests/, __graft_entry__.smoke() and the cpu_baseline legs of bench.py only.
+#include "mio_oracle.hpp"
+#include "../include/mio_cuda.h"
+
+#include <cstring>
+
+using namespace orc;
+
+namespace
+{
+
+int ncomp_of(int model)
+{
+    return model == MIO_MODEL_OSECIR ? 10 : 27;
+}
+
+int64_t pset_size(int model, int G)
+{
+    return MIO_PSET_HEADER + int64_t(model == MIO_MODEL_OSECIR ? MIO_OSECIR_AGE_STRIDE : 0) * G;
+}
+
+int64_t ctable_size(int G, int max_loc, int max_pts)
+{
+    return 1 + max_loc + int64_t(max_loc) * (max_pts + int64_t(2 + max_pts) * G * G);
+}
+
+DampingExprGroup contacts_from_flat(const double* ct, int G, int max_loc, int max_pts)
+{
+    DampingExprGroup g;
+    const int L          = int(ct[0]);
+    const int64_t stride = max_pts + int64_t(2 + max_pts) * G * G;
+    for (int l = 0; l < L; ++l) {
+        const int K      = int(ct[1 + l]);
+        const double* p  = ct + 1 + max_loc + l * stride;
+        const double* tm = p;
+        const double* B  = p + max_pts;
+        const double* M  = B + G * G;
+        const double* D  = M + G * G;
+        Mat b(G, G), m(G, G);
+        std::copy(B, B + G * G, b.a.begin());
+        std::copy(M, M + G * G, m.a.begin());
+        DampingExpr e(b, m);
+        std::vector<double> times(tm, tm + K);
+        std::vector<Mat> mats;
+        for (int k = 0; k < K; ++k) {
+            Mat d(G, G);
+            std::copy(D + int64_t(k) * G * G, D + int64_t(k + 1) * G * G, d.a.begin());
+            mats.push_back(d);
+        }
+        e.dampings.set_cache(times, mats);
+        g.m.push_back(e);
+    }
+    return g;
+}
+
+osecir::Model osecir_from_flat(int G, const double* pset, const double* local, const double* ct, int max_loc,
+                               int max_pts, const double* y0)
+{
+    osecir::Model m(G);
+    auto& p                       = m.parameters;
+    p.StartDay                    = pset[MIO_PH_START_DAY];
+    p.Seasonality                 = pset[MIO_PH_SEASONALITY];
+    p.TestAndTraceCapacityMaxRisk = pset[MIO_PH_TNT_MAX_RISK];
+    p.commuter_nondetection       = pset[MIO_PH_COMMUTER_NONDETECTION];
+    p.start_commuter_detection    = pset[MIO_PH_START_COMMUTER_DETECTION];
+    p.end_commuter_detection      = pset[MIO_PH_END_COMMUTER_DETECTION];
+    p.ICUCapacity                 = local[MIO_NL_ICU_CAPACITY];
+    p.TestAndTraceCapacity        = local[MIO_NL_TNT_CAPACITY];
+    for (int i = 0; i < G; ++i) {
+        const double* a                        = pset + MIO_PSET_HEADER + i * MIO_OSECIR_AGE_STRIDE;
+        p.TimeExposed[i]                       = a[MIO_PA_TIME_EXPOSED];
+        p.TimeInfectedNoSymptoms[i]            = a[MIO_PA_TIME_INS];
+        p.TimeInfectedSymptoms[i]              = a[MIO_PA_TIME_ISY];
+        p.TimeInfectedSevere[i]                = a[MIO_PA_TIME_ISEV];
+        p.TimeInfectedCritical[i]              = a[MIO_PA_TIME_ICR];
+        p.TransmissionProbabilityOnContact[i]  = a[MIO_PA_TRANS_PROB];
+        p.RelativeTransmissionNoSymptoms[i]    = a[MIO_PA_REL_TRANS_NOSYMP];
+        p.RecoveredPerInfectedNoSymptoms[i]    = a[MIO_PA_REC_PER_INS];
+        p.RiskOfInfectionFromSymptomatic[i]    = a[MIO_PA_RISK_SYMP];
+        p.MaxRiskOfInfectionFromSymptomatic[i] = a[MIO_PA_MAX_RISK_SYMP];
+        p.SeverePerInfectedSymptoms[i]         = a[MIO_PA_SEV_PER_ISY];
+        p.CriticalPerSevere[i]                 = a[MIO_PA_CRIT_PER_SEV];
+        p.DeathsPerSevere[i]                   = a[MIO_PA_DEATHS_PER_SEV];
+        p.DeathsPerCritical[i]                 = a[MIO_PA_DEATHS_PER_CRIT];
+    }
+    p.ContactPatterns = contacts_from_flat(ct, G, max_loc, max_pts);
+    std::copy(y0, y0 + size_t(G) * osecir::NC, m.populations.begin());
+    return m;
+}
+
+std::unique_ptr<IntegratorCore> make_core(const mio_integrator_desc& d)
+{
+    switch (d.kind) {
+    case MIO_INTEGRATOR_CK54:
+        return std::make_unique<CashKarp54Core>(d.abs_tol, d.rel_tol, d.dt_min, d.dt_max);
+    case MIO_INTEGRATOR_RKF45:
+        return std::make_unique<RKF45Core>(d.abs_tol, d.rel_tol, d.dt_min, d.dt_max);
+    default:
+        return std::make_unique<EulerCore>();
+    }
+}
+
+} // namespace
+
+extern "C" {
+
+// Dampings::update_cache on K raw dampings of shape rows x cols; returns the number of cache entries (without the
+// two sentinels) and writes change times and accumulated matrices.
+int orc_dampings_cache(int rows, int cols, int K, const double* times, const int* levels, const int* types,
+                       const double* mats, double* out_times, double* out_mats)
+{
+    Dampings d(rows, cols);
+    const int sz = rows * cols;
+    for (int k = 0; k < K; ++k) {
+        Damping dm{times[k], levels[k], types[k], Mat(rows, cols)};
+        std::copy(mats + int64_t(k) * sz, mats + int64_t(k + 1) * sz, dm.m.a.begin());
+        d.add(dm);
+    }
+    int n = int(d.cache.size()) - 2;
+    for (int k = 0; k < n; ++k) {
+        out_times[k] = d.cache[k + 1].second;
+        std::copy(d.cache[k + 1].first.a.begin(), d.cache[k + 1].first.a.end(), out_mats + int64_t(k) * sz);
+    }
+    return n;
+}
+
+// ContactMatrixGroup::get_matrix_at(t) from a flat contact table
+void orc_contact_matrix_at(const double* ct, int G, int max_loc, int max_pts, double t, double* out)
+{
+    auto g = contacts_from_flat(ct, G, max_loc, max_pts);
+    for (int i = 0; i < G; ++i) {
+        for (int j = 0; j < G; ++j) {
+            out[i * G + j] = g.at(t, i, j);
+        }
+    }
+}
+
+// osecir right-hand side (get_derivatives with pop, y distinct)
+void orc_osecir_rhs(int G, const double* pset, const double* local, const double* ct, int max_loc, int max_pts,
+                    const double* pop, const double* y, double t, double* dydt)
+{
+    Vec zero(size_t(G) * osecir::NC, 0.0);
+    auto m = osecir_from_flat(G, pset, local, ct, max_loc, max_pts, zero.data());
+    Vec p(pop, pop + zero.size()), yy(y, y + zero.size()), d(zero.size());
+    m.get_derivatives(p, yy, t, d);
+    std::copy(d.begin(), d.end(), dydt);
+}
+
+// mio::simulate (compartments/simulation.h) for one node. Returns the number of time points (all of them are counted,
+// at most max_pts are written); counters = {accepted, rejected, forced}.
+int orc_simulate(int model, int G, const double* pset, const double* local, const double* ct, int max_loc,
+                 int max_pts_ct, const double* y0, double t0, double tmax, double dt,
+                 const mio_integrator_desc* integ, int max_pts, double* out_t, double* out_y, double* out_dt,
+                 int64_t* counters)
+{
+    if (model != MIO_MODEL_OSECIR) {
+        return -1;
+    }
+    auto m = osecir_from_flat(G, pset, local, ct, max_loc, max_pts_ct, y0);
+    Simulation<osecir::Model> sim(m, t0, dt);
+    sim.set_integrator_core(make_core(*integ));
+    sim.advance(tmax);
+    const int n  = int(sim.result.n());
+    const int ne = G * ncomp_of(model);
+    for (int k = 0; k < std::min(n, max_pts); ++k) {
+        out_t[k] = sim.result.times[k];
+        std::copy(sim.result.values[k].begin(), sim.result.values[k].end(), out_y + int64_t(k) * ne);
+    }
+    if (out_dt) {
+        *out_dt = sim.dt;
+    }
+    if (counters) {
+        counters[0] = sim.integrator.n_steps;
+        counters[1] = sim.integrator.core->n_rejected;
+        counters[2] = sim.integrator.core->n_forced;
+    }
+    return n;
+}
+
+// make_mobility_sim + GraphSimulation::advance for ONE run described by the flat descriptors of mio_cuda.h.
+//   out_state[N][n]          final get_result().get_last_value() of every node
+//   out_dt[N]                final integrator dt of every node
+//   out_counters[N][4]       accepted, rejected, forced, underflow fix-ups (as destination)
+//   out_halfsteps            optional [num_graph_steps][N][n]: node states after every graph step's edge phase
+//   max_halfsteps            capacity of out_halfsteps (in graph steps)
+// returns number of graph steps taken, or <0 on error.
+int orc_graph_simulate(const mio_graph_desc* desc, const mio_run_data* run, double t_max, double* out_state,
+                       double* out_dt, int64_t* out_counters, double* out_halfsteps, int max_halfsteps)
+{
+    if (desc->model != MIO_MODEL_OSECIR) {
+        return -1;
+    }
+    const int G = desc->num_groups, N = desc->num_nodes, E = desc->num_edges;
+    const int n       = G * ncomp_of(desc->model);
+    const int64_t psz = pset_size(desc->model, G);
+    const int64_t csz = ctable_size(G, desc->ct_max_loc, desc->ct_max_pts);
+    GraphSim<osecir::Model> g(desc->t0, desc->dt_graph);
+    for (int k = 0; k < N; ++k) {
+        const int ps = desc->node_pset ? desc->node_pset[k] : 0;
+        const int ci = desc->node_ctable ? desc->node_ctable[k] : 0;
+        auto m       = osecir_from_flat(G, run->psets + ps * psz, run->node_local + int64_t(k) * MIO_NODE_LOCAL,
+                                        run->ctables + ci * csz, desc->ct_max_loc, desc->ct_max_pts,
+                                        run->y0 + int64_t(k) * n);
+        g.add_node(m, desc->t0, run->dt0 ? run->dt0[k] : 0.1);
+        g.nodes.back().sim.set_integrator_core(make_core(desc->integrator));
+    }
+    for (int e = 0; e < E; ++e) {
+        Vec c(desc->edge_coeff + int64_t(e) * n, desc->edge_coeff + int64_t(e + 1) * n);
+        MobilityEdge me(c);
+        if (run->mobtables && desc->mob_max_pts > 0) {
+            const double* mt = run->mobtables;
+            const int K      = int(mt[0]);
+            std::vector<double> times(mt + 1, mt + 1 + K);
+            std::vector<Mat> mats;
+            for (int k = 0; k < K; ++k) {
+                Mat d(n, 1);
+                std::copy(mt + 1 + desc->mob_max_pts + int64_t(k) * n,
+                          mt + 1 + desc->mob_max_pts + int64_t(k + 1) * n, d.a.begin());
+                mats.push_back(d);
+            }
+            me.coefficients.m[0].dampings.set_cache(times, mats);
+        }
+        g.add_edge(desc->edge_start[e], desc->edge_end[e], me);
+    }
+    // GraphSimulation::advance, unrolled here only to snapshot the state after each graph step
+    int steps  = 0;
+    double dts = g.dt;
+    while (g.t < t_max) {
+        if (g.t + dts > t_max) {
+            dts = t_max - g.t;
+        }
+        for (auto& nd : g.nodes) {
+            nd.advance(g.t, dts);
+        }
+        g.t += dts;
+        for (auto& e : g.edges) {
+            e.property.apply_mobility(g.t, dts, g.nodes[e.start], g.nodes[e.end]);
+        }
+        if (out_halfsteps && steps < max_halfsteps) {
+            for (int k = 0; k < N; ++k) {
+                std::copy(g.nodes[k].sim.result.last().begin(), g.nodes[k].sim.result.last().end(),
+                          out_halfsteps + (int64_t(steps) * N + k) * n);
+            }
+        }
+        ++steps;
+    }
+    for (int k = 0; k < N; ++k) {
+        std::copy(g.nodes[k].sim.result.last().begin(), g.nodes[k].sim.result.last().end(),
+                  out_state + int64_t(k) * n);
+        if (out_dt) {
+            out_dt[k] = g.nodes[k].sim.dt;
+        }
+        if (out_counters) {
+            out_counters[k * 4 + 0] = g.nodes[k].sim.integrator.n_steps;
+            out_counters[k * 4 + 1] = g.nodes[k].sim.integrator.core->n_rejected;
+            out_counters[k * 4 + 2] = g.nodes[k].sim.integrator.core->n_forced;
+            out_counters[k * 4 + 3] = 0;
+        }
+    }
+    if (out_counters) {
+        for (auto& e : g.edges) {
+            out_counters[e.end * 4 + 3] += e.property.stats.underflows;
+        }
+    }
+    return steps;
+}
+
+} // extern "C"
