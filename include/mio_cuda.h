@@ -207,6 +207,10 @@ MIO_API int mio_cuda_get_daily(mio_handle* h, int32_t slot0, int32_t count, int3
 MIO_API int mio_cuda_get_trajectory(mio_handle* h, int32_t slot0, int32_t count, int32_t* npts, double* times,
                                     double* values);
 
+/* statistics: kernels launched by this handle so far; (run, step) pairs whose return phase needed the literal
+ * in-order replay because of underflow fix-ups */
+MIO_API int mio_cuda_get_stats(mio_handle* h, int64_t* launches, int64_t* exact_replays);
+
 #ifdef __cplusplus
 }
 #endif

@@ -1,0 +1,761 @@
+// capi.cu -- C-ABI (include/mio_cuda.h) over the CUDA kernels: handle management, run upload, the
+// GraphSimulation::advance loop (cpp/memilio/mobility/graph_simulation.h:101-120) and result download.
+#include "../../include/mio_cuda.h"
+#include "kernels.h"
+
+#include <algorithm>
+#include <cmath>
+#include <cstdio>
+#include <cstring>
+#include <limits>
+#include <numeric>
+#include <string>
+#include <vector>
+
+using namespace miocu;
+
+namespace
+{
+
+thread_local std::string g_last_error;
+
+int fail(int code, const std::string& msg)
+{
+    g_last_error = msg;
+    return code;
+}
+
+#define CUDA_TRY(expr)                                                                                                 \
+    do {                                                                                                               \
+        cudaError_t err__ = (expr);                                                                                    \
+        if (err__ != cudaSuccess) {                                                                                    \
+            return fail(MIO_UNKNOWN_ERROR, std::string(#expr) + ": " + cudaGetErrorString(err__));                     \
+        }                                                                                                              \
+    } while (0)
+
+template <class T>
+cudaError_t dev_alloc(T** p, size_t count)
+{
+    *p = nullptr;
+    if (count == 0) {
+        return cudaSuccess;
+    }
+    return cudaMalloc((void**)p, count * sizeof(T));
+}
+
+} // namespace
+
+struct mio_handle {
+    mio_graph_desc desc;
+    Geometry geo;
+    int device       = 0;
+    cudaStream_t stream = nullptr;
+    int max_runs = 0, active_runs = 0;
+    // graph (device)
+    int *d_node_pset = nullptr, *d_node_ctable = nullptr;
+    int *d_node_order = nullptr, *d_inc_ptr = nullptr, *d_inc_edge = nullptr, *d_inc_other = nullptr,
+        *d_inc_out = nullptr, *d_edge_start = nullptr, *d_edge_end = nullptr;
+    double* d_coeff = nullptr;
+    // per run (device)
+    double *d_run_block = nullptr, *d_node_local = nullptr, *d_t_node = nullptr, *d_dt_node = nullptr;
+    int* d_counters     = nullptr;
+    double* d_y[4]      = {nullptr, nullptr, nullptr, nullptr};
+    double *d_fac = nullptr, *d_aux = nullptr;
+    int* d_run_flags = nullptr;
+    double* d_daily  = nullptr;
+    int* d_traj_npts = nullptr;
+    double *d_traj_times = nullptr, *d_traj_values = nullptr;
+    // simulation state (GraphSimulationBase::m_t and the edges' common toggle / stored mobile population)
+    double t            = 0.0;
+    bool toggle         = false; // MobilityEdge::m_return_mobile_population
+    bool have_mobile    = false; // a mobile population is stored (between departure and return)
+    double t_dep        = 0.0, return_time = 0.0;
+    int cur = 0, snap_idx = -1, v0_idx = -1;
+    int day0 = 0, days_recorded = 0;
+    // statistics
+    long long launches = 0;
+    long long* d_stats = nullptr; // [0] exact replays of return steps
+};
+
+namespace
+{
+
+int64_t pset_size(int model, int G)
+{
+    return MIO_PSET_HEADER + int64_t(model == MIO_MODEL_OSECIR ? MIO_OSECIR_AGE_STRIDE : 0) * G;
+}
+int64_t ctable_size(int G, int max_loc, int max_pts)
+{
+    return 1 + max_loc + int64_t(max_loc) * (max_pts + int64_t(2 + max_pts) * G * G);
+}
+int64_t mobtable_size(int n, int mob_max_pts)
+{
+    return 1 + mob_max_pts + int64_t(mob_max_pts) * n;
+}
+
+// raw parameter set (mio_cuda.h layout) -> derived device record (device_common.cuh). The coefficient expressions
+// keep the operand order of cpp/models/ode_secir/model.h:152-211 so that coef*y is bit-identical to the reference.
+void derive_pset(const double* raw, int G, double* out)
+{
+    for (int k = 0; k < PHDR; ++k) {
+        out[k] = 0.0;
+    }
+    out[hSTART_DAY]       = raw[MIO_PH_START_DAY];
+    out[hSEASONALITY]     = raw[MIO_PH_SEASONALITY];
+    out[hTNT_MAX_RISK]    = raw[MIO_PH_TNT_MAX_RISK];
+    out[hNONDETECTION]    = raw[MIO_PH_COMMUTER_NONDETECTION];
+    out[hSTART_DETECTION] = raw[MIO_PH_START_COMMUTER_DETECTION];
+    out[hEND_DETECTION]   = raw[MIO_PH_END_COMMUTER_DETECTION];
+    for (int i = 0; i < G; ++i) {
+        const double* a    = raw + MIO_PSET_HEADER + i * MIO_OSECIR_AGE_STRIDE;
+        double* r          = out + PHDR + i * AGE_REC;
+        const double T_E   = a[MIO_PA_TIME_EXPOSED];
+        const double T_INS = a[MIO_PA_TIME_INS];
+        const double T_ISy = a[MIO_PA_TIME_ISY];
+        const double T_ISev = a[MIO_PA_TIME_ISEV];
+        const double T_ICr = a[MIO_PA_TIME_ICR];
+        const double rho   = a[MIO_PA_REC_PER_INS];
+        const double sev   = a[MIO_PA_SEV_PER_ISY];
+        const double crit  = a[MIO_PA_CRIT_PER_SEV];
+        const double dps   = a[MIO_PA_DEATHS_PER_SEV];
+        const double dpc   = a[MIO_PA_DEATHS_PER_CRIT];
+        r[rE_INS]          = 1.0 / T_E;
+        r[rINS_ISy]        = (1 - rho) * (1 / T_INS);
+        r[rINS_R]          = rho * (1.0 / T_INS);
+        r[rISy_ISev]       = sev / T_ISy;
+        r[rISy_R]          = (1 - sev) / T_ISy;
+        r[rISev_ICr0]      = crit / T_ISev;
+        r[rISev_R]         = (1.0 - crit - dps) / T_ISev;
+        r[rISev_D0]        = (dps + (crit - crit)) / T_ISev;
+        r[rICr_D]          = dpc / T_ICr;
+        r[rICr_R]          = (1.0 - dpc) / T_ICr;
+        r[rTNT]            = (1 - rho) / T_INS;
+        r[rP]              = a[MIO_PA_TRANS_PROB];
+        r[rREL]            = a[MIO_PA_REL_TRANS_NOSYMP];
+        r[rRISK]           = a[MIO_PA_RISK_SYMP];
+        r[rMAXRISK]        = a[MIO_PA_MAX_RISK_SYMP];
+        r[rCRIT]           = crit;
+        r[rT_ISEV]         = T_ISev;
+        r[rDPS]            = dps;
+        r[18]              = 0.0;
+        r[19]              = 0.0;
+    }
+}
+
+void destroy(mio_handle* h)
+{
+    if (!h) {
+        return;
+    }
+    cudaSetDevice(h->device);
+    void* ptrs[] = {h->d_node_pset,  h->d_node_ctable, h->d_node_order, h->d_inc_ptr,   h->d_inc_edge,
+                    h->d_inc_other,  h->d_inc_out,     h->d_edge_start, h->d_edge_end,  h->d_coeff,
+                    h->d_run_block,  h->d_node_local,  h->d_t_node,     h->d_dt_node,   h->d_counters,
+                    h->d_y[0],       h->d_y[1],        h->d_y[2],       h->d_y[3],      h->d_fac,
+                    h->d_aux,        h->d_run_flags,   h->d_daily,      h->d_traj_npts, h->d_traj_times,
+                    h->d_traj_values, h->d_stats};
+    for (void* p : ptrs) {
+        if (p) {
+            cudaFree(p);
+        }
+    }
+    if (h->stream) {
+        cudaStreamDestroy(h->stream);
+    }
+    delete h;
+}
+
+DeviceState device_state(const mio_handle* h)
+{
+    DeviceState st;
+    st.run_block   = h->d_run_block;
+    st.node_local  = h->d_node_local;
+    st.node_pset   = h->d_node_pset;
+    st.node_ctable = h->d_node_ctable;
+    st.t_node      = h->d_t_node;
+    st.dt_node     = h->d_dt_node;
+    st.counters    = h->d_counters;
+    return st;
+}
+
+int free_buffer(const mio_handle* h, int a, int b, int c)
+{
+    for (int i = 0; i < 4; ++i) {
+        if (i != a && i != b && i != c && i != h->snap_idx && i != h->v0_idx) {
+            return i;
+        }
+    }
+    return -1;
+}
+
+} // namespace
+
+extern "C" {
+
+const char* mio_cuda_last_error_string(void)
+{
+    return g_last_error.c_str();
+}
+
+int mio_cuda_version(void)
+{
+    return 100;
+}
+
+int mio_cuda_device_count(void)
+{
+    int n = 0;
+    if (cudaGetDeviceCount(&n) != cudaSuccess) {
+        return 0;
+    }
+    return n;
+}
+
+int mio_num_compartments(int model)
+{
+    return model == MIO_MODEL_OSECIR ? 10 : (model == MIO_MODEL_OSECIRVVS ? 27 : -1);
+}
+int mio_pset_age_stride(int model)
+{
+    return model == MIO_MODEL_OSECIR ? MIO_OSECIR_AGE_STRIDE : -1;
+}
+int64_t mio_pset_size(int model, int num_groups)
+{
+    return pset_size(model, num_groups);
+}
+int64_t mio_ctable_size(int num_groups, int ct_max_loc, int ct_max_pts)
+{
+    return ctable_size(num_groups, ct_max_loc, ct_max_pts);
+}
+int64_t mio_mobtable_size(int model, int num_groups, int mob_max_pts)
+{
+    return mobtable_size(num_groups * mio_num_compartments(model), mob_max_pts);
+}
+
+int mio_cuda_graph_create(const mio_graph_desc* d, int device, mio_handle** out)
+{
+    if (!d || !out) {
+        return fail(MIO_INVALID_VALUE, "null argument");
+    }
+    *out = nullptr;
+    if (d->model != MIO_MODEL_OSECIR) {
+        return fail(MIO_INVALID_VALUE, "model kind not supported by this build (osecir only)");
+    }
+    if (d->num_groups < 1 || d->num_groups > MIO_MAX_GROUPS || d->num_nodes < 1 || d->num_edges < 0 ||
+        d->max_runs < 1 || d->num_psets < 1 || d->num_ctables < 1 || d->ct_max_loc < 1 || d->ct_max_pts < 0 ||
+        d->mob_max_pts < 0) {
+        return fail(MIO_INVALID_VALUE, "invalid graph descriptor sizes");
+    }
+    if (!(d->dt_graph > 0.0)) {
+        return fail(MIO_INVALID_VALUE, "dt_graph must be positive");
+    }
+    if (d->integrator.kind < 0 || d->integrator.kind > 2) {
+        return fail(MIO_INVALID_VALUE, "unknown integrator kind");
+    }
+    if (d->num_edges > 0 && (!d->edge_start || !d->edge_end || !d->edge_coeff)) {
+        return fail(MIO_INVALID_VALUE, "edge arrays missing");
+    }
+    int ndev = 0;
+    if (cudaGetDeviceCount(&ndev) != cudaSuccess || ndev == 0) {
+        return fail(MIO_UNKNOWN_ERROR, "no CUDA device available (this library has no CPU fallback)");
+    }
+    if (device < 0 || device >= ndev) {
+        return fail(MIO_OUT_OF_RANGE, "device index out of range");
+    }
+    CUDA_TRY(cudaSetDevice(device));
+    cudaDeviceProp prop;
+    CUDA_TRY(cudaGetDeviceProperties(&prop, device));
+    if (prop.major != 10) {
+        return fail(MIO_UNKNOWN_ERROR, "device is not sm_100 (kernels are built for sm_100a only)");
+    }
+    const int G = d->num_groups, N = d->num_nodes, E = d->num_edges, n = G * NC;
+    for (int e = 0; e < E; ++e) {
+        if (d->edge_start[e] < 0 || d->edge_start[e] >= N || d->edge_end[e] < 0 || d->edge_end[e] >= N ||
+            d->edge_start[e] == d->edge_end[e]) {
+            return fail(MIO_OUT_OF_RANGE, "edge endpoint out of range");
+        }
+        if (e > 0 && !(d->edge_start[e - 1] < d->edge_start[e] ||
+                       (d->edge_start[e - 1] == d->edge_start[e] && d->edge_end[e - 1] < d->edge_end[e]))) {
+            return fail(MIO_INVALID_VALUE, "edges must be sorted by (start,end) like Graph::add_edge keeps them");
+        }
+    }
+    for (int k = 0; k < N; ++k) {
+        if ((d->node_pset && (d->node_pset[k] < 0 || d->node_pset[k] >= d->num_psets)) ||
+            (d->node_ctable && (d->node_ctable[k] < 0 || d->node_ctable[k] >= d->num_ctables))) {
+            return fail(MIO_OUT_OF_RANGE, "node parameter-set / contact-table index out of range");
+        }
+    }
+    auto* h     = new mio_handle();
+    h->desc     = *d;
+    h->device   = device;
+    h->max_runs = h->active_runs = d->max_runs;
+    Geometry& geo    = h->geo;
+    geo.G            = G;
+    geo.N            = N;
+    geo.E            = E;
+    geo.n            = n;
+    geo.num_psets    = d->num_psets;
+    geo.num_ctables  = d->num_ctables;
+    geo.ct_max_loc   = d->ct_max_loc;
+    geo.ct_max_pts   = d->ct_max_pts;
+    geo.mob_max_pts  = d->mob_max_pts;
+    geo.pset_stride  = PHDR + AGE_REC * G;
+    geo.ctable_stride = (int)ctable_size(G, d->ct_max_loc, d->ct_max_pts);
+    geo.ct_off       = geo.num_psets * geo.pset_stride;
+    geo.mob_off      = geo.ct_off + geo.num_ctables * geo.ctable_stride;
+    int total        = geo.mob_off + (d->mob_max_pts > 0 ? (int)mobtable_size(n, d->mob_max_pts) : 0);
+    geo.block_stride = (total + 1) & ~1; // cp.async.bulk wants multiples of 16 bytes
+    if ((size_t)geo.block_stride * 8 > 200 * 1024) {
+        delete h;
+        return fail(MIO_OUT_OF_RANGE, "per-run parameter block exceeds the shared memory of one CTA");
+    }
+    h->t    = d->t0;
+    h->day0 = (int)std::ceil(d->t0 - 1e-14);
+
+#define H_TRY(expr)                                                                                                    \
+    do {                                                                                                               \
+        cudaError_t err__ = (expr);                                                                                    \
+        if (err__ != cudaSuccess) {                                                                                    \
+            std::string m = std::string(#expr) + ": " + cudaGetErrorString(err__);                                     \
+            destroy(h);                                                                                                \
+            return fail(MIO_UNKNOWN_ERROR, m);                                                                         \
+        }                                                                                                              \
+    } while (0)
+
+    H_TRY(cudaStreamCreateWithFlags(&h->stream, cudaStreamNonBlocking));
+    // graph
+    if (d->node_pset) {
+        H_TRY(dev_alloc(&h->d_node_pset, (size_t)N));
+        H_TRY(cudaMemcpy(h->d_node_pset, d->node_pset, sizeof(int) * N, cudaMemcpyHostToDevice));
+    }
+    if (d->node_ctable) {
+        H_TRY(dev_alloc(&h->d_node_ctable, (size_t)N));
+        H_TRY(cudaMemcpy(h->d_node_ctable, d->node_ctable, sizeof(int) * N, cudaMemcpyHostToDevice));
+    }
+    if (E > 0) {
+        // incidence lists in global edge order
+        std::vector<int> inc_ptr(N + 1, 0), deg(N, 0);
+        for (int e = 0; e < E; ++e) {
+            ++deg[d->edge_start[e]];
+            ++deg[d->edge_end[e]];
+        }
+        for (int k = 0; k < N; ++k) {
+            inc_ptr[k + 1] = inc_ptr[k] + deg[k];
+        }
+        std::vector<int> fill(inc_ptr.begin(), inc_ptr.end() - 1), inc_edge(2 * E), inc_other(2 * E), inc_out(2 * E);
+        for (int e = 0; e < E; ++e) { // ascending e => every node's list is sorted by e
+            int s = d->edge_start[e], t = d->edge_end[e];
+            inc_edge[fill[s]] = e, inc_other[fill[s]] = t, inc_out[fill[s]] = 1, ++fill[s];
+            inc_edge[fill[t]] = e, inc_other[fill[t]] = s, inc_out[fill[t]] = 0, ++fill[t];
+        }
+        std::vector<int> order(N);
+        std::iota(order.begin(), order.end(), 0);
+        std::stable_sort(order.begin(), order.end(), [&](int a, int b) {
+            return deg[a] > deg[b];
+        });
+        H_TRY(dev_alloc(&h->d_node_order, (size_t)N));
+        H_TRY(dev_alloc(&h->d_inc_ptr, (size_t)N + 1));
+        H_TRY(dev_alloc(&h->d_inc_edge, (size_t)2 * E));
+        H_TRY(dev_alloc(&h->d_inc_other, (size_t)2 * E));
+        H_TRY(dev_alloc(&h->d_inc_out, (size_t)2 * E));
+        H_TRY(dev_alloc(&h->d_edge_start, (size_t)E));
+        H_TRY(dev_alloc(&h->d_edge_end, (size_t)E));
+        H_TRY(dev_alloc(&h->d_coeff, (size_t)E * n));
+        H_TRY(cudaMemcpy(h->d_node_order, order.data(), sizeof(int) * N, cudaMemcpyHostToDevice));
+        H_TRY(cudaMemcpy(h->d_inc_ptr, inc_ptr.data(), sizeof(int) * (N + 1), cudaMemcpyHostToDevice));
+        H_TRY(cudaMemcpy(h->d_inc_edge, inc_edge.data(), sizeof(int) * 2 * E, cudaMemcpyHostToDevice));
+        H_TRY(cudaMemcpy(h->d_inc_other, inc_other.data(), sizeof(int) * 2 * E, cudaMemcpyHostToDevice));
+        H_TRY(cudaMemcpy(h->d_inc_out, inc_out.data(), sizeof(int) * 2 * E, cudaMemcpyHostToDevice));
+        H_TRY(cudaMemcpy(h->d_edge_start, d->edge_start, sizeof(int) * E, cudaMemcpyHostToDevice));
+        H_TRY(cudaMemcpy(h->d_edge_end, d->edge_end, sizeof(int) * E, cudaMemcpyHostToDevice));
+        H_TRY(cudaMemcpy(h->d_coeff, d->edge_coeff, sizeof(double) * (size_t)E * n, cudaMemcpyHostToDevice));
+    }
+    // per-run state
+    const size_t R = (size_t)d->max_runs;
+    H_TRY(dev_alloc(&h->d_run_block, R * geo.block_stride));
+    H_TRY(dev_alloc(&h->d_node_local, R * N * 2));
+    H_TRY(dev_alloc(&h->d_t_node, R * N));
+    H_TRY(dev_alloc(&h->d_dt_node, R * N));
+    H_TRY(dev_alloc(&h->d_counters, R * N * 4));
+    const int nbuf = E > 0 ? 4 : 2;
+    for (int b = 0; b < nbuf; ++b) {
+        H_TRY(dev_alloc(&h->d_y[b], R * N * n));
+    }
+    if (E > 0) {
+        H_TRY(dev_alloc(&h->d_fac, R * N * G));
+        H_TRY(dev_alloc(&h->d_aux, R * N * G * 4));
+        H_TRY(dev_alloc(&h->d_run_flags, R));
+        H_TRY(cudaMemset(h->d_run_flags, 0, sizeof(int) * R));
+        H_TRY(dev_alloc(&h->d_stats, (size_t)4));
+        H_TRY(cudaMemset(h->d_stats, 0, sizeof(long long) * 4));
+    }
+    if (d->record_daily) {
+        if (d->max_days < 1) {
+            destroy(h);
+            return fail(MIO_INVALID_VALUE, "record_daily needs max_days >= 1");
+        }
+        H_TRY(dev_alloc(&h->d_daily, R * N * (size_t)d->max_days * n));
+    }
+    if (d->traj_capacity > 0) {
+        H_TRY(dev_alloc(&h->d_traj_npts, R * N));
+        H_TRY(dev_alloc(&h->d_traj_times, R * N * (size_t)d->traj_capacity));
+        H_TRY(dev_alloc(&h->d_traj_values, R * N * (size_t)d->traj_capacity * n));
+    }
+    H_TRY(cudaMemset(h->d_counters, 0, sizeof(int) * R * N * 4));
+#undef H_TRY
+    // the descriptor's host pointers are not valid after this call
+    h->desc.edge_start = h->desc.edge_end = nullptr;
+    h->desc.edge_coeff                    = nullptr;
+    h->desc.node_pset = h->desc.node_ctable = nullptr;
+    *out = h;
+    return MIO_OK;
+}
+
+void mio_cuda_graph_destroy(mio_handle* h)
+{
+    destroy(h);
+}
+
+int mio_cuda_set_runs(mio_handle* h, int32_t slot0, int32_t count, const mio_run_data* data)
+{
+    if (!h || !data || !data->psets || !data->ctables || !data->node_local || !data->y0) {
+        return fail(MIO_INVALID_VALUE, "null argument");
+    }
+    if (slot0 < 0 || count < 0 || slot0 + count > h->max_runs) {
+        return fail(MIO_OUT_OF_RANGE, "run slots out of range");
+    }
+    if (h->geo.mob_max_pts > 0 && !data->mobtables) {
+        return fail(MIO_INVALID_VALUE, "graph was created with mob_max_pts > 0 but no mobility tables were given");
+    }
+    if (count == 0) {
+        return MIO_OK;
+    }
+    CUDA_TRY(cudaSetDevice(h->device));
+    const Geometry& geo = h->geo;
+    const int G = geo.G, N = geo.N, n = geo.n;
+    const int64_t psz = pset_size(h->desc.model, G);
+    const int64_t csz = geo.ctable_stride;
+    const int64_t msz = geo.mob_max_pts > 0 ? mobtable_size(n, geo.mob_max_pts) : 0;
+    // build the device run blocks: derived parameter sets | contact tables | mobility table
+    std::vector<double> block((size_t)count * geo.block_stride, 0.0);
+    for (int r = 0; r < count; ++r) {
+        double* b = block.data() + (size_t)r * geo.block_stride;
+        for (int p = 0; p < geo.num_psets; ++p) {
+            derive_pset(data->psets + ((size_t)r * geo.num_psets + p) * psz, G, b + p * geo.pset_stride);
+        }
+        std::memcpy(b + geo.ct_off, data->ctables + (size_t)r * geo.num_ctables * csz,
+                    sizeof(double) * geo.num_ctables * csz);
+        for (int c = 0; c < geo.num_ctables; ++c) {
+            const double* ct = b + geo.ct_off + c * csz;
+            const int L      = (int)ct[0];
+            if (L < 1 || L > geo.ct_max_loc) {
+                return fail(MIO_INVALID_VALUE, "contact table: number of locations out of range");
+            }
+            for (int l = 0; l < L; ++l) {
+                if (ct[1 + l] < 0 || ct[1 + l] > geo.ct_max_pts) {
+                    return fail(MIO_INVALID_VALUE, "contact table: number of change points out of range");
+                }
+            }
+        }
+        if (msz > 0) {
+            std::memcpy(b + geo.mob_off, data->mobtables + (size_t)r * msz, sizeof(double) * msz);
+            if (b[geo.mob_off] < 0 || b[geo.mob_off] > geo.mob_max_pts) {
+                return fail(MIO_INVALID_VALUE, "mobility table: number of change points out of range");
+            }
+        }
+    }
+    const size_t s0 = (size_t)slot0;
+    CUDA_TRY(cudaMemcpyAsync(h->d_run_block + s0 * geo.block_stride, block.data(), sizeof(double) * block.size(),
+                             cudaMemcpyHostToDevice, h->stream));
+    CUDA_TRY(cudaMemcpyAsync(h->d_node_local + s0 * N * 2, data->node_local, sizeof(double) * (size_t)count * N * 2,
+                             cudaMemcpyHostToDevice, h->stream));
+    CUDA_TRY(cudaMemcpyAsync(h->d_y[h->cur] + s0 * N * n, data->y0, sizeof(double) * (size_t)count * N * n,
+                             cudaMemcpyHostToDevice, h->stream));
+    std::vector<double> tn((size_t)count * N, h->desc.t0), dtn((size_t)count * N, 0.1);
+    if (data->dt0) {
+        std::copy(data->dt0, data->dt0 + (size_t)count * N, dtn.begin());
+    }
+    for (double v : dtn) {
+        if (!(v > 0.0)) {
+            return fail(MIO_INVALID_VALUE, "initial integrator dt must be positive");
+        }
+    }
+    CUDA_TRY(cudaMemcpyAsync(h->d_t_node + s0 * N, tn.data(), sizeof(double) * tn.size(), cudaMemcpyHostToDevice,
+                             h->stream));
+    CUDA_TRY(cudaMemcpyAsync(h->d_dt_node + s0 * N, dtn.data(), sizeof(double) * dtn.size(), cudaMemcpyHostToDevice,
+                             h->stream));
+    CUDA_TRY(cudaMemsetAsync(h->d_counters + s0 * N * 4, 0, sizeof(int) * (size_t)count * N * 4, h->stream));
+    if (h->d_daily) {
+        // day 0 = initial value (interpolate_simulation_result, analyze_result.h:228-231)
+        std::vector<double> tmp; // strided copy: slot day 0 of each (run,node)
+        const size_t md = (size_t)h->desc.max_days;
+        CUDA_TRY(cudaMemcpy2DAsync(h->d_daily + s0 * N * md * n, sizeof(double) * md * n, data->y0,
+                                   sizeof(double) * n, sizeof(double) * n, (size_t)count * N,
+                                   cudaMemcpyHostToDevice, h->stream));
+        h->days_recorded = std::max(h->days_recorded, 1);
+    }
+    if (h->d_traj_npts) {
+        const size_t cap = (size_t)h->desc.traj_capacity;
+        std::vector<int> one((size_t)count * N, 1);
+        CUDA_TRY(cudaMemcpyAsync(h->d_traj_npts + s0 * N, one.data(), sizeof(int) * one.size(),
+                                 cudaMemcpyHostToDevice, h->stream));
+        CUDA_TRY(cudaMemcpy2DAsync(h->d_traj_times + s0 * N * cap, sizeof(double) * cap, tn.data(), sizeof(double),
+                                   sizeof(double), (size_t)count * N, cudaMemcpyHostToDevice, h->stream));
+        CUDA_TRY(cudaMemcpy2DAsync(h->d_traj_values + s0 * N * cap * n, sizeof(double) * cap * n, data->y0,
+                                   sizeof(double) * n, sizeof(double) * n, (size_t)count * N,
+                                   cudaMemcpyHostToDevice, h->stream));
+    }
+    CUDA_TRY(cudaStreamSynchronize(h->stream));
+    return MIO_OK;
+}
+
+int mio_cuda_set_active_runs(mio_handle* h, int32_t count)
+{
+    if (!h || count < 0 || count > h->max_runs) {
+        return fail(MIO_OUT_OF_RANGE, "active run count out of range");
+    }
+    h->active_runs = count;
+    return MIO_OK;
+}
+
+// GraphSimulation::advance, graph_simulation.h:101-120
+int mio_cuda_advance(mio_handle* h, double t_max)
+{
+    if (!h) {
+        return fail(MIO_INVALID_VALUE, "null handle");
+    }
+    CUDA_TRY(cudaSetDevice(h->device));
+    const Geometry& geo = h->geo;
+    const int R         = h->active_runs;
+    if (R == 0) {
+        return MIO_OK;
+    }
+    double dt = h->desc.dt_graph;
+    while (h->t < t_max) {
+        if (h->t + dt > t_max) {
+            dt = t_max - h->t;
+        }
+        const bool will_depart = geo.E > 0 && !h->toggle;
+        // node phase
+        const int out_idx = free_buffer(h, h->cur, -1, -1);
+        if (out_idx < 0 || !h->d_y[out_idx]) {
+            return fail(MIO_UNKNOWN_ERROR, "internal: no free state buffer");
+        }
+        IntegrateArgs ia;
+        ia.geo        = geo;
+        ia.st         = device_state(h);
+        ia.y_in       = h->d_y[h->cur];
+        ia.y_out      = h->d_y[out_idx];
+        ia.fac_out    = will_depart ? h->d_fac : nullptr;
+        ia.t_end      = h->t + dt;
+        ia.integrator = h->desc.integrator.kind;
+        ia.abs_tol    = h->desc.integrator.abs_tol;
+        ia.rel_tol    = h->desc.integrator.rel_tol;
+        ia.dt_min     = h->desc.integrator.dt_min;
+        ia.dt_max     = h->desc.integrator.dt_max;
+        ia.traj       = TrajectoryBuffers{h->desc.traj_capacity, h->d_traj_npts, h->d_traj_times, h->d_traj_values};
+        ia.num_runs   = R;
+        CUDA_TRY(launch_integrate(ia, h->stream));
+        ++h->launches;
+        h->cur = out_idx;
+        h->t += dt;
+        // edge phase, MobilityEdge::apply_mobility for all edges
+        if (geo.E > 0) {
+            EdgeArgs ea;
+            ea.geo            = geo;
+            ea.st             = device_state(h);
+            ea.inc            = Incidence{h->d_node_order, h->d_inc_ptr,    h->d_inc_edge, h->d_inc_other,
+                                          h->d_inc_out,    h->d_edge_start, h->d_edge_end, h->d_coeff};
+            ea.fac            = h->d_fac;
+            ea.aux            = h->d_aux;
+            ea.run_flags      = h->d_run_flags;
+            ea.stats          = h->d_stats;
+            ea.num_runs       = R;
+            ea.dt             = dt;
+            ea.t              = h->t;
+            ea.daily_out      = nullptr;
+            ea.day_index      = 0;
+            ea.max_days       = 0;
+            if (h->have_mobile && h->return_time <= h->t) {
+                const int ret_idx = free_buffer(h, h->cur, -1, -1);
+                if (ret_idx < 0) {
+                    return fail(MIO_UNKNOWN_ERROR, "internal: no free state buffer");
+                }
+                ea.snap  = h->d_y[h->snap_idx];
+                ea.v0    = h->d_y[h->v0_idx];
+                ea.y_in  = h->d_y[h->cur];
+                ea.y_out = h->d_y[ret_idx];
+                ea.t_dep = h->t_dep;
+                CUDA_TRY(launch_return(ea, h->stream));
+                ++h->launches;
+                // runs that need the order dependent underflow fix-up are replayed literally (the kernel exits
+                // at once for unflagged runs and clears the flag, so no host round trip is needed)
+                CUDA_TRY(launch_return_exact(ea, h->stream));
+                ++h->launches;
+                h->cur         = ret_idx;
+                h->have_mobile = false;
+                h->snap_idx = h->v0_idx = -1;
+            }
+            if (!h->toggle) {
+                if (h->have_mobile) {
+                    return fail(MIO_INVALID_VALUE, "irregular stepping: a second departure before the previous "
+                                                   "commuters returned is not supported");
+                }
+                const int dep_idx = free_buffer(h, h->cur, -1, -1);
+                if (dep_idx < 0) {
+                    return fail(MIO_UNKNOWN_ERROR, "internal: no free state buffer");
+                }
+                ea.snap  = h->d_y[h->cur];
+                ea.v0    = nullptr;
+                ea.y_in  = h->d_y[h->cur];
+                ea.y_out = h->d_y[dep_idx];
+                ea.t_dep = h->t;
+                CUDA_TRY(launch_depart(ea, h->stream));
+                ++h->launches;
+                h->snap_idx    = h->cur;
+                h->v0_idx      = dep_idx;
+                h->cur         = dep_idx;
+                h->have_mobile = true;
+                h->t_dep       = h->t;
+                h->return_time = h->t + dt;
+            }
+            h->toggle = !h->toggle;
+        }
+        // daily record: the value the reference's interpolate_simulation_result yields at integer days
+        if (h->d_daily) {
+            const double day = std::round(h->t);
+            if (std::fabs(h->t - day) <= 1e-10 * std::max(1.0, std::fabs(day))) {
+                const int slot = (int)day - h->day0;
+                if (slot >= 0 && slot < h->desc.max_days) {
+                    CUDA_TRY(launch_record_daily(geo, h->d_y[h->cur], h->d_daily, slot, h->desc.max_days, R,
+                                                 h->stream));
+                    ++h->launches;
+                    h->days_recorded = std::max(h->days_recorded, slot + 1);
+                }
+            }
+        }
+    }
+    CUDA_TRY(cudaStreamSynchronize(h->stream));
+    return MIO_OK;
+}
+
+int mio_cuda_get_time(mio_handle* h, double* t)
+{
+    if (!h || !t) {
+        return fail(MIO_INVALID_VALUE, "null argument");
+    }
+    *t = h->t;
+    return MIO_OK;
+}
+
+static int check_slots(mio_handle* h, int32_t slot0, int32_t count, const void* out)
+{
+    if (!h || !out) {
+        return fail(MIO_INVALID_VALUE, "null argument");
+    }
+    if (slot0 < 0 || count < 0 || slot0 + count > h->max_runs) {
+        return fail(MIO_OUT_OF_RANGE, "run slots out of range");
+    }
+    return MIO_OK;
+}
+
+int mio_cuda_get_state(mio_handle* h, int32_t slot0, int32_t count, double* out)
+{
+    if (int rc = check_slots(h, slot0, count, out)) {
+        return rc;
+    }
+    CUDA_TRY(cudaSetDevice(h->device));
+    const size_t per = (size_t)h->geo.N * h->geo.n;
+    CUDA_TRY(cudaMemcpy(out, h->d_y[h->cur] + (size_t)slot0 * per, sizeof(double) * per * count,
+                        cudaMemcpyDeviceToHost));
+    return MIO_OK;
+}
+
+int mio_cuda_get_node_dt(mio_handle* h, int32_t slot0, int32_t count, double* out)
+{
+    if (int rc = check_slots(h, slot0, count, out)) {
+        return rc;
+    }
+    CUDA_TRY(cudaSetDevice(h->device));
+    CUDA_TRY(cudaMemcpy(out, h->d_dt_node + (size_t)slot0 * h->geo.N, sizeof(double) * (size_t)count * h->geo.N,
+                        cudaMemcpyDeviceToHost));
+    return MIO_OK;
+}
+
+int mio_cuda_get_counters(mio_handle* h, int32_t slot0, int32_t count, int64_t* out)
+{
+    if (int rc = check_slots(h, slot0, count, out)) {
+        return rc;
+    }
+    CUDA_TRY(cudaSetDevice(h->device));
+    const size_t m = (size_t)count * h->geo.N * 4;
+    std::vector<int> tmp(m);
+    CUDA_TRY(cudaMemcpy(tmp.data(), h->d_counters + (size_t)slot0 * h->geo.N * 4, sizeof(int) * m,
+                        cudaMemcpyDeviceToHost));
+    for (size_t i = 0; i < m; ++i) {
+        out[i] = tmp[i];
+    }
+    return MIO_OK;
+}
+
+int mio_cuda_get_daily(mio_handle* h, int32_t slot0, int32_t count, int32_t* num_days, double* out,
+                       int64_t out_capacity)
+{
+    if (int rc = check_slots(h, slot0, count, out)) {
+        return rc;
+    }
+    if (!h->d_daily || !num_days) {
+        return fail(MIO_INVALID_VALUE, "graph was created without record_daily");
+    }
+    CUDA_TRY(cudaSetDevice(h->device));
+    const size_t nd = (size_t)h->days_recorded, md = (size_t)h->desc.max_days, n = (size_t)h->geo.n;
+    const size_t rows = (size_t)count * h->geo.N;
+    if ((int64_t)(rows * nd * n) > out_capacity) {
+        return fail(MIO_OUT_OF_RANGE, "output buffer too small for the daily record");
+    }
+    *num_days = (int32_t)nd;
+    CUDA_TRY(cudaMemcpy2D(out, sizeof(double) * nd * n, h->d_daily + (size_t)slot0 * h->geo.N * md * n,
+                          sizeof(double) * md * n, sizeof(double) * nd * n, rows, cudaMemcpyDeviceToHost));
+    return MIO_OK;
+}
+
+int mio_cuda_get_trajectory(mio_handle* h, int32_t slot0, int32_t count, int32_t* npts, double* times,
+                            double* values)
+{
+    if (int rc = check_slots(h, slot0, count, npts)) {
+        return rc;
+    }
+    if (!h->d_traj_npts || !times || !values) {
+        return fail(MIO_INVALID_VALUE, "graph was created without traj_capacity, or null output");
+    }
+    CUDA_TRY(cudaSetDevice(h->device));
+    const size_t rows = (size_t)count * h->geo.N, cap = (size_t)h->desc.traj_capacity, n = (size_t)h->geo.n;
+    const size_t off = (size_t)slot0 * h->geo.N;
+    CUDA_TRY(cudaMemcpy(npts, h->d_traj_npts + off, sizeof(int) * rows, cudaMemcpyDeviceToHost));
+    CUDA_TRY(cudaMemcpy(times, h->d_traj_times + off * cap, sizeof(double) * rows * cap, cudaMemcpyDeviceToHost));
+    CUDA_TRY(cudaMemcpy(values, h->d_traj_values + off * cap * n, sizeof(double) * rows * cap * n,
+                        cudaMemcpyDeviceToHost));
+    return MIO_OK;
+}
+
+int mio_cuda_get_stats(mio_handle* h, int64_t* launches, int64_t* exact_replays)
+{
+    if (!h) {
+        return fail(MIO_INVALID_VALUE, "null handle");
+    }
+    if (launches) {
+        *launches = h->launches;
+    }
+    if (exact_replays) {
+        *exact_replays = 0;
+        if (h->d_stats) {
+            long long v = 0;
+            CUDA_TRY(cudaSetDevice(h->device));
+            CUDA_TRY(cudaMemcpy(&v, h->d_stats, sizeof(long long), cudaMemcpyDeviceToHost));
+            *exact_replays = v;
+        }
+    }
+    return MIO_OK;
+}
+
+} // extern "C"

@@ -1,0 +1,121 @@
+"""Synthetic Germany-shaped county graph (BASELINE.json configs[2..4], SURVEY.md section 8d "Config 3").
+
+No mobility or population data ships with the reference (data/README.md), so the graph is generated: log-normal
+county populations, gravity-law commuter matrix, the reference's own edge threshold and coefficient formula
+(`set_edges`, cpp/memilio/mobility/graph.h:402-440: coefficient = commuters / working population * age weight for the
+mobile compartments, edge kept iff commuter share > 4e-5).
+"""
+from __future__ import annotations
+
+from typing import Optional
+
+import numpy as np
+
+from . import cdefs, flat
+from .flat import ContactLocation
+from .problem import GraphProblem
+
+AGE_SHARES = np.array([0.047, 0.092, 0.225, 0.345, 0.215, 0.076])
+COMMUTING_WEIGHTS = np.array([0.0, 0.0, 1.0, 1.0, 0.33, 0.0])  # pycode/.../bindings/models/osecir.cpp:194
+MOBILE_COMPARTMENTS = (flat.S, flat.E, flat.INS, flat.ISY, flat.R)  # pycode/.../bindings/models/osecir.cpp:191-193
+
+
+def county_graph(N: int = 400, seed: int = 20261017, max_out_degree: int = 25, G: int = 6,
+                 commuter_share: float = 0.3):
+    """Returns (population[N][G], edge_start, edge_end, edge_coeff[E][G*10]) in reference edge order."""
+    rng = np.random.default_rng(seed)
+    pop_total = np.round(np.exp(rng.normal(11.9, 0.75, N)))
+    shares = AGE_SHARES[:G] / AGE_SHARES[:G].sum()
+    weights = COMMUTING_WEIGHTS[:G] if G == 6 else np.ones(G)
+    pop = pop_total[:, None] * shares[None, :]
+    xy = rng.uniform(0, 1, (N, 2)) * np.array([640.0, 870.0])
+    d = np.linalg.norm(xy[:, None, :] - xy[None, :, :], axis=2)
+    np.fill_diagonal(d, np.inf)
+    working = (pop * weights[None, :]).sum(axis=1)
+    grav = pop_total[:, None] * pop_total[None, :] / np.maximum(d, 5.0) ** 2
+    m = grav / grav.sum(axis=1, keepdims=True) * (commuter_share * working)[:, None]  # absolute commuters i -> j
+    coeff_ij = m / working[:, None]
+    keep = coeff_ij > 4e-5
+    if max_out_degree is not None:
+        for i in range(N):
+            idx = np.flatnonzero(keep[i])
+            if idx.size > max_out_degree:
+                drop = idx[np.argsort(coeff_ij[i, idx])[:-max_out_degree]]
+                keep[i, drop] = False
+    es, ee = np.nonzero(keep)  # row-major => sorted by (start, end)
+    n = G * 10
+    coeff = np.zeros((es.size, n))
+    for a in range(G):
+        for c in MOBILE_COMPARTMENTS:
+            coeff[:, a * 10 + c] = coeff_ij[es, ee] * weights[a]
+    return pop, es.astype(np.int32), ee.astype(np.int32), coeff
+
+
+def covid_midpoint_pset(G: int = 6, seasonality: float = 0.2) -> np.ndarray:
+    """Midpoints of the uniform ranges of set_covid_parameters
+    (cpp/examples/ode_secir_parameter_study_graph.cpp:91-159)."""
+    mid = lambda lo, hi: 0.5 * (np.asarray(hi, dtype=np.float64) + np.asarray(lo, dtype=np.float64))
+    six = lambda a: np.asarray(a, dtype=np.float64)[:G] if G <= 6 else np.resize(a, G)
+    return flat.osecir_pset(
+        G, StartDay=0.0, Seasonality=seasonality,
+        TimeExposed=mid(2.67, 4.0), TimeInfectedNoSymptoms=mid(1.2, 2.53),
+        TimeInfectedSymptoms=six(mid([5.6255, 5.6255, 5.6646, 5.5631, 5.501, 5.465],
+                                     [8.427, 8.427, 8.4684, 8.3139, 8.169, 8.085])),
+        TimeInfectedSevere=six(mid([3.925, 3.925, 4.85, 6.4, 7.2, 9.], [6.075, 6.075, 7., 8.7, 9.8, 13.])),
+        TimeInfectedCritical=six(mid([4.95, 4.95, 4.86, 14.14, 14.4, 10.], [8.95, 8.95, 8.86, 20.58, 19.8, 13.2])),
+        TransmissionProbabilityOnContact=six(mid([0.02, 0.05, 0.05, 0.05, 0.08, 0.15],
+                                                 [0.04, 0.07, 0.07, 0.07, 0.10, 0.20])),
+        RelativeTransmissionNoSymptoms=1.0, RiskOfInfectionFromSymptomatic=mid(0.1, 0.3),
+        MaxRiskOfInfectionFromSymptomatic=mid(0.3, 0.5),
+        RecoveredPerInfectedNoSymptoms=six(mid([0.2, 0.2, 0.15, 0.15, 0.15, 0.15], [0.3, 0.3, 0.25, 0.25, 0.25, 0.25])),
+        SeverePerInfectedSymptoms=six(mid([0.006, 0.006, 0.015, 0.049, 0.15, 0.20],
+                                          [0.009, 0.009, 0.023, 0.074, 0.18, 0.25])),
+        CriticalPerSevere=six(mid([0.05, 0.05, 0.05, 0.10, 0.25, 0.35], [0.10, 0.10, 0.10, 0.20, 0.35, 0.45])),
+        DeathsPerCritical=six(mid([0.00, 0.00, 0.10, 0.10, 0.30, 0.5], [0.10, 0.10, 0.18, 0.18, 0.50, 0.7])))
+
+
+def county_problem(N: int = 400, runs: int = 1, seed: int = 20261017, G: int = 6, max_out_degree: int = 25,
+                   n_seeded: int = 10, contact_damping: Optional[float] = 0.6, damping_day: float = 30.0,
+                   cont_freq: float = 10.0, perturb: float = 0.0, tnt_capacity_factor: float = 7.5e-5,
+                   integrator: Optional[cdefs.IntegratorDesc] = None, dt_graph: float = 0.5) -> GraphProblem:
+    """Config 3 (runs=1) / config 4 shaped inputs. `perturb` > 0 draws run-specific parameters with numpy (uniform
+    +-perturb around the midpoints) -- used by parity tests that only need *some* per-run variation; the bit-exact
+    MEmilio sampling path is memilio_b200.sampling."""
+    pop, es, ee, coeff = county_graph(N, seed, max_out_degree, G)
+    n = G * 10
+    rng = np.random.default_rng(seed + 1)
+    y0 = np.zeros((N, G, 10))
+    y0[:, :, flat.S] = pop
+    seeded = rng.choice(N, size=min(n_seeded, N), replace=False)
+    for k in seeded:
+        e0 = 1e-4 * pop[k]
+        y0[k, :, flat.E] = e0
+        y0[k, :, flat.S] -= e0
+    local = np.zeros((N, 2))
+    local[:, 0] = flat.DBL_MAX  # ICUCapacity default
+    local[:, 1] = pop.sum(axis=1) * tnt_capacity_factor
+    pset = covid_midpoint_pset(G)
+    base = np.full((G, G), cont_freq / G)
+    locs = [ContactLocation(base, None, [damping_day], [np.full((G, G), contact_damping)])] \
+        if contact_damping is not None else [ContactLocation(base)]
+    ct = flat.contact_table(G, locs, 1, 2)
+    psets = np.broadcast_to(pset, (runs, 1, pset.size)).copy()
+    ctables = np.broadcast_to(ct, (runs, 1, ct.size)).copy()
+    locals_ = np.broadcast_to(local, (runs, N, 2)).copy()
+    y0s = np.broadcast_to(y0.reshape(N, n), (runs, N, n)).copy()
+    if perturb > 0.0:
+        prng = np.random.default_rng(seed + 2)
+        rec = psets[:, 0, flat.PSET_HEADER:].reshape(runs, G, flat.OSECIR_AGE_STRIDE)
+        rec[:, :, :14] *= prng.uniform(1 - perturb, 1 + perturb, (runs, G, 14))
+        psets[:, 0, flat.PH["Seasonality"]] = prng.uniform(0.1, 0.3, runs)
+        locals_[:, :, 1] *= prng.uniform(0.8, 1.2, (runs, N))
+        y0s *= prng.uniform(0.9, 1.1, (runs, N, n))
+        if contact_damping is not None:
+            for r in range(runs):
+                d = prng.uniform(0.4, 0.8)
+                ctables[r, 0] = flat.contact_table(
+                    G, [ContactLocation(base, None, [damping_day], [np.full((G, G), d)])], 1, 2)
+    return GraphProblem(model=flat.MODEL_OSECIR, num_groups=G, num_nodes=N, edge_start=es, edge_end=ee,
+                        edge_coeff=coeff, psets=psets, ctables=ctables, node_local=locals_, y0=y0s, ct_max_loc=1,
+                        ct_max_pts=2, integrator=integrator if integrator is not None else cdefs.integrator_desc(),
+                        t0=0.0, dt_graph=dt_graph)

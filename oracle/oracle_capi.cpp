@@ -267,4 +267,26 @@ int orc_graph_simulate(const mio_graph_desc* desc, const mio_run_data* run, doub
     return steps;
 }
 
+// The call sequence of TestMobility.edgeApplyMobility (cpp/tests/test_mobility.cpp:154-215): two identical G=1 nodes,
+// one edge with coefficient vector coeff[n]; apply_mobility at t (departure), advance both nodes by dt, apply_mobility
+// (return), advance, apply_mobility (departure again). out[3][2][n] = node1/node2 last values after each apply.
+void orc_edge_apply_sequence(int G, const double* pset, const double* local, const double* ct, int max_loc,
+                             int max_pts, const double* y0, const double* coeff, double t, double dt, double* out)
+{
+    auto m      = osecir_from_flat(G, pset, local, ct, max_loc, max_pts, y0);
+    const int n = G * osecir::NC;
+    SimulationNode<osecir::Model> node1(m, t), node2(m, t);
+    MobilityEdge edge(Vec(coeff, coeff + n));
+    for (int phase = 0; phase < 3; ++phase) {
+        if (phase > 0) {
+            node1.advance(t, dt);
+            node2.advance(t, dt);
+            t += dt;
+        }
+        edge.apply_mobility(t, dt, node1, node2);
+        std::copy(node1.sim.result.last().begin(), node1.sim.result.last().end(), out + (phase * 2 + 0) * n);
+        std::copy(node2.sim.result.last().begin(), node2.sim.result.last().end(), out + (phase * 2 + 1) * n);
+    }
+}
+
 } // extern "C"

@@ -94,3 +94,13 @@ def graph_simulate(p: GraphProblem, run: int, t_max: float, halfsteps: int = 0):
                                      cdefs.lptr(cnt), cdefs.dptr(hs) if halfsteps else None, halfsteps)
     assert steps >= 0
     return dict(state=state, dt=dt, counters=cnt, steps=steps, halfsteps=hs[:min(steps, halfsteps)])
+
+
+def edge_apply_sequence(G, pset, local, ct, max_loc, max_pts, y0, coeff, t, dt):
+    n = G * 10
+    out = np.zeros((3, 2, n))
+    args = [np.ascontiguousarray(a, dtype=np.float64) for a in (pset, local, ct, y0, coeff)]
+    lib().orc_edge_apply_sequence(G, cdefs.dptr(args[0]), cdefs.dptr(args[1]), cdefs.dptr(args[2]), max_loc, max_pts,
+                                  cdefs.dptr(args[3]), cdefs.dptr(args[4]), C.c_double(t), C.c_double(dt),
+                                  cdefs.dptr(out))
+    return out

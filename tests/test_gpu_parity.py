@@ -1,0 +1,129 @@
+"""Parity of the CUDA path (through the C-ABI) against the CPU oracle and the reference's golden vectors.
+Tolerance: compartment trajectories within 1e-8 relative (FP64, same tableau and step control); accepted / rejected
+step counts equal (BASELINE.json north_star)."""
+import numpy as np
+import pytest
+
+import oracle_lib
+import scenarios
+from memilio_b200 import capi, flat, synthetic
+
+pytestmark = pytest.mark.gpu
+
+RTOL = 1e-8
+
+
+def assert_close(a, b, rtol=RTOL, atol=1e-9, what=""):
+    a = np.asarray(a)
+    b = np.asarray(b)
+    err = np.abs(a - b) - (atol + rtol * np.abs(b))
+    assert np.all(err <= 0), f"{what}: max violation {err.max():.3e} at {np.unravel_index(err.argmax(), err.shape)}"
+
+
+@pytest.mark.parametrize("name", list(scenarios.GOLDEN_CASES))
+def test_single_node_trajectories_match_golden_and_oracle(name):
+    s = scenarios.golden_case(name)
+    p = scenarios.golden_problem(name)
+    t_o, y_o, dt_o, cnt_o = oracle_lib.simulate(s["G"], s["pset"], s["local"], s["ct"], s["ct_max_loc"],
+                                                s["ct_max_pts"], s["y0"], s["t0"], s["tmax"], s["dt0"],
+                                                s["integrator"])
+    with capi.GraphSimulation(p, traj_capacity=128) as sim:
+        sim.advance(s["tmax"])
+        npts, times, values = sim.trajectory()
+        cnt = sim.counters()[0, 0]
+        dt = sim.node_dt()[0, 0]
+    n = int(npts[0, 0])
+    ref = s["csv"]
+    # identical accepted step count = identical number of time points as the reference's golden file
+    assert n == ref.shape[0] == len(t_o)
+    assert cnt[0] == cnt_o[0] and cnt[1] == cnt_o[1] and cnt[2] == cnt_o[2]
+    np.testing.assert_allclose(times[0, 0, :n], ref[:, 0], rtol=0, atol=1e-10)
+    ys = scenarios.age_sum(values[0, 0, :n], s["G"])
+    np.testing.assert_allclose(ys, ref[:, 1:], rtol=0, atol=max(s["tol"], 1e-9))
+    assert_close(values[0, 0, :n], y_o, what="trajectory vs oracle")
+    assert_close(times[0, 0, :n], t_o, rtol=1e-12, atol=1e-12, what="time points vs oracle")
+    assert abs(dt - dt_o) <= 1e-9 * abs(dt_o)
+
+
+def test_example_ode_secir_graph_every_half_day():
+    # BASELINE config 2: cpp/examples/ode_secir_graph.cpp
+    p = scenarios.example_ode_secir_graph()
+    ref = oracle_lib.graph_simulate(p, 0, 30.0, halfsteps=60)
+    with capi.GraphSimulation(p) as sim:
+        for k in range(60):
+            sim.advance(0.5 * (k + 1))
+            assert_close(sim.state()[0], ref["halfsteps"][k], what=f"state after graph step {k}")
+        cnt = sim.counters()[0]
+        assert sim.t == 30.0
+        np.testing.assert_array_equal(cnt[:, :3], ref["counters"][:, :3])
+        np.testing.assert_array_equal(cnt[:, 3], ref["counters"][:, 3])
+        assert_close(sim.node_dt()[0], ref["dt"], rtol=1e-8, what="node dt")
+
+
+def test_example_graph_single_advance_equals_stepwise():
+    p = scenarios.example_ode_secir_graph()
+    ref = oracle_lib.graph_simulate(p, 0, 30.0)
+    with capi.GraphSimulation(p) as sim:
+        sim.advance(30.0)
+        assert_close(sim.state()[0], ref["state"], what="final state")
+
+
+@pytest.mark.parametrize("G,N", [(6, 40), (3, 25), (1, 37), (2, 16)])
+def test_county_graph_ensemble_matches_oracle(G, N):
+    # a small Germany-shaped graph, several runs with different parameters, seeded so that the first days hit the
+    # return-phase underflow fix-up (order dependent path) and the contact damping ramp at day 5
+    runs = 5
+    p = synthetic.county_problem(N=N, runs=runs, G=G, max_out_degree=8, n_seeded=3, damping_day=5.0, perturb=0.1)
+    tmax = 12.0
+    with capi.GraphSimulation(p, record_daily=True, max_days=13) as sim:
+        sim.advance(tmax)
+        state = sim.state()
+        cnt = sim.counters()
+        dts = sim.node_dt()
+        daily = sim.daily()
+        st = sim.stats()
+    assert daily.shape == (runs, N, 13, p.n)
+    total_underflow = 0
+    for r in range(runs):
+        ref = oracle_lib.graph_simulate(p, r, tmax, halfsteps=24)
+        assert_close(state[r], ref["state"], what=f"run {r} final state")
+        np.testing.assert_array_equal(cnt[r][:, :3], ref["counters"][:, :3])
+        np.testing.assert_array_equal(cnt[r][:, 3], ref["counters"][:, 3])
+        assert_close(dts[r], ref["dt"], rtol=1e-7, what="node dt")
+        # daily record = state after the edge phase at integer days (what interpolate_simulation_result returns)
+        np.testing.assert_array_equal(daily[r][:, 0], p.y0[r])
+        for d in range(1, 13):
+            assert_close(daily[r][:, d], ref["halfsteps"][2 * d - 1], what=f"run {r} day {d}")
+        total_underflow += int(ref["counters"][:, 3].sum())
+        # population is conserved by construction of the exchange
+        assert abs(state[r].sum() - p.y0[r].sum()) < 1e-6 * p.y0[r].sum()
+    if G == 6:
+        assert total_underflow > 0 and st["exact_replays"] > 0  # the order dependent path was exercised
+
+
+def test_full_size_county_graph_single_run():
+    # BASELINE config 3: 400 counties, ~10k edges, one run, 100 days
+    p = synthetic.county_problem(N=400, runs=1)
+    assert p.num_edges == 10000
+    ref = oracle_lib.graph_simulate(p, 0, 100.0)
+    with capi.GraphSimulation(p) as sim:
+        sim.advance(100.0)
+        state = sim.state()[0]
+        cnt = sim.counters()[0]
+    assert_close(state, ref["state"], what="config 3 final state")
+    mism = int((cnt[:, :3] != ref["counters"][:, :3]).any(axis=1).sum())
+    assert mism == 0, f"{mism} nodes with different accepted/rejected/forced step counts"
+    np.testing.assert_array_equal(cnt[:, 3], ref["counters"][:, 3])
+
+
+def test_error_behaviour():
+    p = scenarios.example_ode_secir_graph()
+    with capi.GraphSimulation(p) as sim:
+        with pytest.raises(capi.MioCudaError) as e:
+            sim.set_runs(1, p, 0, 1)  # slot out of range
+        assert e.value.code == 2
+    p.edge_start[:] = [1, 0]
+    p.edge_end[:] = [0, 1]
+    with pytest.raises(capi.MioCudaError) as e:
+        capi.GraphSimulation(p)  # edges not in reference order
+    assert e.value.code == 3
