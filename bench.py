@@ -1,0 +1,318 @@
+#!/usr/bin/env python
+"""bench.py -- Graph-ODE-SECIR ensemble throughput on B200 (BASELINE.json metric: node-days/s = runs x counties x days).
+
+One "step" = one pass of the hot path over one batch: R runs of the synthetic 400-county ODE-SECIR graph (6 age groups,
+~10k commuter edges, dt 0.5) advanced over T days with GraphSimulation::advance semantics (adaptive Cash-Karp node
+integration + commuter departure/return). `value` times the device work with the inputs resident in HBM; `e2e` times the
+same step through the C-ABI with host buffers (H2D of the sampled runs, advance, D2H of the result).
+
+    python bench.py [--gpus N] [--steps K] [--warmup W] [--impl reference]
+
+For N > 1 launch under torchrun (one rank per GPU); runs shard over ranks with no data-path collective ("weak").
+`--impl reference` times the reference's CPU path (the oracle port of it, see oracle/) on the host cores.
+"""
+from __future__ import annotations
+
+import argparse
+import json
+import os
+import subprocess
+import sys
+import threading
+import time
+
+import numpy as np
+
+ROOT = os.path.dirname(os.path.abspath(__file__))
+sys.path.insert(0, ROOT)
+
+# algorithmic work per unit, see DESIGN.md "Roofline"
+FLOP_PER_CK54_ATTEMPT = 7.7e3  # 6 RHS (650) + stage axpys (1800) + solution (720) + error (720) + norm (540)
+EDGE_BYTES_PER_RUN_DAY = 10.8e6  # explicit traveler state, N=400, E=10000, n=60
+
+
+def parse():
+    ap = argparse.ArgumentParser()
+    ap.add_argument("--gpus", type=int, default=1)
+    ap.add_argument("--steps", type=int, default=3)
+    ap.add_argument("--warmup", type=int, default=3)
+    ap.add_argument("--impl", default="b200", choices=["b200", "reference"])
+    ap.add_argument("--runs", type=int, default=10000, help="ensemble runs per GPU (weak scaling)")
+    ap.add_argument("--days", type=float, default=100.0)
+    ap.add_argument("--nodes", type=int, default=400)
+    ap.add_argument("--cpu-sample-runs", type=int, default=0, help="runs of the CPU baseline sample (0 = one per core)")
+    ap.add_argument("--no-cpu-baseline", action="store_true")
+    return ap.parse_args()
+
+
+class ClockSampler:
+    """Samples nvidia-smi clocks / throttle reasons during the timed region (B200_PROFILING.md clocks line)."""
+    Q = ("index,clocks.sm,clocks.max.sm,power.draw,clocks_event_reasons.active,clocks_event_reasons.hw_slowdown,"
+         "clocks_event_reasons.hw_thermal_slowdown,clocks_event_reasons.sw_thermal_slowdown,"
+         "clocks_event_reasons.sw_power_cap")
+
+    def __init__(self, device):
+        self.device = device
+        self.lines = []
+        self.proc = None
+
+    def start(self):
+        try:
+            self.proc = subprocess.Popen(["nvidia-smi", f"--id={self.device}", f"--query-gpu={self.Q}",
+                                          "--format=csv,noheader,nounits", "-lms", "200"], stdout=subprocess.PIPE,
+                                         stderr=subprocess.DEVNULL, text=True)
+            self.thread = threading.Thread(target=self._read, daemon=True)
+            self.thread.start()
+        except OSError:
+            self.proc = None
+
+    def _read(self):
+        for line in self.proc.stdout:
+            self.lines.append(line.strip())
+
+    def stop(self):
+        if not self.proc:
+            return {"sm_mhz": None, "sm_max_mhz": None, "reasons": ["unavailable"]}
+        self.proc.terminate()
+        try:
+            self.proc.wait(timeout=2)
+        except subprocess.TimeoutExpired:
+            self.proc.kill()
+        sm, smax, reasons = [], [], set()
+        for ln in self.lines:
+            f = [x.strip() for x in ln.split(",")]
+            if len(f) < 9:
+                continue
+            try:
+                sm.append(float(f[1]))
+                smax.append(float(f[2]))
+            except ValueError:
+                continue
+            for name, v in zip(("hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"), f[5:9]):
+                if v.lower().startswith("active"):
+                    reasons.add(name)
+        busy = [c for c in sm if c > 0]
+        return {"sm_mhz": float(np.median(busy)) if busy else None, "sm_max_mhz": max(smax) if smax else None,
+                "reasons": sorted(reasons), "samples": len(sm)}
+
+
+def workload_config(args):
+    return {"workload": f"ParameterStudy ensemble, synthetic {args.nodes}-county ODE-SECIR graph "
+                        f"(BASELINE configs[3]): {args.runs} runs/GPU x {args.nodes} counties x {args.days:g} days",
+            "runs_per_gpu": args.runs, "counties": args.nodes, "edges": None, "age_groups": 6, "days": args.days,
+            "dt_graph": 0.5, "integrator": "cash_karp54 abs 1e-10 rel 1e-5", "parallelism": f"runs sharded x{args.gpus}",
+            "l2_policy": "inputs larger than L2 (state 4 x %.2f GB per GPU)" % (args.runs * args.nodes * 480 / 1e9)}
+
+
+def cpu_baseline(problem, days, sample_runs, threads):
+    """The reference's CPU path (oracle port) on the host cores: `sample_runs` runs partitioned over `threads`
+    workers like distribute_runs (parameter_studies.h:354-367). Returns (node-days/s, seconds)."""
+    sys.path.insert(0, os.path.join(ROOT, "tests"))
+    import oracle_lib
+    from concurrent.futures import ThreadPoolExecutor
+    oracle_lib.lib()
+    runs = [r % problem.num_runs for r in range(sample_runs)]
+    t0 = time.perf_counter()
+    with ThreadPoolExecutor(max_workers=threads) as ex:  # ctypes releases the GIL during the call
+        list(ex.map(lambda r: oracle_lib.graph_simulate(problem, r, days)["steps"], runs))
+    dt = time.perf_counter() - t0
+    return sample_runs * problem.num_nodes * days / dt, dt
+
+
+def run_reference(args, rank, world):
+    """--impl reference: the reference's own CPU implementation of the path (oracle port; the reference itself
+    cannot be built here) on all host threads. Rank 0 only."""
+    if rank != 0:
+        return
+    from memilio_b200 import synthetic
+    cores = os.cpu_count() or 1
+    sample = args.cpu_sample_runs or cores
+    problem = synthetic.county_problem(N=args.nodes, runs=max(sample, 1), perturb=0.1)
+    for _ in range(min(args.warmup, 1)):
+        cpu_baseline(problem, min(args.days, 2.0), cores, cores)
+    vals, secs = [], []
+    for _ in range(args.steps):
+        v, s = cpu_baseline(problem, args.days, sample, cores)
+        vals.append(v)
+        secs.append(s)
+    value = float(np.sum(sample * args.nodes * args.days * len(vals)) / np.sum(secs))
+    cfg = workload_config(args)
+    cfg["edges"] = problem.num_edges
+    sample_txt = f"{sample} runs x {args.nodes} counties x {args.days:g} days per step over {cores} threads"
+    print(json.dumps({
+        "impl": "reference", "metric": "graph_ode_secir_node_days_per_s", "value": value, "unit": "node-days/s",
+        "n_gpus": args.gpus, "steps": args.steps, "warmup": args.warmup, "ms_per_step": 1e3 * float(np.mean(secs)),
+        "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "f64", "data": "synthetic",
+        "config": cfg,
+        "cpu_baseline": {"value": value, "unit": "node-days/s", "cores": cores, "kind": "port", "sample": sample_txt},
+        "e2e": {"value": value, "unit": "node-days/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
+        "gpu_launches": 0}))
+
+
+def main():
+    args = parse()
+    rank = int(os.environ.get("RANK", "0"))
+    world = int(os.environ.get("WORLD_SIZE", "1"))
+    local_rank = int(os.environ.get("LOCAL_RANK", "0"))
+    if args.impl == "reference":
+        run_reference(args, rank, world)
+        return
+
+    import torch
+    import torch.distributed as dist
+    from memilio_b200 import capi, synthetic
+    if not torch.cuda.is_available():
+        raise SystemExit("bench.py needs a CUDA device: the B200 path has no CPU fallback")
+    torch.cuda.set_device(local_rank)
+    if world > 1:
+        dist.init_process_group("nccl", device_id=torch.device("cuda", local_rank))
+
+    def barrier():
+        if world > 1:
+            dist.barrier()
+        torch.cuda.synchronize()
+
+    R, N, T = args.runs, args.nodes, args.days
+    # synthetic inputs of the benchmark shape; every rank owns a distinct block of runs (seed offset by rank)
+    problem = synthetic.county_problem(N=N, runs=R, perturb=0.1, seed=20261017)
+    if rank > 0:
+        rr = np.random.default_rng(1000 + rank)
+        problem.y0 *= rr.uniform(0.95, 1.05, (R, 1, 1))
+    # pinned host staging for the e2e leg
+    pinned = {}
+    for name in ("y0", "node_local", "psets", "ctables"):
+        a = getattr(problem, name)
+        tns = torch.empty(a.shape, dtype=torch.float64).pin_memory()
+        tns.numpy()[...] = a
+        pinned[name] = tns
+        setattr(problem, name, tns.numpy())
+    out_pinned = torch.empty((R, N, problem.n), dtype=torch.float64).pin_memory()
+
+    sim = capi.GraphSimulation(problem, device=local_rank, max_runs=R, upload=False)
+    stream = torch.cuda.ExternalStream(sim.stream_ptr(), device=torch.device("cuda", local_rank))
+    from memilio_b200 import cdefs
+
+    def fresh():
+        """rewind the handle to t0 and upload the runs (H2D) -- untimed for `value`, timed for `e2e`"""
+        sim.reset()
+        sim.set_runs(0, problem, 0, R)
+
+    h2d = problem.y0.nbytes + problem.node_local.nbytes + problem.psets.nbytes + problem.ctables.nbytes
+    d2h = out_pinned.numel() * 8
+
+    def step_device():
+        fresh()
+        torch.cuda.synchronize()
+        e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        e0.record(stream)
+        sim.advance(T)
+        e1.record(stream)
+        e1.synchronize()
+        return e0.elapsed_time(e1)
+
+    def step_e2e():
+        t0 = time.perf_counter()
+        fresh()
+        sim.advance(T)
+        capi._check(capi.lib().mio_cuda_get_state(sim._h, 0, R, cdefs.dptr(out_pinned.numpy())))
+        torch.cuda.synchronize()
+        return (time.perf_counter() - t0) * 1e3
+
+    for _ in range(args.warmup):
+        step_device()
+    # ---- timed: device leg -------------------------------------------------------------------------------------
+    sim.set_profiling(False)
+    clocks = ClockSampler(local_rank)
+    barrier()
+    clocks.start()
+    ms_dev = []
+    prof = None
+    launches = 0
+    attempts = 0
+    for k in range(args.steps):
+        fresh()
+        sim.set_profiling(True)
+        torch.cuda.synchronize()
+        e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        e0.record(stream)
+        sim.advance(T)
+        e1.record(stream)
+        e1.synchronize()
+        ms_dev.append(e0.elapsed_time(e1))
+        p = sim.profile()
+        prof = p if prof is None else {c: (prof[c][0] + p[c][0], prof[c][1] + p[c][1]) for c in p}
+        launches += sum(v[1] for v in p.values())
+        cnt = sim.counters()
+        attempts += int(cnt[:, :, 0].sum() + cnt[:, :, 1].sum())
+    barrier()
+    clock_info = clocks.stop()
+    replays = sim.stats()["exact_replays"]
+    # ---- timed: end-to-end leg (host buffers in, result out) --------------------------------------------------------
+    step_e2e()
+    barrier()
+    ms_e2e = [step_e2e() for _ in range(args.steps)]
+    barrier()
+
+    t_dev = torch.tensor([float(np.sum(ms_dev)), float(np.sum(ms_e2e))], device="cuda", dtype=torch.float64)
+    agg = torch.tensor([float(attempts), float(launches)], device="cuda", dtype=torch.float64)
+    if world > 1:
+        dist.all_reduce(t_dev, op=dist.ReduceOp.MAX)
+        dist.all_reduce(agg, op=dist.ReduceOp.SUM)
+    tot_dev_ms, tot_e2e_ms = [float(x) for x in t_dev.tolist()]
+    units = world * R * N * T * args.steps
+    value = units / (tot_dev_ms * 1e-3)
+    e2e = units / (tot_e2e_ms * 1e-3)
+
+    if rank == 0:
+        peaks = {}
+        if os.path.exists(os.path.join(ROOT, "MEASURED_PEAKS.json")):
+            with open(os.path.join(ROOT, "MEASURED_PEAKS.json")) as f:
+                peaks = json.load(f)
+        hbm_peak = peaks.get("hbm_gbs", 6650.0)
+        hbm_src = "measured (MEASURED_PEAKS.json)" if "hbm_gbs" in peaks else "fallback"
+        fp64_peak = capi.measure_fp64_peak(local_rank, 0.5)
+        kernel_ms = {c: prof[c][0] / args.steps for c in prof}
+        dominant = max(kernel_ms, key=kernel_ms.get)
+        integ_s = prof["integrate"][0] * 1e-3
+        att_rank0 = attempts
+        fp64_achieved = att_rank0 * FLOP_PER_CK54_ATTEMPT / integ_s / 1e12 if integ_s > 0 else 0.0
+        edge_s = (prof["depart"][0] + prof["return"][0] + prof["return_exact"][0]) * 1e-3
+        edge_gbs = EDGE_BYTES_PER_RUN_DAY * R * T * args.steps / edge_s / 1e9 if edge_s > 0 else 0.0
+        roof_fp64 = {"kernel": "integrate_nodes_kernel", "bound": "fp64", "achieved": fp64_achieved, "peak": fp64_peak,
+                     "unit": "TFLOP/s", "frac": fp64_achieved / fp64_peak if fp64_peak else None, "traffic": None,
+                     "peak_source": "measured in this run (DFMA chains, mio_cuda_measure_fp64_peak)",
+                     "attempts_per_launch": att_rank0 / max(prof["integrate"][1], 1),
+                     "flop_per_attempt": FLOP_PER_CK54_ATTEMPT}
+        roof_edge = {"kernel": "depart_kernel+return_kernel", "bound": "hbm", "achieved": edge_gbs, "peak": hbm_peak,
+                     "unit": "GB/s", "frac": edge_gbs / hbm_peak, "traffic": None, "peak_source": hbm_src,
+                     "algorithmic_bytes_per_run_day": EDGE_BYTES_PER_RUN_DAY}
+        line = {
+            "metric": "graph_ode_secir_node_days_per_s", "value": value, "unit": "node-days/s", "n_gpus": world,
+            "steps": args.steps, "warmup": args.warmup, "ms_per_step": tot_dev_ms / args.steps,
+            "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "f64", "data": "synthetic",
+            "config": dict(workload_config(args), edges=problem.num_edges),
+            "e2e": {"value": e2e, "unit": "node-days/s", "h2d_bytes_per_step": int(h2d), "d2h_bytes_per_step": int(d2h),
+                    "ms_per_step": tot_e2e_ms / args.steps},
+            "gpu_launches": int(agg[1].item()),
+            "clocks": clock_info,
+            "roofline": roof_edge if dominant in ("depart", "return", "return_exact") else roof_fp64,
+            "roofline_node_phase": roof_fp64, "roofline_edge_phase": roof_edge,
+            "kernel_ms_per_step": kernel_ms, "dominant_kernel": dominant,
+            "rk_attempts_per_node_day": float(agg[0].item()) / units,
+            "exact_return_replays": int(replays),
+        }
+        if not args.no_cpu_baseline:
+            cores = os.cpu_count() or 1
+            sample = args.cpu_sample_runs or cores
+            v, s = cpu_baseline(problem, T, sample, cores)
+            line["cpu_baseline"] = {"value": v, "unit": "node-days/s", "cores": cores, "kind": "port",
+                                    "sample": f"{sample} runs x {N} counties x {T:g} days over {cores} threads "
+                                              f"({s:.1f} s)"}
+        print(json.dumps(line))
+    sim.close()
+    if world > 1:
+        dist.destroy_process_group()
+
+
+if __name__ == "__main__":
+    main()

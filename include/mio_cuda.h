@@ -187,6 +187,8 @@ MIO_API void mio_cuda_graph_destroy(mio_handle* h);
 
 /* (re)initialise run slots [slot0, slot0+count): parameters, initial state, t = t0 */
 MIO_API int mio_cuda_set_runs(mio_handle* h, int32_t slot0, int32_t count, const mio_run_data* data);
+/* rewind the simulation clock and the edges' departure/return toggle to t0; follow with set_runs for every slot */
+MIO_API int mio_cuda_reset(mio_handle* h);
 /* number of slots that take part in advance() (default max_runs) */
 MIO_API int mio_cuda_set_active_runs(mio_handle* h, int32_t count);
 
@@ -210,6 +212,23 @@ MIO_API int mio_cuda_get_trajectory(mio_handle* h, int32_t slot0, int32_t count,
 /* statistics: kernels launched by this handle so far; (run, step) pairs whose return phase needed the literal
  * in-order replay because of underflow fix-ups */
 MIO_API int mio_cuda_get_stats(mio_handle* h, int64_t* launches, int64_t* exact_replays);
+
+/* ---- measurement hooks ------------------------------------------------------------------------------------------ */
+#define MIO_NUM_KERNEL_CLASSES 5
+#define MIO_KC_INTEGRATE 0    /* node phase: adaptive RK integration of every (run, node) */
+#define MIO_KC_DEPART 1       /* edge phase: commuter departure gather */
+#define MIO_KC_RETURN 2       /* edge phase: commuter return gather (optimistic) */
+#define MIO_KC_RETURN_EXACT 3 /* edge phase: in-order replay of runs with underflow fix-ups */
+#define MIO_KC_RECORD 4       /* daily record copy */
+/* the CUDA stream (cudaStream_t) all kernels of this handle are launched on */
+MIO_API int mio_cuda_get_stream(mio_handle* h, void** stream);
+/* per-kernel-class device time, measured with CUDA events on that stream while profiling is on; resets the sums */
+MIO_API int mio_cuda_set_profiling(mio_handle* h, int on);
+MIO_API int mio_cuda_get_profile(mio_handle* h, double* ms /*[5]*/, int64_t* launches /*[5]*/);
+/* device pointer of the live node state [max_runs][N][n] (valid until the next advance) */
+MIO_API int mio_cuda_device_state_ptr(mio_handle* h, void** y, int64_t* num_doubles);
+/* sustained FP64 FMA throughput of the device (DFMA chains on all SMs), the roofline denominator of the node phase */
+MIO_API int mio_cuda_measure_fp64_peak(int device, double seconds, double* tflops);
 
 #ifdef __cplusplus
 }

@@ -20,10 +20,12 @@ _LIB = None
 EXPORTS = [
     "mio_cuda_last_error_string", "mio_cuda_version", "mio_cuda_device_count", "mio_num_compartments",
     "mio_pset_age_stride", "mio_pset_size", "mio_ctable_size", "mio_mobtable_size", "mio_cuda_graph_create",
-    "mio_cuda_graph_destroy", "mio_cuda_set_runs", "mio_cuda_set_active_runs", "mio_cuda_advance", "mio_cuda_get_time",
+    "mio_cuda_graph_destroy", "mio_cuda_reset", "mio_cuda_set_runs", "mio_cuda_set_active_runs", "mio_cuda_advance", "mio_cuda_get_time",
     "mio_cuda_get_state", "mio_cuda_get_node_dt", "mio_cuda_get_counters", "mio_cuda_get_daily",
-    "mio_cuda_get_trajectory", "mio_cuda_get_stats",
+    "mio_cuda_get_trajectory", "mio_cuda_get_stats", "mio_cuda_get_stream", "mio_cuda_set_profiling",
+    "mio_cuda_get_profile", "mio_cuda_device_state_ptr", "mio_cuda_measure_fp64_peak",
 ]
+KERNEL_CLASSES = ["integrate", "depart", "return", "return_exact", "record"]
 
 
 class MioCudaError(RuntimeError):
@@ -46,6 +48,7 @@ def lib():
         L.mio_cuda_graph_destroy.restype = None
         L.mio_cuda_set_runs.argtypes = [C.c_void_p, C.c_int32, C.c_int32, C.POINTER(cdefs.RunData)]
         L.mio_cuda_set_active_runs.argtypes = [C.c_void_p, C.c_int32]
+        L.mio_cuda_reset.argtypes = [C.c_void_p]
         L.mio_cuda_advance.argtypes = [C.c_void_p, C.c_double]
         L.mio_cuda_get_time.argtypes = [C.c_void_p, C.POINTER(C.c_double)]
         L.mio_cuda_get_state.argtypes = [C.c_void_p, C.c_int32, C.c_int32, cdefs.c_double_p]
@@ -56,6 +59,11 @@ def lib():
         L.mio_cuda_get_trajectory.argtypes = [C.c_void_p, C.c_int32, C.c_int32, cdefs.c_int32_p, cdefs.c_double_p,
                                               cdefs.c_double_p]
         L.mio_cuda_get_stats.argtypes = [C.c_void_p, cdefs.c_int64_p, cdefs.c_int64_p]
+        L.mio_cuda_get_stream.argtypes = [C.c_void_p, C.POINTER(C.c_void_p)]
+        L.mio_cuda_set_profiling.argtypes = [C.c_void_p, C.c_int]
+        L.mio_cuda_get_profile.argtypes = [C.c_void_p, cdefs.c_double_p, cdefs.c_int64_p]
+        L.mio_cuda_device_state_ptr.argtypes = [C.c_void_p, C.POINTER(C.c_void_p), C.POINTER(C.c_int64)]
+        L.mio_cuda_measure_fp64_peak.argtypes = [C.c_int, C.c_double, C.POINTER(C.c_double)]
         _LIB = L
     return _LIB
 
@@ -84,6 +92,9 @@ class GraphSimulation:
     def set_runs(self, slot0: int, problem: GraphProblem, run0: int, count: int):
         rd = problem.run_data(run0, count)
         _check(lib().mio_cuda_set_runs(self._h, slot0, count, C.byref(rd)))
+
+    def reset(self):
+        _check(lib().mio_cuda_reset(self._h))
 
     def set_active_runs(self, count: int):
         _check(lib().mio_cuda_set_active_runs(self._h, count))
@@ -140,6 +151,28 @@ class GraphSimulation:
         _check(lib().mio_cuda_get_stats(self._h, cdefs.lptr(a), cdefs.lptr(b)))
         return dict(launches=int(a[0]), exact_replays=int(b[0]))
 
+    def stream_ptr(self) -> int:
+        """cudaStream_t of the handle (wrap with torch.cuda.ExternalStream to time with torch events)."""
+        sp = C.c_void_p()
+        _check(lib().mio_cuda_get_stream(self._h, C.byref(sp)))
+        return int(sp.value or 0)
+
+    def set_profiling(self, on: bool):
+        _check(lib().mio_cuda_set_profiling(self._h, int(on)))
+
+    def profile(self):
+        """{kernel class: (device ms, launches)} accumulated since set_profiling(True)."""
+        ms = np.zeros(len(KERNEL_CLASSES))
+        ln = np.zeros(len(KERNEL_CLASSES), dtype=np.int64)
+        _check(lib().mio_cuda_get_profile(self._h, cdefs.dptr(ms), cdefs.lptr(ln)))
+        return {k: (float(ms[i]), int(ln[i])) for i, k in enumerate(KERNEL_CLASSES)}
+
+    def device_state_ptr(self):
+        ptr = C.c_void_p()
+        nd = C.c_int64()
+        _check(lib().mio_cuda_device_state_ptr(self._h, C.byref(ptr), C.byref(nd)))
+        return int(ptr.value), int(nd.value)
+
     def close(self):
         if self._h:
             lib().mio_cuda_graph_destroy(self._h)
@@ -156,6 +189,13 @@ class GraphSimulation:
 
     def __exit__(self, *exc):
         self.close()
+
+
+def measure_fp64_peak(device: int = 0, seconds: float = 0.5) -> float:
+    """Measured FP64 FMA throughput in TFLOP/s (DFMA chains on all SMs)."""
+    out = C.c_double()
+    _check(lib().mio_cuda_measure_fp64_peak(device, seconds, C.byref(out)))
+    return out.value
 
 
 def make_mobility_sim(problem: GraphProblem, **kw) -> GraphSimulation:

@@ -75,6 +75,16 @@ struct mio_handle {
     // statistics
     long long launches = 0;
     long long* d_stats = nullptr; // [0] exact replays of return steps
+    // optional per-kernel-class device timing (CUDA events on the launching stream)
+    bool profiling = false;
+    struct Span {
+        int cls;
+        cudaEvent_t a, b;
+    };
+    std::vector<Span> spans;
+    std::vector<cudaEvent_t> event_pool;
+    double prof_ms[MIO_NUM_KERNEL_CLASSES]        = {0, 0, 0, 0, 0};
+    long long prof_launches[MIO_NUM_KERNEL_CLASSES] = {0, 0, 0, 0, 0};
 };
 
 namespace
@@ -159,6 +169,13 @@ void destroy(mio_handle* h)
             cudaFree(p);
         }
     }
+    for (auto& sp : h->spans) {
+        cudaEventDestroy(sp.a);
+        cudaEventDestroy(sp.b);
+    }
+    for (auto e : h->event_pool) {
+        cudaEventDestroy(e);
+    }
     if (h->stream) {
         cudaStreamDestroy(h->stream);
     }
@@ -176,6 +193,56 @@ DeviceState device_state(const mio_handle* h)
     st.dt_node     = h->d_dt_node;
     st.counters    = h->d_counters;
     return st;
+}
+
+cudaEvent_t get_event(mio_handle* h)
+{
+    if (!h->event_pool.empty()) {
+        cudaEvent_t e = h->event_pool.back();
+        h->event_pool.pop_back();
+        return e;
+    }
+    cudaEvent_t e;
+    cudaEventCreate(&e);
+    return e;
+}
+
+struct ScopedSpan {
+    mio_handle* h;
+    int cls;
+    cudaEvent_t a = nullptr;
+    ScopedSpan(mio_handle* h_, int cls_)
+        : h(h_)
+        , cls(cls_)
+    {
+        ++h->prof_launches[cls];
+        ++h->launches;
+        if (h->profiling) {
+            a = get_event(h);
+            cudaEventRecord(a, h->stream);
+        }
+    }
+    ~ScopedSpan()
+    {
+        if (h->profiling) {
+            cudaEvent_t b = get_event(h);
+            cudaEventRecord(b, h->stream);
+            h->spans.push_back({cls, a, b});
+        }
+    }
+};
+
+void collect_spans(mio_handle* h)
+{
+    for (auto& s : h->spans) {
+        float ms = 0.f;
+        if (cudaEventElapsedTime(&ms, s.a, s.b) == cudaSuccess) {
+            h->prof_ms[s.cls] += ms;
+        }
+        h->event_pool.push_back(s.a);
+        h->event_pool.push_back(s.b);
+    }
+    h->spans.clear();
 }
 
 int free_buffer(const mio_handle* h, int a, int b, int c)
@@ -509,6 +576,25 @@ int mio_cuda_set_runs(mio_handle* h, int32_t slot0, int32_t count, const mio_run
     return MIO_OK;
 }
 
+// rewind the graph simulation to t0 (run slots keep their data until set_runs overwrites them)
+int mio_cuda_reset(mio_handle* h)
+{
+    if (!h) {
+        return fail(MIO_INVALID_VALUE, "null handle");
+    }
+    CUDA_TRY(cudaSetDevice(h->device));
+    h->t           = h->desc.t0;
+    h->toggle      = false;
+    h->have_mobile = false;
+    h->snap_idx = h->v0_idx = -1;
+    h->days_recorded        = 0;
+    CUDA_TRY(cudaMemsetAsync(h->d_counters, 0, sizeof(int) * (size_t)h->max_runs * h->geo.N * 4, h->stream));
+    if (h->d_run_flags) {
+        CUDA_TRY(cudaMemsetAsync(h->d_run_flags, 0, sizeof(int) * (size_t)h->max_runs, h->stream));
+    }
+    return MIO_OK;
+}
+
 int mio_cuda_set_active_runs(mio_handle* h, int32_t count)
 {
     if (!h || count < 0 || count > h->max_runs) {
@@ -555,8 +641,10 @@ int mio_cuda_advance(mio_handle* h, double t_max)
         ia.dt_max     = h->desc.integrator.dt_max;
         ia.traj       = TrajectoryBuffers{h->desc.traj_capacity, h->d_traj_npts, h->d_traj_times, h->d_traj_values};
         ia.num_runs   = R;
-        CUDA_TRY(launch_integrate(ia, h->stream));
-        ++h->launches;
+        {
+            ScopedSpan sp(h, MIO_KC_INTEGRATE);
+            CUDA_TRY(launch_integrate(ia, h->stream));
+        }
         h->cur = out_idx;
         h->t += dt;
         // edge phase, MobilityEdge::apply_mobility for all edges
@@ -586,12 +674,16 @@ int mio_cuda_advance(mio_handle* h, double t_max)
                 ea.y_in  = h->d_y[h->cur];
                 ea.y_out = h->d_y[ret_idx];
                 ea.t_dep = h->t_dep;
-                CUDA_TRY(launch_return(ea, h->stream));
-                ++h->launches;
+                {
+                    ScopedSpan sp(h, MIO_KC_RETURN);
+                    CUDA_TRY(launch_return(ea, h->stream));
+                }
                 // runs that need the order dependent underflow fix-up are replayed literally (the kernel exits
                 // at once for unflagged runs and clears the flag, so no host round trip is needed)
-                CUDA_TRY(launch_return_exact(ea, h->stream));
-                ++h->launches;
+                {
+                    ScopedSpan sp(h, MIO_KC_RETURN_EXACT);
+                    CUDA_TRY(launch_return_exact(ea, h->stream));
+                }
                 h->cur         = ret_idx;
                 h->have_mobile = false;
                 h->snap_idx = h->v0_idx = -1;
@@ -610,8 +702,10 @@ int mio_cuda_advance(mio_handle* h, double t_max)
                 ea.y_in  = h->d_y[h->cur];
                 ea.y_out = h->d_y[dep_idx];
                 ea.t_dep = h->t;
-                CUDA_TRY(launch_depart(ea, h->stream));
-                ++h->launches;
+                {
+                    ScopedSpan sp(h, MIO_KC_DEPART);
+                    CUDA_TRY(launch_depart(ea, h->stream));
+                }
                 h->snap_idx    = h->cur;
                 h->v0_idx      = dep_idx;
                 h->cur         = dep_idx;
@@ -627,15 +721,16 @@ int mio_cuda_advance(mio_handle* h, double t_max)
             if (std::fabs(h->t - day) <= 1e-10 * std::max(1.0, std::fabs(day))) {
                 const int slot = (int)day - h->day0;
                 if (slot >= 0 && slot < h->desc.max_days) {
+                    ScopedSpan sp(h, MIO_KC_RECORD);
                     CUDA_TRY(launch_record_daily(geo, h->d_y[h->cur], h->d_daily, slot, h->desc.max_days, R,
                                                  h->stream));
-                    ++h->launches;
                     h->days_recorded = std::max(h->days_recorded, slot + 1);
                 }
             }
         }
     }
     CUDA_TRY(cudaStreamSynchronize(h->stream));
+    collect_spans(h);
     return MIO_OK;
 }
 
@@ -755,6 +850,50 @@ int mio_cuda_get_stats(mio_handle* h, int64_t* launches, int64_t* exact_replays)
             *exact_replays = v;
         }
     }
+    return MIO_OK;
+}
+
+int mio_cuda_get_stream(mio_handle* h, void** stream)
+{
+    if (!h || !stream) {
+        return fail(MIO_INVALID_VALUE, "null argument");
+    }
+    *stream = (void*)h->stream;
+    return MIO_OK;
+}
+
+int mio_cuda_set_profiling(mio_handle* h, int on)
+{
+    if (!h) {
+        return fail(MIO_INVALID_VALUE, "null handle");
+    }
+    h->profiling = on != 0;
+    for (int k = 0; k < MIO_NUM_KERNEL_CLASSES; ++k) {
+        h->prof_ms[k]       = 0.0;
+        h->prof_launches[k] = 0;
+    }
+    return MIO_OK;
+}
+
+int mio_cuda_get_profile(mio_handle* h, double* ms, int64_t* launches)
+{
+    if (!h || !ms || !launches) {
+        return fail(MIO_INVALID_VALUE, "null argument");
+    }
+    for (int k = 0; k < MIO_NUM_KERNEL_CLASSES; ++k) {
+        ms[k]       = h->prof_ms[k];
+        launches[k] = h->prof_launches[k];
+    }
+    return MIO_OK;
+}
+
+int mio_cuda_device_state_ptr(mio_handle* h, void** y, int64_t* num_doubles)
+{
+    if (!h || !y || !num_doubles) {
+        return fail(MIO_INVALID_VALUE, "null argument");
+    }
+    *y           = (void*)h->d_y[h->cur];
+    *num_doubles = (int64_t)h->max_runs * h->geo.N * h->geo.n;
     return MIO_OK;
 }
 
