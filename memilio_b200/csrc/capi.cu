@@ -53,14 +53,15 @@ struct mio_handle {
     int max_runs = 0, active_runs = 0;
     // graph (device)
     int *d_node_pset = nullptr, *d_node_ctable = nullptr;
-    int *d_node_order = nullptr, *d_inc_ptr = nullptr, *d_inc_edge = nullptr, *d_inc_other = nullptr,
-        *d_inc_out = nullptr, *d_edge_start = nullptr, *d_edge_end = nullptr;
-    double* d_coeff = nullptr;
+    int *d_order_in = nullptr, *d_order_out = nullptr, *d_in_ptr = nullptr, *d_in_split = nullptr, *d_in_src = nullptr,
+        *d_out_ptr = nullptr, *d_out_dst = nullptr, *d_edge_start = nullptr, *d_edge_end = nullptr;
+    double *d_coeff = nullptr, *d_w_in = nullptr, *d_w_out = nullptr, *d_s_out = nullptr, *d_umask = nullptr;
+    int factorized = 0;
     // per run (device)
     double *d_run_block = nullptr, *d_node_local = nullptr, *d_t_node = nullptr, *d_dt_node = nullptr;
     int* d_counters     = nullptr;
     double* d_y[4]      = {nullptr, nullptr, nullptr, nullptr};
-    double *d_fac = nullptr, *d_aux = nullptr;
+    double *d_fac = nullptr, *d_aux = nullptr, *d_u = nullptr, *d_vis = nullptr;
     int* d_run_flags = nullptr;
     double* d_daily  = nullptr;
     int* d_traj_npts = nullptr;
@@ -158,8 +159,10 @@ void destroy(mio_handle* h)
         return;
     }
     cudaSetDevice(h->device);
-    void* ptrs[] = {h->d_node_pset,  h->d_node_ctable, h->d_node_order, h->d_inc_ptr,   h->d_inc_edge,
-                    h->d_inc_other,  h->d_inc_out,     h->d_edge_start, h->d_edge_end,  h->d_coeff,
+    void* ptrs[] = {h->d_node_pset,  h->d_node_ctable, h->d_order_in,   h->d_order_out, h->d_in_ptr,
+                    h->d_in_split,   h->d_in_src,      h->d_out_ptr,    h->d_out_dst,   h->d_w_in,
+                    h->d_w_out,      h->d_s_out,       h->d_umask,      h->d_u,         h->d_vis,
+                    h->d_edge_start, h->d_edge_end,    h->d_coeff,
                     h->d_run_block,  h->d_node_local,  h->d_t_node,     h->d_dt_node,   h->d_counters,
                     h->d_y[0],       h->d_y[1],        h->d_y[2],       h->d_y[3],      h->d_fac,
                     h->d_aux,        h->d_run_flags,   h->d_daily,      h->d_traj_npts, h->d_traj_times,
@@ -400,42 +403,117 @@ int mio_cuda_graph_create(const mio_graph_desc* d, int device, mio_handle** out)
         H_TRY(cudaMemcpy(h->d_node_ctable, d->node_ctable, sizeof(int) * N, cudaMemcpyHostToDevice));
     }
     if (E > 0) {
-        // incidence lists in global edge order
-        std::vector<int> inc_ptr(N + 1, 0), deg(N, 0);
+        for (size_t i = 0; i < (size_t)E * n; ++i) {
+            if (!(d->edge_coeff[i] >= 0.0)) {
+                destroy(h);
+                return fail(MIO_INVALID_VALUE, "mobility coefficients must be non-negative");
+            }
+        }
+        // outgoing CSR = reference edge order; incoming CSR sorted by (dst, src)
+        std::vector<int> out_ptr(N + 1, 0), in_ptr(N + 1, 0), in_split(N, 0);
         for (int e = 0; e < E; ++e) {
-            ++deg[d->edge_start[e]];
-            ++deg[d->edge_end[e]];
+            ++out_ptr[d->edge_start[e] + 1];
+            ++in_ptr[d->edge_end[e] + 1];
+            if (d->edge_start[e] < d->edge_end[e]) {
+                ++in_split[d->edge_end[e]];
+            }
         }
         for (int k = 0; k < N; ++k) {
-            inc_ptr[k + 1] = inc_ptr[k] + deg[k];
+            out_ptr[k + 1] += out_ptr[k];
+            in_ptr[k + 1] += in_ptr[k];
         }
-        std::vector<int> fill(inc_ptr.begin(), inc_ptr.end() - 1), inc_edge(2 * E), inc_other(2 * E), inc_out(2 * E);
-        for (int e = 0; e < E; ++e) { // ascending e => every node's list is sorted by e
-            int s = d->edge_start[e], t = d->edge_end[e];
-            inc_edge[fill[s]] = e, inc_other[fill[s]] = t, inc_out[fill[s]] = 1, ++fill[s];
-            inc_edge[fill[t]] = e, inc_other[fill[t]] = s, inc_out[fill[t]] = 0, ++fill[t];
+        std::vector<int> fill(in_ptr.begin(), in_ptr.end() - 1), in_src(E), in_edge(E);
+        for (int e = 0; e < E; ++e) { // ascending (src, dst) => every destination's list is sorted by src
+            const int t  = d->edge_end[e];
+            in_src[fill[t]]  = d->edge_start[e];
+            in_edge[fill[t]] = e;
+            ++fill[t];
         }
-        std::vector<int> order(N);
-        std::iota(order.begin(), order.end(), 0);
-        std::stable_sort(order.begin(), order.end(), [&](int a, int b) {
-            return deg[a] > deg[b];
+        // factorized form: coeff[e][i][c] == w[e][i] * mask[i][c] with a 0/1 mask, exactly
+        std::vector<double> umask(n, 0.0), w_age((size_t)E * G, 0.0);
+        for (int e = 0; e < E; ++e) {
+            for (int j = 0; j < n; ++j) {
+                if (d->edge_coeff[(size_t)e * n + j] != 0.0) {
+                    umask[j] = 1.0;
+                }
+            }
+        }
+        bool fact = true;
+        for (int e = 0; e < E && fact; ++e) {
+            for (int i = 0; i < G && fact; ++i) {
+                double w = 0.0;
+                for (int c = 0; c < NC; ++c) {
+                    if (umask[i * NC + c] != 0.0) {
+                        w = d->edge_coeff[(size_t)e * n + i * NC + c];
+                        break;
+                    }
+                }
+                for (int c = 0; c < NC; ++c) {
+                    if (d->edge_coeff[(size_t)e * n + i * NC + c] != w * umask[i * NC + c]) {
+                        fact = false;
+                    }
+                }
+                w_age[(size_t)e * G + i] = w;
+            }
+        }
+        h->factorized = fact ? 1 : 0;
+        if (!fact) {
+            std::fill(umask.begin(), umask.end(), 1.0);
+        }
+        std::vector<double> w_in(fact ? (size_t)E * G : (size_t)E * n), w_out((size_t)E * G * 2),
+            s_out((size_t)N * n, 0.0);
+        for (int pos = 0; pos < E; ++pos) {
+            const int e = in_edge[pos];
+            if (fact) {
+                std::copy(w_age.begin() + (size_t)e * G, w_age.begin() + (size_t)(e + 1) * G,
+                          w_in.begin() + (size_t)pos * G);
+            }
+            else {
+                std::copy(d->edge_coeff + (size_t)e * n, d->edge_coeff + (size_t)(e + 1) * n,
+                          w_in.begin() + (size_t)pos * n);
+            }
+        }
+        for (int e = 0; e < E; ++e) {
+            for (int i = 0; i < G; ++i) {
+                w_out[((size_t)e * G + i) * 2 + 0] = d->edge_coeff[(size_t)e * n + i * NC + cS];
+                w_out[((size_t)e * G + i) * 2 + 1] = d->edge_coeff[(size_t)e * n + i * NC + cISev];
+            }
+            for (int j = 0; j < n; ++j) {
+                s_out[(size_t)d->edge_start[e] * n + j] += d->edge_coeff[(size_t)e * n + j];
+            }
+        }
+        std::vector<int> order_in(N), order_out(N);
+        std::iota(order_in.begin(), order_in.end(), 0);
+        std::iota(order_out.begin(), order_out.end(), 0);
+        std::stable_sort(order_in.begin(), order_in.end(), [&](int a, int b) {
+            return in_ptr[a + 1] - in_ptr[a] > in_ptr[b + 1] - in_ptr[b];
         });
-        H_TRY(dev_alloc(&h->d_node_order, (size_t)N));
-        H_TRY(dev_alloc(&h->d_inc_ptr, (size_t)N + 1));
-        H_TRY(dev_alloc(&h->d_inc_edge, (size_t)2 * E));
-        H_TRY(dev_alloc(&h->d_inc_other, (size_t)2 * E));
-        H_TRY(dev_alloc(&h->d_inc_out, (size_t)2 * E));
-        H_TRY(dev_alloc(&h->d_edge_start, (size_t)E));
-        H_TRY(dev_alloc(&h->d_edge_end, (size_t)E));
-        H_TRY(dev_alloc(&h->d_coeff, (size_t)E * n));
-        H_TRY(cudaMemcpy(h->d_node_order, order.data(), sizeof(int) * N, cudaMemcpyHostToDevice));
-        H_TRY(cudaMemcpy(h->d_inc_ptr, inc_ptr.data(), sizeof(int) * (N + 1), cudaMemcpyHostToDevice));
-        H_TRY(cudaMemcpy(h->d_inc_edge, inc_edge.data(), sizeof(int) * 2 * E, cudaMemcpyHostToDevice));
-        H_TRY(cudaMemcpy(h->d_inc_other, inc_other.data(), sizeof(int) * 2 * E, cudaMemcpyHostToDevice));
-        H_TRY(cudaMemcpy(h->d_inc_out, inc_out.data(), sizeof(int) * 2 * E, cudaMemcpyHostToDevice));
-        H_TRY(cudaMemcpy(h->d_edge_start, d->edge_start, sizeof(int) * E, cudaMemcpyHostToDevice));
-        H_TRY(cudaMemcpy(h->d_edge_end, d->edge_end, sizeof(int) * E, cudaMemcpyHostToDevice));
-        H_TRY(cudaMemcpy(h->d_coeff, d->edge_coeff, sizeof(double) * (size_t)E * n, cudaMemcpyHostToDevice));
+        std::stable_sort(order_out.begin(), order_out.end(), [&](int a, int b) {
+            return out_ptr[a + 1] - out_ptr[a] > out_ptr[b + 1] - out_ptr[b];
+        });
+        auto up_i = [&](int** dst, const std::vector<int>& v) {
+            cudaError_t er = dev_alloc(dst, v.size());
+            return er != cudaSuccess ? er : cudaMemcpy(*dst, v.data(), sizeof(int) * v.size(), cudaMemcpyHostToDevice);
+        };
+        auto up_d = [&](double** dst, const double* v, size_t cnt) {
+            cudaError_t er = dev_alloc(dst, cnt);
+            return er != cudaSuccess ? er : cudaMemcpy(*dst, v, sizeof(double) * cnt, cudaMemcpyHostToDevice);
+        };
+        std::vector<int> es(d->edge_start, d->edge_start + E), ee(d->edge_end, d->edge_end + E);
+        H_TRY(up_i(&h->d_order_in, order_in));
+        H_TRY(up_i(&h->d_order_out, order_out));
+        H_TRY(up_i(&h->d_in_ptr, in_ptr));
+        H_TRY(up_i(&h->d_in_split, in_split));
+        H_TRY(up_i(&h->d_in_src, in_src));
+        H_TRY(up_i(&h->d_out_ptr, out_ptr));
+        H_TRY(up_i(&h->d_out_dst, ee));
+        H_TRY(up_i(&h->d_edge_start, es));
+        H_TRY(up_i(&h->d_edge_end, ee));
+        H_TRY(up_d(&h->d_coeff, d->edge_coeff, (size_t)E * n));
+        H_TRY(up_d(&h->d_w_in, w_in.data(), w_in.size()));
+        H_TRY(up_d(&h->d_w_out, w_out.data(), w_out.size()));
+        H_TRY(up_d(&h->d_s_out, s_out.data(), s_out.size()));
+        H_TRY(up_d(&h->d_umask, umask.data(), umask.size()));
     }
     // per-run state
     const size_t R = (size_t)d->max_runs;
@@ -451,6 +529,8 @@ int mio_cuda_graph_create(const mio_graph_desc* d, int device, mio_handle** out)
     if (E > 0) {
         H_TRY(dev_alloc(&h->d_fac, R * N * G));
         H_TRY(dev_alloc(&h->d_aux, R * N * G * 4));
+        H_TRY(dev_alloc(&h->d_u, R * N * n));
+        H_TRY(dev_alloc(&h->d_vis, R * N * 2 * n));
         H_TRY(dev_alloc(&h->d_run_flags, R));
         H_TRY(cudaMemset(h->d_run_flags, 0, sizeof(int) * R));
         H_TRY(dev_alloc(&h->d_stats, (size_t)4));
@@ -633,6 +713,8 @@ int mio_cuda_advance(mio_handle* h, double t_max)
         ia.y_in       = h->d_y[h->cur];
         ia.y_out      = h->d_y[out_idx];
         ia.fac_out    = will_depart ? h->d_fac : nullptr;
+        ia.u_out      = will_depart ? h->d_u : nullptr;
+        ia.umask      = h->d_umask;
         ia.t_end      = h->t + dt;
         ia.integrator = h->desc.integrator.kind;
         ia.abs_tol    = h->desc.integrator.abs_tol;
@@ -652,25 +734,24 @@ int mio_cuda_advance(mio_handle* h, double t_max)
             EdgeArgs ea;
             ea.geo            = geo;
             ea.st             = device_state(h);
-            ea.inc            = Incidence{h->d_node_order, h->d_inc_ptr,    h->d_inc_edge, h->d_inc_other,
-                                          h->d_inc_out,    h->d_edge_start, h->d_edge_end, h->d_coeff};
+            ea.csr = GraphCsr{h->d_order_in, h->d_order_out, h->d_in_ptr,  h->d_in_split, h->d_in_src,
+                              h->d_w_in,     h->d_out_ptr,   h->d_out_dst, h->d_w_out,    h->d_s_out,
+                              h->d_umask,    h->factorized,  h->d_edge_start, h->d_edge_end, h->d_coeff};
             ea.fac            = h->d_fac;
+            ea.u              = h->d_u;
+            ea.vis            = h->d_vis;
             ea.aux            = h->d_aux;
             ea.run_flags      = h->d_run_flags;
             ea.stats          = h->d_stats;
             ea.num_runs       = R;
             ea.dt             = dt;
             ea.t              = h->t;
-            ea.daily_out      = nullptr;
-            ea.day_index      = 0;
-            ea.max_days       = 0;
             if (h->have_mobile && h->return_time <= h->t) {
                 const int ret_idx = free_buffer(h, h->cur, -1, -1);
                 if (ret_idx < 0) {
                     return fail(MIO_UNKNOWN_ERROR, "internal: no free state buffer");
                 }
                 ea.snap  = h->d_y[h->snap_idx];
-                ea.v0    = h->d_y[h->v0_idx];
                 ea.y_in  = h->d_y[h->cur];
                 ea.y_out = h->d_y[ret_idx];
                 ea.t_dep = h->t_dep;
@@ -698,7 +779,6 @@ int mio_cuda_advance(mio_handle* h, double t_max)
                     return fail(MIO_UNKNOWN_ERROR, "internal: no free state buffer");
                 }
                 ea.snap  = h->d_y[h->cur];
-                ea.v0    = nullptr;
                 ea.y_in  = h->d_y[h->cur];
                 ea.y_out = h->d_y[dep_idx];
                 ea.t_dep = h->t;

@@ -7,13 +7,13 @@
 //
 // Formulation: the reference walks the edges in (start,end) order and updates both end nodes in place. Every
 // contribution of an edge depends only on per-node snapshots (m_last_state of the source, post-departure state of the
-// destination), so the loop is re-expressed as a *gather per node*: the lane group that owns node k walks k's incident
-// edges in the same global order and applies the same additions/subtractions to k's state held in registers. No
-// atomics, deterministic, and the floating point summation order per node equals the reference's. The traveler state
-// of an edge is not stored between departure and return; it is recomputed from the source snapshot (bit-identical),
-// which turns E*n doubles of HBM traffic per run and exchange into L2-resident snapshot reads.
-// The one order dependent piece, the underflow fix-up of returns (:579-596), is detected by the gather (run_flags) and
-// such runs are replayed for that step by return_exact_kernel with the literal sequential semantics.
+// destination) and is linear in the source's snapshot, so the loop is re-expressed as two sparse matrix-vector
+// gathers per node (visitors over the incoming-edge CSR at departure; destination coefficients over the outgoing-edge
+// CSR at return) plus one Euler step per node, see depart_kernel / return_kernel. No atomics, deterministic; per node
+// the blocks are combined in the reference's order (sources < k, own outgoing edges, sources > k). The traveler state
+// of an edge is not stored: per destination node the summed visitor vectors are kept instead (2n doubles per node
+// rather than n per edge). The one order dependent piece, the underflow fix-up of returns (:579-596), is detected
+// (run_flags) and such runs are replayed for that step by return_exact_kernel with the literal sequential semantics.
 #include "device_common.cuh"
 #include "kernels.h"
 
@@ -100,8 +100,8 @@ __device__ __forceinline__ void euler_return(const LaneCoef& c, double slam, dou
 }
 
 template <int G>
-__device__ __forceinline__ void edge_lane_setup(const Geometry& geo, const Incidence& inc, int num_runs,
-                                                EdgeLane<G>& L, bool& cta_active)
+__device__ __forceinline__ void edge_lane_setup(const Geometry& geo, const int* order, int num_runs, EdgeLane<G>& L,
+                                                bool& cta_active)
 {
     constexpr int NPW   = 32 / G;
     constexpr int WARPS = EDGE_THREADS / 32;
@@ -112,14 +112,57 @@ __device__ __forceinline__ void edge_lane_setup(const Geometry& geo, const Incid
     const int warp      = threadIdx.x >> 5;
     const int item      = (chunk * WARPS + warp) * NPW + L.g.lane / G;
     L.valid             = cta_active && !L.g.spare() && item < geo.N;
-    L.node              = L.valid ? inc.node_order[item] : 0;
+    L.node              = L.valid ? order[item] : 0;
     L.rn                = (size_t)(cta_active ? L.run : 0) * geo.N + L.node;
 }
 
+__device__ __forceinline__ int warp_max(int v)
+{
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) {
+        v = max(v, __shfl_xor_sync(0xffffffffu, v, o));
+    }
+    return v;
+}
+
+// V += coeff_e * u_src over the incoming edges [beg, beg+cnt) of this lane's node (SpMV row, edge order)
+template <bool FACT, int G>
+__device__ __forceinline__ void gather_visitors(const EdgeArgs& a, const Geometry& geo, int run, int gl, int beg,
+                                                int cnt, int max_cnt, double (&V)[NC])
+{
+    for (int it = 0; it < max_cnt; ++it) {
+        const bool act = it < cnt;
+        const int pos  = beg + (act ? it : 0);
+        const int src  = a.csr.in_src[pos];
+        double us[NC];
+        load10(a.u + ((size_t)run * geo.N + src) * geo.n + gl * NC, us);
+        if (FACT) {
+            const double w = act ? a.csr.w_in[(size_t)pos * G + gl] : 0.0;
+#pragma unroll
+            for (int i = 0; i < NC; ++i) {
+                V[i] += w * us[i];
+            }
+        }
+        else {
+            double w[NC];
+            load10(a.csr.w_in + (size_t)pos * geo.n + gl * NC, w);
+            if (act) {
+#pragma unroll
+                for (int i = 0; i < NC; ++i) {
+                    V[i] += w[i] * us[i];
+                }
+            }
+        }
+    }
+}
+
 // ---------------------------------------------------------------------------------------------------------------
-// Departure: y_out = y_in + sum(incoming mobile) - sum(outgoing mobile) in edge order; then the return coefficients of
-// this node as a destination (lambda_i, ICU adjusted rates) from v0 = y_out at time t.
-template <int G>
+// Departure (all edges, one launch). With m_e = coeff_e * u_from (the mobile population of edge e) the in-place edge
+// loop leaves node k at  y_k + sum_{e into k} m_e - sum_{e out of k} m_e. The visitors are gathered per destination
+// (SpMV over the incoming-edge CSR; V1: sources < k, V3: sources > k, i.e. before / after k's own outgoing edges in
+// the reference order) and kept for the return phase; the emigrants are s_out_k * u_k.
+// Then the return coefficients of k as a destination (lambda_i, ICU adjusted rates) from v0 = y_out at time t.
+template <int G, bool FACT>
 __global__ void __launch_bounds__(EDGE_THREADS) depart_kernel(EdgeArgs a)
 {
     extern __shared__ __align__(16) double smem[];
@@ -127,84 +170,56 @@ __global__ void __launch_bounds__(EDGE_THREADS) depart_kernel(EdgeArgs a)
     const Geometry& geo = a.geo;
     EdgeLane<G> L;
     bool cta_active;
-    edge_lane_setup<G>(geo, a.inc, a.num_runs, L, cta_active);
+    edge_lane_setup<G>(geo, a.csr.order_in, a.num_runs, L, cta_active);
     if (!cta_active) {
         return;
     }
     stage_run_block(smem, a.st.run_block + (size_t)L.run * geo.block_stride, geo.block_stride * 8, &mbar);
     const Group<G>& g  = L.g;
-    const double* mob  = geo.mob_max_pts > 0 ? smem + geo.mob_off : nullptr;
-    const bool damped  = mob != nullptr && mob[0] > 0.0;
     const int ps_own   = a.st.node_pset ? a.st.node_pset[L.node] : 0;
     const double* pset = smem + ps_own * geo.pset_stride;
 
-    double y[NC], snapk[NC], damp[NC];
+    double y[NC], uk[NC], so[NC];
     load10(a.y_in + L.rn * geo.n + g.gl * NC, y);
-    load10(a.snap + L.rn * geo.n + g.gl * NC, snapk);
-    const double fack = a.fac[L.rn * G + g.gl];
-    mobility_damping_eval(damped ? mob : nullptr, geo.mob_max_pts, geo.n, g.gl, a.t, damp);
-    const double nd_own = nondetection_at(pset, a.t);
+    load10(a.u + L.rn * geo.n + g.gl * NC, uk);
+    load10(a.csr.s_out + (size_t)L.node * geo.n + g.gl * NC, so);
 
-    const int beg = L.valid ? a.inc.inc_ptr[L.node] : 0;
-    const int cnt = L.valid ? a.inc.inc_ptr[L.node + 1] - beg : 0;
-    int max_cnt   = cnt;
+    const int beg   = L.valid ? a.csr.in_ptr[L.node] : 0;
+    const int cnt   = L.valid ? a.csr.in_ptr[L.node + 1] - beg : 0;
+    const int split = L.valid ? a.csr.in_split[L.node] : 0;
+    double V1[NC], V3[NC];
 #pragma unroll
-    for (int o = 16; o > 0; o >>= 1) {
-        max_cnt = max(max_cnt, __shfl_xor_sync(0xffffffffu, max_cnt, o));
+    for (int i = 0; i < NC; ++i) {
+        V1[i] = 0.0;
+        V3[i] = 0.0;
     }
-    for (int it = 0; it < max_cnt; ++it) {
-        const bool act = it < cnt;
-        const int idx  = beg + (act ? it : 0);
-        const int e    = act ? a.inc.inc_edge[idx] : 0;
-        const int o    = act ? a.inc.inc_other[idx] : 0;
-        const bool out = act ? (a.inc.inc_out[idx] != 0) : true;
-        double m[NC], mu[2];
-        bool pos;
-        double nd = nd_own;
-        if (out) {
-            pos = damped ? mobile_at_departure<true>(a.inc.coeff + (size_t)e * geo.n + g.gl * NC, damp, snapk, fack,
-                                                     nd, m, mu)
-                         : mobile_at_departure<false>(a.inc.coeff + (size_t)e * geo.n + g.gl * NC, damp, snapk, fack,
-                                                      nd, m, mu);
-        }
-        else {
-            const size_t ro = (size_t)L.run * geo.N + o;
-            double so[NC];
-            load10(a.snap + ro * geo.n + g.gl * NC, so);
-            const double fo = a.fac[ro * G + g.gl];
-            if (geo.num_psets > 1) {
-                nd = nondetection_at(smem + a.st.node_pset[o] * geo.pset_stride, a.t);
-            }
-            pos = damped ? mobile_at_departure<true>(a.inc.coeff + (size_t)e * geo.n + g.gl * NC, damp, so, fo, nd,
-                                                     m, mu)
-                         : mobile_at_departure<false>(a.inc.coeff + (size_t)e * geo.n + g.gl * NC, damp, so, fo, nd,
-                                                      m, mu);
-        }
-        // (coeffs(t) > 0).any(), instant.h:605-606
-        const bool any = g.any(act && pos);
-        if (act && any) {
-            if (out) {
-                if (nd != 1.0) { // test_commuters acts on the source node, ode_secir/model.h:733-736
-                    y[cINS] -= mu[0] * (1 - nd);
-                    y[cINSC] += mu[0] * (1 - nd);
-                    y[cISy] -= mu[1] * (1 - nd);
-                    y[cISyC] += mu[1] * (1 - nd);
-                }
+    gather_visitors<FACT, G>(a, geo, L.run, g.gl, beg, split, warp_max(split), V1);
+    gather_visitors<FACT, G>(a, geo, L.run, g.gl, beg + split, cnt - split, warp_max(cnt - split), V3);
+
+    // test_commuters (ode_secir/model.h:717-742): detected commuters stay, in the *Confirmed compartments
+    const double nd = nondetection_at(pset, a.t);
+    if (nd != 1.0) {
+        // u holds the tested (travelling) population; the untested one is rebuilt from the snapshot (= y here)
+        const double* mob = geo.mob_max_pts > 0 ? smem + geo.mob_off : nullptr;
+        double damp[NC];
+        mobility_damping_eval((mob != nullptr && mob[0] > 0.0) ? mob : nullptr, geo.mob_max_pts, geo.n, g.gl, a.t,
+                              damp);
+        const double fk       = a.fac[L.rn * G + g.gl];
+        const double lost_ins = so[cINS] * (y[cINS] * (1.0 - damp[cINS]) * a.csr.umask[g.gl * NC + cINS]);
+        const double lost_isy = so[cISy] * (y[cISy] * (1.0 - damp[cISy]) * fk * a.csr.umask[g.gl * NC + cISy]);
+        y[cINS] -= lost_ins * (1 - nd);
+        y[cINSC] += lost_ins * (1 - nd);
+        y[cISy] -= lost_isy * (1 - nd);
+        y[cISyC] += lost_isy * (1 - nd);
+    }
 #pragma unroll
-                for (int i = 0; i < NC; ++i) {
-                    y[i] -= m[i];
-                }
-            }
-            else {
-#pragma unroll
-                for (int i = 0; i < NC; ++i) {
-                    y[i] += m[i];
-                }
-            }
-        }
+    for (int i = 0; i < NC; ++i) {
+        y[i] = ((y[i] + V1[i]) - so[i] * uk[i]) + V3[i];
     }
     if (L.valid) {
         store10(a.y_out + L.rn * geo.n + g.gl * NC, y);
+        store10(a.vis + (L.rn * 2 + 0) * geo.n + g.gl * NC, V1);
+        store10(a.vis + (L.rn * 2 + 1) * geo.n + g.gl * NC, V3);
     }
     // return coefficients of this node as destination: get_flows with pop = v0 (ode_secir/model.h:90-153)
     {
@@ -251,8 +266,17 @@ __global__ void __launch_bounds__(EDGE_THREADS) depart_kernel(EdgeArgs a)
 }
 
 // ---------------------------------------------------------------------------------------------------------------
-// Return (optimistic gather): y_out = y_in + sum(returning own commuters) - sum(returning visitors), edge order.
-template <int G>
+// Return (all edges, one launch). calculate_mobility_returns is one explicit Euler step m + dt*A_dest*m of the
+// destination's model, linear in the traveler vector m, so the sums over edges commute with it:
+//   visitors leaving k :  (I + dt*A_k) V1  and  (I + dt*A_k) V3                   (V from the departure gather)
+//   own commuters back :  sum_e (I + dt*A_dst(e)) coeff_e*u_k = (I + dt*A0)(s_out*u_k) + dt*(destination dependent
+//                         flows: S->E with sum_e coeff_e[S]*lambda_dst, ISev->ICr/D with the ICU adjusted rates)
+// Order kept from the reference: visitors from sources < k, then own commuters, then visitors from sources > k.
+// The underflow fix-up (instant.h:579-596) triggers iff the node's running value goes negative at an incoming edge;
+// the running value decreases monotonically along the incoming edges (returning visitor vectors are non-negative as
+// long as dt*rate <= 1, checked), so it is enough to test it after the first and after the last block. Flagged runs
+// are replayed literally by return_exact_kernel.
+template <int G, bool FACT>
 __global__ void __launch_bounds__(EDGE_THREADS) return_kernel(EdgeArgs a)
 {
     extern __shared__ __align__(16) double smem[];
@@ -260,23 +284,14 @@ __global__ void __launch_bounds__(EDGE_THREADS) return_kernel(EdgeArgs a)
     const Geometry& geo = a.geo;
     EdgeLane<G> L;
     bool cta_active;
-    edge_lane_setup<G>(geo, a.inc, a.num_runs, L, cta_active);
+    edge_lane_setup<G>(geo, a.csr.order_out, a.num_runs, L, cta_active);
     if (!cta_active) {
         return;
     }
     stage_run_block(smem, a.st.run_block + (size_t)L.run * geo.block_stride, geo.block_stride * 8, &mbar);
     const Group<G>& g  = L.g;
-    const double* mob  = geo.mob_max_pts > 0 ? smem + geo.mob_off : nullptr;
-    const bool damped  = mob != nullptr && mob[0] > 0.0;
     const int ps_own   = a.st.node_pset ? a.st.node_pset[L.node] : 0;
     const double* pset = smem + ps_own * geo.pset_stride;
-
-    double y[NC], snapk[NC], damp[NC];
-    load10(a.y_in + L.rn * geo.n + g.gl * NC, y);
-    load10(a.snap + L.rn * geo.n + g.gl * NC, snapk);
-    const double fack = a.fac[L.rn * G + g.gl];
-    mobility_damping_eval(damped ? mob : nullptr, geo.mob_max_pts, geo.n, g.gl, a.t_dep, damp);
-    const double nd_own = nondetection_at(pset, a.t_dep);
     LaneCoef c_own;
     c_own.load(pset + PHDR + g.gl * AGE_REC);
     double slam_own, ricr_own, rd_own;
@@ -287,70 +302,97 @@ __global__ void __launch_bounds__(EDGE_THREADS) return_kernel(EdgeArgs a)
         ricr_own = a0.y;
         rd_own   = a1.x;
     }
-    const int beg = L.valid ? a.inc.inc_ptr[L.node] : 0;
-    const int cnt = L.valid ? a.inc.inc_ptr[L.node + 1] - beg : 0;
-    int max_cnt   = cnt;
-#pragma unroll
-    for (int o = 16; o > 0; o >>= 1) {
-        max_cnt = max(max_cnt, __shfl_xor_sync(0xffffffffu, max_cnt, o));
-    }
+    double y[NC], V[NC];
+    load10(a.y_in + L.rn * geo.n + g.gl * NC, y);
     bool underflow = false;
-    for (int it = 0; it < max_cnt; ++it) {
-        const bool act = it < cnt;
-        const int idx  = beg + (act ? it : 0);
-        const int e    = act ? a.inc.inc_edge[idx] : 0;
-        const int o    = act ? a.inc.inc_other[idx] : 0;
-        const bool out = act ? (a.inc.inc_out[idx] != 0) : true;
-        const size_t ro = (size_t)L.run * geo.N + o;
-        double m[NC], mu[2];
-        bool pos;
-        if (out) {
-            pos = damped ? mobile_at_departure<true>(a.inc.coeff + (size_t)e * geo.n + g.gl * NC, damp, snapk, fack,
-                                                     nd_own, m, mu)
-                         : mobile_at_departure<false>(a.inc.coeff + (size_t)e * geo.n + g.gl * NC, damp, snapk, fack,
-                                                      nd_own, m, mu);
-            // destination = other node: its return coefficients and (if parameter sets differ) its rates
-            const double2* ax = reinterpret_cast<const double2*>(a.aux + (ro * G + g.gl) * AUX);
-            double2 a0 = ax[0], a1 = ax[1];
-            if (geo.num_psets > 1) {
-                LaneCoef c_o;
-                c_o.load(smem + a.st.node_pset[o] * geo.pset_stride + PHDR + g.gl * AGE_REC);
-                euler_return(c_o, a0.x, a0.y, a1.x, a.dt, m);
+    // monotonicity guard: returning visitor vectors stay non-negative iff dt * (outflow rate) <= 1
+    {
+        const double rmax = fmax(fmax(fmax(slam_own, c_own.rE_INS), fmax(c_own.rINS_ISy + c_own.rINS_R,
+                                                                         c_own.rISy_ISev + c_own.rISy_R)),
+                                 fmax(ricr_own + c_own.rISev_R + rd_own, c_own.rICr_D + c_own.rICr_R));
+        underflow = !(a.dt * rmax <= 1.0);
+    }
+    // visitors from sources < k
+    load10(a.vis + (L.rn * 2 + 0) * geo.n + g.gl * NC, V);
+    euler_return(c_own, slam_own, ricr_own, rd_own, a.dt, V);
+#pragma unroll
+    for (int i = 0; i < NC; ++i) {
+        y[i] -= V[i];
+        underflow = underflow || (y[i] < 0.0);
+    }
+    // own commuters
+    {
+        double uk[NC], so[NC], q[NC];
+        load10(a.u + L.rn * geo.n + g.gl * NC, uk);
+        const int beg = L.valid ? a.csr.out_ptr[L.node] : 0;
+        const int cnt = L.valid ? a.csr.out_ptr[L.node + 1] - beg : 0;
+        const int mx  = warp_max(cnt);
+        if (geo.num_psets == 1) {
+            load10(a.csr.s_out + (size_t)L.node * geo.n + g.gl * NC, so);
+            double a_slam = 0.0, a_icr = 0.0, a_d = 0.0;
+            for (int it = 0; it < mx; ++it) {
+                const bool act  = it < cnt;
+                const int e     = beg + (act ? it : 0);
+                const int dst   = a.csr.out_dst[e];
+                const double2 w = reinterpret_cast<const double2*>(a.csr.w_out)[(size_t)e * G + g.gl];
+                const double2* ax =
+                    reinterpret_cast<const double2*>(a.aux + (((size_t)L.run * geo.N + dst) * G + g.gl) * AUX);
+                const double2 a0 = ax[0], a1 = ax[1];
+                if (act) {
+                    a_slam += w.x * a0.x;
+                    a_icr += w.y * a0.y;
+                    a_d += w.y * a1.x;
+                }
             }
-            else {
-                euler_return(c_own, a0.x, a0.y, a1.x, a.dt, m);
+#pragma unroll
+            for (int i = 0; i < NC; ++i) {
+                q[i] = so[i] * uk[i];
+            }
+            double k[NC];
+            const LaneCoef& c = c_own;
+            flows_to_dydt(a_slam * uk[cS], c.rE_INS * q[cE], c.rINS_ISy * q[cINS], c.rINS_R * q[cINS],
+                          c.rINS_ISy * q[cINSC], c.rINS_R * q[cINSC], c.rISy_ISev * q[cISy], c.rISy_R * q[cISy],
+                          c.rISy_ISev * q[cISyC], c.rISy_R * q[cISyC], a_icr * uk[cISev], c.rISev_R * q[cISev],
+                          a_d * uk[cISev], c.rICr_D * q[cICr], c.rICr_R * q[cICr], k);
+#pragma unroll
+            for (int i = 0; i < NC; ++i) {
+                y[i] += q[i] + a.dt * k[i];
             }
         }
         else {
-            double so[NC];
-            load10(a.snap + ro * geo.n + g.gl * NC, so);
-            const double fo = a.fac[ro * G + g.gl];
-            double nd       = nd_own;
-            if (geo.num_psets > 1) {
-                nd = nondetection_at(smem + a.st.node_pset[o] * geo.pset_stride, a.t_dep);
-            }
-            pos = damped ? mobile_at_departure<true>(a.inc.coeff + (size_t)e * geo.n + g.gl * NC, damp, so, fo, nd,
-                                                     m, mu)
-                         : mobile_at_departure<false>(a.inc.coeff + (size_t)e * geo.n + g.gl * NC, damp, so, fo, nd,
-                                                      m, mu);
-            euler_return(c_own, slam_own, ricr_own, rd_own, a.dt, m);
-        }
-        const bool any = g.any(act && pos);
-        if (act && any) {
-            if (out) {
+            // parameter sets differ between nodes: Euler step per edge with the destination's own rates
+            for (int it = 0; it < mx; ++it) {
+                const bool act = it < cnt;
+                const int e    = beg + (act ? it : 0);
+                const int dst  = a.csr.out_dst[e];
+                double m[NC];
+                load10(a.csr.coeff + (size_t)e * geo.n + g.gl * NC, m);
 #pragma unroll
                 for (int i = 0; i < NC; ++i) {
-                    y[i] += m[i];
+                    m[i] *= uk[i];
                 }
-            }
-            else {
+                LaneCoef c_o;
+                c_o.load(smem + a.st.node_pset[dst] * geo.pset_stride + PHDR + g.gl * AGE_REC);
+                const double2* ax =
+                    reinterpret_cast<const double2*>(a.aux + (((size_t)L.run * geo.N + dst) * G + g.gl) * AUX);
+                const double2 a0 = ax[0], a1 = ax[1];
+                euler_return(c_o, a0.x, a0.y, a1.x, a.dt, m);
+                if (act) {
 #pragma unroll
-                for (int i = 0; i < NC; ++i) {
-                    y[i] -= m[i];
-                    underflow = underflow || (y[i] < 0.0);
+                    for (int i = 0; i < NC; ++i) {
+                        y[i] += m[i];
+                    }
                 }
             }
         }
+    }
+    // visitors from sources > k
+    load10(a.vis + (L.rn * 2 + 1) * geo.n + g.gl * NC, V);
+    euler_return(c_own, slam_own, ricr_own, rd_own, a.dt, V);
+#pragma unroll
+    for (int i = 0; i < NC; ++i) {
+        y[i] -= V[i];
+        underflow = underflow || (y[i] < 0.0);
     }
     if (L.valid) {
         store10(a.y_out + L.rn * geo.n + g.gl * NC, y);
@@ -395,8 +437,8 @@ __global__ void __launch_bounds__(32) return_exact_kernel(EdgeArgs a)
     mobility_damping_eval(damped ? mob : nullptr, geo.mob_max_pts, geo.n, gl, a.t_dep, damp);
     const unsigned gmask = (1u << G) - 1u;
     for (int e = 0; e < geo.E; ++e) {
-        const int from   = a.inc.edge_start[e];
-        const int to     = a.inc.edge_end[e];
+        const int from   = a.csr.edge_start[e];
+        const int to     = a.csr.edge_end[e];
         const size_t rf  = (size_t)run * geo.N + from;
         const size_t rt  = (size_t)run * geo.N + to;
         const int ps_f   = a.st.node_pset ? a.st.node_pset[from] : 0;
@@ -406,8 +448,8 @@ __global__ void __launch_bounds__(32) return_exact_kernel(EdgeArgs a)
         load10(a.snap + rf * geo.n + gl * NC, sf);
         const double ff = a.fac[rf * G + gl];
         const bool pos =
-            damped ? mobile_at_departure<true>(a.inc.coeff + (size_t)e * geo.n + gl * NC, damp, sf, ff, nd, m, mu)
-                   : mobile_at_departure<false>(a.inc.coeff + (size_t)e * geo.n + gl * NC, damp, sf, ff, nd, m, mu);
+            damped ? mobile_at_departure<true>(a.csr.coeff + (size_t)e * geo.n + gl * NC, damp, sf, ff, nd, m, mu)
+                   : mobile_at_departure<false>(a.csr.coeff + (size_t)e * geo.n + gl * NC, damp, sf, ff, nd, m, mu);
         const bool any = (__ballot_sync(gmask, pos) & gmask) != 0u;
         if (!any) {
             continue;
@@ -481,24 +523,34 @@ static cudaError_t launch_edges_g(const EdgeArgs& a, int which, cudaStream_t str
     const int chunks    = (a.geo.N + NPW * WARPS - 1) / (NPW * WARPS);
     const size_t grid   = (size_t)chunks * a.num_runs;
     const size_t shmem  = (size_t)a.geo.block_stride * 8;
+#define MIO_EDGE_LAUNCH(KERN, GRID, THREADS)                                                                           \
+    do {                                                                                                               \
+        auto kern = KERN;                                                                                              \
+        if (shmem > 48 * 1024) {                                                                                       \
+            cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)shmem);                       \
+        }                                                                                                              \
+        kern<<<(unsigned)(GRID), THREADS, shmem, stream>>>(a);                                                         \
+    } while (0)
     if (which == 0) {
-        if (shmem > 48 * 1024) {
-            cudaFuncSetAttribute(depart_kernel<G>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)shmem);
+        if (a.csr.factorized) {
+            MIO_EDGE_LAUNCH((depart_kernel<G, true>), grid, EDGE_THREADS);
         }
-        depart_kernel<G><<<(unsigned)grid, EDGE_THREADS, shmem, stream>>>(a);
+        else {
+            MIO_EDGE_LAUNCH((depart_kernel<G, false>), grid, EDGE_THREADS);
+        }
     }
     else if (which == 1) {
-        if (shmem > 48 * 1024) {
-            cudaFuncSetAttribute(return_kernel<G>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)shmem);
+        if (a.csr.factorized) {
+            MIO_EDGE_LAUNCH((return_kernel<G, true>), grid, EDGE_THREADS);
         }
-        return_kernel<G><<<(unsigned)grid, EDGE_THREADS, shmem, stream>>>(a);
+        else {
+            MIO_EDGE_LAUNCH((return_kernel<G, false>), grid, EDGE_THREADS);
+        }
     }
     else {
-        if (shmem > 48 * 1024) {
-            cudaFuncSetAttribute(return_exact_kernel<G>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)shmem);
-        }
-        return_exact_kernel<G><<<(unsigned)a.num_runs, 32, shmem, stream>>>(a);
+        MIO_EDGE_LAUNCH((return_exact_kernel<G>), a.num_runs, 32);
     }
+#undef MIO_EDGE_LAUNCH
     return cudaGetLastError();
 }
 

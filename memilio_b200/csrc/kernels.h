@@ -21,7 +21,11 @@ struct IntegrateArgs {
     DeviceState st;
     const double* y_in;
     double* y_out;
-    double* fac_out; // [R][N][G] mobility factor of the InfectedSymptoms compartment of the new snapshot (may be null)
+    // written only by the node phase that precedes a departure (null otherwise):
+    double* fac_out; // [R][N][G] get_mobility_factors of the new snapshot (InfectedSymptoms entry; the others are 1)
+    double* u_out;   // [R][N][n] emigration base vector: snapshot * (1 - mobility damping) * factor * nondetection,
+                     //           masked to the mobile compartments; mobile population of edge e = coeff_e * u_from
+    const double* umask; // [n]
     double t_end;
     int integrator;
     double abs_tol, rel_tol, dt_min, dt_max;
@@ -29,13 +33,22 @@ struct IntegrateArgs {
     int num_runs;
 };
 
-// incidence lists of the graph: for every node the incident edges in global (reference) edge order
-struct Incidence {
-    const int* node_order; // [N] processing order of the edge kernels (heaviest nodes first)
-    const int* inc_ptr;    // [N+1]
-    const int* inc_edge;   // [2E] edge index
-    const int* inc_other;  // [2E] the other node
-    const int* inc_out;    // [2E] 1: this node is the edge's start (outgoing), 0: incoming
+// Graph in the two forms the edge phase uses.
+struct GraphCsr {
+    // aggregated (SpMV) form
+    const int* order_in;  // [N] nodes by descending in-degree  (departure kernel processing order)
+    const int* order_out; // [N] nodes by descending out-degree (return kernel processing order)
+    const int* in_ptr;    // [N+1] incoming edges sorted by (dst, src)
+    const int* in_split;  // [N] incoming edges with src < dst: they precede dst's outgoing edges in reference order
+    const int* in_src;    // [E]
+    const double* w_in;   // factorized: [E][G] scalar per (edge, age); dense: [E][n]; incoming-CSR order
+    const int* out_ptr;   // [N+1] outgoing edges = reference edge order
+    const int* out_dst;   // [E]
+    const double* w_out;  // [E][G][2] coefficient of the Susceptible and InfectedSevere compartment per age
+    const double* s_out;  // [N][n] sum of the coefficient vectors of a node's outgoing edges (edge order)
+    const double* umask;  // [n] 1/0 mobile compartment mask (all ones in dense mode)
+    int factorized;       // coeff[e][i][c] == w[e][i] * umask[i][c] holds exactly for every edge
+    // literal form (exact replay of the sequential edge loop)
     const int* edge_start; // [E]
     const int* edge_end;   // [E]
     const double* coeff;   // [E][n]
@@ -44,21 +57,20 @@ struct Incidence {
 struct EdgeArgs {
     Geometry geo;
     DeviceState st;
-    Incidence inc;
-    const double* snap;     // [R][N][n] m_last_state of the departure step
-    const double* fac;      // [R][N][G] mobility factors of snap
-    const double* y_in;     // [R][N][n] live state before this edge phase
-    double* y_out;          // [R][N][n] live state after this edge phase
-    const double* v0;       // return only: [R][N][n] state right after the departure exchange (pop of the Euler step)
-    double* aux;            // [R][N][G][2] departure: written (lambda_i, critAdj_i of v0); return: read
-    int* run_flags;         // [R] return only: set to 1 when an underflow fix-up is needed (exact pass required)
-    long long* stats;       // [0] += number of (run, step) replays done by the exact kernel
-    double t;               // time of this edge phase (m_t after the node phase)
-    double t_dep;           // return only: departure time of the returning commuters
-    double dt;              // dt of this graph step
+    GraphCsr csr;
+    const double* snap;  // [R][N][n] m_last_state of the departure step
+    const double* fac;   // [R][N][G] mobility factors of snap
+    const double* u;     // [R][N][n] emigration base vectors of the departure step
+    const double* y_in;  // [R][N][n] live state before this edge phase
+    double* y_out;       // [R][N][n] live state after this edge phase
+    double* vis;         // [R][N][2][n] visitors held by a node between departure and return: V1 (from src < dst), V3
+    double* aux;         // [R][N][G][4] return coefficients of a node as destination (written at departure)
+    int* run_flags;      // [R] return: set to 1 when an underflow fix-up is needed (exact replay required)
+    long long* stats;    // [0] += number of (run, step) replays done by the exact kernel
+    double t;            // time of this edge phase (m_t after the node phase)
+    double t_dep;        // return only: departure time of the returning commuters
+    double dt;           // dt of this graph step
     int num_runs;
-    double* daily_out;      // optional [R][N][max_days][n]: record y_out as day `day_index`
-    int day_index, max_days;
 };
 
 cudaError_t launch_integrate(const IntegrateArgs& a, cudaStream_t stream);
