@@ -213,6 +213,92 @@ MIO_API int mio_cuda_get_trajectory(mio_handle* h, int32_t slot0, int32_t count,
  * in-order replay because of underflow fix-ups */
 MIO_API int mio_cuda_get_stats(mio_handle* h, int64_t* launches, int64_t* exact_replays);
 
+/* ---- ParameterStudy sampling (host C++, no device needed) --------------------------------------------------------
+ * Replaces, per run: ParameterStudy::run_impl's counter logic (cpp/memilio/compartments/parameter_studies.h:304-339),
+ * osecir::draw_sample(Graph&) (cpp/models/ode_secir/parameter_space.h:207-251) with draw_sample_infection :155-191 and
+ * draw_sample_demographics :125-148, UncertainValue::draw_sample (cpp/memilio/utils/uncertain_value.h:181-188),
+ * ParameterDistribution*::sample (cpp/memilio/utils/parameter_distributions.h), UncertainContactMatrix::
+ * draw_sample_dampings / make_matrix (cpp/memilio/epidemiology/uncertain_matrix.h:165-200), apply_dampings /
+ * make_contact_damping_matrix / make_mobility_damping_vector (epidemiology/damping_sampling.h:256-307),
+ * Dampings::update_cache (epidemiology/damping.h:571-660) and Parameters::apply_constraints
+ * (ode_secir/parameters.h:465-615). Random numbers: threefry2x32-20 keyed by std::seed_seq(seeds)
+ * (utils/random_number_generator.h:195-218,320-331) under the libstdc++ distributions, exactly as the reference.
+ */
+#define MIO_DIST_NONE 0        /* UncertainValue without distribution: draw_sample() keeps the value, no RNG draw */
+#define MIO_DIST_UNIFORM 1     /* ParameterDistributionUniform(a = lower, b = upper) */
+#define MIO_DIST_NORMAL 2      /* ParameterDistributionNormal(lower, upper, mean = a, stddev = b, quantile) */
+#define MIO_DIST_LOGNORMAL 3   /* ParameterDistributionLogNormal(log_mean = a, log_stddev = b) */
+#define MIO_DIST_EXPONENTIAL 4 /* ParameterDistributionExponential(rate = a) */
+#define MIO_DIST_CONSTANT 5    /* ParameterDistributionConstant(a) */
+
+typedef struct {
+    int32_t kind; /* MIO_DIST_* */
+    int32_t reserved;
+    double value; /* UncertainValue::m_value before sampling */
+    double a, b;
+    double lower, upper, quantile; /* normal only */
+} mio_uncertain_value;
+
+/* DampingSampling, cpp/memilio/epidemiology/damping_sampling.h:40-120 */
+typedef struct {
+    mio_uncertain_value value;
+    int32_t level, type;
+    double time;
+    uint64_t matrix_mask; /* bit l set: the damping applies to contact location l (get_matrix_indices) */
+    double group_weights[MIO_MAX_GROUPS];
+} mio_damping_sampling;
+
+typedef struct {
+    int32_t model;         /* MIO_MODEL_OSECIR */
+    int32_t num_groups;    /* G */
+    int32_t num_nodes;     /* N */
+    int32_t num_locations; /* L contact matrices of ContactPatterns */
+    int32_t num_dampings;  /* entries of UncertainContactMatrix::get_dampings() */
+    int32_t num_holiday_sets; /* distinct school holiday period lists (0 = no holidays anywhere) */
+    int32_t ct_max_pts;    /* capacity of the produced contact tables (change points per location) */
+    int32_t mob_max_pts;   /* capacity of the produced mobility tables; 0 = do not produce mobility tables */
+    int32_t mobility_location; /* member of the edges' MobilityCoefficientGroup that carries the baseline (set_edges:
+                                  ContactLocation::Work, graph.h:420-440; 0 for single-member groups) */
+    int32_t num_seeds;     /* <= 8; RandomNumberGenerator::seed(seeds) */
+    uint32_t seeds[8];
+    uint64_t rng_counter;  /* m_rng.get_counter() before run() (0 for a fresh study) */
+    const mio_uncertain_value* header;      /* [MIO_PSET_HEADER]  of node 0 (the shared parameter model) */
+    const mio_uncertain_value* age_params;  /* [G][mio_pset_age_stride] of node 0 */
+    const mio_uncertain_value* node_local;  /* [N][MIO_NODE_LOCAL] */
+    const mio_uncertain_value* populations; /* [N][n] */
+    const double* baseline;                 /* [L][G*G] */
+    const double* minimum;                  /* [L][G*G] */
+    const mio_damping_sampling* dampings;   /* [num_dampings] */
+    const mio_damping_sampling* school_holiday_damping; /* NULL = the default (value 0, no distribution, level/type 0) */
+    const int32_t* node_holiday_set;        /* [N] index into the holiday sets, -1 = none; NULL = none */
+    const int32_t* holiday_ptr;             /* [num_holiday_sets + 1] */
+    const double* holiday_periods;          /* [holiday_ptr[last]][2] = (start, end) */
+} mio_study_desc;
+
+typedef struct mio_study mio_study;
+
+MIO_API int mio_study_create(const mio_study_desc* desc, mio_study** out);
+MIO_API void mio_study_destroy(mio_study* s);
+/* number of contact tables per run the study produces (= max(1, num_holiday_sets + [some node has none])) and the
+ * node -> contact table map to pass as mio_graph_desc.node_ctable */
+MIO_API int mio_study_num_ctables(const mio_study* s);
+MIO_API int mio_study_node_ctable(const mio_study* s, int32_t* node_ctable /*[N]*/);
+/* draw_sample(graph) for runs [run0, run0 + count) of the study, each with the RNG counter
+ * rng_counter + (run_idx << 32). Outputs use the layouts of mio_run_data (ct_max_loc = num_locations);
+ * mobtables may be NULL when mob_max_pts == 0; draws (optional) receives the number of random numbers each run used. */
+MIO_API int mio_study_sample_runs(mio_study* s, int64_t run0, int32_t count, double* psets, double* ctables,
+                                  double* node_local, double* y0, double* mobtables, uint64_t* draws);
+/* ParameterStudy::distribute_runs (parameter_studies.h:354-367): first run and run count of `rank` */
+MIO_API int mio_study_distribute_runs(int64_t num_runs, int32_t num_procs, int32_t rank, int64_t* run0, int64_t* count);
+/* raw generator output: RandomNumberGenerator::operator() for `count` consecutive counters (known-answer tests) */
+MIO_API int mio_study_rng_raw(const uint32_t* seeds, int32_t num_seeds, uint64_t counter, int32_t count, uint64_t* out,
+                              uint64_t* key_out);
+/* Dampings::update_cache for K raw dampings of shape rows x cols (matrices row-major); returns the accumulated
+ * dampings and their change times in the layout the contact / mobility tables use. *num_out = cache entries. */
+MIO_API int mio_damping_cache_build(int32_t rows, int32_t cols, int32_t K, const double* times, const int32_t* levels,
+                                    const int32_t* types, const double* mats, int32_t* num_out, double* out_times,
+                                    double* out_mats);
+
 /* ---- measurement hooks ------------------------------------------------------------------------------------------ */
 #define MIO_NUM_KERNEL_CLASSES 5
 #define MIO_KC_INTEGRATE 0    /* node phase: adaptive RK integration of every (run, node) */

@@ -10,7 +10,7 @@ HERE = os.path.dirname(os.path.abspath(__file__))
 CSRC = os.path.join(HERE, "csrc")
 LIB = os.path.join(CSRC, "libmio_cuda.so")
 CU_SOURCES = ["integrate.cu", "edges.cu", "capi.cu", "peak.cu"]
-CXX_SOURCES = []
+CXX_SOURCES = ["study.cpp"]
 NVCC_FLAGS = ["-gencode", "arch=compute_100a,code=sm_100a", "-O3", "-lineinfo", "-std=c++17", "-Xcompiler",
               "-fPIC,-fvisibility=hidden,-O2", "-Xptxas", "-v", "--expt-relaxed-constexpr"]
 

@@ -24,6 +24,8 @@ EXPORTS = [
     "mio_cuda_get_state", "mio_cuda_get_node_dt", "mio_cuda_get_counters", "mio_cuda_get_daily",
     "mio_cuda_get_trajectory", "mio_cuda_get_stats", "mio_cuda_get_stream", "mio_cuda_set_profiling",
     "mio_cuda_get_profile", "mio_cuda_device_state_ptr", "mio_cuda_measure_fp64_peak",
+    "mio_study_create", "mio_study_destroy", "mio_study_num_ctables", "mio_study_node_ctable",
+    "mio_study_sample_runs", "mio_study_distribute_runs", "mio_study_rng_raw", "mio_damping_cache_build",
 ]
 KERNEL_CLASSES = ["integrate", "depart", "return", "return_exact", "record"]
 

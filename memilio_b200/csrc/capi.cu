@@ -45,6 +45,12 @@ cudaError_t dev_alloc(T** p, size_t count)
 
 } // namespace
 
+// shared with the host-only translation units (study.cpp)
+int mio_set_last_error(int code, const std::string& msg)
+{
+    return fail(code, msg);
+}
+
 struct mio_handle {
     mio_graph_desc desc;
     Geometry geo;

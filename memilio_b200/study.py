@@ -1,0 +1,342 @@
+"""ParameterStudy on the B200 backend (host-side mirror of cpp/memilio/compartments/parameter_studies.h:47-374).
+
+Sampling (`osecir::draw_sample(graph)`, cpp/models/ode_secir/parameter_space.h:207-251) runs in the C library
+(csrc/study.cpp, bit-exact with the reference's libstdc++ sampling); runs are processed in batches on the GPU.
+"""
+from __future__ import annotations
+
+import ctypes as C
+import dataclasses
+from typing import Callable, List, Optional, Sequence, Tuple
+
+import numpy as np
+
+from . import cdefs, flat
+from .problem import GraphProblem
+
+DIST_NONE, DIST_UNIFORM, DIST_NORMAL, DIST_LOGNORMAL, DIST_EXPONENTIAL, DIST_CONSTANT = range(6)
+MAX_GROUPS = 8
+
+
+class UncertainValue(C.Structure):
+    """mio::UncertainValue (cpp/memilio/utils/uncertain_value.h:45-258) as a POD."""
+    _fields_ = [("kind", C.c_int32), ("reserved", C.c_int32), ("value", C.c_double), ("a", C.c_double),
+                ("b", C.c_double), ("lower", C.c_double), ("upper", C.c_double), ("quantile", C.c_double)]
+
+
+class DampingSampling(C.Structure):
+    _fields_ = [("value", UncertainValue), ("level", C.c_int32), ("type", C.c_int32), ("time", C.c_double),
+                ("matrix_mask", C.c_uint64), ("group_weights", C.c_double * MAX_GROUPS)]
+
+
+class StudyDesc(C.Structure):
+    _fields_ = [("model", C.c_int32), ("num_groups", C.c_int32), ("num_nodes", C.c_int32),
+                ("num_locations", C.c_int32), ("num_dampings", C.c_int32), ("num_holiday_sets", C.c_int32),
+                ("ct_max_pts", C.c_int32), ("mob_max_pts", C.c_int32), ("mobility_location", C.c_int32),
+                ("num_seeds", C.c_int32), ("seeds", C.c_uint32 * 8), ("rng_counter", C.c_uint64),
+                ("header", C.POINTER(UncertainValue)), ("age_params", C.POINTER(UncertainValue)),
+                ("node_local", C.POINTER(UncertainValue)), ("populations", C.POINTER(UncertainValue)),
+                ("baseline", cdefs.c_double_p), ("minimum", cdefs.c_double_p),
+                ("dampings", C.POINTER(DampingSampling)), ("school_holiday_damping", C.POINTER(DampingSampling)),
+                ("node_holiday_set", cdefs.c_int32_p), ("holiday_ptr", cdefs.c_int32_p),
+                ("holiday_periods", cdefs.c_double_p)]
+
+
+UV_DTYPE = np.dtype([("kind", np.int32), ("reserved", np.int32), ("value", np.float64), ("a", np.float64),
+                     ("b", np.float64), ("lower", np.float64), ("upper", np.float64), ("quantile", np.float64)])
+assert UV_DTYPE.itemsize == C.sizeof(UncertainValue)
+
+
+def uv_array(shape) -> np.ndarray:
+    return np.zeros(shape, dtype=UV_DTYPE)
+
+
+def set_value(arr, idx, value):
+    arr[idx]["kind"] = DIST_NONE
+    arr[idx]["value"] = value
+
+
+def set_uniform(arr, idx, lo, hi):
+    """assign_uniform_distribution, cpp/examples/ode_secir_parameter_study_graph.cpp:45-49"""
+    arr[idx]["kind"] = DIST_UNIFORM
+    arr[idx]["value"] = 0.5 * (np.asarray(hi) + np.asarray(lo))
+    arr[idx]["a"] = lo
+    arr[idx]["b"] = hi
+
+
+def set_normal(arr, idx, lower, upper, mean, stddev, quantile=2.5758):
+    arr[idx]["kind"] = DIST_NORMAL
+    arr[idx]["value"] = mean
+    arr[idx]["a"] = mean
+    arr[idx]["b"] = stddev
+    arr[idx]["lower"] = lower
+    arr[idx]["upper"] = upper
+    arr[idx]["quantile"] = quantile
+
+
+@dataclasses.dataclass
+class Damping:
+    """DampingSampling, cpp/memilio/epidemiology/damping_sampling.h:40-120"""
+    value: np.ndarray  # one-element UV array
+    time: float
+    level: int = 0
+    type: int = 0
+    matrices: Sequence[int] = (0,)
+    group_weights: Optional[Sequence[float]] = None
+
+
+@dataclasses.dataclass
+class StudyGraph:
+    """The parameter graph a ParameterStudy samples from: `mio::Graph<osecir::Model, MobilityParameters>` with
+    UncertainValues (cpp/memilio/mobility/graph.h:145-300)."""
+    num_groups: int
+    num_nodes: int
+    header: np.ndarray  # UV[8]
+    age_params: np.ndarray  # UV[G][16]
+    node_local: np.ndarray  # UV[N][2]
+    populations: np.ndarray  # UV[N][n]
+    baseline: np.ndarray  # [L][G][G]
+    minimum: Optional[np.ndarray]
+    edge_start: np.ndarray
+    edge_end: np.ndarray
+    edge_coeff: np.ndarray
+    dampings: List[Damping] = dataclasses.field(default_factory=list)
+    school_holiday_damping: Optional[Damping] = None
+    node_holiday_set: Optional[np.ndarray] = None
+    holiday_sets: Sequence[Sequence[Tuple[float, float]]] = ()
+    mobility_location: int = 0
+    damp_mobility: bool = True
+    model: int = flat.MODEL_OSECIR
+
+    @property
+    def n(self):
+        return self.num_groups * flat.num_compartments(self.model)
+
+    @property
+    def num_locations(self):
+        return int(np.asarray(self.baseline).shape[0])
+
+
+def _lib():
+    from . import capi
+    L = capi.lib()
+    if not getattr(L, "_study_bound", False):
+        L.mio_study_create.argtypes = [C.POINTER(StudyDesc), C.POINTER(C.c_void_p)]
+        L.mio_study_destroy.argtypes = [C.c_void_p]
+        L.mio_study_destroy.restype = None
+        L.mio_study_num_ctables.argtypes = [C.c_void_p]
+        L.mio_study_node_ctable.argtypes = [C.c_void_p, cdefs.c_int32_p]
+        L.mio_study_sample_runs.argtypes = [C.c_void_p, C.c_int64, C.c_int32, cdefs.c_double_p, cdefs.c_double_p,
+                                            cdefs.c_double_p, cdefs.c_double_p, cdefs.c_double_p,
+                                            C.POINTER(C.c_uint64)]
+        L.mio_study_distribute_runs.argtypes = [C.c_int64, C.c_int32, C.c_int32, C.POINTER(C.c_int64),
+                                                C.POINTER(C.c_int64)]
+        L.mio_study_rng_raw.argtypes = [C.POINTER(C.c_uint32), C.c_int32, C.c_uint64, C.c_int32,
+                                        C.POINTER(C.c_uint64), C.POINTER(C.c_uint64)]
+        L.mio_damping_cache_build.argtypes = [C.c_int32, C.c_int32, C.c_int32, cdefs.c_double_p, cdefs.c_int32_p,
+                                              cdefs.c_int32_p, cdefs.c_double_p, C.POINTER(C.c_int32),
+                                              cdefs.c_double_p, cdefs.c_double_p]
+        L._study_bound = True
+    return L
+
+
+def _check(rc):
+    from . import capi
+    capi._check(rc)
+
+
+def _ds_struct(d: Damping, G: int) -> DampingSampling:
+    s = DampingSampling()
+    C.memmove(C.byref(s.value), d.value.ctypes.data, C.sizeof(UncertainValue))
+    s.level, s.type, s.time = d.level, d.type, d.time
+    mask = 0
+    for l in d.matrices:
+        mask |= 1 << int(l)
+    s.matrix_mask = mask
+    w = np.ones(G) if d.group_weights is None else np.asarray(d.group_weights, dtype=np.float64)
+    for i in range(G):
+        s.group_weights[i] = w[i]
+    return s
+
+
+def build_desc(g: StudyGraph, seeds: Sequence[int], rng_counter: int, ct_max_pts: int, mob_max_pts: int):
+    """(StudyDesc, keep-alive list) for the C library and the oracle."""
+    G, N = g.num_groups, g.num_nodes
+    d = StudyDesc()
+    d.model, d.num_groups, d.num_nodes, d.num_locations = g.model, G, N, g.num_locations
+    d.num_dampings = len(g.dampings)
+    d.num_holiday_sets = len(g.holiday_sets)
+    d.ct_max_pts, d.mob_max_pts, d.mobility_location = ct_max_pts, mob_max_pts, g.mobility_location
+    d.num_seeds = len(seeds)
+    for i, sd in enumerate(seeds):
+        d.seeds[i] = int(sd)
+    d.rng_counter = int(rng_counter)
+    keep = []
+
+    def uvp(a, shape):
+        a = np.ascontiguousarray(a, dtype=UV_DTYPE).reshape(shape)
+        keep.append(a)
+        return a.ctypes.data_as(C.POINTER(UncertainValue))
+
+    d.header = uvp(g.header, (flat.PSET_HEADER,))
+    d.age_params = uvp(g.age_params, (G, flat.OSECIR_AGE_STRIDE))
+    d.node_local = uvp(g.node_local, (N, 2))
+    d.populations = uvp(g.populations, (N, g.n))
+    base = np.ascontiguousarray(g.baseline, dtype=np.float64).reshape(g.num_locations, G, G)
+    keep.append(base)
+    d.baseline = cdefs.dptr(base)
+    if g.minimum is not None:
+        mn = np.ascontiguousarray(g.minimum, dtype=np.float64).reshape(g.num_locations, G, G)
+        keep.append(mn)
+        d.minimum = cdefs.dptr(mn)
+    if g.dampings:
+        arr = (DampingSampling * len(g.dampings))(*[_ds_struct(x, G) for x in g.dampings])
+        keep.append(arr)
+        d.dampings = C.cast(arr, C.POINTER(DampingSampling))
+    if g.school_holiday_damping is not None:
+        hs = _ds_struct(g.school_holiday_damping, G)
+        keep.append(hs)
+        d.school_holiday_damping = C.pointer(hs)
+    if len(g.holiday_sets) > 0:
+        ptr = np.zeros(len(g.holiday_sets) + 1, dtype=np.int32)
+        periods = []
+        for k, hs_ in enumerate(g.holiday_sets):
+            periods += [list(p) for p in hs_]
+            ptr[k + 1] = len(periods)
+        periods = np.ascontiguousarray(np.asarray(periods, dtype=np.float64).reshape(-1, 2))
+        ns = np.ascontiguousarray(g.node_holiday_set, dtype=np.int32)
+        keep += [ptr, periods, ns]
+        d.holiday_ptr, d.holiday_periods, d.node_holiday_set = cdefs.iptr(ptr), cdefs.dptr(periods), cdefs.iptr(ns)
+    return d, keep
+
+
+def distribute_runs(num_runs: int, num_procs: int, rank: int) -> Tuple[int, int]:
+    """ParameterStudy::distribute_runs (parameter_studies.h:354-367): (first run, count) of `rank`."""
+    a, b = C.c_int64(), C.c_int64()
+    _check(_lib().mio_study_distribute_runs(num_runs, num_procs, rank, C.byref(a), C.byref(b)))
+    return a.value, b.value
+
+
+def rng_raw(seeds, counter, count):
+    s = (C.c_uint32 * len(seeds))(*[int(x) for x in seeds])
+    out = (C.c_uint64 * count)()
+    key = C.c_uint64()
+    _check(_lib().mio_study_rng_raw(s, len(seeds), C.c_uint64(counter), count, out, C.byref(key)))
+    return np.array(out[:], dtype=np.uint64), int(key.value)
+
+
+def damping_cache(rows, cols, times, levels, types, mats):
+    K = len(times)
+    times = np.ascontiguousarray(times, dtype=np.float64)
+    levels = np.ascontiguousarray(levels, dtype=np.int32)
+    types = np.ascontiguousarray(types, dtype=np.int32)
+    mats = np.ascontiguousarray(mats, dtype=np.float64).reshape(K, rows * cols)
+    ot = np.zeros(max(K, 1))
+    om = np.zeros((max(K, 1), rows * cols))
+    n = C.c_int32()
+    _check(_lib().mio_damping_cache_build(rows, cols, K, cdefs.dptr(times), cdefs.iptr(levels), cdefs.iptr(types),
+                                          cdefs.dptr(mats), C.byref(n), cdefs.dptr(ot), cdefs.dptr(om)))
+    return ot[:n.value].copy(), om[:n.value].reshape(n.value, rows, cols).copy()
+
+
+class ParameterStudy:
+    """`mio::ParameterStudy(params_graph, t0, tmax, dt, num_runs)` (parameter_studies.h:84) for a Graph-ODE-SECIR
+    study. `run` keeps the reference's semantics: run r is sampled with RNG counter `counter + (r << 32)`, advanced
+    to tmax, then handed to `process_result`; after `run` the counter moves on by `num_runs << 32`."""
+
+    def __init__(self, graph: StudyGraph, t0: float, tmax: float, dt: float, num_runs: int,
+                 seeds: Sequence[int] = (1, 2, 3, 4, 5, 6), ct_max_pts: int = 4, mob_max_pts: Optional[int] = None,
+                 integrator: Optional[cdefs.IntegratorDesc] = None):
+        self.graph, self.t0, self.tmax, self.dt, self.num_runs = graph, t0, tmax, dt, num_runs
+        self.seeds = list(seeds)
+        self.rng_counter = 0
+        self.ct_max_pts = ct_max_pts
+        if mob_max_pts is None:
+            mob_max_pts = ct_max_pts if (graph.damp_mobility and graph.dampings) else 0
+        self.mob_max_pts = mob_max_pts
+        self.integrator = integrator if integrator is not None else cdefs.integrator_desc()
+        self._h = None
+        self._keep = None
+
+    # -- sampling ---------------------------------------------------------------------------------------------
+    def _study(self):
+        if self._h is None:
+            d, keep = build_desc(self.graph, self.seeds, self.rng_counter, self.ct_max_pts, self.mob_max_pts)
+            h = C.c_void_p()
+            _check(_lib().mio_study_create(C.byref(d), C.byref(h)))
+            self._h, self._keep = h, keep
+        return self._h
+
+    def _invalidate(self):
+        if self._h is not None:
+            _lib().mio_study_destroy(self._h)
+            self._h = None
+
+    def seed(self, seeds):
+        self.seeds = list(seeds)
+        self._invalidate()
+
+    def sample(self, run0: int, count: int) -> GraphProblem:
+        """The sampled graphs of runs [run0, run0+count) as flat run data (what create_simulation would build)."""
+        h = self._study()
+        g = self.graph
+        G, N, n = g.num_groups, g.num_nodes, g.n
+        nct = _lib().mio_study_num_ctables(h)
+        node_ct = np.zeros(N, dtype=np.int32)
+        _check(_lib().mio_study_node_ctable(h, cdefs.iptr(node_ct)))
+        psets = np.zeros((count, 1, flat.pset_size(g.model, G)))
+        ctables = np.zeros((count, nct, flat.ctable_size(G, g.num_locations, self.ct_max_pts)))
+        local = np.zeros((count, N, 2))
+        y0 = np.zeros((count, N, n))
+        mob = np.zeros((count, flat.mobtable_size(n, self.mob_max_pts))) if self.mob_max_pts > 0 else None
+        draws = (C.c_uint64 * max(count, 1))()
+        _check(_lib().mio_study_sample_runs(h, run0, count, cdefs.dptr(psets), cdefs.dptr(ctables), cdefs.dptr(local),
+                                            cdefs.dptr(y0), cdefs.dptr(mob), draws))
+        self.last_draws = np.array(draws[:count], dtype=np.uint64)
+        return GraphProblem(model=g.model, num_groups=G, num_nodes=N, edge_start=g.edge_start, edge_end=g.edge_end,
+                            edge_coeff=g.edge_coeff, psets=psets, ctables=ctables, node_local=local, y0=y0,
+                            ct_max_loc=g.num_locations, ct_max_pts=self.ct_max_pts,
+                            node_ctable=node_ct if nct > 1 else None, mobtables=mob, mob_max_pts=self.mob_max_pts,
+                            integrator=self.integrator, t0=self.t0, dt_graph=self.dt)
+
+    # -- run ----------------------------------------------------------------------------------------------------
+    def run(self, process_result: Optional[Callable] = None, batch: int = 1024, device: int = 0, rank: int = 0,
+            world: int = 1, record_daily: bool = True):
+        """ParameterStudy::run (parameter_studies.h:158-217): this rank's block of runs (distribute_runs), in batches.
+        `process_result(run_idx, daily[N][days][n] or state[N][n])` is called per run in run order; its results are
+        returned as a list (like the ensemble_result vector)."""
+        from . import capi
+        run0, count = distribute_runs(self.num_runs, world, rank)
+        out = []
+        sim = None
+        days = int(np.floor(self.tmax + 1e-14) - np.ceil(self.t0 - 1e-14)) + 1
+        done = 0
+        while done < count:
+            b = min(batch, count - done)
+            p = self.sample(run0 + done, b)
+            if sim is None:
+                sim = capi.GraphSimulation(p, device=device, max_runs=min(batch, count), record_daily=record_daily,
+                                           max_days=days, upload=False)
+            sim.reset()
+            sim.set_active_runs(b)
+            sim.set_runs(0, p, 0, b)
+            sim.advance(self.tmax)
+            res = sim.daily(0, b) if record_daily else sim.state(0, b)
+            for r in range(b):
+                out.append(process_result(run0 + done + r, res[r]) if process_result else res[r])
+            done += b
+        if sim is not None:
+            sim.close()
+        # parameter_studies.h:339: future calls of run() produce different parameters
+        self.rng_counter += self.num_runs << 32
+        self._invalidate()
+        return out
+
+    def close(self):
+        self._invalidate()
+
+    def __del__(self):
+        try:
+            self._invalidate()
+        except Exception:
+            pass

@@ -119,3 +119,71 @@ def county_problem(N: int = 400, runs: int = 1, seed: int = 20261017, G: int = 6
                         edge_coeff=coeff, psets=psets, ctables=ctables, node_local=locals_, y0=y0s, ct_max_loc=1,
                         ct_max_pts=2, integrator=integrator if integrator is not None else cdefs.integrator_desc(),
                         t0=0.0, dt_graph=dt_graph)
+
+
+# uniform ranges of set_covid_parameters, cpp/examples/ode_secir_parameter_study_graph.cpp:91-159
+COVID_UNIFORM = dict(
+    TimeExposed=(2.67, 4.0), TimeInfectedNoSymptoms=(1.2, 2.53),
+    TimeInfectedSymptoms=([5.6255, 5.6255, 5.6646, 5.5631, 5.501, 5.465], [8.427, 8.427, 8.4684, 8.3139, 8.169, 8.085]),
+    TimeInfectedSevere=([3.925, 3.925, 4.85, 6.4, 7.2, 9.], [6.075, 6.075, 7., 8.7, 9.8, 13.]),
+    TimeInfectedCritical=([4.95, 4.95, 4.86, 14.14, 14.4, 10.], [8.95, 8.95, 8.86, 20.58, 19.8, 13.2]),
+    TransmissionProbabilityOnContact=([0.02, 0.05, 0.05, 0.05, 0.08, 0.15], [0.04, 0.07, 0.07, 0.07, 0.10, 0.20]),
+    RelativeTransmissionNoSymptoms=(1.0, 1.0),
+    RiskOfInfectionFromSymptomatic=(0.1, 0.3), MaxRiskOfInfectionFromSymptomatic=(0.3, 0.5),
+    RecoveredPerInfectedNoSymptoms=([0.2, 0.2, 0.15, 0.15, 0.15, 0.15], [0.3, 0.3, 0.25, 0.25, 0.25, 0.25]),
+    SeverePerInfectedSymptoms=([0.006, 0.006, 0.015, 0.049, 0.15, 0.20], [0.009, 0.009, 0.023, 0.074, 0.18, 0.25]),
+    CriticalPerSevere=([0.05, 0.05, 0.05, 0.10, 0.25, 0.35], [0.10, 0.10, 0.10, 0.20, 0.35, 0.45]),
+    DeathsPerCritical=([0.00, 0.00, 0.10, 0.10, 0.30, 0.5], [0.10, 0.10, 0.18, 0.18, 0.50, 0.7]),
+)
+
+
+def covid_study_graph(N: int = 400, seed: int = 20261017, G: int = 6, max_out_degree: int = 25, n_seeded: int = 10,
+                      cont_freq: float = 10.0, damping_day: Optional[float] = 30.0, pop_uncertainty: float = 0.1,
+                      tnt_capacity_factor: float = 7.5e-5):
+    """Config 4: the synthetic county graph as a *parameter graph* with the uniform distributions of
+    set_covid_parameters, +-10 % uniform uncertainty on the seeded compartments and 0.8-1.2 on the test-and-trace
+    capacity (cpp/memilio/mobility/graph.h:350-351,376-378), one sampled contact damping U(0.4, 0.8) at
+    `damping_day` that also damps the mobility coefficients (parameter_space.h:241-248)."""
+    from . import study as st
+    pop, es, ee, coeff = county_graph(N, seed, max_out_degree, G)
+    n = G * 10
+    header = st.uv_array(flat.PSET_HEADER)
+    st.set_value(header, flat.PH["StartDay"], 0.0)
+    st.set_uniform(header, flat.PH["Seasonality"], 0.1, 0.3)
+    st.set_value(header, flat.PH["TestAndTraceCapacityMaxRisk"], 5.0)
+    age = st.uv_array((G, flat.OSECIR_AGE_STRIDE))
+    for name, slot in flat.PA.items():
+        age[:, slot]["value"] = flat.PA_DEFAULT[name]
+    for name, (lo, hi) in COVID_UNIFORM.items():
+        lo = np.broadcast_to(np.asarray(lo, dtype=np.float64)[:G] if np.ndim(lo) else lo, (G,))
+        hi = np.broadcast_to(np.asarray(hi, dtype=np.float64)[:G] if np.ndim(hi) else hi, (G,))
+        for i in range(G):
+            st.set_uniform(age, (i, flat.PA[name]), lo[i], hi[i])
+    rng = np.random.default_rng(seed + 1)
+    y0 = np.zeros((N, G, 10))
+    y0[:, :, flat.S] = pop
+    seeded = rng.choice(N, size=min(n_seeded, N), replace=False)
+    for k in seeded:
+        e0 = 1e-4 * pop[k]
+        y0[k, :, flat.E] = e0
+        y0[k, :, flat.S] -= e0
+    pops = st.uv_array((N, n))
+    pops["value"] = y0.reshape(N, n)
+    if pop_uncertainty > 0:
+        for k in seeded:
+            for i in range(G):
+                v = y0[k, i, flat.E]
+                st.set_uniform(pops, (k, i * 10 + flat.E), (1 - pop_uncertainty) * v, (1 + pop_uncertainty) * v)
+    local = st.uv_array((N, 2))
+    st.set_value(local, (slice(None), 0), flat.DBL_MAX)
+    tnt = pop.sum(axis=1) * tnt_capacity_factor
+    for k in range(N):
+        st.set_uniform(local, (k, 1), 0.8 * tnt[k], 1.2 * tnt[k])
+    dampings = []
+    if damping_day is not None:
+        v = st.uv_array(1)
+        st.set_uniform(v, 0, 0.4, 0.8)
+        dampings.append(st.Damping(value=v, time=damping_day, level=0, type=0, matrices=(0,)))
+    return st.StudyGraph(num_groups=G, num_nodes=N, header=header, age_params=age, node_local=local,
+                         populations=pops, baseline=np.full((1, G, G), cont_freq / G), minimum=None, edge_start=es,
+                         edge_end=ee, edge_coeff=coeff, dampings=dampings)

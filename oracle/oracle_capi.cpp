@@ -2,6 +2,7 @@
 // They take the same flat descriptors as the CUDA C-ABI (include/mio_cuda.h) so that tests feed identical bytes to
 // both sides. Loaded with ctypes by tests/, __graft_entry__.smoke() and the cpu_baseline legs of bench.py only.
 #include "mio_oracle.hpp"
+#include "mio_oracle_sampling.hpp"
 #include "../include/mio_cuda.h"
 
 #include <cstring>
@@ -287,6 +288,233 @@ void orc_edge_apply_sequence(int G, const double* pset, const double* local, con
         std::copy(node1.sim.result.last().begin(), node1.sim.result.last().end(), out + (phase * 2 + 0) * n);
         std::copy(node2.sim.result.last().begin(), node2.sim.result.last().end(), out + (phase * 2 + 1) * n);
     }
+}
+
+// ---- ParameterStudy sampling (oracle side of mio_study_sample_runs) ---------------------------------------------
+static orc::sampling::UncertainValue uv_from(const mio_uncertain_value& u)
+{
+    orc::sampling::UncertainValue v;
+    v.value = u.value;
+    if (u.kind != MIO_DIST_NONE) {
+        orc::sampling::Distribution d;
+        d.kind     = u.kind;
+        d.a        = u.a;
+        d.b        = u.b;
+        d.lower    = u.lower;
+        d.upper    = u.upper;
+        d.quantile = u.quantile;
+        v.dist     = d;
+    }
+    return v;
+}
+
+static orc::sampling::DampingSampling ds_from(const mio_damping_sampling& s, int G)
+{
+    orc::sampling::DampingSampling d;
+    d.value = uv_from(s.value);
+    d.level = s.level;
+    d.type  = s.type;
+    d.time  = s.time;
+    for (size_t l = 0; l < 64; ++l) {
+        if ((s.matrix_mask >> l) & 1u) {
+            d.matrices.push_back(l);
+        }
+    }
+    d.groups.assign(s.group_weights, s.group_weights + G);
+    return d;
+}
+
+// raw RandomNumberGenerator output and key for `count` consecutive counters
+void orc_rng_raw(const uint32_t* seeds, int num_seeds, uint64_t counter, int count, uint64_t* out, uint64_t* key_out)
+{
+    orc::sampling::RandomNumberGenerator rng;
+    rng.seed(std::vector<uint32_t>(seeds, seeds + num_seeds));
+    rng.counter = counter;
+    if (key_out) {
+        *key_out = rng.key;
+    }
+    for (int i = 0; i < count; ++i) {
+        out[i] = rng();
+    }
+}
+
+// threefry2x32-20 on explicit counter/key words (Random123 known-answer tests)
+void orc_threefry2x32(const uint32_t* ctr, const uint32_t* key, uint32_t* out)
+{
+    auto r = orc::sampling::threefry2x32({{ctr[0], ctr[1]}}, {{key[0], key[1]}});
+    out[0] = r.v[0];
+    out[1] = r.v[1];
+}
+
+// one uniform / normal draw sequence (distribution level checks)
+void orc_draw_values(const uint32_t* seeds, int num_seeds, uint64_t counter, const mio_uncertain_value* u, int count,
+                     double* out)
+{
+    orc::sampling::RandomNumberGenerator rng;
+    rng.seed(std::vector<uint32_t>(seeds, seeds + num_seeds));
+    rng.counter = counter;
+    for (int i = 0; i < count; ++i) {
+        auto v = uv_from(u[i]);
+        out[i] = v.draw_sample(rng);
+    }
+}
+
+// ParameterStudy::run_impl sampling step for runs [run0, run0+count): copy the parameter graph, set the counter,
+// osecir::draw_sample(copy); outputs in the flat layouts of mio_run_data. Returns 0 on success.
+int orc_study_sample_runs(const mio_study_desc* d, int64_t run0, int count, double* psets, double* ctables,
+                          double* node_local, double* y0, double* mobtables, uint64_t* draws)
+{
+    namespace sp = orc::sampling;
+    const int G = d->num_groups, N = d->num_nodes, L = d->num_locations, n = G * 10;
+    // the parameter graph: every node carries node 0's parameter distributions (only node 0's are ever used)
+    sp::GraphU graph;
+    graph.n                 = n;
+    graph.mobility_location = d->mobility_location;
+    sp::SecirParamsU p0;
+    p0.G                            = G;
+    p0.StartDay                     = uv_from(d->header[MIO_PH_START_DAY]);
+    p0.Seasonality                  = uv_from(d->header[MIO_PH_SEASONALITY]);
+    p0.TestAndTraceCapacityMaxRisk  = uv_from(d->header[MIO_PH_TNT_MAX_RISK]);
+    p0.commuter_nondetection        = uv_from(d->header[MIO_PH_COMMUTER_NONDETECTION]);
+    p0.start_commuter_detection     = uv_from(d->header[MIO_PH_START_COMMUTER_DETECTION]);
+    p0.end_commuter_detection       = uv_from(d->header[MIO_PH_END_COMMUTER_DETECTION]);
+    p0.age.assign(sp::NumTags, std::vector<sp::UncertainValue>(G));
+    for (int i = 0; i < G; ++i) {
+        for (int tag = 0; tag < sp::NumTags; ++tag) {
+            p0.age[tag][i] = uv_from(d->age_params[i * MIO_OSECIR_AGE_STRIDE + tag]);
+        }
+    }
+    for (int l = 0; l < L; ++l) {
+        Mat b(G, G), m(G, G);
+        std::copy(d->baseline + int64_t(l) * G * G, d->baseline + int64_t(l + 1) * G * G, b.a.begin());
+        if (d->minimum) {
+            std::copy(d->minimum + int64_t(l) * G * G, d->minimum + int64_t(l + 1) * G * G, m.a.begin());
+        }
+        p0.baseline.push_back(b);
+        p0.minimum.push_back(m);
+    }
+    for (int k = 0; k < d->num_dampings; ++k) {
+        p0.dampings.push_back(ds_from(d->dampings[k], G));
+    }
+    if (d->school_holiday_damping) {
+        p0.school_holiday_damping = ds_from(*d->school_holiday_damping, G);
+    }
+    else {
+        p0.school_holiday_damping.groups.assign(G, 0.0);
+    }
+    int num_tables = 1;
+    bool any_none  = false;
+    if (d->num_holiday_sets > 0) {
+        for (int k = 0; k < N; ++k) {
+            any_none = any_none || d->node_holiday_set[k] < 0;
+        }
+        num_tables = d->num_holiday_sets + (any_none ? 1 : 0);
+    }
+    for (int k = 0; k < N; ++k) {
+        sp::NodeModelU node;
+        node.parameters                      = p0;
+        node.parameters.ICUCapacity          = uv_from(d->node_local[k * 2 + MIO_NL_ICU_CAPACITY]);
+        node.parameters.TestAndTraceCapacity = uv_from(d->node_local[k * 2 + MIO_NL_TNT_CAPACITY]);
+        if (d->num_holiday_sets > 0 && d->node_holiday_set[k] >= 0) {
+            const int hs = d->node_holiday_set[k];
+            for (int h = d->holiday_ptr[hs]; h < d->holiday_ptr[hs + 1]; ++h) {
+                node.parameters.school_holidays.emplace_back(d->holiday_periods[h * 2], d->holiday_periods[h * 2 + 1]);
+            }
+        }
+        for (int j = 0; j < n; ++j) {
+            node.populations.push_back(uv_from(d->populations[int64_t(k) * n + j]));
+        }
+        graph.nodes.push_back(node);
+    }
+    sp::RandomNumberGenerator rng;
+    rng.seed(std::vector<uint32_t>(d->seeds, d->seeds + d->num_seeds));
+    const int64_t psz = pset_size(MIO_MODEL_OSECIR, G);
+    const int64_t csz = ctable_size(G, L, d->ct_max_pts);
+    const int64_t msz = d->mob_max_pts > 0 ? 1 + d->mob_max_pts + int64_t(d->mob_max_pts) * n : 0;
+    const int64_t lstr = d->ct_max_pts + int64_t(2 + d->ct_max_pts) * G * G;
+    for (int r = 0; r < count; ++r) {
+        const uint64_t c0 = d->rng_counter + (uint64_t(run0 + r) << 32);
+        rng.counter       = c0;
+        auto copy         = graph;
+        auto [nodes, mob] = sp::draw_sample(copy, rng);
+        if (draws) {
+            draws[r] = rng.counter - c0;
+        }
+        // all nodes share the sampled parameter set: flatten node 0's
+        double* ps = psets + r * psz;
+        std::fill(ps, ps + psz, 0.0);
+        const auto& q                     = nodes[0].parameters;
+        ps[MIO_PH_START_DAY]              = q.StartDay.value;
+        ps[MIO_PH_SEASONALITY]            = q.Seasonality.value;
+        ps[MIO_PH_TNT_MAX_RISK]           = q.TestAndTraceCapacityMaxRisk.value;
+        ps[MIO_PH_COMMUTER_NONDETECTION]  = q.commuter_nondetection.value;
+        ps[MIO_PH_START_COMMUTER_DETECTION] = q.start_commuter_detection.value;
+        ps[MIO_PH_END_COMMUTER_DETECTION] = q.end_commuter_detection.value;
+        ps[MIO_PH_RESERVED6]              = d->header[MIO_PH_RESERVED6].value;
+        ps[MIO_PH_RESERVED7]              = d->header[MIO_PH_RESERVED7].value;
+        for (int i = 0; i < G; ++i) {
+            for (int tag = 0; tag < sp::NumTags; ++tag) {
+                ps[MIO_PSET_HEADER + i * MIO_OSECIR_AGE_STRIDE + tag] = q.age[tag][i].value;
+            }
+            for (int tag = sp::NumTags; tag < MIO_OSECIR_AGE_STRIDE; ++tag) {
+                ps[MIO_PSET_HEADER + i * MIO_OSECIR_AGE_STRIDE + tag] = d->age_params[i * MIO_OSECIR_AGE_STRIDE + tag].value;
+            }
+        }
+        for (int k = 0; k < N; ++k) {
+            node_local[(int64_t(r) * N + k) * 2 + 0] = nodes[k].parameters.ICUCapacity.value;
+            node_local[(int64_t(r) * N + k) * 2 + 1] = nodes[k].parameters.TestAndTraceCapacity.value;
+            for (int j = 0; j < n; ++j) {
+                y0[(int64_t(r) * N + k) * n + j] = nodes[k].populations[j].value;
+            }
+        }
+        // contact tables: one per holiday set, taken from the first node that uses it
+        for (int tbl = 0; tbl < num_tables; ++tbl) {
+            int rep = 0;
+            if (d->num_holiday_sets > 0) {
+                for (int k = 0; k < N; ++k) {
+                    const int hs = d->node_holiday_set[k] < 0 ? d->num_holiday_sets : d->node_holiday_set[k];
+                    if (hs == tbl) {
+                        rep = k;
+                        break;
+                    }
+                }
+            }
+            double* ct = ctables + (int64_t(r) * num_tables + tbl) * csz;
+            std::fill(ct, ct + csz, 0.0);
+            ct[0] = L;
+            for (int l = 0; l < L; ++l) {
+                const auto& dm = nodes[rep].parameters.cont_freq_dampings[l];
+                const int K    = int(dm.cache.size()) - 2;
+                if (K > d->ct_max_pts) {
+                    return 2;
+                }
+                ct[1 + l] = K;
+                double* p = ct + 1 + L + l * lstr;
+                for (int k = 0; k < K; ++k) {
+                    p[k] = dm.cache[k + 1].second;
+                    std::copy(dm.cache[k + 1].first.a.begin(), dm.cache[k + 1].first.a.end(),
+                              p + d->ct_max_pts + int64_t(2 + k) * G * G);
+                }
+                std::copy(q.baseline[l].a.begin(), q.baseline[l].a.end(), p + d->ct_max_pts);
+                std::copy(q.minimum[l].a.begin(), q.minimum[l].a.end(), p + d->ct_max_pts + G * G);
+            }
+        }
+        if (msz > 0 && mobtables) {
+            double* mt = mobtables + r * msz;
+            std::fill(mt, mt + msz, 0.0);
+            const int K = int(mob.cache.size()) - 2;
+            if (K > d->mob_max_pts) {
+                return 2;
+            }
+            mt[0] = K;
+            for (int k = 0; k < K; ++k) {
+                mt[1 + k] = mob.cache[k + 1].second;
+                std::copy(mob.cache[k + 1].first.a.begin(), mob.cache[k + 1].first.a.end(),
+                          mt + 1 + d->mob_max_pts + int64_t(k) * n);
+            }
+        }
+    }
+    return 0;
 }
 
 } // extern "C"
