@@ -42,6 +42,7 @@ def parse():
     ap.add_argument("--nodes", type=int, default=400)
     ap.add_argument("--cpu-sample-runs", type=int, default=0, help="runs of the CPU baseline sample (0 = one per core)")
     ap.add_argument("--no-cpu-baseline", action="store_true")
+    ap.add_argument("--e2e-batches", type=int, default=4, help="batches of the end-to-end leg (sampling overlaps GPU)")
     return ap.parse_args()
 
 
@@ -101,7 +102,9 @@ def workload_config(args):
                         f"(BASELINE configs[3]): {args.runs} runs/GPU x {args.nodes} counties x {args.days:g} days",
             "runs_per_gpu": args.runs, "counties": args.nodes, "edges": None, "age_groups": 6, "days": args.days,
             "dt_graph": 0.5, "integrator": "cash_karp54 abs 1e-10 rel 1e-5", "parallelism": f"runs sharded x{args.gpus}",
-            "l2_policy": "inputs larger than L2 (state 4 x %.2f GB per GPU)" % (args.runs * args.nodes * 480 / 1e9)}
+            "l2_policy": "inputs larger than L2 (state 4 x %.2f GB per GPU)" % (args.runs * args.nodes * 480 / 1e9),
+            "sampling": "osecir::draw_sample(graph) semantics, threefry2x32 seeds {1..6}, uniform ranges of set_covid_parameters",
+            "outputs": "per-node daily p05/p25/p50/p75/p95 + mean of age-summed compartments and of the node-summed state"}
 
 
 def cpu_baseline(problem, days, sample_runs, threads):
@@ -126,8 +129,10 @@ def run_reference(args, rank, world):
         return
     from memilio_b200 import synthetic
     cores = os.cpu_count() or 1
-    sample = args.cpu_sample_runs or cores
-    problem = synthetic.county_problem(N=args.nodes, runs=max(sample, 1), perturb=0.1)
+    sample = args.cpu_sample_runs or 4 * cores
+    from memilio_b200 import study
+    ps = study.ParameterStudy(synthetic.covid_study_graph(N=args.nodes), 0.0, args.days, 0.5, max(sample, 1))
+    problem = ps.sample(0, max(sample, 1))
     for _ in range(min(args.warmup, 1)):
         cpu_baseline(problem, min(args.days, 2.0), cores, cores)
     vals, secs = [], []
@@ -160,7 +165,8 @@ def main():
 
     import torch
     import torch.distributed as dist
-    from memilio_b200 import capi, synthetic
+    from concurrent.futures import ThreadPoolExecutor
+    from memilio_b200 import capi, ensemble, study, synthetic
     if not torch.cuda.is_available():
         raise SystemExit("bench.py needs a CUDA device: the B200 path has no CPU fallback")
     torch.cuda.set_device(local_rank)
@@ -173,92 +179,120 @@ def main():
         torch.cuda.synchronize()
 
     R, N, T = args.runs, args.nodes, args.days
-    # synthetic inputs of the benchmark shape; every rank owns a distinct block of runs (seed offset by rank)
-    problem = synthetic.county_problem(N=N, runs=R, perturb=0.1, seed=20261017)
-    if rank > 0:
-        rr = np.random.default_rng(1000 + rank)
-        problem.y0 *= rr.uniform(0.95, 1.05, (R, 1, 1))
-    # pinned host staging for the e2e leg
-    pinned = {}
-    for name in ("y0", "node_local", "psets", "ctables"):
+    days = int(T) + 1
+    # ParameterStudy over the synthetic county graph; weak scaling: R runs per GPU, rank r owns the contiguous block
+    # distribute_runs(world*R, world, r) of ONE global study (seeds {1..6}), sampled bit-exactly like the reference
+    graph = synthetic.covid_study_graph(N=N)
+    ps = study.ParameterStudy(graph, 0.0, T, 0.5, world * R)
+    run0, count = study.distribute_runs(world * R, world, rank)
+    assert count == R
+    t_s = time.perf_counter()
+    problem = ps.sample(run0, R)
+    host_sampling_s = time.perf_counter() - t_s
+    # pinned host staging
+    for name in ("y0", "node_local", "psets", "ctables", "mobtables"):
         a = getattr(problem, name)
         tns = torch.empty(a.shape, dtype=torch.float64).pin_memory()
         tns.numpy()[...] = a
-        pinned[name] = tns
         setattr(problem, name, tns.numpy())
-    out_pinned = torch.empty((R, N, problem.n), dtype=torch.float64).pin_memory()
+        setattr(problem, "_pin_" + name, tns)
+    h2d = sum(getattr(problem, n_).nbytes for n_ in ("y0", "node_local", "psets", "ctables", "mobtables"))
 
     sim = capi.GraphSimulation(problem, device=local_rank, max_runs=R, upload=False)
+    rec = ensemble.EnsembleRecord(graph.num_groups, N, days, capacity_runs=R, mode=ensemble.ENS_AGE_SUM,
+                                  device=local_rank)
+    rec_t = rec.as_torch()
+    ncol = rec.info()["num_columns"]
+    d2h = (len(ensemble.DEFAULT_PERCENTILES) + 1) * ncol * 8
     stream = torch.cuda.ExternalStream(sim.stream_ptr(), device=torch.device("cuda", local_rank))
-    from memilio_b200 import cdefs
 
     def fresh():
-        """rewind the handle to t0 and upload the runs (H2D) -- untimed for `value`, timed for `e2e`"""
+        """rewind the handle to t0 and upload the runs (H2D) -- untimed for `value`"""
         sim.reset()
+        rec.attach(sim, 0)
         sim.set_runs(0, problem, 0, R)
 
-    h2d = problem.y0.nbytes + problem.node_local.nbytes + problem.psets.nbytes + problem.ctables.nbytes
-    d2h = out_pinned.numel() * 8
+    def reduce():
+        return ensemble.reduce_distributed(rec_t, R, rank, world)
 
-    def step_device():
+    def step_device(profile=False):
         fresh()
+        sim.set_profiling(profile)
         torch.cuda.synchronize()
-        e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        e0, e1, e2 = (torch.cuda.Event(enable_timing=True) for _ in range(3))
         e0.record(stream)
-        sim.advance(T)
+        sim.advance(T)  # synchronises the handle's stream before it returns
         e1.record(stream)
-        e1.synchronize()
-        return e0.elapsed_time(e1)
-
-    def step_e2e():
-        t0 = time.perf_counter()
-        fresh()
-        sim.advance(T)
-        capi._check(capi.lib().mio_cuda_get_state(sim._h, 0, R, cdefs.dptr(out_pinned.numpy())))
-        torch.cuda.synchronize()
-        return (time.perf_counter() - t0) * 1e3
+        reduce()        # synchronous: exchange (N>1), selection kernels, gather on rank 0
+        e2.record(stream)
+        e2.synchronize()
+        return e0.elapsed_time(e2), e1.elapsed_time(e2)
 
     for _ in range(args.warmup):
         step_device()
-    # ---- timed: device leg -------------------------------------------------------------------------------------
-    sim.set_profiling(False)
+    # ---- timed: device leg (inputs resident in HBM) -----------------------------------------------------------------
     clocks = ClockSampler(local_rank)
     barrier()
     clocks.start()
-    ms_dev = []
+    ms_dev, ms_red = [], []
     prof = None
     launches = 0
     attempts = 0
     for k in range(args.steps):
-        fresh()
-        sim.set_profiling(True)
-        torch.cuda.synchronize()
-        e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
-        e0.record(stream)
-        sim.advance(T)
-        e1.record(stream)
-        e1.synchronize()
-        ms_dev.append(e0.elapsed_time(e1))
+        a, b = step_device(profile=True)
+        ms_dev.append(a)
+        ms_red.append(b)
         p = sim.profile()
         prof = p if prof is None else {c: (prof[c][0] + p[c][0], prof[c][1] + p[c][1]) for c in p}
-        launches += sum(v[1] for v in p.values())
+        launches += sum(v[1] for v in p.values()) + 1  # + the selection kernel
         cnt = sim.counters()
         attempts += int(cnt[:, :, 0].sum() + cnt[:, :, 1].sum())
     barrier()
     clock_info = clocks.stop()
     replays = sim.stats()["exact_replays"]
-    # ---- timed: end-to-end leg (host buffers in, result out) --------------------------------------------------------
+    sim.set_profiling(False)
+
+    # ---- timed: end-to-end leg: what a user of ParameterStudy.run pays, from distributions to percentiles ------------
+    # host sampling (C library) of batch b+1 overlaps the GPU work of batch b; H2D of every batch and D2H of the
+    # reduced result are inside the timed region.
+    nb = max(1, min(args.e2e_batches, R))
+    bounds = [(i * R // nb, (i + 1) * R // nb) for i in range(nb)]
+    bmax = max(b - a for a, b in bounds)
+    sim2 = capi.GraphSimulation(problem, device=local_rank, max_runs=bmax, upload=False)
+    pool = ThreadPoolExecutor(max_workers=1)
+
+    def step_e2e():
+        t0 = time.perf_counter()
+        fut = pool.submit(ps.sample, run0 + bounds[0][0], bounds[0][1] - bounds[0][0])
+        for i, (a, b) in enumerate(bounds):
+            pb = fut.result()
+            if i + 1 < nb:
+                fut = pool.submit(ps.sample, run0 + bounds[i + 1][0], bounds[i + 1][1] - bounds[i + 1][0])
+            sim2.reset()
+            sim2.set_active_runs(b - a)
+            rec.attach(sim2, a)
+            sim2.set_runs(0, pb, 0, b - a)
+            sim2.advance(T)
+        out = reduce()
+        torch.cuda.synchronize()
+        return (time.perf_counter() - t0) * 1e3, out
+
     step_e2e()
     barrier()
-    ms_e2e = [step_e2e() for _ in range(args.steps)]
+    e2e_runs = [step_e2e() for _ in range(args.steps)]
+    ms_e2e = [x[0] for x in e2e_runs]
     barrier()
+    if rank == 0 and e2e_runs[-1][1][0] is not None:
+        pct = e2e_runs[-1][1][0]
+        assert np.isfinite(pct).all()
 
-    t_dev = torch.tensor([float(np.sum(ms_dev)), float(np.sum(ms_e2e))], device="cuda", dtype=torch.float64)
+    t_dev = torch.tensor([float(np.sum(ms_dev)), float(np.sum(ms_e2e)), float(np.sum(ms_red)), host_sampling_s],
+                         device="cuda", dtype=torch.float64)
     agg = torch.tensor([float(attempts), float(launches)], device="cuda", dtype=torch.float64)
     if world > 1:
         dist.all_reduce(t_dev, op=dist.ReduceOp.MAX)
         dist.all_reduce(agg, op=dist.ReduceOp.SUM)
-    tot_dev_ms, tot_e2e_ms = [float(x) for x in t_dev.tolist()]
+    tot_dev_ms, tot_e2e_ms, tot_red_ms, samp_s = [float(x) for x in t_dev.tolist()]
     units = world * R * N * T * args.steps
     value = units / (tot_dev_ms * 1e-3)
     e2e = units / (tot_e2e_ms * 1e-3)
@@ -269,30 +303,37 @@ def main():
             with open(os.path.join(ROOT, "MEASURED_PEAKS.json")) as f:
                 peaks = json.load(f)
         hbm_peak = peaks.get("hbm_gbs", 6650.0)
-        hbm_src = "measured (MEASURED_PEAKS.json)" if "hbm_gbs" in peaks else "fallback"
+        hbm_src = "measured (MEASURED_PEAKS.json)" if "hbm_gbs" in peaks else "fallback (B200_PROFILING.md)"
         fp64_peak = capi.measure_fp64_peak(local_rank, 0.5)
         kernel_ms = {c: prof[c][0] / args.steps for c in prof}
+        kernel_ms["select"] = tot_red_ms / args.steps
         dominant = max(kernel_ms, key=kernel_ms.get)
         integ_s = prof["integrate"][0] * 1e-3
-        att_rank0 = attempts
-        fp64_achieved = att_rank0 * FLOP_PER_CK54_ATTEMPT / integ_s / 1e12 if integ_s > 0 else 0.0
+        fp64_achieved = attempts * FLOP_PER_CK54_ATTEMPT / integ_s / 1e12 if integ_s > 0 else 0.0
         edge_s = (prof["depart"][0] + prof["return"][0] + prof["return_exact"][0]) * 1e-3
         edge_gbs = EDGE_BYTES_PER_RUN_DAY * R * T * args.steps / edge_s / 1e9 if edge_s > 0 else 0.0
+        traffic = ncu_traffic(R)
         roof_fp64 = {"kernel": "integrate_nodes_kernel", "bound": "fp64", "achieved": fp64_achieved, "peak": fp64_peak,
-                     "unit": "TFLOP/s", "frac": fp64_achieved / fp64_peak if fp64_peak else None, "traffic": None,
-                     "peak_source": "measured in this run (DFMA chains, mio_cuda_measure_fp64_peak)",
-                     "attempts_per_launch": att_rank0 / max(prof["integrate"][1], 1),
+                     "unit": "TFLOP/s", "frac": fp64_achieved / fp64_peak if fp64_peak else None,
+                     "traffic": traffic.get("integrate"),
+                     "peak_source": "measured in this run (DFMA chains on all SMs, mio_cuda_measure_fp64_peak); "
+                                    "MEASURED_PEAKS.json has no FP64 figure",
+                     "attempts_per_launch": attempts / max(prof["integrate"][1], 1),
                      "flop_per_attempt": FLOP_PER_CK54_ATTEMPT}
-        roof_edge = {"kernel": "depart_kernel+return_kernel", "bound": "hbm", "achieved": edge_gbs, "peak": hbm_peak,
-                     "unit": "GB/s", "frac": edge_gbs / hbm_peak, "traffic": None, "peak_source": hbm_src,
-                     "algorithmic_bytes_per_run_day": EDGE_BYTES_PER_RUN_DAY}
+        roof_edge = {"kernel": "depart_kernel+return_kernel(+return_exact)", "bound": "hbm", "achieved": edge_gbs,
+                     "peak": hbm_peak, "unit": "GB/s", "frac": edge_gbs / hbm_peak,
+                     "traffic": (traffic.get("depart", 0) + traffic.get("return", 0)) or None,
+                     "peak_source": hbm_src, "algorithmic_bytes_per_run_day": EDGE_BYTES_PER_RUN_DAY,
+                     "note": "algorithmic bytes are SURVEY 8d's explicit-traveler-state figure; the aggregated "
+                             "formulation moves fewer DRAM bytes (see traffic), so achieved can exceed DRAM throughput"}
         line = {
             "metric": "graph_ode_secir_node_days_per_s", "value": value, "unit": "node-days/s", "n_gpus": world,
             "steps": args.steps, "warmup": args.warmup, "ms_per_step": tot_dev_ms / args.steps,
             "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "f64", "data": "synthetic",
-            "config": dict(workload_config(args), edges=problem.num_edges),
+            "config": dict(workload_config(args), edges=int(problem.num_edges)),
             "e2e": {"value": e2e, "unit": "node-days/s", "h2d_bytes_per_step": int(h2d), "d2h_bytes_per_step": int(d2h),
-                    "ms_per_step": tot_e2e_ms / args.steps},
+                    "ms_per_step": tot_e2e_ms / args.steps, "batches": nb,
+                    "includes": "host sampling (overlapped), H2D of sampled runs, advance, percentile reduction, D2H"},
             "gpu_launches": int(agg[1].item()),
             "clocks": clock_info,
             "roofline": roof_edge if dominant in ("depart", "return", "return_exact") else roof_fp64,
@@ -300,18 +341,32 @@ def main():
             "kernel_ms_per_step": kernel_ms, "dominant_kernel": dominant,
             "rk_attempts_per_node_day": float(agg[0].item()) / units,
             "exact_return_replays": int(replays),
+            "host_sampling_s_per_step": samp_s,
         }
         if not args.no_cpu_baseline:
             cores = os.cpu_count() or 1
-            sample = args.cpu_sample_runs or cores
+            sample = args.cpu_sample_runs or 4 * cores
             v, s = cpu_baseline(problem, T, sample, cores)
             line["cpu_baseline"] = {"value": v, "unit": "node-days/s", "cores": cores, "kind": "port",
                                     "sample": f"{sample} runs x {N} counties x {T:g} days over {cores} threads "
                                               f"({s:.1f} s)"}
         print(json.dumps(line))
     sim.close()
+    sim2.close()
+    rec.close()
     if world > 1:
         dist.destroy_process_group()
+
+
+def ncu_traffic(R):
+    """DRAM bytes per launch of each kernel from the committed ncu --set full capture (profiles/ncu_traffic.json:
+    dram__bytes_read.sum + dram__bytes_write.sum at the captured run count), scaled linearly to this run count."""
+    path = os.path.join(ROOT, "profiles", "ncu_traffic.json")
+    if not os.path.exists(path):
+        return {}
+    with open(path) as f:
+        t = json.load(f)
+    return {k: v["bytes_per_launch"] * R / v["runs"] for k, v in t["kernels"].items()}
 
 
 if __name__ == "__main__":

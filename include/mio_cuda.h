@@ -299,18 +299,49 @@ MIO_API int mio_damping_cache_build(int32_t rows, int32_t cols, int32_t K, const
                                     const int32_t* types, const double* mats, int32_t* num_out, double* out_times,
                                     double* out_mats);
 
+/* ---- ensemble results -------------------------------------------------------------------------------------------
+ * Device-resident record of the interpolated (daily) results of all runs of a study and their reduction.
+ * Replaces interpolate_simulation_result / sum_nodes / ensemble_mean / ensemble_percentile
+ * (cpp/memilio/data/analyze_result.h:186-343) as used by save_results (cpp/memilio/io/result_io.h:135-202).
+ * The record is a column-major matrix [column][run]: per-node columns (node k, day d, element e) ->
+ * (k * num_days + d) * El + e with El = n (MIO_ENS_FULL) or C (MIO_ENS_AGE_SUM: age groups summed per compartment),
+ * followed by the node-summed full-resolution columns N*num_days*El + d * n + j (sum_nodes).
+ */
+#define MIO_ENS_FULL 0
+#define MIO_ENS_AGE_SUM 1
+typedef struct mio_ensemble mio_ensemble;
+MIO_API int mio_cuda_ensemble_create(int device, int32_t model, int32_t num_groups, int32_t num_nodes,
+                                     int32_t num_days, int32_t mode, int64_t capacity_runs, mio_ensemble** out);
+MIO_API void mio_cuda_ensemble_destroy(mio_ensemble* e);
+/* from now on set_runs() records day 0 and advance() every further integer day of the active run slots into the
+ * runs [run_offset, run_offset + active) of the record (t0 must be an integer day); e = NULL detaches */
+MIO_API int mio_cuda_attach_ensemble(mio_handle* h, mio_ensemble* e, int64_t run_offset);
+MIO_API int mio_cuda_ensemble_info(mio_ensemble* e, int64_t* num_columns, int64_t* stride, int64_t* num_runs,
+                                   void** device_ptr);
+/* ensemble_percentile (order statistic size_t(num_runs * p) per column, exact) and ensemble_mean over the recorded
+ * runs. Host outputs percentiles[num_p][num_columns], mean[num_columns]; either may be NULL. num_p <= 8. */
+MIO_API int mio_cuda_ensemble_reduce(mio_ensemble* e, int32_t num_p, const double* p, double* percentiles,
+                                     double* mean);
+/* the same reduction for columns whose runs are spread over up to 8 device segments (multi-GPU: after the
+ * run-sharded -> column-sharded exchange); segment s holds [num_columns][seg_stride[s]] doubles, seg_count[s] runs */
+MIO_API int mio_cuda_select_percentiles(int device, int32_t num_segments, const void* const* seg_ptr,
+                                        const int64_t* seg_stride, const int64_t* seg_count, int64_t num_columns,
+                                        int32_t num_p, const double* p, double* percentiles, double* mean);
+
 /* ---- measurement hooks ------------------------------------------------------------------------------------------ */
-#define MIO_NUM_KERNEL_CLASSES 5
+#define MIO_NUM_KERNEL_CLASSES 6
 #define MIO_KC_INTEGRATE 0    /* node phase: adaptive RK integration of every (run, node) */
 #define MIO_KC_DEPART 1       /* edge phase: commuter departure gather */
 #define MIO_KC_RETURN 2       /* edge phase: commuter return gather (optimistic) */
 #define MIO_KC_RETURN_EXACT 3 /* edge phase: in-order replay of runs with underflow fix-ups */
 #define MIO_KC_RECORD 4       /* daily record copy */
+#define MIO_KC_ENSEMBLE 5     /* ensemble record (transpose + node sum) */
 /* the CUDA stream (cudaStream_t) all kernels of this handle are launched on */
 MIO_API int mio_cuda_get_stream(mio_handle* h, void** stream);
 /* per-kernel-class device time, measured with CUDA events on that stream while profiling is on; resets the sums */
 MIO_API int mio_cuda_set_profiling(mio_handle* h, int on);
-MIO_API int mio_cuda_get_profile(mio_handle* h, double* ms /*[5]*/, int64_t* launches /*[5]*/);
+MIO_API int mio_cuda_get_profile(mio_handle* h, double* ms /*[MIO_NUM_KERNEL_CLASSES]*/,
+                                 int64_t* launches /*[MIO_NUM_KERNEL_CLASSES]*/);
 /* device pointer of the live node state [max_runs][N][n] (valid until the next advance) */
 MIO_API int mio_cuda_device_state_ptr(mio_handle* h, void** y, int64_t* num_doubles);
 /* sustained FP64 FMA throughput of the device (DFMA chains on all SMs), the roofline denominator of the node phase */

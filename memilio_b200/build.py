@@ -9,7 +9,7 @@ import sys
 HERE = os.path.dirname(os.path.abspath(__file__))
 CSRC = os.path.join(HERE, "csrc")
 LIB = os.path.join(CSRC, "libmio_cuda.so")
-CU_SOURCES = ["integrate.cu", "edges.cu", "capi.cu", "peak.cu"]
+CU_SOURCES = ["integrate.cu", "edges.cu", "reduce.cu", "capi.cu", "peak.cu"]
 CXX_SOURCES = ["study.cpp"]
 NVCC_FLAGS = ["-gencode", "arch=compute_100a,code=sm_100a", "-O3", "-lineinfo", "-std=c++17", "-Xcompiler",
               "-fPIC,-fvisibility=hidden,-O2", "-Xptxas", "-v", "--expt-relaxed-constexpr"]
@@ -28,30 +28,33 @@ def needs_build() -> bool:
     return any(os.path.getmtime(d) > t for d in deps)
 
 
-def build(force: bool = False, verbose: bool = False) -> str:
-    if not force and not needs_build():
+def build(force: bool = False, verbose: bool = False, defines=(), out: str = LIB, objdir: str = CSRC) -> str:
+    """Compile every CUDA / C++ source for sm_100a and link the C-ABI library. `defines` (e.g. launch-shape macros of
+    kernels.h) and `out` let tools/build_variants.py produce tuning variants next to the default library."""
+    if out == LIB and not force and not needs_build():
         return LIB
+    os.makedirs(objdir, exist_ok=True)
     objs = []
     logs = []
     for src in CU_SOURCES + CXX_SOURCES:
-        obj = os.path.join(CSRC, os.path.splitext(src)[0] + ".o")
-        cmd = [_nvcc()] + NVCC_FLAGS + ["-c", os.path.join(CSRC, src), "-o", obj]
+        obj = os.path.join(objdir, os.path.splitext(src)[0] + ".o")
+        cmd = [_nvcc()] + NVCC_FLAGS + ["-D" + d for d in defines] + ["-c", os.path.join(CSRC, src), "-o", obj]
         r = subprocess.run(cmd, capture_output=True, text=True)
         logs.append(r.stderr)
         if r.returncode != 0:
             sys.stderr.write(r.stdout + r.stderr)
             raise RuntimeError("nvcc failed for " + src)
         objs.append(obj)
-    cmd = [_nvcc(), "-shared", "-o", LIB] + objs + ["-gencode", "arch=compute_100a,code=sm_100a"]
+    cmd = [_nvcc(), "-shared", "-o", out] + objs + ["-gencode", "arch=compute_100a,code=sm_100a"]
     r = subprocess.run(cmd, capture_output=True, text=True)
     if r.returncode != 0:
         sys.stderr.write(r.stdout + r.stderr)
         raise RuntimeError("link failed")
-    with open(os.path.join(CSRC, "ptxas.log"), "w") as f:
+    with open(os.path.join(objdir, "ptxas.log"), "w") as f:
         f.write("\n".join(logs))
     if verbose:
         print("\n".join(logs))
-    return LIB
+    return out
 
 
 if __name__ == "__main__":

@@ -14,7 +14,7 @@ from . import cdefs, flat
 from .problem import GraphProblem
 
 _HERE = os.path.dirname(os.path.abspath(__file__))
-LIB_PATH = os.path.join(_HERE, "csrc", "libmio_cuda.so")
+LIB_PATH = os.environ.get("MIO_CUDA_LIB") or os.path.join(_HERE, "csrc", "libmio_cuda.so")  # tuning variants
 _LIB = None
 
 EXPORTS = [
@@ -26,8 +26,10 @@ EXPORTS = [
     "mio_cuda_get_profile", "mio_cuda_device_state_ptr", "mio_cuda_measure_fp64_peak",
     "mio_study_create", "mio_study_destroy", "mio_study_num_ctables", "mio_study_node_ctable",
     "mio_study_sample_runs", "mio_study_distribute_runs", "mio_study_rng_raw", "mio_damping_cache_build",
+    "mio_cuda_ensemble_create", "mio_cuda_ensemble_destroy", "mio_cuda_attach_ensemble", "mio_cuda_ensemble_info",
+    "mio_cuda_ensemble_reduce", "mio_cuda_select_percentiles",
 ]
-KERNEL_CLASSES = ["integrate", "depart", "return", "return_exact", "record"]
+KERNEL_CLASSES = ["integrate", "depart", "return", "return_exact", "record", "ensemble"]
 
 
 class MioCudaError(RuntimeError):

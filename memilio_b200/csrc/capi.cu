@@ -51,8 +51,17 @@ int mio_set_last_error(int code, const std::string& msg)
     return fail(code, msg);
 }
 
+struct mio_ensemble {
+    int device = 0;
+    int G = 0, C = 0, N = 0, num_days = 0, mode = 0;
+    long long capacity = 0, num_runs = 0, num_columns = 0;
+    double* d_data = nullptr; // [num_columns][capacity]
+};
+
 struct mio_handle {
     mio_graph_desc desc;
+    mio_ensemble* ens      = nullptr;
+    long long ens_offset   = 0;
     Geometry geo;
     int device       = 0;
     cudaStream_t stream = nullptr;
@@ -90,8 +99,8 @@ struct mio_handle {
     };
     std::vector<Span> spans;
     std::vector<cudaEvent_t> event_pool;
-    double prof_ms[MIO_NUM_KERNEL_CLASSES]        = {0, 0, 0, 0, 0};
-    long long prof_launches[MIO_NUM_KERNEL_CLASSES] = {0, 0, 0, 0, 0};
+    double prof_ms[MIO_NUM_KERNEL_CLASSES]        = {0, 0, 0, 0, 0, 0};
+    long long prof_launches[MIO_NUM_KERNEL_CLASSES] = {0, 0, 0, 0, 0, 0};
 };
 
 namespace
@@ -658,6 +667,17 @@ int mio_cuda_set_runs(mio_handle* h, int32_t slot0, int32_t count, const mio_run
                                    sizeof(double) * n, sizeof(double) * n, (size_t)count * N,
                                    cudaMemcpyHostToDevice, h->stream));
     }
+    if (h->ens) {
+        if (h->ens_offset + slot0 + count > h->ens->capacity) {
+            return fail(MIO_OUT_OF_RANGE, "ensemble record: run capacity exceeded");
+        }
+        ++h->launches;
+        ++h->prof_launches[MIO_KC_ENSEMBLE];
+        CUDA_TRY(launch_record_ensemble(h->d_y[h->cur] + s0 * N * n, h->ens->d_data, N, G, NC, count, 0,
+                                        h->ens->num_days, h->ens->mode, h->ens_offset + slot0, h->ens->capacity,
+                                        h->stream));
+        h->ens->num_runs = std::max(h->ens->num_runs, h->ens_offset + slot0 + count);
+    }
     CUDA_TRY(cudaStreamSynchronize(h->stream));
     return MIO_OK;
 }
@@ -701,6 +721,9 @@ int mio_cuda_advance(mio_handle* h, double t_max)
     const int R         = h->active_runs;
     if (R == 0) {
         return MIO_OK;
+    }
+    if (h->ens && h->ens_offset + R > h->ens->capacity) {
+        return fail(MIO_OUT_OF_RANGE, "ensemble record: run_offset + active runs exceeds the capacity");
     }
     double dt = h->desc.dt_graph;
     while (h->t < t_max) {
@@ -802,11 +825,17 @@ int mio_cuda_advance(mio_handle* h, double t_max)
             h->toggle = !h->toggle;
         }
         // daily record: the value the reference's interpolate_simulation_result yields at integer days
-        if (h->d_daily) {
+        if (h->d_daily || h->ens) {
             const double day = std::round(h->t);
             if (std::fabs(h->t - day) <= 1e-10 * std::max(1.0, std::fabs(day))) {
                 const int slot = (int)day - h->day0;
-                if (slot >= 0 && slot < h->desc.max_days) {
+                if (h->ens && slot >= 0 && slot < h->ens->num_days) {
+                    ScopedSpan sp(h, MIO_KC_ENSEMBLE);
+                    CUDA_TRY(launch_record_ensemble(h->d_y[h->cur], h->ens->d_data, geo.N, geo.G, NC, R, slot,
+                                                    h->ens->num_days, h->ens->mode, h->ens_offset, h->ens->capacity,
+                                                    h->stream));
+                }
+                if (h->d_daily && slot >= 0 && slot < h->desc.max_days) {
                     ScopedSpan sp(h, MIO_KC_RECORD);
                     CUDA_TRY(launch_record_daily(geo, h->d_y[h->cur], h->d_daily, slot, h->desc.max_days, R,
                                                  h->stream));
@@ -981,6 +1010,172 @@ int mio_cuda_device_state_ptr(mio_handle* h, void** y, int64_t* num_doubles)
     *y           = (void*)h->d_y[h->cur];
     *num_doubles = (int64_t)h->max_runs * h->geo.N * h->geo.n;
     return MIO_OK;
+}
+
+// ---- ensemble record and reduction ------------------------------------------------------------------------------
+int mio_cuda_ensemble_create(int device, int32_t model, int32_t num_groups, int32_t num_nodes, int32_t num_days,
+                             int32_t mode, int64_t capacity_runs, mio_ensemble** out)
+{
+    if (!out) {
+        return fail(MIO_INVALID_VALUE, "null argument");
+    }
+    *out = nullptr;
+    if (model != MIO_MODEL_OSECIR || num_groups < 1 || num_groups > MIO_MAX_GROUPS || num_nodes < 1 || num_days < 1 ||
+        capacity_runs < 1 || (mode != MIO_ENS_FULL && mode != MIO_ENS_AGE_SUM)) {
+        return fail(MIO_INVALID_VALUE, "invalid ensemble record sizes");
+    }
+    int ndev = 0;
+    if (cudaGetDeviceCount(&ndev) != cudaSuccess || ndev == 0) {
+        return fail(MIO_UNKNOWN_ERROR, "no CUDA device available (this library has no CPU fallback)");
+    }
+    if (device < 0 || device >= ndev) {
+        return fail(MIO_OUT_OF_RANGE, "device index out of range");
+    }
+    CUDA_TRY(cudaSetDevice(device));
+    auto* e        = new mio_ensemble();
+    e->device      = device;
+    e->G           = num_groups;
+    e->C           = NC;
+    e->N           = num_nodes;
+    e->num_days    = num_days;
+    e->mode        = mode;
+    e->capacity    = capacity_runs;
+    const int n    = num_groups * NC;
+    const int El   = mode == MIO_ENS_AGE_SUM ? NC : n;
+    e->num_columns = (long long)num_nodes * num_days * El + (long long)num_days * n;
+    cudaError_t er = dev_alloc(&e->d_data, (size_t)e->num_columns * (size_t)capacity_runs);
+    if (er != cudaSuccess) {
+        delete e;
+        return fail(MIO_UNKNOWN_ERROR, std::string("ensemble record allocation: ") + cudaGetErrorString(er));
+    }
+    *out = e;
+    return MIO_OK;
+}
+
+void mio_cuda_ensemble_destroy(mio_ensemble* e)
+{
+    if (e) {
+        cudaSetDevice(e->device);
+        cudaFree(e->d_data);
+        delete e;
+    }
+}
+
+int mio_cuda_attach_ensemble(mio_handle* h, mio_ensemble* e, int64_t run_offset)
+{
+    if (!h) {
+        return fail(MIO_INVALID_VALUE, "null handle");
+    }
+    if (e) {
+        if (e->device != h->device || e->G != h->geo.G || e->N != h->geo.N) {
+            return fail(MIO_INVALID_VALUE, "ensemble record does not match the graph (device, groups or nodes)");
+        }
+        if (run_offset < 0 || run_offset >= e->capacity) {
+            return fail(MIO_OUT_OF_RANGE, "ensemble record: run_offset exceeds the capacity");
+        }
+        if (std::floor(h->desc.t0) != h->desc.t0) {
+            return fail(MIO_INVALID_VALUE, "ensemble record needs an integer t0");
+        }
+    }
+    h->ens        = e;
+    h->ens_offset = run_offset;
+    return MIO_OK;
+}
+
+int mio_cuda_ensemble_info(mio_ensemble* e, int64_t* num_columns, int64_t* stride, int64_t* num_runs,
+                           void** device_ptr)
+{
+    if (!e) {
+        return fail(MIO_INVALID_VALUE, "null argument");
+    }
+    if (num_columns) {
+        *num_columns = e->num_columns;
+    }
+    if (stride) {
+        *stride = e->capacity;
+    }
+    if (num_runs) {
+        *num_runs = e->num_runs;
+    }
+    if (device_ptr) {
+        *device_ptr = e->d_data;
+    }
+    return MIO_OK;
+}
+
+int mio_cuda_select_percentiles(int device, int32_t num_segments, const void* const* seg_ptr,
+                                const int64_t* seg_stride, const int64_t* seg_count, int64_t num_columns,
+                                int32_t num_p, const double* p, double* percentiles, double* mean)
+{
+    if (num_segments < 1 || num_segments > SEL_MAX_SEG || !seg_ptr || !seg_stride || !seg_count || num_columns < 0 ||
+        num_p < 0 || num_p > SEL_MAX_P || (num_p > 0 && (!p || !percentiles))) {
+        return fail(MIO_INVALID_VALUE, "invalid arguments");
+    }
+    CUDA_TRY(cudaSetDevice(device));
+    SelectArgs a{};
+    a.num_segments = num_segments;
+    a.total        = 0;
+    for (int s = 0; s < num_segments; ++s) {
+        if (seg_count[s] < 0 || seg_count[s] > seg_stride[s] || (!seg_ptr[s] && seg_count[s] > 0)) {
+            return fail(MIO_INVALID_VALUE, "invalid segment");
+        }
+        a.seg_ptr[s]    = static_cast<const double*>(seg_ptr[s]);
+        a.seg_stride[s] = seg_stride[s];
+        a.seg_count[s]  = seg_count[s];
+        a.total += seg_count[s];
+    }
+    if (a.total == 0) {
+        return fail(MIO_INVALID_VALUE, "no runs recorded");
+    }
+    a.num_p = num_p;
+    for (int q = 0; q < num_p; ++q) {
+        // analyze_result.h:318,338: assert(p > 0 && p < 1); index static_cast<size_t>(num_runs * p)
+        if (!(p[q] > 0.0 && p[q] < 1.0)) {
+            return fail(MIO_INVALID_VALUE, "percentile must lie in (0, 1)");
+        }
+        a.rank[q] = (long long)(size_t)((double)a.total * p[q]);
+    }
+    a.num_columns = num_columns;
+    double *d_sel = nullptr, *d_mean = nullptr;
+    if (num_p > 0) {
+        CUDA_TRY(dev_alloc(&d_sel, (size_t)num_p * num_columns));
+    }
+    if (mean) {
+        cudaError_t er = dev_alloc(&d_mean, (size_t)num_columns);
+        if (er != cudaSuccess) {
+            cudaFree(d_sel);
+            return fail(MIO_UNKNOWN_ERROR, cudaGetErrorString(er));
+        }
+    }
+    a.out_select   = d_sel;
+    a.out_mean     = d_mean;
+    cudaError_t er = cudaDeviceSynchronize(); // the record kernels run on the handles' streams
+    if (er == cudaSuccess) {
+        er = launch_select(a, nullptr);
+    }
+    if (er == cudaSuccess && d_sel) {
+        er = cudaMemcpy(percentiles, d_sel, sizeof(double) * (size_t)num_p * num_columns, cudaMemcpyDeviceToHost);
+    }
+    if (er == cudaSuccess && d_mean) {
+        er = cudaMemcpy(mean, d_mean, sizeof(double) * (size_t)num_columns, cudaMemcpyDeviceToHost);
+    }
+    cudaFree(d_sel);
+    cudaFree(d_mean);
+    if (er != cudaSuccess) {
+        return fail(MIO_UNKNOWN_ERROR, std::string("select_percentiles: ") + cudaGetErrorString(er));
+    }
+    return MIO_OK;
+}
+
+int mio_cuda_ensemble_reduce(mio_ensemble* e, int32_t num_p, const double* p, double* percentiles, double* mean)
+{
+    if (!e) {
+        return fail(MIO_INVALID_VALUE, "null argument");
+    }
+    const void* ptr      = e->d_data;
+    const int64_t stride = e->capacity, count = e->num_runs;
+    return mio_cuda_select_percentiles(e->device, 1, &ptr, &stride, &count, e->num_columns, num_p, p, percentiles,
+                                       mean);
 }
 
 } // extern "C"

@@ -163,7 +163,7 @@ __device__ __forceinline__ void gather_visitors(const EdgeArgs& a, const Geometr
 // the reference order) and kept for the return phase; the emigrants are s_out_k * u_k.
 // Then the return coefficients of k as a destination (lambda_i, ICU adjusted rates) from v0 = y_out at time t.
 template <int G, bool FACT>
-__global__ void __launch_bounds__(EDGE_THREADS) depart_kernel(EdgeArgs a)
+__global__ void __launch_bounds__(EDGE_THREADS, MIO_DEPART_MINBLOCKS) depart_kernel(EdgeArgs a)
 {
     extern __shared__ __align__(16) double smem[];
     __shared__ __align__(8) uint64_t mbar;
@@ -277,7 +277,7 @@ __global__ void __launch_bounds__(EDGE_THREADS) depart_kernel(EdgeArgs a)
 // long as dt*rate <= 1, checked), so it is enough to test it after the first and after the last block. Flagged runs
 // are replayed literally by return_exact_kernel.
 template <int G, bool FACT>
-__global__ void __launch_bounds__(EDGE_THREADS) return_kernel(EdgeArgs a)
+__global__ void __launch_bounds__(EDGE_THREADS, MIO_RETURN_MINBLOCKS) return_kernel(EdgeArgs a)
 {
     extern __shared__ __align__(16) double smem[];
     __shared__ __align__(8) uint64_t mbar;

@@ -6,8 +6,24 @@
 namespace miocu
 {
 
-constexpr int INTEGRATE_THREADS = 256;
-constexpr int EDGE_THREADS      = 256;
+// launch shapes (tunable at build time; see tools/build_variants.py and profiles/ for the measurements behind them)
+#ifndef MIO_INTEGRATE_THREADS
+#define MIO_INTEGRATE_THREADS 256
+#endif
+#ifndef MIO_INTEGRATE_MINBLOCKS
+#define MIO_INTEGRATE_MINBLOCKS 1
+#endif
+#ifndef MIO_EDGE_THREADS
+#define MIO_EDGE_THREADS 256
+#endif
+#ifndef MIO_DEPART_MINBLOCKS
+#define MIO_DEPART_MINBLOCKS 1
+#endif
+#ifndef MIO_RETURN_MINBLOCKS
+#define MIO_RETURN_MINBLOCKS 1
+#endif
+constexpr int INTEGRATE_THREADS = MIO_INTEGRATE_THREADS;
+constexpr int EDGE_THREADS      = MIO_EDGE_THREADS;
 
 struct TrajectoryBuffers {
     int capacity;   // 0 = off
@@ -81,5 +97,32 @@ cudaError_t launch_return(const EdgeArgs& a, cudaStream_t stream);
 cudaError_t launch_return_exact(const EdgeArgs& a, cudaStream_t stream);
 cudaError_t launch_record_daily(const Geometry& geo, const double* y, double* daily, int day_index, int max_days,
                                 int num_runs, cudaStream_t stream);
+
+// ---- ensemble reduction (reduce.cu) -------------------------------------------------------------------------------
+constexpr int SEL_MAX_P    = 8;
+constexpr int SEL_MAX_SEG  = 8;
+constexpr int SEL_BITS     = 11;
+constexpr int SEL_BINS     = 1 << SEL_BITS;
+constexpr int SEL_THREADS  = 256;
+
+struct SelectArgs {
+    const double* seg_ptr[SEL_MAX_SEG]; // segment s holds rows [col][seg_stride[s]], seg_count[s] valid runs each
+    long long seg_stride[SEL_MAX_SEG];
+    long long seg_count[SEL_MAX_SEG];
+    int num_segments;
+    int num_p;
+    long long rank[SEL_MAX_P]; // zero based order statistic, size_t(num_runs * p)
+    long long num_columns;
+    long long total;           // sum of seg_count
+    double* out_select;        // [num_p][num_columns] or null
+    double* out_mean;          // [num_columns] or null
+};
+
+
+// y[R][N][n] of the current integer day -> columns of the ensemble matrix (per-node part and node-summed part)
+cudaError_t launch_record_ensemble(const double* y, double* ens, int N, int G, int C, int num_runs, int day,
+                                   int num_days, int age_sum, long long run_offset, long long stride,
+                                   cudaStream_t stream);
+cudaError_t launch_select(const SelectArgs& a, cudaStream_t stream);
 
 } // namespace miocu

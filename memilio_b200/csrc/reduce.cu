@@ -1,0 +1,228 @@
+// reduce.cu -- ensemble post-processing on the device: the interpolated (daily) results of all runs are kept as one
+// column-major matrix [column][run] and reduced at the end of the study.
+//
+// Replaces cpp/memilio/data/analyze_result.h:186-265 (interpolate_simulation_result: with dt_graph = 0.5 every integer
+// day is a time point of the node series, so the day value is the state after that step's edge phase), :267-287
+// (sum_nodes), :289-314 (ensemble_mean), :316-343 (ensemble_percentile: sort over runs, index size_t(num_runs * p)).
+//
+// Columns: (node k, day d, element e) -> (k * D + d) * El + e for the per-node results (El = n, or C when the age
+// groups are summed), followed by the node-summed full-resolution result (day d, element j) -> N*D*El + d * n + j.
+// The order statistic is found by an exact radix select on the order-preserving 64 bit image of the doubles, all
+// requested percentiles in the same passes; no approximation. HBM bound: 6 passes over the column.
+#include "kernels.h"
+
+#include <cstdint>
+
+namespace miocu
+{
+
+// ---------------------------------------------------------------------------------------------------------------
+// y[R][N][n] at an integer day -> ens[col][run_offset + r]
+__global__ void __launch_bounds__(256) record_ensemble_kernel(const double* __restrict__ y, double* __restrict__ ens,
+                                                              int N, int G, int C, int num_runs, int day, int num_days,
+                                                              int age_sum, long long run_offset, long long stride)
+{
+    extern __shared__ double tile[]; // [32][n + 1]
+    const int n    = G * C;
+    const int node = blockIdx.y;
+    const int r0   = blockIdx.x * 32;
+    const int rows = min(32, num_runs - r0);
+    for (int idx = threadIdx.x; idx < rows * n; idx += blockDim.x) {
+        const int rr = idx / n, e = idx - rr * n;
+        tile[rr * (n + 1) + e] = y[((size_t)(r0 + rr) * N + node) * n + e];
+    }
+    __syncthreads();
+    const int El   = age_sum ? C : n;
+    const int lane = threadIdx.x & 31, w = threadIdx.x >> 5, nw = blockDim.x >> 5;
+    if (lane < rows) {
+        for (int el = w; el < El; el += nw) {
+            double v;
+            if (age_sum) {
+                v = 0.0;
+                for (int a = 0; a < G; ++a) {
+                    v += tile[lane * (n + 1) + a * C + el];
+                }
+            }
+            else {
+                v = tile[lane * (n + 1) + el];
+            }
+            ens[((size_t)(node * num_days + day) * El + el) * stride + run_offset + r0 + lane] = v;
+        }
+    }
+}
+
+// sum_nodes: ens[base + day*n + j][run] = sum_k y[run][k][j], nodes added in index order
+__global__ void __launch_bounds__(128) record_node_sum_kernel(const double* __restrict__ y, double* __restrict__ ens,
+                                                              int N, int n, int num_runs, int day, long long base_col,
+                                                              long long run_offset, long long stride)
+{
+    const int run = blockIdx.x;
+    const int j   = threadIdx.x;
+    if (run >= num_runs || j >= n) {
+        return;
+    }
+    const double* p = y + (size_t)run * N * n + j;
+    double s        = 0.0;
+    for (int k = 0; k < N; ++k) {
+        s += p[(size_t)k * n];
+    }
+    ens[(size_t)(base_col + (long long)day * n + j) * stride + run_offset + run] = s;
+}
+
+// ---------------------------------------------------------------------------------------------------------------
+__device__ __forceinline__ unsigned long long ordered_key(double v)
+{
+    unsigned long long b = (unsigned long long)__double_as_longlong(v);
+    return (b & 0x8000000000000000ull) ? ~b : (b | 0x8000000000000000ull);
+}
+__device__ __forceinline__ double key_to_double(unsigned long long k)
+{
+    unsigned long long b = (k & 0x8000000000000000ull) ? (k & 0x7fffffffffffffffull) : ~k;
+    return __longlong_as_double((long long)b);
+}
+
+// One CTA per column. Pass over the digits from the most significant; every percentile keeps its own prefix.
+__global__ void __launch_bounds__(SEL_THREADS) select_percentiles_kernel(SelectArgs a)
+{
+    extern __shared__ unsigned int hist_dyn[]; // [num_p][SEL_BINS]
+    unsigned int(*hist)[SEL_BINS] = reinterpret_cast<unsigned int(*)[SEL_BINS]>(hist_dyn);
+    __shared__ unsigned long long prefix[SEL_MAX_P];
+    __shared__ long long remaining[SEL_MAX_P];
+    __shared__ double red[SEL_THREADS];
+    const long long col = blockIdx.x;
+    const int tid       = threadIdx.x;
+    if (a.out_mean != nullptr) {
+        // ensemble_mean: sum of value / num_runs (fixed summation tree => deterministic)
+        double s           = 0.0;
+        const double denom = (double)a.total;
+        for (int sg = 0; sg < a.num_segments; ++sg) {
+            const double* p = a.seg_ptr[sg] + (size_t)col * a.seg_stride[sg];
+            for (long long i = tid; i < a.seg_count[sg]; i += SEL_THREADS) {
+                s += p[i] / denom;
+            }
+        }
+        red[tid] = s;
+        __syncthreads();
+        for (int o = SEL_THREADS / 2; o > 0; o >>= 1) {
+            if (tid < o) {
+                red[tid] += red[tid + o];
+            }
+            __syncthreads();
+        }
+        if (tid == 0) {
+            a.out_mean[col] = red[0];
+        }
+    }
+    if (a.out_select == nullptr || a.num_p == 0) {
+        return;
+    }
+    if (tid < a.num_p) {
+        prefix[tid]    = 0ull;
+        remaining[tid] = a.rank[tid];
+    }
+    int shift = 64;
+    while (shift > 0) {
+        const int bits = shift >= 20 + SEL_BITS ? SEL_BITS : (shift > 10 ? 10 : shift); // 11,11,11,11,10,10
+        shift -= bits;
+        const unsigned int nb = 1u << bits;
+        for (int i = tid; i < a.num_p * SEL_BINS; i += SEL_THREADS) {
+            (&hist[0][0])[i] = 0u;
+        }
+        __syncthreads();
+        const bool first = (shift + bits) == 64;
+        for (int sg = 0; sg < a.num_segments; ++sg) {
+            const double* p = a.seg_ptr[sg] + (size_t)col * a.seg_stride[sg];
+            for (long long i = tid; i < a.seg_count[sg]; i += SEL_THREADS) {
+                const unsigned long long k = ordered_key(p[i]);
+                const unsigned int digit   = (unsigned int)(k >> shift) & (nb - 1u);
+                if (first) {
+                    // all percentiles share the empty prefix. The leading digit (sign + exponent bits) is the same
+                    // for most runs of a column: aggregate equal digits inside the warp before touching shared memory
+                    const unsigned int act  = __activemask();
+                    const unsigned int same = __match_any_sync(act, digit);
+                    if ((int)(threadIdx.x & 31) == __ffs(same) - 1) {
+                        atomicAdd(&hist[0][digit], (unsigned int)__popc(same));
+                    }
+                }
+                else {
+                    const unsigned long long hi = k >> (shift + bits);
+                    for (int q = 0; q < a.num_p; ++q) {
+                        if (hi == prefix[q]) {
+                            atomicAdd(&hist[q][digit], 1u);
+                        }
+                    }
+                }
+            }
+        }
+        __syncthreads();
+        // warp q locates the digit of percentile q: per-lane partial sums, warp scan, then a short in-lane search
+        {
+            const int wq = tid >> 5, lane = tid & 31;
+            if (wq < a.num_p) {
+                const unsigned int* h = first ? hist[0] : hist[wq];
+                const int per         = (int)(nb / 32u);
+                unsigned int sum      = 0;
+                for (int i = 0; i < per; ++i) {
+                    sum += h[lane * per + i];
+                }
+                unsigned int inc = sum;
+                for (int o = 1; o < 32; o <<= 1) {
+                    const unsigned int t = __shfl_up_sync(0xffffffffu, inc, o);
+                    if (lane >= o) {
+                        inc += t;
+                    }
+                }
+                const unsigned int exc = inc - sum;
+                const long long rem    = remaining[wq];
+                const bool mine        = rem >= (long long)exc && rem < (long long)inc;
+                const unsigned int who = __ballot_sync(0xffffffffu, mine);
+                if (who != 0u && lane == __ffs(who) - 1) {
+                    long long r    = rem - exc;
+                    unsigned int d = lane * per;
+                    for (;; ++d) {
+                        const unsigned int c = h[d];
+                        if (r < (long long)c) {
+                            break;
+                        }
+                        r -= c;
+                    }
+                    remaining[wq] = r;
+                    prefix[wq]    = (prefix[wq] << bits) | (unsigned long long)d;
+                }
+            }
+        }
+        __syncthreads();
+    }
+    if (tid < a.num_p) {
+        a.out_select[(size_t)tid * a.num_columns + col] = key_to_double(prefix[tid]);
+    }
+}
+
+cudaError_t launch_record_ensemble(const double* y, double* ens, int N, int G, int C, int num_runs, int day,
+                                   int num_days, int age_sum, long long run_offset, long long stride,
+                                   cudaStream_t stream)
+{
+    const int n = G * C;
+    dim3 grid((num_runs + 31) / 32, N);
+    record_ensemble_kernel<<<grid, 256, sizeof(double) * 32 * (n + 1), stream>>>(y, ens, N, G, C, num_runs, day,
+                                                                                 num_days, age_sum, run_offset, stride);
+    const long long base = (long long)N * num_days * (age_sum ? C : n);
+    record_node_sum_kernel<<<num_runs, ((n + 31) / 32) * 32, 0, stream>>>(y, ens, N, n, num_runs, day, base, run_offset,
+                                                                         stride);
+    return cudaGetLastError();
+}
+
+cudaError_t launch_select(const SelectArgs& a, cudaStream_t stream)
+{
+    if (a.num_columns == 0) {
+        return cudaSuccess;
+    }
+    const int shmem = (int)sizeof(unsigned int) * SEL_BINS * (a.num_p > 0 ? a.num_p : 1);
+    // static shared (prefixes, reduction scratch) comes on top: always raise the dynamic limit to the maximum used
+    cudaFuncSetAttribute(select_percentiles_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize,
+                         (int)sizeof(unsigned int) * SEL_BINS * SEL_MAX_P);
+    select_percentiles_kernel<<<(unsigned)a.num_columns, SEL_THREADS, shmem, stream>>>(a);
+    return cudaGetLastError();
+}
+
+} // namespace miocu

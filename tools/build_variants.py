@@ -1,0 +1,25 @@
+#!/usr/bin/env python
+"""Build launch-shape variants of the library under memilio_b200/csrc/variants/ for A/B timing on the GPU box."""
+import os
+import sys
+
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+sys.path.insert(0, ROOT)
+from memilio_b200 import build as b  # noqa: E402
+
+VARIANTS = {
+    "i128x3": ["MIO_INTEGRATE_THREADS=128", "MIO_INTEGRATE_MINBLOCKS=3"],
+    "i128x4": ["MIO_INTEGRATE_THREADS=128", "MIO_INTEGRATE_MINBLOCKS=4"],
+    "i256x2": ["MIO_INTEGRATE_MINBLOCKS=2"],
+    "e256x2": ["MIO_DEPART_MINBLOCKS=2", "MIO_RETURN_MINBLOCKS=3"],
+    "e256x4": ["MIO_DEPART_MINBLOCKS=4", "MIO_RETURN_MINBLOCKS=4"],
+    "e128x6": ["MIO_EDGE_THREADS=128", "MIO_DEPART_MINBLOCKS=6", "MIO_RETURN_MINBLOCKS=8"],
+}
+
+if __name__ == "__main__":
+    names = sys.argv[1:] or list(VARIANTS)
+    for name in names:
+        d = os.path.join(b.CSRC, "variants", name)
+        out = os.path.join(b.CSRC, "variants", f"libmio_cuda_{name}.so")
+        b.build(force=True, defines=VARIANTS[name], out=out, objdir=d)
+        print(out)
