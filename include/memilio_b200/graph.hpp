@@ -362,7 +362,8 @@ PackedGraph pack_graph(const GraphT& g, int ct_max_pts_min = 1)
         p.edge_start.push_back(int32_t(e.start_node_idx));
         p.edge_end.push_back(int32_t(e.end_node_idx));
         const auto& grp = e.property.get_parameters().get_coefficients();
-        std::vector<double> c(size_t(p.n), 0.0);
+        const size_t nn = size_t(p.n);
+        std::vector<double> c(nn, 0.0);
         for (size_t mbr = 0; mbr < grp.get_num_matrices(); ++mbr) {
             if (grp[mbr].get_baseline().size() != p.n) {
                 throw std::runtime_error("pack_graph: mobility coefficient vector has the wrong size");
@@ -383,11 +384,13 @@ PackedGraph pack_graph(const GraphT& g, int ct_max_pts_min = 1)
                     types.push_back(d.type);
                     mats.insert(mats.end(), d.v.data(), d.v.data() + p.n);
                 }
-                std::vector<double> ot(size_t(Kd)), om(size_t(Kd) * p.n);
+                const size_t Ku = size_t(Kd);
+                std::vector<double> ot(Ku), om(Ku * size_t(p.n));
                 int32_t nout = 0;
                 cuda_check(mio_damping_cache_build(p.n, 1, Kd, times.data(), levels.data(), types.data(), mats.data(),
                                                    &nout, ot.data(), om.data()));
-                std::vector<double> tbl(size_t(1 + Kd + Kd * p.n), 0.0);
+                const size_t tsz = size_t(1 + Kd + Kd * p.n);
+                std::vector<double> tbl(tsz, 0.0);
                 tbl[0] = nout;
                 std::copy(ot.begin(), ot.begin() + nout, tbl.begin() + 1);
                 std::copy(om.begin(), om.begin() + size_t(nout) * p.n, tbl.begin() + 1 + Kd);
@@ -507,7 +510,8 @@ public:
             m_dev  = std::make_shared<detail::DeviceGraph>(p, m_dt, 1, int(p.psets.size()), int(p.ctables.size()), 0);
             m_dev->set_run(0, p, int(p.psets.size()), int(p.ctables.size()));
         }
-        std::vector<double> state(size_t(m_dev->N()) * m_dev->n());
+        const size_t total = size_t(m_dev->N()) * size_t(m_dev->n());
+        std::vector<double> state(total);
         FP dt = m_dt;
         while (m_t < t_max) {
             if (m_t + dt > t_max) {
@@ -518,7 +522,8 @@ public:
             cuda_check(mio_cuda_get_state(m_dev->get(), 0, 1, state.data()));
             append_time_point(m_t, state.data());
         }
-        std::vector<double> dts(size_t(m_dev->N()));
+        const size_t Nn = size_t(m_dev->N());
+        std::vector<double> dts(Nn);
         cuda_check(mio_cuda_get_node_dt(m_dev->get(), 0, 1, dts.data()));
         for (size_t k = 0; k < m_graph.nodes().size(); ++k) {
             m_graph.nodes()[k].property.get_simulation().get_dt() = dts[k];

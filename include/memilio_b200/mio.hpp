@@ -436,6 +436,9 @@ private:
     std::vector<T> m_v;
 };
 
+template <class T, class... Tags>
+using CustomIndexArray = AgeArray<T>; // only AgeGroup-indexed arrays occur on this path
+
 // ---- TimeSeries (utils/time_series.h:57-620): columns [t, y_0 .. y_{n-1}] ------------------------------------------
 template <class FP = ScalarType>
 class TimeSeries
@@ -879,3 +882,4 @@ using DefaultIntegratorCore = AdaptiveCoreT<MIO_INTEGRATOR_CK54>;  // compartmen
 #include "osecir.hpp"
 #include "graph.hpp"
 #include "study.hpp"
+#include "io.hpp"

@@ -420,7 +420,8 @@ constexpr int NC = int(InfectionState::Count);
 template <class FP>
 std::vector<double> contact_table(const ContactMatrixGroup<FP>& cm, int G, int max_loc, int max_pts)
 {
-    std::vector<double> ct(size_t(mio_ctable_size(G, max_loc, max_pts)), 0.0);
+    const size_t csz = size_t(mio_ctable_size(G, max_loc, max_pts));
+    std::vector<double> ct(csz, 0.0);
     const int L = int(cm.get_num_matrices());
     if (L > max_loc) {
         throw std::runtime_error("contact table: too many contact locations");
@@ -430,9 +431,9 @@ std::vector<double> contact_table(const ContactMatrixGroup<FP>& cm, int G, int m
     for (int l = 0; l < L; ++l) {
         const auto& m = cm[size_t(l)];
         const int K   = int(m.get_dampings().size());
-        std::vector<double> times(size_t(K)), mats(size_t(K) * G * G), ot(size_t(std::max(K, 1))),
-            om(size_t(std::max(K, 1)) * G * G);
-        std::vector<int32_t> levels(size_t(K)), types(size_t(K));
+        const size_t Ku = size_t(K), K1 = size_t(std::max(K, 1)), GG = size_t(G) * size_t(G);
+        std::vector<double> times(Ku), mats(Ku * GG), ot(K1), om(K1 * GG);
+        std::vector<int32_t> levels(Ku), types(Ku);
         for (int k = 0; k < K; ++k) {
             const auto& d    = m.get_dampings()[size_t(k)];
             times[size_t(k)] = d.time;
@@ -535,7 +536,8 @@ public:
         d.integrator    = m_core->desc();
         d.t0            = m_result.get_last_time();
         d.dt_graph      = std::numeric_limits<double>::infinity();
-        std::vector<double> pset(size_t(mio_pset_size(MIO_MODEL_OSECIR, G)), 0.0), local(MIO_NODE_LOCAL);
+        const size_t psz = size_t(mio_pset_size(MIO_MODEL_OSECIR, G));
+        std::vector<double> pset(psz, 0.0), local(MIO_NODE_LOCAL);
         m_model.parameters.pack_values(pset.data(), local.data());
         std::vector<double> ct = detail::contact_table(cm, G, L, K);
         std::vector<double> y0(m_result.get_last_value().data(), m_result.get_last_value().data() + n);
@@ -546,7 +548,8 @@ public:
             cuda_check(mio_cuda_set_runs(h, 0, 1, &rd));
             cuda_check(mio_cuda_advance(h, tmax));
             int32_t npts = 0;
-            std::vector<double> times(size_t(d.traj_capacity)), values(size_t(d.traj_capacity) * n);
+            const size_t cap = size_t(d.traj_capacity);
+            std::vector<double> times(cap), values(cap * size_t(n));
             cuda_check(mio_cuda_get_trajectory(h, 0, 1, &npts, times.data(), values.data()));
             if (npts > d.traj_capacity) {
                 throw std::runtime_error("Simulation::advance: more integrator steps than the trajectory capacity");

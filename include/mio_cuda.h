@@ -328,6 +328,11 @@ MIO_API int mio_cuda_select_percentiles(int device, int32_t num_segments, const 
                                         const int64_t* seg_stride, const int64_t* seg_count, int64_t num_columns,
                                         int32_t num_p, const double* p, double* percentiles, double* mean);
 
+/* convenience for host callers (the C++ facade's ensemble_percentile / ensemble_mean): host matrix
+ * columns[num_columns][num_runs] -> percentiles[num_p][num_columns] and/or mean[num_columns], computed on the device */
+MIO_API int mio_cuda_reduce_host_columns(const double* columns, int64_t num_columns, int64_t num_runs, int32_t num_p,
+                                         const double* p, double* percentiles, double* mean);
+
 /* ---- measurement hooks ------------------------------------------------------------------------------------------ */
 #define MIO_NUM_KERNEL_CLASSES 6
 #define MIO_KC_INTEGRATE 0    /* node phase: adaptive RK integration of every (run, node) */

@@ -27,7 +27,7 @@ EXPORTS = [
     "mio_study_create", "mio_study_destroy", "mio_study_num_ctables", "mio_study_node_ctable",
     "mio_study_sample_runs", "mio_study_distribute_runs", "mio_study_rng_raw", "mio_damping_cache_build",
     "mio_cuda_ensemble_create", "mio_cuda_ensemble_destroy", "mio_cuda_attach_ensemble", "mio_cuda_ensemble_info",
-    "mio_cuda_ensemble_reduce", "mio_cuda_select_percentiles",
+    "mio_cuda_ensemble_reduce", "mio_cuda_select_percentiles", "mio_cuda_reduce_host_columns",
 ]
 KERNEL_CLASSES = ["integrate", "depart", "return", "return_exact", "record", "ensemble"]
 

@@ -72,6 +72,8 @@ struct mio_handle {
         *d_out_ptr = nullptr, *d_out_dst = nullptr, *d_edge_start = nullptr, *d_edge_end = nullptr;
     double *d_coeff = nullptr, *d_w_in = nullptr, *d_w_out = nullptr, *d_s_out = nullptr, *d_umask = nullptr;
     int factorized = 0;
+    int num_mob = 0;
+    int mob_comp[NC] = {0, 0, 0, 0, 0, 0, 0, 0, 0, 0};
     // per run (device)
     double *d_run_block = nullptr, *d_node_local = nullptr, *d_t_node = nullptr, *d_dt_node = nullptr;
     int* d_counters     = nullptr;
@@ -475,6 +477,26 @@ int mio_cuda_graph_create(const mio_graph_desc* d, int device, mio_handle** out)
         if (!fact) {
             std::fill(umask.begin(), umask.end(), 1.0);
         }
+        // mobile compartments = union of the mask over the age groups; the list is padded with a non-mobile
+        // compartment (its emigration base entries are zero) or, if all ten are mobile, is simply complete
+        {
+            int pad = -1;
+            for (int cc = 0; cc < NC; ++cc) {
+                bool any = false;
+                for (int i = 0; i < G; ++i) {
+                    any = any || umask[i * NC + cc] != 0.0;
+                }
+                if (any) {
+                    h->mob_comp[h->num_mob++] = cc;
+                }
+                else if (pad < 0) {
+                    pad = cc;
+                }
+            }
+            for (int m = h->num_mob; m < NC; ++m) {
+                h->mob_comp[m] = pad < 0 ? 0 : pad;
+            }
+        }
         std::vector<double> w_in(fact ? (size_t)E * G : (size_t)E * n), w_out((size_t)E * G * 2),
             s_out((size_t)N * n, 0.0);
         for (int pos = 0; pos < E; ++pos) {
@@ -765,7 +787,9 @@ int mio_cuda_advance(mio_handle* h, double t_max)
             ea.st             = device_state(h);
             ea.csr = GraphCsr{h->d_order_in, h->d_order_out, h->d_in_ptr,  h->d_in_split, h->d_in_src,
                               h->d_w_in,     h->d_out_ptr,   h->d_out_dst, h->d_w_out,    h->d_s_out,
-                              h->d_umask,    h->factorized,  h->d_edge_start, h->d_edge_end, h->d_coeff};
+                              h->d_umask,    h->factorized,  h->num_mob,   {0},           h->d_edge_start,
+                              h->d_edge_end, h->d_coeff};
+            std::copy(h->mob_comp, h->mob_comp + NC, ea.csr.mob_comp);
             ea.fac            = h->d_fac;
             ea.u              = h->d_u;
             ea.vis            = h->d_vis;
@@ -1176,6 +1200,33 @@ int mio_cuda_ensemble_reduce(mio_ensemble* e, int32_t num_p, const double* p, do
     const int64_t stride = e->capacity, count = e->num_runs;
     return mio_cuda_select_percentiles(e->device, 1, &ptr, &stride, &count, e->num_columns, num_p, p, percentiles,
                                        mean);
+}
+
+int mio_cuda_reduce_host_columns(const double* columns, int64_t num_columns, int64_t num_runs, int32_t num_p,
+                                 const double* p, double* percentiles, double* mean)
+{
+    if (!columns || num_columns < 0 || num_runs < 1) {
+        return fail(MIO_INVALID_VALUE, "invalid arguments");
+    }
+    int ndev = 0;
+    if (cudaGetDeviceCount(&ndev) != cudaSuccess || ndev == 0) {
+        return fail(MIO_UNKNOWN_ERROR, "no CUDA device available (this library has no CPU fallback)");
+    }
+    int device = 0;
+    CUDA_TRY(cudaGetDevice(&device));
+    double* d = nullptr;
+    CUDA_TRY(dev_alloc(&d, (size_t)num_columns * (size_t)num_runs));
+    cudaError_t er = cudaMemcpy(d, columns, sizeof(double) * (size_t)num_columns * (size_t)num_runs,
+                                cudaMemcpyHostToDevice);
+    if (er != cudaSuccess) {
+        cudaFree(d);
+        return fail(MIO_UNKNOWN_ERROR, cudaGetErrorString(er));
+    }
+    const void* ptr = d;
+    int rc = mio_cuda_select_percentiles(device, 1, &ptr, &num_runs, &num_runs, num_columns, num_p, p, percentiles,
+                                         mean);
+    cudaFree(d);
+    return rc;
 }
 
 } // extern "C"

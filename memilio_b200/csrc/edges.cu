@@ -162,40 +162,19 @@ __device__ __forceinline__ void gather_visitors(const EdgeArgs& a, const Geometr
 // (SpMV over the incoming-edge CSR; V1: sources < k, V3: sources > k, i.e. before / after k's own outgoing edges in
 // the reference order) and kept for the return phase; the emigrants are s_out_k * u_k.
 // Then the return coefficients of k as a destination (lambda_i, ICU adjusted rates) from v0 = y_out at time t.
-template <int G, bool FACT>
-__global__ void __launch_bounds__(EDGE_THREADS, MIO_DEPART_MINBLOCKS) depart_kernel(EdgeArgs a)
+// Everything of the departure after the visitor gather: test_commuters bookkeeping, the in-place node update in the
+// reference's block order, and the return coefficients of the node as a destination.
+template <int G>
+__device__ __forceinline__ void depart_node_update(const EdgeArgs& a, const Geometry& geo, const EdgeLane<G>& L,
+                                                   const double* smem, const double (&V1)[NC], const double (&V3)[NC])
 {
-    extern __shared__ __align__(16) double smem[];
-    __shared__ __align__(8) uint64_t mbar;
-    const Geometry& geo = a.geo;
-    EdgeLane<G> L;
-    bool cta_active;
-    edge_lane_setup<G>(geo, a.csr.order_in, a.num_runs, L, cta_active);
-    if (!cta_active) {
-        return;
-    }
-    stage_run_block(smem, a.st.run_block + (size_t)L.run * geo.block_stride, geo.block_stride * 8, &mbar);
     const Group<G>& g  = L.g;
     const int ps_own   = a.st.node_pset ? a.st.node_pset[L.node] : 0;
     const double* pset = smem + ps_own * geo.pset_stride;
-
     double y[NC], uk[NC], so[NC];
     load10(a.y_in + L.rn * geo.n + g.gl * NC, y);
     load10(a.u + L.rn * geo.n + g.gl * NC, uk);
     load10(a.csr.s_out + (size_t)L.node * geo.n + g.gl * NC, so);
-
-    const int beg   = L.valid ? a.csr.in_ptr[L.node] : 0;
-    const int cnt   = L.valid ? a.csr.in_ptr[L.node + 1] - beg : 0;
-    const int split = L.valid ? a.csr.in_split[L.node] : 0;
-    double V1[NC], V3[NC];
-#pragma unroll
-    for (int i = 0; i < NC; ++i) {
-        V1[i] = 0.0;
-        V3[i] = 0.0;
-    }
-    gather_visitors<FACT, G>(a, geo, L.run, g.gl, beg, split, warp_max(split), V1);
-    gather_visitors<FACT, G>(a, geo, L.run, g.gl, beg + split, cnt - split, warp_max(cnt - split), V3);
-
     // test_commuters (ode_secir/model.h:717-742): detected commuters stay, in the *Confirmed compartments
     const double nd = nondetection_at(pset, a.t);
     if (nd != 1.0) {
@@ -262,6 +241,125 @@ __global__ void __launch_bounds__(EDGE_THREADS, MIO_DEPART_MINBLOCKS) depart_ker
             reinterpret_cast<double2*>(ax)[0] = make_double2((season * c.rP) * lam, rISev_ICr);
             reinterpret_cast<double2*>(ax)[1] = make_double2(rISev_D, 0.0);
         }
+    }
+}
+
+template <int G, bool FACT>
+__global__ void __launch_bounds__(EDGE_THREADS, MIO_DEPART_MINBLOCKS) depart_kernel(EdgeArgs a)
+{
+    extern __shared__ __align__(16) double smem[];
+    __shared__ __align__(8) uint64_t mbar;
+    const Geometry& geo = a.geo;
+    EdgeLane<G> L;
+    bool cta_active;
+    edge_lane_setup<G>(geo, a.csr.order_in, a.num_runs, L, cta_active);
+    if (!cta_active) {
+        return;
+    }
+    stage_run_block(smem, a.st.run_block + (size_t)L.run * geo.block_stride, geo.block_stride * 8, &mbar);
+    const Group<G>& g = L.g;
+    const int beg     = L.valid ? a.csr.in_ptr[L.node] : 0;
+    const int cnt     = L.valid ? a.csr.in_ptr[L.node + 1] - beg : 0;
+    const int split   = L.valid ? a.csr.in_split[L.node] : 0;
+    double V1[NC], V3[NC];
+#pragma unroll
+    for (int i = 0; i < NC; ++i) {
+        V1[i] = 0.0;
+        V3[i] = 0.0;
+    }
+    gather_visitors<FACT, G>(a, geo, L.run, g.gl, beg, split, warp_max(split), V1);
+    gather_visitors<FACT, G>(a, geo, L.run, g.gl, beg + split, cnt - split, warp_max(cnt - split), V3);
+    depart_node_update<G>(a, geo, L, smem, V1, V3);
+}
+
+// ---------------------------------------------------------------------------------------------------------------
+// Departure with the run's emigration base vectors staged in shared memory (factorized coefficients only).
+// The gather of depart_kernel reads E*n doubles per run through L2 (48 GB per launch at R = 10^4) and is bound by L2
+// bandwidth; here one CTA owns one run, copies the M mobile compartments of u[run] (N*G*M doubles, 96 KB for the
+// 400-county graph) into shared memory once, and every incoming edge is then a shared-memory read.
+constexpr int DEPART_SMEM_THREADS = 256;
+
+template <int G, int M>
+__global__ void __launch_bounds__(DEPART_SMEM_THREADS, 2) depart_smem_kernel(EdgeArgs a)
+{
+    extern __shared__ __align__(16) double smem[];
+    __shared__ __align__(8) uint64_t mbar;
+    const Geometry& geo = a.geo;
+    constexpr int NPW   = 32 / G;
+    constexpr int WARPS = DEPART_SMEM_THREADS / 32;
+    const int run       = blockIdx.x;
+    if (run >= a.num_runs) {
+        return;
+    }
+    stage_run_block(smem, a.st.run_block + (size_t)run * geo.block_stride, geo.block_stride * 8, &mbar);
+    double* us = smem + geo.block_stride;
+    {
+        const double* ug = a.u + (size_t)run * geo.N * geo.n;
+        const int total  = geo.N * G * M;
+        for (int idx = threadIdx.x; idx < total; idx += DEPART_SMEM_THREADS) {
+            const int m    = idx % M;
+            const int rest = idx / M; // node * G + age
+            us[idx]        = ug[(size_t)rest * NC + a.csr.mob_comp[m]];
+        }
+    }
+    __syncthreads();
+    EdgeLane<G> L;
+    L.run            = run;
+    const int warp   = threadIdx.x >> 5;
+    const int passes = (geo.N + NPW * WARPS - 1) / (NPW * WARPS);
+    for (int pass = 0; pass < passes; ++pass) {
+        const int item = (pass * WARPS + warp) * NPW + L.g.lane / G;
+        L.valid        = !L.g.spare() && item < geo.N;
+        L.node         = L.valid ? a.csr.order_in[item] : 0;
+        L.rn           = (size_t)run * geo.N + L.node;
+        const int gl   = L.g.gl;
+        const int beg   = L.valid ? a.csr.in_ptr[L.node] : 0;
+        const int cnt   = L.valid ? a.csr.in_ptr[L.node + 1] - beg : 0;
+        const int split = L.valid ? a.csr.in_split[L.node] : 0;
+        double v1[M], v3[M];
+#pragma unroll
+        for (int m = 0; m < M; ++m) {
+            v1[m] = 0.0;
+            v3[m] = 0.0;
+        }
+        const int mx = warp_max(cnt);
+        for (int it = 0; it < mx; ++it) {
+            const bool act = it < cnt;
+            const int pos  = beg + (act ? it : 0);
+            const int src  = a.csr.in_src[pos];
+            const double w = act ? a.csr.w_in[(size_t)pos * G + gl] : 0.0;
+            const double* p = us + (src * G + gl) * M;
+            if (it < split) {
+#pragma unroll
+                for (int m = 0; m < M; ++m) {
+                    v1[m] += w * p[m];
+                }
+            }
+            else {
+#pragma unroll
+                for (int m = 0; m < M; ++m) {
+                    v3[m] += w * p[m];
+                }
+            }
+        }
+        double V1[NC], V3[NC];
+#pragma unroll
+        for (int i = 0; i < NC; ++i) {
+            V1[i] = 0.0;
+            V3[i] = 0.0;
+        }
+#pragma unroll
+        for (int m = 0; m < M; ++m) {
+            const int c = a.csr.mob_comp[m];
+#pragma unroll
+            for (int i = 0; i < NC; ++i) { // register arrays: select instead of a dynamic index
+                if (i == c) {
+                    V1[i] += v1[m];
+                    V3[i] += v3[m];
+                }
+            }
+        }
+        depart_node_update<G>(a, geo, L, smem, V1, V3);
     }
 }
 
@@ -532,7 +630,22 @@ static cudaError_t launch_edges_g(const EdgeArgs& a, int which, cudaStream_t str
         kern<<<(unsigned)(GRID), THREADS, shmem, stream>>>(a);                                                         \
     } while (0)
     if (which == 0) {
-        if (a.csr.factorized) {
+        const int M          = a.csr.num_mob <= 5 ? 5 : NC;
+        const size_t shmem_u = shmem + sizeof(double) * (size_t)a.geo.N * G * M;
+        if (a.csr.factorized && a.csr.num_mob > 0 && shmem_u <= 110 * 1024) {
+            // two CTAs per SM keep both the FP64 tail and the shared-memory gather busy
+            if (M == 5) {
+                auto kern = depart_smem_kernel<G, 5>;
+                cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)shmem_u);
+                kern<<<(unsigned)a.num_runs, DEPART_SMEM_THREADS, shmem_u, stream>>>(a);
+            }
+            else {
+                auto kern = depart_smem_kernel<G, NC>;
+                cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)shmem_u);
+                kern<<<(unsigned)a.num_runs, DEPART_SMEM_THREADS, shmem_u, stream>>>(a);
+            }
+        }
+        else if (a.csr.factorized) {
             MIO_EDGE_LAUNCH((depart_kernel<G, true>), grid, EDGE_THREADS);
         }
         else {

@@ -64,6 +64,8 @@ struct GraphCsr {
     const double* s_out;  // [N][n] sum of the coefficient vectors of a node's outgoing edges (edge order)
     const double* umask;  // [n] 1/0 mobile compartment mask (all ones in dense mode)
     int factorized;       // coeff[e][i][c] == w[e][i] * umask[i][c] holds exactly for every edge
+    int num_mob;          // number of mobile compartments (union over the age groups of the mask)
+    int mob_comp[NC];     // their indices, padded by repeating a non-mobile compartment (whose u is zero)
     // literal form (exact replay of the sequential edge loop)
     const int* edge_start; // [E]
     const int* edge_end;   // [E]

@@ -1,0 +1,115 @@
+"""The C++ facade end to end on the GPU: the restated example programs (examples/*.cpp, MEmilio's API names) are
+built with the host compiler, run, and their printed results compared with the reference's golden vector, the CPU
+oracle and the Python mirror."""
+import os
+import subprocess
+
+import numpy as np
+import pytest
+
+import oracle_lib
+import scenarios
+from memilio_b200 import build, capi, flat, study
+
+pytestmark = pytest.mark.gpu
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+
+
+def run_example(name, *args):
+    build.build()
+    subprocess.run(["make", "-s", "-C", os.path.join(ROOT, "examples")], check=True)
+    r = subprocess.run([os.path.join(ROOT, "examples", "_build", name), *map(str, args)], capture_output=True,
+                       text=True, timeout=600)
+    assert r.returncode == 0, r.stderr[-2000:]
+    return r.stdout
+
+
+def test_single_node_example_reproduces_reference_golden_vector():
+    out = run_example("secir_single")
+    got = np.array([[float(w) for w in ln.split()] for ln in out.strip().splitlines()])
+    ref = scenarios.load_csv("ode-secihurd-compare.csv")
+    assert got.shape == ref.shape  # same accepted adaptive steps as the reference run
+    np.testing.assert_allclose(got[:, 0], ref[:, 0], rtol=1e-8, atol=1e-10)
+    np.testing.assert_allclose(got[:, 1:], ref[:, 1:], rtol=1e-8, atol=1e-8)
+
+
+def test_two_node_graph_example_matches_oracle_every_half_day():
+    out = run_example("graph_two_nodes")
+    rows = np.array([[float(w) for w in ln.split()] for ln in out.strip().splitlines()])
+    p = scenarios.example_ode_secir_graph()
+    ref = oracle_lib.graph_simulate(p, 0, 30.0, halfsteps=60)
+    for k in range(2):
+        node = rows[rows[:, 1] == k]
+        assert node.shape[0] == 61
+        np.testing.assert_array_equal(node[:, 0], np.arange(61) * 0.5)
+        np.testing.assert_array_equal(node[0, 2:], p.y0[0, k])
+        np.testing.assert_allclose(node[1:, 2:], ref["halfsteps"][:, k], rtol=1e-8, atol=1e-9)
+
+
+def _python_twin_of_parameter_study_example():
+    G, N = 6, 3
+    header = study.uv_array(flat.PSET_HEADER)
+    study.set_uniform(header, flat.PH["Seasonality"], 0.1, 0.3)
+    study.set_value(header, flat.PH["TestAndTraceCapacityMaxRisk"], 5.0)
+    age = study.uv_array((G, flat.OSECIR_AGE_STRIDE))
+    for name, slot in flat.PA.items():
+        age[:, slot]["value"] = flat.PA_DEFAULT[name]
+    tsev = ([3.925, 3.925, 4.85, 6.4, 7.2, 9.], [6.075, 6.075, 7., 8.7, 9.8, 13.])
+    prob = ([0.02, 0.05, 0.05, 0.05, 0.08, 0.15], [0.04, 0.07, 0.07, 0.07, 0.10, 0.20])
+    for i in range(G):
+        for name, lo, hi in (("TimeExposed", 2.67, 4.0), ("TimeInfectedNoSymptoms", 1.2, 2.53),
+                             ("TimeInfectedSymptoms", 5.6, 8.4), ("TimeInfectedSevere", tsev[0][i], tsev[1][i]),
+                             ("TimeInfectedCritical", 4.95, 8.95),
+                             ("TransmissionProbabilityOnContact", prob[0][i], prob[1][i]),
+                             ("RelativeTransmissionNoSymptoms", 0.5, 1.0),
+                             ("RiskOfInfectionFromSymptomatic", 0.1, 0.3),
+                             ("MaxRiskOfInfectionFromSymptomatic", 0.3, 0.5),
+                             ("RecoveredPerInfectedNoSymptoms", 0.15, 0.3),
+                             ("SeverePerInfectedSymptoms", 0.006, 0.2), ("CriticalPerSevere", 0.05, 0.35),
+                             ("DeathsPerCritical", 0.0, 0.5)):
+            study.set_uniform(age, (i, flat.PA[name]), lo, hi)
+    local = study.uv_array((N, 2))
+    study.set_value(local, (slice(None), 0), flat.DBL_MAX)
+    for k in range(N):
+        study.set_uniform(local, (k, 1), 20, 40)
+    pops = study.uv_array((N, G * 10))
+    for k in range(N):
+        for i in range(G):
+            study.set_uniform(pops, (k, i * 10 + flat.E), 10, 30)
+            pops[k, i * 10 + flat.E]["value"] = 20
+            study.set_value(pops, (k, i * 10 + flat.S), 10000 - 20)
+    dv = study.uv_array(1)
+    study.set_uniform(dv, 0, 0.3, 0.7)
+    n = G * 10
+    coeff = np.stack([np.full(n, c) for c in (0.05, 0.1, 0.15, 0.2)])
+    return study.StudyGraph(num_groups=G, num_nodes=N, header=header, age_params=age, node_local=local,
+                            populations=pops, baseline=np.full((1, G, G), 10.0 / G), minimum=None,
+                            edge_start=np.array([0, 1, 1, 2]), edge_end=np.array([1, 0, 2, 1]), edge_coeff=coeff,
+                            dampings=[study.Damping(value=dv, time=4.0, matrices=(0,))])
+
+
+def test_parameter_study_example_equals_python_mirror_and_numpy_percentile():
+    runs, days = 7, 8
+    out = run_example("parameter_study", runs, days)
+    per_run, p50 = [], []
+    for ln in out.strip().splitlines():
+        w = ln.split()
+        (p50 if w[0] == "p50" else per_run).append([float(x) for x in (w[1:] if w[0] == "p50" else w)])
+    per_run = np.array(per_run)
+    p50 = np.array(p50)
+    assert per_run.shape == (runs * 3 * (days + 1), 3 + 60)
+    got = per_run[:, 3:].reshape(runs, 3, days + 1, 60)
+    # the same study through the Python mirror: same seeds, same draw order => identical sampled runs
+    ps = study.ParameterStudy(_python_twin_of_parameter_study_example(), 0.0, float(days), 0.5, runs,
+                              seeds=(1, 2, 3, 4, 5, 6))
+    p = ps.sample(0, runs)
+    with capi.GraphSimulation(p, record_daily=True, max_days=days + 1) as sim:
+        sim.advance(float(days))
+        daily = sim.daily()
+    # the facade interpolates linearly between graph steps like the reference (y1 + (y2 - y1) * 1.0 at a day that is a
+    # time point): within an ulp of the recorded day value
+    np.testing.assert_allclose(got, daily, rtol=1e-14, atol=1e-300)
+    np.testing.assert_array_equal(got[:, :, 0], p.y0)
+    # ensemble_percentile: order statistic int(runs * 0.5) of the printed per-run values
+    want = np.sort(got, axis=0)[int(runs * 0.5)]
+    np.testing.assert_array_equal(p50[:, 2:].reshape(3, days + 1, 60), want)
