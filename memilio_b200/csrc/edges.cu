@@ -294,12 +294,27 @@ __global__ void __launch_bounds__(DEPART_SMEM_THREADS, 2) depart_smem_kernel(Edg
     stage_run_block(smem, a.st.run_block + (size_t)run * geo.block_stride, geo.block_stride * 8, &mbar);
     double* us = smem + geo.block_stride;
     {
-        const double* ug = a.u + (size_t)run * geo.N * geo.n;
-        const int total  = geo.N * G * M;
-        for (int idx = threadIdx.x; idx < total; idx += DEPART_SMEM_THREADS) {
-            const int m    = idx % M;
-            const int rest = idx / M; // node * G + age
-            us[idx]        = ug[(size_t)rest * NC + a.csr.mob_comp[m]];
+        // one (node, age) record of 10 doubles per thread and iteration: five 16-byte loads in flight per thread
+        const double2* ug = reinterpret_cast<const double2*>(a.u + (size_t)run * geo.N * geo.n);
+        const int total   = geo.N * G;
+        for (int rec = threadIdx.x; rec < total; rec += DEPART_SMEM_THREADS) {
+            double v[NC];
+#pragma unroll
+            for (int i = 0; i < NC / 2; ++i) {
+                const double2 x = __ldg(ug + (size_t)rec * (NC / 2) + i);
+                v[2 * i]        = x.x;
+                v[2 * i + 1]    = x.y;
+            }
+#pragma unroll
+            for (int m = 0; m < M; ++m) {
+                const int c = a.csr.mob_comp[m];
+                double x    = 0.0;
+#pragma unroll
+                for (int i = 0; i < NC; ++i) {
+                    x = (i == c) ? v[i] : x;
+                }
+                us[rec * M + m] = x;
+            }
         }
     }
     __syncthreads();
@@ -322,23 +337,30 @@ __global__ void __launch_bounds__(DEPART_SMEM_THREADS, 2) depart_smem_kernel(Edg
             v1[m] = 0.0;
             v3[m] = 0.0;
         }
-        const int mx = warp_max(cnt);
-        for (int it = 0; it < mx; ++it) {
-            const bool act = it < cnt;
-            const int pos  = beg + (act ? it : 0);
-            const int src  = a.csr.in_src[pos];
-            const double w = act ? a.csr.w_in[(size_t)pos * G + gl] : 0.0;
-            const double* p = us + (src * G + gl) * M;
-            if (it < split) {
+        // the edge list and weights come from global memory (L2): fetch a batch of BATCH edges first, then do the
+        // shared-memory reads and FMAs, so that BATCH independent loads are in flight per lane
+        constexpr int BATCH = 8;
+        const int mx        = warp_max(cnt);
+        for (int it0 = 0; it0 < mx; it0 += BATCH) {
+            int src[BATCH];
+            double w[BATCH];
 #pragma unroll
-                for (int m = 0; m < M; ++m) {
-                    v1[m] += w * p[m];
-                }
+            for (int j = 0; j < BATCH; ++j) {
+                const bool act = it0 + j < cnt;
+                const int pos  = beg + (act ? it0 + j : 0);
+                src[j]         = __ldg(a.csr.in_src + pos);
+                w[j]           = act ? __ldg(a.csr.w_in + (size_t)pos * G + gl) : 0.0;
             }
-            else {
+#pragma unroll
+            for (int j = 0; j < BATCH; ++j) {
+                const double* p  = us + (src[j] * G + gl) * M;
+                const bool first = it0 + j < split;
+                const double w1 = first ? w[j] : 0.0, w3 = first ? 0.0 : w[j];
 #pragma unroll
                 for (int m = 0; m < M; ++m) {
-                    v3[m] += w * p[m];
+                    const double x = p[m];
+                    v1[m] += w1 * x;
+                    v3[m] += w3 * x;
                 }
             }
         }
@@ -375,7 +397,8 @@ __global__ void __launch_bounds__(DEPART_SMEM_THREADS, 2) depart_smem_kernel(Edg
 // long as dt*rate <= 1, checked), so it is enough to test it after the first and after the last block. Flagged runs
 // are replayed literally by return_exact_kernel.
 template <int G, bool FACT>
-__global__ void __launch_bounds__(EDGE_THREADS, MIO_RETURN_MINBLOCKS) return_kernel(EdgeArgs a)
+__global__ void __launch_bounds__(EDGE_THREADS, MIO_RETURN_MINBLOCKS < 2 ? 2 : MIO_RETURN_MINBLOCKS)
+    return_kernel(EdgeArgs a)
 {
     extern __shared__ __align__(16) double smem[];
     __shared__ __align__(8) uint64_t mbar;
@@ -428,18 +451,32 @@ __global__ void __launch_bounds__(EDGE_THREADS, MIO_RETURN_MINBLOCKS) return_ker
         if (geo.num_psets == 1) {
             load10(a.csr.s_out + (size_t)L.node * geo.n + g.gl * NC, so);
             double a_slam = 0.0, a_icr = 0.0, a_d = 0.0;
-            for (int it = 0; it < mx; ++it) {
-                const bool act  = it < cnt;
-                const int e     = beg + (act ? it : 0);
-                const int dst   = a.csr.out_dst[e];
-                const double2 w = reinterpret_cast<const double2*>(a.csr.w_out)[(size_t)e * G + g.gl];
-                const double2* ax =
-                    reinterpret_cast<const double2*>(a.aux + (((size_t)L.run * geo.N + dst) * G + g.gl) * AUX);
-                const double2 a0 = ax[0], a1 = ax[1];
-                if (act) {
-                    a_slam += w.x * a0.x;
-                    a_icr += w.y * a0.y;
-                    a_d += w.y * a1.x;
+            constexpr int BATCH = 4;
+            for (int it0 = 0; it0 < mx; it0 += BATCH) {
+                int dst[BATCH];
+                double2 w[BATCH], a0[BATCH], a1[BATCH];
+#pragma unroll
+                for (int j = 0; j < BATCH; ++j) {
+                    const bool act = it0 + j < cnt;
+                    const int e    = beg + (act ? it0 + j : 0);
+                    dst[j]         = __ldg(a.csr.out_dst + e);
+                    w[j] = __ldg(reinterpret_cast<const double2*>(a.csr.w_out) + (size_t)e * G + g.gl);
+                    if (!act) {
+                        w[j] = make_double2(0.0, 0.0);
+                    }
+                }
+#pragma unroll
+                for (int j = 0; j < BATCH; ++j) {
+                    const double2* ax =
+                        reinterpret_cast<const double2*>(a.aux + (((size_t)L.run * geo.N + dst[j]) * G + g.gl) * AUX);
+                    a0[j] = ax[0];
+                    a1[j] = ax[1];
+                }
+#pragma unroll
+                for (int j = 0; j < BATCH; ++j) {
+                    a_slam += w[j].x * a0[j].x;
+                    a_icr += w[j].y * a0[j].y;
+                    a_d += w[j].y * a1[j].x;
                 }
             }
 #pragma unroll
