@@ -99,6 +99,24 @@ typedef enum {
 #define MIO_PA_DEATHS_PER_SEV 12 /* DeathsPerSevere */
 #define MIO_PA_DEATHS_PER_CRIT 13 /* DeathsPerCritical */
 
+/* osecirvvs: header slot 2 holds TestAndTraceCapacityMaxRiskSymptoms, slots 6/7 the two extra scalars
+ * (cpp/models/ode_secirvvs/parameters.h:62-155) */
+#define MIO_PH_TNT_MAX_RISK_NOSYMP 6   /* TestAndTraceCapacityMaxRiskNoSymptoms (osecirvvs) */
+#define MIO_PH_START_DAY_NEW_VARIANT 7 /* StartDayNewVariant (osecirvvs) */
+/* osecirvvs age record (32 doubles): slots 0..13 as for osecir, then the tags of ode_secirvvs/parameters.h:422-625 */
+#define MIO_OSECIRVVS_AGE_STRIDE 32
+#define MIO_PV_REDUC_EXPOSED_PI 14      /* ReducExposedPartialImmunity */
+#define MIO_PV_REDUC_EXPOSED_II 15      /* ReducExposedImprovedImmunity */
+#define MIO_PV_REDUC_INF_SYMP_PI 16     /* ReducInfectedSymptomsPartialImmunity */
+#define MIO_PV_REDUC_INF_SYMP_II 17     /* ReducInfectedSymptomsImprovedImmunity */
+#define MIO_PV_REDUC_SEV_CRIT_DEAD_PI 18 /* ReducInfectedSevereCriticalDeadPartialImmunity */
+#define MIO_PV_REDUC_SEV_CRIT_DEAD_II 19 /* ReducInfectedSevereCriticalDeadImprovedImmunity */
+#define MIO_PV_REDUC_TIME_MILD 20       /* ReducTimeInfectedMild */
+#define MIO_PV_INFECTIOUSNESS_NEW_VARIANT 21 /* InfectiousnessNewVariant */
+#define MIO_PV_VACCINATION_GAP 22
+#define MIO_PV_DAYS_UNTIL_EFFECTIVE_PI 23
+#define MIO_PV_DAYS_UNTIL_EFFECTIVE_II 24
+
 /* per-node local parameters: [ICUCapacity, TestAndTraceCapacity] (sampled per node, parameter_space.h:125-148) */
 #define MIO_NODE_LOCAL 2
 #define MIO_NL_ICU_CAPACITY 0
@@ -151,6 +169,12 @@ typedef struct {
     mio_integrator_desc integrator;
     double t0;
     double dt_graph;     /* GraphSimulation m_dt; +inf for make_no_mobility_sim */
+    /* osecirvvs only: cumulative vaccinations DailyPartialVaccinations / DailyFullVaccinations
+     * (ode_secirvvs/parameters.h:470-497), run-invariant, [N][G][vacc_days]; NULL / 0 for osecir */
+    int32_t vacc_days;
+    int32_t reserved2;
+    const double* vacc_partial;
+    const double* vacc_full;
 } mio_graph_desc;
 
 typedef struct {

@@ -45,6 +45,25 @@ PA_DEFAULT = dict(TimeExposed=1., TimeInfectedNoSymptoms=1., TimeInfectedSymptom
                   MaxRiskOfInfectionFromSymptomatic=1., SeverePerInfectedSymptoms=0., CriticalPerSevere=0.,
                   DeathsPerSevere=0., DeathsPerCritical=0.)
 
+# osecirvvs (cpp/models/ode_secirvvs/parameters.h): header slot 2 = TestAndTraceCapacityMaxRiskSymptoms
+OSECIRVVS_AGE_STRIDE = 32
+PHV = dict(PH, TestAndTraceCapacityMaxRiskSymptoms=2, TestAndTraceCapacityMaxRiskNoSymptoms=6, StartDayNewVariant=7)
+del PHV["TestAndTraceCapacityMaxRisk"]
+PV = dict(PA, ReducExposedPartialImmunity=14, ReducExposedImprovedImmunity=15, ReducInfectedSymptomsPartialImmunity=16,
+          ReducInfectedSymptomsImprovedImmunity=17, ReducInfectedSevereCriticalDeadPartialImmunity=18,
+          ReducInfectedSevereCriticalDeadImprovedImmunity=19, ReducTimeInfectedMild=20, InfectiousnessNewVariant=21,
+          VaccinationGap=22, DaysUntilEffectivePartialImmunity=23, DaysUntilEffectiveImprovedImmunity=24)
+PV_DEFAULT = dict(PA_DEFAULT, ReducExposedPartialImmunity=1., ReducExposedImprovedImmunity=1.,
+                  ReducInfectedSymptomsPartialImmunity=1., ReducInfectedSymptomsImprovedImmunity=1.,
+                  ReducInfectedSevereCriticalDeadPartialImmunity=1.,
+                  ReducInfectedSevereCriticalDeadImprovedImmunity=1., ReducTimeInfectedMild=0.5,
+                  InfectiousnessNewVariant=1., VaccinationGap=49., DaysUntilEffectivePartialImmunity=14.,
+                  DaysUntilEffectiveImprovedImmunity=7.)
+# osecirvvs InfectionState, ode_secirvvs/infection_state.h:36-67
+(V_SN, V_SPI, V_EN, V_EPI, V_EII, V_INSN, V_INSPI, V_INSII, V_INSNC, V_INSPIC, V_INSIIC, V_ISYN, V_ISYPI, V_ISYII,
+ V_ISYNC, V_ISYPIC, V_ISYIIC, V_ISEVN, V_ISEVPI, V_ISEVII, V_ICRN, V_ICRPI, V_ICRII, V_SII, V_DN, V_DPI,
+ V_DII) = range(27)
+
 # InfectionState, ode_secir/infection_state.h:33-47
 S, E, INS, INSC, ISY, ISYC, ISEV, ICR, R, D = range(10)
 
@@ -53,9 +72,12 @@ def num_compartments(model: int) -> int:
     return OSECIR_NCOMP if model == MODEL_OSECIR else OSECIRVVS_NCOMP
 
 
+def age_stride(model: int) -> int:
+    return OSECIR_AGE_STRIDE if model == MODEL_OSECIR else OSECIRVVS_AGE_STRIDE
+
+
 def pset_size(model: int, G: int) -> int:
-    assert model == MODEL_OSECIR
-    return PSET_HEADER + OSECIR_AGE_STRIDE * G
+    return PSET_HEADER + age_stride(model) * G
 
 
 def ctable_size(G: int, max_loc: int, max_pts: int) -> int:
@@ -81,6 +103,68 @@ def osecir_pset(G: int, **kw) -> np.ndarray:
         else:
             raise KeyError(name)
     return p
+
+
+def osecirvvs_pset(G: int, **kw) -> np.ndarray:
+    """One osecirvvs parameter set (defaults of ode_secirvvs/parameters.h get_default())."""
+    p = np.zeros(pset_size(MODEL_OSECIRVVS, G))
+    p[PHV["TestAndTraceCapacityMaxRiskSymptoms"]] = 15.0
+    p[PHV["TestAndTraceCapacityMaxRiskNoSymptoms"]] = 2.0
+    p[PHV["StartDayNewVariant"]] = DBL_MAX
+    rec = p[PSET_HEADER:].reshape(G, OSECIRVVS_AGE_STRIDE)
+    for name, slot in PV.items():
+        rec[:, slot] = PV_DEFAULT[name]
+    for name, val in kw.items():
+        if name in PHV:
+            p[PHV[name]] = float(val)
+        elif name in PV:
+            rec[:, PV[name]] = np.broadcast_to(np.asarray(val, dtype=np.float64), (G,))
+        else:
+            raise KeyError(name)
+    return p
+
+
+def osecirvvs_apply_constraints(p: np.ndarray, G: int, local: Optional[np.ndarray] = None) -> bool:
+    """osecirvvs Parameters::apply_constraints, ode_secirvvs/parameters.h:705-946, on a flat parameter set."""
+    corrected = False
+
+    def fix(arr, idx, bad, to):
+        nonlocal corrected
+        if bad:
+            arr[idx] = to
+            corrected = True
+    fix(p, PHV["Seasonality"], p[PHV["Seasonality"]] < 0.0 or p[PHV["Seasonality"]] > 0.5, 0.0)
+    if local is not None:
+        for k in range(2):
+            fix(local, k, local[k] < 0.0, 0.0)
+    for name in ("TestAndTraceCapacityMaxRiskSymptoms", "TestAndTraceCapacityMaxRiskNoSymptoms"):
+        fix(p, PHV[name], p[PHV[name]] < 0.0, 0.0)
+    rec = p[PSET_HEADER:].reshape(G, OSECIRVVS_AGE_STRIDE)
+    for i in range(G):
+        r = rec[i]
+        for name in ("TimeExposed", "TimeInfectedNoSymptoms", "TimeInfectedSymptoms", "TimeInfectedSevere",
+                     "TimeInfectedCritical"):
+            fix(r, PV[name], r[PV[name]] < 0.1, 0.1)
+        s = PV["TransmissionProbabilityOnContact"]
+        fix(r, s, r[s] < 0.0 or r[s] > 1.0, 0.0)
+        s = PV["RelativeTransmissionNoSymptoms"]
+        fix(r, s, r[s] < 0.0, 0.0)
+        for name in ("RecoveredPerInfectedNoSymptoms", "RiskOfInfectionFromSymptomatic", "SeverePerInfectedSymptoms",
+                     "CriticalPerSevere", "DeathsPerSevere"):
+            s = PV[name]
+            fix(r, s, r[s] < 0.0 or r[s] > 1.0, 0.0)
+        fix(r, PV["DeathsPerSevere"], r[PV["CriticalPerSevere"]] + r[PV["DeathsPerSevere"]] > 1.0, 0.0)
+        s = PV["DeathsPerCritical"]
+        fix(r, s, r[s] < 0.0 or r[s] > 1.0, 0.0)
+        for name in ("DaysUntilEffectivePartialImmunity", "DaysUntilEffectiveImprovedImmunity", "VaccinationGap"):
+            fix(r, PV[name], r[PV[name]] < 0.0, 0.0)
+        for name in ("ReducExposedPartialImmunity", "ReducExposedImprovedImmunity",
+                     "ReducInfectedSymptomsPartialImmunity", "ReducInfectedSymptomsImprovedImmunity",
+                     "ReducInfectedSevereCriticalDeadPartialImmunity",
+                     "ReducInfectedSevereCriticalDeadImprovedImmunity", "ReducTimeInfectedMild"):
+            fix(r, PV[name], r[PV[name]] <= 0.0 or r[PV[name]] > 1.0, 1.0)
+        fix(r, PV["InfectiousnessNewVariant"], r[PV["InfectiousnessNewVariant"]] < 0.0, 1.0)
+    return corrected
 
 
 def osecir_apply_constraints(p: np.ndarray, G: int, local: Optional[np.ndarray] = None) -> bool:

@@ -37,6 +37,8 @@ class GraphProblem:
     t0: float = 0.0
     dt_graph: float = 0.5
     sim_kind: int = flat.SIM_MODEL
+    vacc_partial: Optional[np.ndarray] = None  # osecirvvs: [N][G][days] cumulative DailyPartialVaccinations
+    vacc_full: Optional[np.ndarray] = None  # osecirvvs: [N][G][days] cumulative DailyFullVaccinations
 
     def __post_init__(self):
         self.edge_start = np.ascontiguousarray(self.edge_start, dtype=np.int32)
@@ -63,6 +65,10 @@ class GraphProblem:
         if self.mobtables is not None:
             self.mobtables = np.ascontiguousarray(self.mobtables, dtype=np.float64).reshape(R, -1)
             assert self.mobtables.shape[1] == flat.mobtable_size(n, self.mob_max_pts)
+        for name in ("vacc_partial", "vacc_full"):
+            if getattr(self, name) is not None:
+                setattr(self, name, np.ascontiguousarray(getattr(self, name), dtype=np.float64).reshape(
+                    self.num_nodes, self.num_groups, -1))
 
     @property
     def n(self) -> int:
@@ -109,6 +115,10 @@ class GraphProblem:
         d.integrator = self.integrator
         d.t0 = self.t0
         d.dt_graph = self.dt_graph
+        if self.vacc_partial is not None:
+            d.vacc_days = int(self.vacc_partial.shape[2])
+            d.vacc_partial = cdefs.dptr(self.vacc_partial)
+            d.vacc_full = cdefs.dptr(self.vacc_full)
         return d
 
     def run_data(self, run0: int = 0, count: Optional[int] = None) -> cdefs.RunData:

@@ -3,6 +3,7 @@
 // both sides. Loaded with ctypes by tests/, __graft_entry__.smoke() and the cpu_baseline legs of bench.py only.
 #include "mio_oracle.hpp"
 #include "mio_oracle_sampling.hpp"
+#include "mio_oracle_vvs.hpp"
 #include "../include/mio_cuda.h"
 
 #include <cstring>
@@ -19,7 +20,7 @@ int ncomp_of(int model)
 
 int64_t pset_size(int model, int G)
 {
-    return MIO_PSET_HEADER + int64_t(model == MIO_MODEL_OSECIR ? MIO_OSECIR_AGE_STRIDE : 0) * G;
+    return MIO_PSET_HEADER + int64_t(model == MIO_MODEL_OSECIR ? MIO_OSECIR_AGE_STRIDE : MIO_OSECIRVVS_AGE_STRIDE) * G;
 }
 
 int64_t ctable_size(int G, int max_loc, int max_pts)
@@ -88,6 +89,61 @@ osecir::Model osecir_from_flat(int G, const double* pset, const double* local, c
     }
     p.ContactPatterns = contacts_from_flat(ct, G, max_loc, max_pts);
     std::copy(y0, y0 + size_t(G) * osecir::NC, m.populations.begin());
+    return m;
+}
+
+osecirvvs::Model osecirvvs_from_flat(int G, const double* pset, const double* local, const double* ct, int max_loc,
+                                     int max_pts, const double* y0, int vacc_days, const double* vacc_partial,
+                                     const double* vacc_full)
+{
+    osecirvvs::Model m(G);
+    auto& p                                 = m.parameters;
+    p.StartDay                              = pset[MIO_PH_START_DAY];
+    p.Seasonality                           = pset[MIO_PH_SEASONALITY];
+    p.TestAndTraceCapacityMaxRiskSymptoms   = pset[MIO_PH_TNT_MAX_RISK];
+    p.TestAndTraceCapacityMaxRiskNoSymptoms = pset[MIO_PH_TNT_MAX_RISK_NOSYMP];
+    p.StartDayNewVariant                    = pset[MIO_PH_START_DAY_NEW_VARIANT];
+    p.commuter_nondetection                 = pset[MIO_PH_COMMUTER_NONDETECTION];
+    p.start_commuter_detection              = pset[MIO_PH_START_COMMUTER_DETECTION];
+    p.end_commuter_detection                = pset[MIO_PH_END_COMMUTER_DETECTION];
+    p.ICUCapacity                           = local[MIO_NL_ICU_CAPACITY];
+    p.TestAndTraceCapacity                  = local[MIO_NL_TNT_CAPACITY];
+    for (int i = 0; i < G; ++i) {
+        const double* a                        = pset + MIO_PSET_HEADER + i * MIO_OSECIRVVS_AGE_STRIDE;
+        p.TimeExposed[i]                       = a[MIO_PA_TIME_EXPOSED];
+        p.TimeInfectedNoSymptoms[i]            = a[MIO_PA_TIME_INS];
+        p.TimeInfectedSymptoms[i]              = a[MIO_PA_TIME_ISY];
+        p.TimeInfectedSevere[i]                = a[MIO_PA_TIME_ISEV];
+        p.TimeInfectedCritical[i]              = a[MIO_PA_TIME_ICR];
+        p.TransmissionProbabilityOnContact[i]  = a[MIO_PA_TRANS_PROB];
+        p.RelativeTransmissionNoSymptoms[i]    = a[MIO_PA_REL_TRANS_NOSYMP];
+        p.RecoveredPerInfectedNoSymptoms[i]    = a[MIO_PA_REC_PER_INS];
+        p.RiskOfInfectionFromSymptomatic[i]    = a[MIO_PA_RISK_SYMP];
+        p.MaxRiskOfInfectionFromSymptomatic[i] = a[MIO_PA_MAX_RISK_SYMP];
+        p.SeverePerInfectedSymptoms[i]         = a[MIO_PA_SEV_PER_ISY];
+        p.CriticalPerSevere[i]                 = a[MIO_PA_CRIT_PER_SEV];
+        p.DeathsPerSevere[i]                   = a[MIO_PA_DEATHS_PER_SEV];
+        p.DeathsPerCritical[i]                 = a[MIO_PA_DEATHS_PER_CRIT];
+        p.ReducExposedPartialImmunity[i]       = a[MIO_PV_REDUC_EXPOSED_PI];
+        p.ReducExposedImprovedImmunity[i]      = a[MIO_PV_REDUC_EXPOSED_II];
+        p.ReducInfectedSymptomsPartialImmunity[i]  = a[MIO_PV_REDUC_INF_SYMP_PI];
+        p.ReducInfectedSymptomsImprovedImmunity[i] = a[MIO_PV_REDUC_INF_SYMP_II];
+        p.ReducInfectedSevereCriticalDeadPartialImmunity[i]  = a[MIO_PV_REDUC_SEV_CRIT_DEAD_PI];
+        p.ReducInfectedSevereCriticalDeadImprovedImmunity[i] = a[MIO_PV_REDUC_SEV_CRIT_DEAD_II];
+        p.ReducTimeInfectedMild[i]             = a[MIO_PV_REDUC_TIME_MILD];
+        p.InfectiousnessNewVariant[i]          = a[MIO_PV_INFECTIOUSNESS_NEW_VARIANT];
+        p.VaccinationGap[i]                    = a[MIO_PV_VACCINATION_GAP];
+        p.DaysUntilEffectivePartialImmunity[i] = a[MIO_PV_DAYS_UNTIL_EFFECTIVE_PI];
+        p.DaysUntilEffectiveImprovedImmunity[i] = a[MIO_PV_DAYS_UNTIL_EFFECTIVE_II];
+        if (vacc_days > 0 && vacc_partial && vacc_full) {
+            p.DailyPartialVaccinations[i].assign(vacc_partial + int64_t(i) * vacc_days,
+                                                 vacc_partial + int64_t(i + 1) * vacc_days);
+            p.DailyFullVaccinations[i].assign(vacc_full + int64_t(i) * vacc_days,
+                                              vacc_full + int64_t(i + 1) * vacc_days);
+        }
+    }
+    p.ContactPatterns = contacts_from_flat(ct, G, max_loc, max_pts);
+    std::copy(y0, y0 + size_t(G) * osecirvvs::NC, m.populations.begin());
     return m;
 }
 
@@ -180,6 +236,34 @@ int orc_simulate(int model, int G, const double* pset, const double* local, cons
     return n;
 }
 
+// osecirvvs::Simulation (sim_kind = MIO_SIM_MODEL) or mio::Simulation<osecirvvs::Model> (MIO_SIM_BASE) for one node
+int orc_simulate_vvs(int sim_kind, int G, const double* pset, const double* local, const double* ct, int max_loc,
+                     int max_pts_ct, const double* y0, int vacc_days, const double* vacc_partial,
+                     const double* vacc_full, double t0, double tmax, double dt, const mio_integrator_desc* integ,
+                     int max_pts, double* out_t, double* out_y, double* out_dt, int64_t* counters)
+{
+    auto m = osecirvvs_from_flat(G, pset, local, ct, max_loc, max_pts_ct, y0, vacc_days, vacc_partial, vacc_full);
+    Simulation<osecirvvs::Model> sim(m, t0, dt);
+    sim.model_sim = sim_kind == MIO_SIM_MODEL;
+    sim.set_integrator_core(make_core(*integ));
+    sim.advance(tmax);
+    const int n  = int(sim.result.n());
+    const int ne = G * osecirvvs::NC;
+    for (int k = 0; k < std::min(n, max_pts); ++k) {
+        out_t[k] = sim.result.times[k];
+        std::copy(sim.result.values[k].begin(), sim.result.values[k].end(), out_y + int64_t(k) * ne);
+    }
+    if (out_dt) {
+        *out_dt = sim.dt;
+    }
+    if (counters) {
+        counters[0] = sim.integrator.n_steps;
+        counters[1] = sim.integrator.core->n_rejected;
+        counters[2] = sim.integrator.core->n_forced;
+    }
+    return n;
+}
+
 // make_mobility_sim + GraphSimulation::advance for ONE run described by the flat descriptors of mio_cuda.h.
 //   out_state[N][n]          final get_result().get_last_value() of every node
 //   out_dt[N]                final integrator dt of every node
@@ -187,24 +271,18 @@ int orc_simulate(int model, int G, const double* pset, const double* local, cons
 //   out_halfsteps            optional [num_graph_steps][N][n]: node states after every graph step's edge phase
 //   max_halfsteps            capacity of out_halfsteps (in graph steps)
 // returns number of graph steps taken, or <0 on error.
-int orc_graph_simulate(const mio_graph_desc* desc, const mio_run_data* run, double t_max, double* out_state,
-                       double* out_dt, int64_t* out_counters, double* out_halfsteps, int max_halfsteps)
+} // extern "C"
+
+template <class M, class MakeModel>
+static int graph_simulate_impl(const mio_graph_desc* desc, const mio_run_data* run, double t_max, double* out_state,
+                               double* out_dt, int64_t* out_counters, double* out_halfsteps, int max_halfsteps,
+                               int ncomp, MakeModel&& make_model)
 {
-    if (desc->model != MIO_MODEL_OSECIR) {
-        return -1;
-    }
     const int G = desc->num_groups, N = desc->num_nodes, E = desc->num_edges;
-    const int n       = G * ncomp_of(desc->model);
-    const int64_t psz = pset_size(desc->model, G);
-    const int64_t csz = ctable_size(G, desc->ct_max_loc, desc->ct_max_pts);
-    GraphSim<osecir::Model> g(desc->t0, desc->dt_graph);
+    const int n = G * ncomp;
+    GraphSim<M> g(desc->t0, desc->dt_graph);
     for (int k = 0; k < N; ++k) {
-        const int ps = desc->node_pset ? desc->node_pset[k] : 0;
-        const int ci = desc->node_ctable ? desc->node_ctable[k] : 0;
-        auto m       = osecir_from_flat(G, run->psets + ps * psz, run->node_local + int64_t(k) * MIO_NODE_LOCAL,
-                                        run->ctables + ci * csz, desc->ct_max_loc, desc->ct_max_pts,
-                                        run->y0 + int64_t(k) * n);
-        g.add_node(m, desc->t0, run->dt0 ? run->dt0[k] : 0.1);
+        g.add_node(make_model(k), desc->t0, run->dt0 ? run->dt0[k] : 0.1);
         g.nodes.back().sim.set_integrator_core(make_core(desc->integrator));
     }
     for (int e = 0; e < E; ++e) {
@@ -266,6 +344,44 @@ int orc_graph_simulate(const mio_graph_desc* desc, const mio_run_data* run, doub
         }
     }
     return steps;
+}
+
+extern "C" {
+
+int orc_graph_simulate(const mio_graph_desc* desc, const mio_run_data* run, double t_max, double* out_state,
+                       double* out_dt, int64_t* out_counters, double* out_halfsteps, int max_halfsteps)
+{
+    const int G       = desc->num_groups;
+    const int64_t psz = pset_size(desc->model, G);
+    const int64_t csz = ctable_size(G, desc->ct_max_loc, desc->ct_max_pts);
+    const int n       = G * ncomp_of(desc->model);
+    auto ps_of        = [&](int k) {
+        return run->psets + (desc->node_pset ? desc->node_pset[k] : 0) * psz;
+    };
+    auto ct_of = [&](int k) {
+        return run->ctables + (desc->node_ctable ? desc->node_ctable[k] : 0) * csz;
+    };
+    if (desc->model == MIO_MODEL_OSECIR) {
+        return graph_simulate_impl<osecir::Model>(
+            desc, run, t_max, out_state, out_dt, out_counters, out_halfsteps, max_halfsteps, osecir::NC, [&](int k) {
+                return osecir_from_flat(G, ps_of(k), run->node_local + int64_t(k) * MIO_NODE_LOCAL, ct_of(k),
+                                        desc->ct_max_loc, desc->ct_max_pts, run->y0 + int64_t(k) * n);
+            });
+    }
+    if (desc->model == MIO_MODEL_OSECIRVVS) {
+        return graph_simulate_impl<osecirvvs::Model>(
+            desc, run, t_max, out_state, out_dt, out_counters, out_halfsteps, max_halfsteps, osecirvvs::NC,
+            [&](int k) {
+                const int64_t vo = int64_t(k) * G * desc->vacc_days;
+                auto m = osecirvvs_from_flat(G, ps_of(k), run->node_local + int64_t(k) * MIO_NODE_LOCAL, ct_of(k),
+                                             desc->ct_max_loc, desc->ct_max_pts, run->y0 + int64_t(k) * n,
+                                             desc->vacc_days, desc->vacc_partial ? desc->vacc_partial + vo : nullptr,
+                                             desc->vacc_full ? desc->vacc_full + vo : nullptr);
+                m.model_sim = desc->sim_kind == MIO_SIM_MODEL;
+                return m;
+            });
+    }
+    return -1;
 }
 
 // The call sequence of TestMobility.edgeApplyMobility (cpp/tests/test_mobility.cpp:154-215): two identical G=1 nodes,

@@ -80,6 +80,29 @@ def simulate(G, pset, local, ct, max_loc, max_pts, y0, t0, tmax, dt, integrator=
     return ot[:npts].copy(), oy[:npts].copy(), float(odt[0]), cnt
 
 
+def simulate_vvs(G, pset, local, ct, max_loc, max_pts, y0, t0, tmax, dt, integrator=None, capacity=4096,
+                 sim_kind=flat.SIM_MODEL, vacc_partial=None, vacc_full=None):
+    """osecirvvs::simulate on the oracle. Returns (times[npts], values[npts][n], final dt, counters[3])."""
+    integ = integrator if integrator is not None else cdefs.integrator_desc()
+    n = G * flat.OSECIRVVS_NCOMP
+    args = [np.ascontiguousarray(a, dtype=np.float64) for a in (pset, local, ct, y0)]
+    vp = None if vacc_partial is None else np.ascontiguousarray(vacc_partial, dtype=np.float64).reshape(G, -1)
+    vf = None if vacc_full is None else np.ascontiguousarray(vacc_full, dtype=np.float64).reshape(G, -1)
+    days = 0 if vp is None else vp.shape[1]
+    ot = np.zeros(capacity)
+    oy = np.zeros((capacity, n))
+    odt = np.zeros(1)
+    cnt = np.zeros(3, dtype=np.int64)
+    L = lib()
+    L.orc_simulate_vvs.restype = C.c_int
+    npts = L.orc_simulate_vvs(sim_kind, G, cdefs.dptr(args[0]), cdefs.dptr(args[1]), cdefs.dptr(args[2]), max_loc,
+                              max_pts, cdefs.dptr(args[3]), days, cdefs.dptr(vp), cdefs.dptr(vf), C.c_double(t0),
+                              C.c_double(tmax), C.c_double(dt), C.byref(integ), capacity, cdefs.dptr(ot),
+                              cdefs.dptr(oy), cdefs.dptr(odt), cdefs.lptr(cnt))
+    assert 0 < npts <= capacity
+    return ot[:npts].copy(), oy[:npts].copy(), float(odt[0]), cnt
+
+
 def graph_simulate(p: GraphProblem, run: int, t_max: float, halfsteps: int = 0):
     """GraphSimulation::advance(t_max) of run `run` on the oracle.
     Returns dict(state[N][n], dt[N], counters[N][4], steps, halfsteps[steps][N][n])."""

@@ -22,7 +22,7 @@ def load_csv(name):
     with open(os.path.join(GOLDEN, name)) as f:
         for line in f:
             s = line.strip()
-            if not s or s.startswith("#"):
+            if not s or s.startswith("#") or s[0].isalpha():  # comment or a header line of column names
                 continue
             rows.append([float(w) for w in s.split()])
     return np.asarray(rows)
@@ -94,6 +94,35 @@ def golden_problem(name) -> GraphProblem:
     s = golden_case(name)
     return single_node_problem(s["G"], s["pset"], s["local"], s["ct"], s["y0"], ct_max_loc=s["ct_max_loc"],
                                ct_max_pts=s["ct_max_pts"], integrator=s["integrator"], t0=s["t0"], dt0=s["dt0"])
+
+
+def vvs_golden_case():
+    """pycode/memilio-simulation/tests/test_osecirvvs.py:38-136,170-196: osecirvvs, 1 age group, default integrator,
+    tmax 50 -> ode-secirvvs-compare.csv."""
+    G = 1
+    y0 = np.zeros(flat.OSECIRVVS_NCOMP)
+    y0[flat.V_EN], y0[flat.V_INSN], y0[flat.V_ISYN], y0[flat.V_ISEVN], y0[flat.V_ICRN] = 100, 50, 50, 20, 10
+    y0[flat.V_SII] = 10
+    cur = 0.0
+    for c in range(flat.OSECIRVVS_NCOMP):  # set_difference_from_group_total, populations.h:194-205
+        cur = cur + y0[c]
+    cur -= y0[flat.V_SN]
+    y0[flat.V_SN] = 10000 - cur
+    pset = flat.osecirvvs_pset(G, Seasonality=0.2, TimeExposed=3.2, TimeInfectedNoSymptoms=2.0,
+                               TimeInfectedSymptoms=5.0, TimeInfectedSevere=10.0, TimeInfectedCritical=8.0,
+                               TransmissionProbabilityOnContact=0.05, RelativeTransmissionNoSymptoms=1,
+                               RecoveredPerInfectedNoSymptoms=0.09, RiskOfInfectionFromSymptomatic=0.25,
+                               SeverePerInfectedSymptoms=0.2, CriticalPerSevere=0.25, DeathsPerCritical=0.3,
+                               ReducExposedPartialImmunity=1.0, ReducExposedImprovedImmunity=1.0,
+                               ReducInfectedSymptomsPartialImmunity=1.0, ReducInfectedSymptomsImprovedImmunity=0,
+                               ReducInfectedSevereCriticalDeadPartialImmunity=0,
+                               ReducInfectedSevereCriticalDeadImprovedImmunity=0, ReducTimeInfectedMild=1)
+    local = np.array([10000.0, 10000.0])
+    flat.osecirvvs_apply_constraints(pset, G, local)
+    ct = flat.contact_table(G, [ContactLocation(np.full((1, 1), 10.0), None, [30.0], [np.full((1, 1), 0.7)])], 1, 2)
+    vacc = np.zeros((G, 1000))
+    return dict(G=G, pset=pset, local=local, ct=ct, ct_max_loc=1, ct_max_pts=2, y0=y0, vacc_partial=vacc,
+                vacc_full=vacc.copy(), csv=load_csv("ode-secirvvs-compare.csv"), t0=0.0, tmax=50.0, dt0=0.1, tol=1e-10)
 
 
 def age_sum(values, G):
