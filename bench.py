@@ -27,8 +27,17 @@ ROOT = os.path.dirname(os.path.abspath(__file__))
 sys.path.insert(0, ROOT)
 
 # algorithmic work per unit, see DESIGN.md "Roofline"
-FLOP_PER_CK54_ATTEMPT = 7.7e3  # 6 RHS (650) + stage axpys (1800) + solution (720) + error (720) + norm (540)
-EDGE_BYTES_PER_RUN_DAY = 10.8e6  # explicit traveler state, N=400, E=10000, n=60
+# SURVEY.md 8d. osecir: 6 RHS (650) + stage axpys (1800) + solution (720) + error (720) + norm (540);
+# osecirvvs: 6 RHS (1.9k) + 4860 + 1944 + 1944 + 1460
+FLOP_PER_CK54_ATTEMPT = {"osecir": 7.7e3, "osecirvvs": 21.6e3}
+STATE_DOUBLES = {"osecir": 60, "osecirvvs": 162}
+
+
+def edge_bytes_per_run_day(model, N, E):
+    """SURVEY.md 8d, explicit traveler state: departure writes and return reads E*n*8 bytes, each phase reads two node
+    records and read-modify-writes a third: 2*E*n*8 + 2*N*3*n*8 (10.8 MB for osecir at N=400, E=10000)."""
+    n = STATE_DOUBLES[model]
+    return 2.0 * E * n * 8 + 2.0 * N * 3 * n * 8
 
 
 def parse():
@@ -43,6 +52,11 @@ def parse():
     ap.add_argument("--cpu-sample-runs", type=int, default=0, help="runs of the CPU baseline sample (0 = one per core)")
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--e2e-batches", type=int, default=4, help="batches of the end-to-end leg (sampling overlaps GPU)")
+    ap.add_argument("--model", default="osecir", choices=["osecir", "osecirvvs"],
+                    help="osecir = BASELINE configs[3] (the default bench line); osecirvvs = configs[4]'s model on one GPU")
+    ap.add_argument("--sim-kind", default="model", choices=["model", "base"],
+                    help="osecirvvs node type: osecirvvs::Simulation (vaccination, ADL mobility hooks) or the plain "
+                         "mio::Simulation the reference's graph benchmark instantiates")
     return ap.parse_args()
 
 
@@ -98,6 +112,19 @@ class ClockSampler:
 
 
 def workload_config(args):
+    if args.model == "osecirvvs":
+        return {"workload": f"ensemble of the synthetic {args.nodes}-county ODE-SECIRVVS graph (BASELINE configs[4] "
+                            f"model, one GPU's share): {args.runs} runs/GPU x {args.nodes} counties x {args.days:g} days",
+                "runs_per_gpu": args.runs, "counties": args.nodes, "edges": None, "age_groups": 6, "days": args.days,
+                "dt_graph": 0.5, "integrator": "cash_karp54 abs 1e-10 rel 1e-5",
+                "node_simulation": "osecirvvs::Simulation (day chunks, vaccination)" if args.sim_kind == "model"
+                else "mio::Simulation<osecirvvs::Model> (as cpp/benchmarks/graph_simulation.cpp)",
+                "parallelism": f"runs sharded x{args.gpus}",
+                "l2_policy": "inputs larger than L2 (state 4 x %.2f GB per GPU)" % (args.runs * args.nodes * 1440 / 1e9),
+                "sampling": "parameters of cpp/benchmarks/graph_simulation.cpp, 32 distinct runs with +-10% uniform "
+                            "variation (numpy) tiled to the run count; no MEmilio sampler for osecirvvs yet",
+                "outputs": "per-node daily p05/p25/p50/p75/p95 + mean of age-summed compartments and of the "
+                           "node-summed state"}
     return {"workload": f"ParameterStudy ensemble, synthetic {args.nodes}-county ODE-SECIR graph "
                         f"(BASELINE configs[3]): {args.runs} runs/GPU x {args.nodes} counties x {args.days:g} days",
             "runs_per_gpu": args.runs, "counties": args.nodes, "edges": None, "age_groups": 6, "days": args.days,
@@ -122,6 +149,36 @@ def cpu_baseline(problem, days, sample_runs, threads):
     return sample_runs * problem.num_nodes * days / dt, dt
 
 
+METRIC = {"osecir": "graph_ode_secir_node_days_per_s", "osecirvvs": "graph_ode_secirvvs_node_days_per_s"}
+
+
+def vvs_problem(args, runs):
+    """osecirvvs county ensemble: 32 distinct runs (numpy +-10 % variation) tiled to `runs`."""
+    from memilio_b200 import flat, synthetic
+    distinct = min(32, runs)
+    base = synthetic.county_problem_vvs(N=args.nodes, runs=distinct, days=int(args.days) + 1, perturb=0.1,
+                                        sim_kind=flat.SIM_MODEL if args.sim_kind == "model" else flat.SIM_BASE)
+    reps = (runs + distinct - 1) // distinct
+    for name in ("psets", "ctables", "node_local", "y0"):
+        a = getattr(base, name)
+        setattr(base, name, np.ascontiguousarray(np.concatenate([a] * reps, axis=0)[:runs]))
+    return base
+
+
+class SlicedSampler:
+    """Stands in for ParameterStudy.sample where there is no sampler: hands out slices of pre-built runs."""
+
+    def __init__(self, problem):
+        self.problem = problem
+
+    def sample(self, run0, count):
+        import copy
+        q = copy.copy(self.problem)
+        for name in ("psets", "ctables", "node_local", "y0"):
+            setattr(q, name, getattr(self.problem, name)[run0:run0 + count])
+        return q
+
+
 def run_reference(args, rank, world):
     """--impl reference: the reference's own CPU implementation of the path (oracle port; the reference itself
     cannot be built here) on all host threads. Rank 0 only."""
@@ -131,8 +188,11 @@ def run_reference(args, rank, world):
     cores = os.cpu_count() or 1
     sample = args.cpu_sample_runs or 4 * cores
     from memilio_b200 import study
-    ps = study.ParameterStudy(synthetic.covid_study_graph(N=args.nodes), 0.0, args.days, 0.5, max(sample, 1))
-    problem = ps.sample(0, max(sample, 1))
+    if args.model == "osecirvvs":
+        problem = vvs_problem(args, max(sample, 1))
+    else:
+        ps = study.ParameterStudy(synthetic.covid_study_graph(N=args.nodes), 0.0, args.days, 0.5, max(sample, 1))
+        problem = ps.sample(0, max(sample, 1))
     for _ in range(min(args.warmup, 1)):
         cpu_baseline(problem, min(args.days, 2.0), cores, cores)
     vals, secs = [], []
@@ -145,7 +205,7 @@ def run_reference(args, rank, world):
     cfg["edges"] = problem.num_edges
     sample_txt = f"{sample} runs x {args.nodes} counties x {args.days:g} days per step over {cores} threads"
     print(json.dumps({
-        "impl": "reference", "metric": "graph_ode_secir_node_days_per_s", "value": value, "unit": "node-days/s",
+        "impl": "reference", "metric": METRIC[args.model], "value": value, "unit": "node-days/s",
         "n_gpus": args.gpus, "steps": args.steps, "warmup": args.warmup, "ms_per_step": 1e3 * float(np.mean(secs)),
         "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "f64", "data": "synthetic",
         "config": cfg,
@@ -182,25 +242,36 @@ def main():
     days = int(T) + 1
     # ParameterStudy over the synthetic county graph; weak scaling: R runs per GPU, rank r owns the contiguous block
     # distribute_runs(world*R, world, r) of ONE global study (seeds {1..6}), sampled bit-exactly like the reference
-    graph = synthetic.covid_study_graph(N=N)
-    ps = study.ParameterStudy(graph, 0.0, T, 0.5, world * R)
+    from memilio_b200 import flat
+    model = flat.MODEL_OSECIRVVS if args.model == "osecirvvs" else flat.MODEL_OSECIR
     run0, count = study.distribute_runs(world * R, world, rank)
     assert count == R
     t_s = time.perf_counter()
-    problem = ps.sample(run0, R)
-    host_sampling_s = time.perf_counter() - t_s
+    if args.model == "osecirvvs":
+        problem = vvs_problem(args, R)
+        ps = SlicedSampler(problem)
+        run0 = 0
+        num_groups = problem.num_groups
+    else:
+        graph = synthetic.covid_study_graph(N=N)
+        ps = study.ParameterStudy(graph, 0.0, T, 0.5, world * R)
+        problem = ps.sample(run0, R)
+        num_groups = graph.num_groups
+    host_sampling_s = time.perf_counter() - t_s if args.model == "osecir" else 0.0
     # pinned host staging
-    for name in ("y0", "node_local", "psets", "ctables", "mobtables"):
+    pinned_names = [n_ for n_ in ("y0", "node_local", "psets", "ctables", "mobtables")
+                    if getattr(problem, n_) is not None]
+    for name in pinned_names:
         a = getattr(problem, name)
         tns = torch.empty(a.shape, dtype=torch.float64).pin_memory()
         tns.numpy()[...] = a
         setattr(problem, name, tns.numpy())
         setattr(problem, "_pin_" + name, tns)
-    h2d = sum(getattr(problem, n_).nbytes for n_ in ("y0", "node_local", "psets", "ctables", "mobtables"))
+    h2d = sum(getattr(problem, n_).nbytes for n_ in pinned_names)
 
     sim = capi.GraphSimulation(problem, device=local_rank, max_runs=R, upload=False)
-    rec = ensemble.EnsembleRecord(graph.num_groups, N, days, capacity_runs=R, mode=ensemble.ENS_AGE_SUM,
-                                  device=local_rank)
+    rec = ensemble.EnsembleRecord(num_groups, N, days, capacity_runs=R, mode=ensemble.ENS_AGE_SUM,
+                                  device=local_rank, model=model)
     rec_t = rec.as_torch()
     ncol = rec.info()["num_columns"]
     d2h = (len(ensemble.DEFAULT_PERCENTILES) + 1) * ncol * 8
@@ -309,31 +380,34 @@ def main():
         kernel_ms["select"] = tot_red_ms / args.steps
         dominant = max(kernel_ms, key=kernel_ms.get)
         integ_s = prof["integrate"][0] * 1e-3
-        fp64_achieved = attempts * FLOP_PER_CK54_ATTEMPT / integ_s / 1e12 if integ_s > 0 else 0.0
+        flop_attempt = FLOP_PER_CK54_ATTEMPT[args.model]
+        edge_bytes = edge_bytes_per_run_day(args.model, N, problem.num_edges)
+        fp64_achieved = attempts * flop_attempt / integ_s / 1e12 if integ_s > 0 else 0.0
         edge_s = (prof["depart"][0] + prof["return"][0] + prof["return_exact"][0]) * 1e-3
-        edge_gbs = EDGE_BYTES_PER_RUN_DAY * R * T * args.steps / edge_s / 1e9 if edge_s > 0 else 0.0
-        traffic = ncu_traffic(R)
+        edge_gbs = edge_bytes * R * T * args.steps / edge_s / 1e9 if edge_s > 0 else 0.0
+        traffic = ncu_traffic(R) if args.model == "osecir" else {}
         roof_fp64 = {"kernel": "integrate_nodes_kernel", "bound": "fp64", "achieved": fp64_achieved, "peak": fp64_peak,
                      "unit": "TFLOP/s", "frac": fp64_achieved / fp64_peak if fp64_peak else None,
                      "traffic": traffic.get("integrate"),
                      "peak_source": "measured in this run (DFMA chains on all SMs, mio_cuda_measure_fp64_peak); "
                                     "MEASURED_PEAKS.json has no FP64 figure",
                      "attempts_per_launch": attempts / max(prof["integrate"][1], 1),
-                     "flop_per_attempt": FLOP_PER_CK54_ATTEMPT}
+                     "flop_per_attempt": flop_attempt}
         roof_edge = {"kernel": "depart_kernel+return_kernel(+return_exact)", "bound": "hbm", "achieved": edge_gbs,
                      "peak": hbm_peak, "unit": "GB/s", "frac": edge_gbs / hbm_peak,
                      "traffic": (traffic.get("depart", 0) + traffic.get("return", 0)) or None,
-                     "peak_source": hbm_src, "algorithmic_bytes_per_run_day": EDGE_BYTES_PER_RUN_DAY,
+                     "peak_source": hbm_src, "algorithmic_bytes_per_run_day": edge_bytes,
                      "note": "algorithmic bytes are SURVEY 8d's explicit-traveler-state figure; the aggregated "
                              "formulation moves fewer DRAM bytes (see traffic), so achieved can exceed DRAM throughput"}
         line = {
-            "metric": "graph_ode_secir_node_days_per_s", "value": value, "unit": "node-days/s", "n_gpus": world,
+            "metric": METRIC[args.model], "value": value, "unit": "node-days/s", "n_gpus": world,
             "steps": args.steps, "warmup": args.warmup, "ms_per_step": tot_dev_ms / args.steps,
             "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "f64", "data": "synthetic",
             "config": dict(workload_config(args), edges=int(problem.num_edges)),
             "e2e": {"value": e2e, "unit": "node-days/s", "h2d_bytes_per_step": int(h2d), "d2h_bytes_per_step": int(d2h),
                     "ms_per_step": tot_e2e_ms / args.steps, "batches": nb,
-                    "includes": "host sampling (overlapped), H2D of sampled runs, advance, percentile reduction, D2H"},
+                    "includes": ("host sampling (overlapped), " if args.model == "osecir" else "") +
+                                "H2D of the runs' parameters and initial values, advance, percentile reduction, D2H"},
             "gpu_launches": int(agg[1].item()),
             "clocks": clock_info,
             "roofline": roof_edge if dominant in ("depart", "return", "return_exact") else roof_fp64,

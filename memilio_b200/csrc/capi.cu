@@ -53,7 +53,7 @@ int mio_set_last_error(int code, const std::string& msg)
 
 struct mio_ensemble {
     int device = 0;
-    int G = 0, C = 0, N = 0, num_days = 0, mode = 0;
+    int G = 0, C = 0, N = 0, num_days = 0, mode = 0, lay = 1;
     long long capacity = 0, num_runs = 0, num_columns = 0;
     double* d_data = nullptr; // [num_columns][capacity]
 };
@@ -79,6 +79,7 @@ struct mio_handle {
     int* d_counters     = nullptr;
     double* d_y[4]      = {nullptr, nullptr, nullptr, nullptr};
     double *d_fac = nullptr, *d_aux = nullptr, *d_u = nullptr, *d_vis = nullptr;
+    double *d_vacc_partial = nullptr, *d_vacc_full = nullptr;
     int* d_run_flags = nullptr;
     double* d_daily  = nullptr;
     int* d_traj_npts = nullptr;
@@ -108,9 +109,13 @@ struct mio_handle {
 namespace
 {
 
+int age_stride(int model)
+{
+    return model == MIO_MODEL_OSECIR ? MIO_OSECIR_AGE_STRIDE : (model == MIO_MODEL_OSECIRVVS ? MIO_OSECIRVVS_AGE_STRIDE : -1);
+}
 int64_t pset_size(int model, int G)
 {
-    return MIO_PSET_HEADER + int64_t(model == MIO_MODEL_OSECIR ? MIO_OSECIR_AGE_STRIDE : 0) * G;
+    return MIO_PSET_HEADER + int64_t(age_stride(model)) * G;
 }
 int64_t ctable_size(int G, int max_loc, int max_pts)
 {
@@ -123,7 +128,7 @@ int64_t mobtable_size(int n, int mob_max_pts)
 
 // raw parameter set (mio_cuda.h layout) -> derived device record (device_common.cuh). The coefficient expressions
 // keep the operand order of cpp/models/ode_secir/model.h:152-211 so that coef*y is bit-identical to the reference.
-void derive_pset(const double* raw, int G, double* out)
+void derive_pset_osecir(const double* raw, int G, double* out)
 {
     for (int k = 0; k < PHDR; ++k) {
         out[k] = 0.0;
@@ -165,8 +170,102 @@ void derive_pset(const double* raw, int G, double* out)
         r[rCRIT]           = crit;
         r[rT_ISEV]         = T_ISev;
         r[rDPS]            = dps;
-        r[18]              = 0.0;
-        r[19]              = 0.0;
+        r[rREDEXP]         = 1.0;
+        r[rINFNV]          = 1.0;
+    }
+}
+
+// osecirvvs: one record per (immunity layer, age group) lane, layer-major. Rate expressions in the operand order of
+// cpp/models/ode_secirvvs/model.h:266-376 (the ICU-dependent ones at "ICU not short", adjusted on the device).
+void derive_pset_osecirvvs(const double* raw, int G, double* out)
+{
+    for (int k = 0; k < PHDR; ++k) {
+        out[k] = 0.0;
+    }
+    out[hSTART_DAY]             = raw[MIO_PH_START_DAY];
+    out[hSEASONALITY]           = raw[MIO_PH_SEASONALITY];
+    out[hTNT_MAX_RISK]          = raw[MIO_PH_TNT_MAX_RISK];
+    out[hNONDETECTION]          = raw[MIO_PH_COMMUTER_NONDETECTION];
+    out[hSTART_DETECTION]       = raw[MIO_PH_START_COMMUTER_DETECTION];
+    out[hEND_DETECTION]         = raw[MIO_PH_END_COMMUTER_DETECTION];
+    out[hTNT_MAX_RISK_NOSYMP]   = raw[MIO_PH_TNT_MAX_RISK_NOSYMP];
+    out[hSTART_DAY_NEW_VARIANT] = raw[MIO_PH_START_DAY_NEW_VARIANT];
+    for (int layer = 0; layer < VVS_LAY; ++layer) {
+        for (int i = 0; i < G; ++i) {
+            const double* a     = raw + MIO_PSET_HEADER + i * MIO_OSECIRVVS_AGE_STRIDE;
+            double* r           = out + PHDR + (layer * G + i) * AGE_REC;
+            const double T_E    = a[MIO_PA_TIME_EXPOSED];
+            const double T_INS  = a[MIO_PA_TIME_INS];
+            const double T_ISy  = a[MIO_PA_TIME_ISY];
+            const double T_ISev = a[MIO_PA_TIME_ISEV];
+            const double T_ICr  = a[MIO_PA_TIME_ICR];
+            const double rho    = a[MIO_PA_REC_PER_INS];
+            const double sev    = a[MIO_PA_SEV_PER_ISY];
+            const double crit   = a[MIO_PA_CRIT_PER_SEV];
+            const double dps    = a[MIO_PA_DEATHS_PER_SEV];
+            const double dpc    = a[MIO_PA_DEATHS_PER_CRIT];
+            const double rtm    = a[MIO_PV_REDUC_TIME_MILD];
+            r[rE_INS]           = 1.0 / T_E;
+            if (layer == 0) {
+                r[rINS_ISy]   = (1 - rho) / T_INS;
+                r[rINS_R]     = rho / T_INS;
+                r[rISy_ISev]  = sev / T_ISy;
+                r[rISy_R]     = (1 - sev) / T_ISy;
+                r[rISev_ICr0] = crit / T_ISev;
+                r[rISev_R]    = (1 - crit - dps) / T_ISev;
+                r[rISev_D0]   = (dps + (crit - crit)) / T_ISev;
+                r[rICr_D]     = dpc / T_ICr;
+                r[rICr_R]     = (1 - dpc) / T_ICr;
+                r[rREDEXP]    = 1.0;
+            }
+            else {
+                const double red_exp  = a[layer == 1 ? MIO_PV_REDUC_EXPOSED_PI : MIO_PV_REDUC_EXPOSED_II];
+                const double red_symp = a[layer == 1 ? MIO_PV_REDUC_INF_SYMP_PI : MIO_PV_REDUC_INF_SYMP_II];
+                const double red_sev  = a[layer == 1 ? MIO_PV_REDUC_SEV_CRIT_DEAD_PI : MIO_PV_REDUC_SEV_CRIT_DEAD_II];
+                r[rINS_ISy]   = (red_symp / red_exp) * (1 - rho) / (T_INS * rtm);
+                r[rINS_R]     = (1 - (red_symp / red_exp) * (1 - rho)) / (T_INS * rtm);
+                r[rISy_ISev]  = red_sev / red_symp * sev / (T_ISy * rtm);
+                r[rISy_R]     = (1 - (red_sev / red_symp) * sev) / (T_ISy * rtm);
+                r[rISev_ICr0] = red_sev / red_sev * crit / T_ISev;
+                r[rISev_R]    = (1 - (red_sev / red_sev) * (crit + dps)) / T_ISev;
+                r[rISev_D0]   = (red_sev / red_sev) * (dps + (crit - crit)) / T_ISev;
+                r[rICr_D]     = (red_sev / red_sev) * dpc / T_ICr;
+                r[rICr_R]     = (1 - (red_sev / red_sev) * dpc) / T_ICr;
+                r[rREDEXP]    = red_exp;
+            }
+            r[rTNT]     = (1 - rho) / T_INS;
+            r[rP]       = a[MIO_PA_TRANS_PROB];
+            r[rREL]     = a[MIO_PA_REL_TRANS_NOSYMP];
+            r[rRISK]    = a[MIO_PA_RISK_SYMP];
+            r[rMAXRISK] = a[MIO_PA_MAX_RISK_SYMP];
+            r[rCRIT]    = crit;
+            r[rT_ISEV]  = T_ISev;
+            r[rDPS]     = dps;
+            r[rINFNV]   = a[MIO_PV_INFECTIOUSNESS_NEW_VARIANT];
+        }
+    }
+}
+
+void derive_pset(int model, const double* raw, int G, double* out)
+{
+    if (model == MIO_MODEL_OSECIRVVS) {
+        derive_pset_osecirvvs(raw, G, out);
+    }
+    else {
+        derive_pset_osecir(raw, G, out);
+    }
+}
+
+// reference element order (age*C + compartment) -> device order [LAY][G][NC] of one node-sized vector; the unused
+// slots get `pad`
+void to_device_layout(int lay, int G, int C_ref, const double* ref, double* dev, double pad = 0.0)
+{
+    const int W = G * lay;
+    std::fill(dev, dev + (size_t)W * NC, pad);
+    for (int i = 0; i < G; ++i) {
+        for (int c = 0; c < C_ref; ++c) {
+            dev[dev_index_of_ref(lay, G, i, c)] = ref[i * C_ref + c];
+        }
     }
 }
 
@@ -183,7 +282,7 @@ void destroy(mio_handle* h)
                     h->d_run_block,  h->d_node_local,  h->d_t_node,     h->d_dt_node,   h->d_counters,
                     h->d_y[0],       h->d_y[1],        h->d_y[2],       h->d_y[3],      h->d_fac,
                     h->d_aux,        h->d_run_flags,   h->d_daily,      h->d_traj_npts, h->d_traj_times,
-                    h->d_traj_values, h->d_stats};
+                    h->d_traj_values, h->d_stats,      h->d_vacc_partial, h->d_vacc_full};
     for (void* p : ptrs) {
         if (p) {
             cudaFree(p);
@@ -212,6 +311,8 @@ DeviceState device_state(const mio_handle* h)
     st.t_node      = h->d_t_node;
     st.dt_node     = h->d_dt_node;
     st.counters    = h->d_counters;
+    st.vacc_partial = h->d_vacc_partial;
+    st.vacc_full    = h->d_vacc_full;
     return st;
 }
 
@@ -304,7 +405,7 @@ int mio_num_compartments(int model)
 }
 int mio_pset_age_stride(int model)
 {
-    return model == MIO_MODEL_OSECIR ? MIO_OSECIR_AGE_STRIDE : -1;
+    return age_stride(model);
 }
 int64_t mio_pset_size(int model, int num_groups)
 {
@@ -325,8 +426,14 @@ int mio_cuda_graph_create(const mio_graph_desc* d, int device, mio_handle** out)
         return fail(MIO_INVALID_VALUE, "null argument");
     }
     *out = nullptr;
-    if (d->model != MIO_MODEL_OSECIR) {
-        return fail(MIO_INVALID_VALUE, "model kind not supported by this build (osecir only)");
+    if (d->model != MIO_MODEL_OSECIR && d->model != MIO_MODEL_OSECIRVVS) {
+        return fail(MIO_INVALID_VALUE, "unknown model kind");
+    }
+    if (d->model == MIO_MODEL_OSECIRVVS && d->sim_kind != MIO_SIM_BASE && d->sim_kind != MIO_SIM_MODEL) {
+        return fail(MIO_INVALID_VALUE, "unknown node simulation kind");
+    }
+    if (d->model == MIO_MODEL_OSECIRVVS && d->vacc_days > 0 && (!d->vacc_partial || !d->vacc_full)) {
+        return fail(MIO_INVALID_VALUE, "vaccination arrays missing");
     }
     if (d->num_groups < 1 || d->num_groups > MIO_MAX_GROUPS || d->num_nodes < 1 || d->num_edges < 0 ||
         d->max_runs < 1 || d->num_psets < 1 || d->num_ctables < 1 || d->ct_max_loc < 1 || d->ct_max_pts < 0 ||
@@ -355,7 +462,10 @@ int mio_cuda_graph_create(const mio_graph_desc* d, int device, mio_handle** out)
     if (prop.major != 10) {
         return fail(MIO_UNKNOWN_ERROR, "device is not sm_100 (kernels are built for sm_100a only)");
     }
-    const int G = d->num_groups, N = d->num_nodes, E = d->num_edges, n = G * NC;
+    const int G = d->num_groups, N = d->num_nodes, E = d->num_edges;
+    const int LAY = d->model == MIO_MODEL_OSECIRVVS ? VVS_LAY : 1;
+    const int W = G * LAY, n = W * NC;
+    const int C_ref = mio_num_compartments(d->model), n_ref = G * C_ref;
     for (int e = 0; e < E; ++e) {
         if (d->edge_start[e] < 0 || d->edge_start[e] >= N || d->edge_end[e] < 0 || d->edge_end[e] >= N ||
             d->edge_start[e] == d->edge_end[e]) {
@@ -381,12 +491,18 @@ int mio_cuda_graph_create(const mio_graph_desc* d, int device, mio_handle** out)
     geo.N            = N;
     geo.E            = E;
     geo.n            = n;
+    geo.LAY          = LAY;
+    geo.W            = W;
+    geo.C_ref        = C_ref;
+    geo.n_ref        = n_ref;
+    geo.sim_kind     = d->model == MIO_MODEL_OSECIRVVS ? d->sim_kind : MIO_SIM_MODEL;
+    geo.vacc_days    = d->model == MIO_MODEL_OSECIRVVS ? d->vacc_days : 0;
     geo.num_psets    = d->num_psets;
     geo.num_ctables  = d->num_ctables;
     geo.ct_max_loc   = d->ct_max_loc;
     geo.ct_max_pts   = d->ct_max_pts;
     geo.mob_max_pts  = d->mob_max_pts;
-    geo.pset_stride  = PHDR + AGE_REC * G;
+    geo.pset_stride  = PHDR + AGE_REC * W;
     geo.ctable_stride = (int)ctable_size(G, d->ct_max_loc, d->ct_max_pts);
     geo.ct_off       = geo.num_psets * geo.pset_stride;
     geo.mob_off      = geo.ct_off + geo.num_ctables * geo.ctable_stride;
@@ -419,13 +535,26 @@ int mio_cuda_graph_create(const mio_graph_desc* d, int device, mio_handle** out)
         H_TRY(dev_alloc(&h->d_node_ctable, (size_t)N));
         H_TRY(cudaMemcpy(h->d_node_ctable, d->node_ctable, sizeof(int) * N, cudaMemcpyHostToDevice));
     }
+    if (geo.vacc_days > 0) {
+        const size_t cnt = (size_t)N * G * geo.vacc_days;
+        H_TRY(dev_alloc(&h->d_vacc_partial, cnt));
+        H_TRY(dev_alloc(&h->d_vacc_full, cnt));
+        H_TRY(cudaMemcpy(h->d_vacc_partial, d->vacc_partial, sizeof(double) * cnt, cudaMemcpyHostToDevice));
+        H_TRY(cudaMemcpy(h->d_vacc_full, d->vacc_full, sizeof(double) * cnt, cudaMemcpyHostToDevice));
+    }
     if (E > 0) {
-        for (size_t i = 0; i < (size_t)E * n; ++i) {
+        for (size_t i = 0; i < (size_t)E * n_ref; ++i) {
             if (!(d->edge_coeff[i] >= 0.0)) {
                 destroy(h);
                 return fail(MIO_INVALID_VALUE, "mobility coefficients must be non-negative");
             }
         }
+        // coefficient vectors in the device's lane order (identity for osecir)
+        std::vector<double> coeff_dev((size_t)E * n);
+        for (int e = 0; e < E; ++e) {
+            to_device_layout(LAY, G, C_ref, d->edge_coeff + (size_t)e * n_ref, coeff_dev.data() + (size_t)e * n);
+        }
+        const double* edge_coeff = coeff_dev.data();
         // outgoing CSR = reference edge order; incoming CSR sorted by (dst, src)
         std::vector<int> out_ptr(N + 1, 0), in_ptr(N + 1, 0), in_split(N, 0);
         for (int e = 0; e < E; ++e) {
@@ -446,44 +575,44 @@ int mio_cuda_graph_create(const mio_graph_desc* d, int device, mio_handle** out)
             in_edge[fill[t]] = e;
             ++fill[t];
         }
-        // factorized form: coeff[e][i][c] == w[e][i] * mask[i][c] with a 0/1 mask, exactly
-        std::vector<double> umask(n, 0.0), w_age((size_t)E * G, 0.0);
+        // factorized form: coeff[e][l][c] == w[e][l] * mask[l][c] with a 0/1 mask, exactly (l = lane of the node)
+        std::vector<double> umask(n, 0.0), w_age((size_t)E * W, 0.0);
         for (int e = 0; e < E; ++e) {
             for (int j = 0; j < n; ++j) {
-                if (d->edge_coeff[(size_t)e * n + j] != 0.0) {
+                if (edge_coeff[(size_t)e * n + j] != 0.0) {
                     umask[j] = 1.0;
                 }
             }
         }
         bool fact = true;
         for (int e = 0; e < E && fact; ++e) {
-            for (int i = 0; i < G && fact; ++i) {
+            for (int i = 0; i < W && fact; ++i) {
                 double w = 0.0;
                 for (int c = 0; c < NC; ++c) {
                     if (umask[i * NC + c] != 0.0) {
-                        w = d->edge_coeff[(size_t)e * n + i * NC + c];
+                        w = edge_coeff[(size_t)e * n + i * NC + c];
                         break;
                     }
                 }
                 for (int c = 0; c < NC; ++c) {
-                    if (d->edge_coeff[(size_t)e * n + i * NC + c] != w * umask[i * NC + c]) {
+                    if (edge_coeff[(size_t)e * n + i * NC + c] != w * umask[i * NC + c]) {
                         fact = false;
                     }
                 }
-                w_age[(size_t)e * G + i] = w;
+                w_age[(size_t)e * W + i] = w;
             }
         }
         h->factorized = fact ? 1 : 0;
         if (!fact) {
             std::fill(umask.begin(), umask.end(), 1.0);
         }
-        // mobile compartments = union of the mask over the age groups; the list is padded with a non-mobile
+        // mobile compartments = union of the mask over the lanes; the list is padded with a non-mobile
         // compartment (its emigration base entries are zero) or, if all ten are mobile, is simply complete
         {
             int pad = -1;
             for (int cc = 0; cc < NC; ++cc) {
                 bool any = false;
-                for (int i = 0; i < G; ++i) {
+                for (int i = 0; i < W; ++i) {
                     any = any || umask[i * NC + cc] != 0.0;
                 }
                 if (any) {
@@ -497,26 +626,26 @@ int mio_cuda_graph_create(const mio_graph_desc* d, int device, mio_handle** out)
                 h->mob_comp[m] = pad < 0 ? 0 : pad;
             }
         }
-        std::vector<double> w_in(fact ? (size_t)E * G : (size_t)E * n), w_out((size_t)E * G * 2),
+        std::vector<double> w_in(fact ? (size_t)E * W : (size_t)E * n), w_out((size_t)E * W * 2),
             s_out((size_t)N * n, 0.0);
         for (int pos = 0; pos < E; ++pos) {
             const int e = in_edge[pos];
             if (fact) {
-                std::copy(w_age.begin() + (size_t)e * G, w_age.begin() + (size_t)(e + 1) * G,
-                          w_in.begin() + (size_t)pos * G);
+                std::copy(w_age.begin() + (size_t)e * W, w_age.begin() + (size_t)(e + 1) * W,
+                          w_in.begin() + (size_t)pos * W);
             }
             else {
-                std::copy(d->edge_coeff + (size_t)e * n, d->edge_coeff + (size_t)(e + 1) * n,
+                std::copy(edge_coeff + (size_t)e * n, edge_coeff + (size_t)(e + 1) * n,
                           w_in.begin() + (size_t)pos * n);
             }
         }
         for (int e = 0; e < E; ++e) {
-            for (int i = 0; i < G; ++i) {
-                w_out[((size_t)e * G + i) * 2 + 0] = d->edge_coeff[(size_t)e * n + i * NC + cS];
-                w_out[((size_t)e * G + i) * 2 + 1] = d->edge_coeff[(size_t)e * n + i * NC + cISev];
+            for (int i = 0; i < W; ++i) {
+                w_out[((size_t)e * W + i) * 2 + 0] = edge_coeff[(size_t)e * n + i * NC + cS];
+                w_out[((size_t)e * W + i) * 2 + 1] = edge_coeff[(size_t)e * n + i * NC + cISev];
             }
             for (int j = 0; j < n; ++j) {
-                s_out[(size_t)d->edge_start[e] * n + j] += d->edge_coeff[(size_t)e * n + j];
+                s_out[(size_t)d->edge_start[e] * n + j] += edge_coeff[(size_t)e * n + j];
             }
         }
         std::vector<int> order_in(N), order_out(N);
@@ -546,7 +675,7 @@ int mio_cuda_graph_create(const mio_graph_desc* d, int device, mio_handle** out)
         H_TRY(up_i(&h->d_out_dst, ee));
         H_TRY(up_i(&h->d_edge_start, es));
         H_TRY(up_i(&h->d_edge_end, ee));
-        H_TRY(up_d(&h->d_coeff, d->edge_coeff, (size_t)E * n));
+        H_TRY(up_d(&h->d_coeff, edge_coeff, (size_t)E * n));
         H_TRY(up_d(&h->d_w_in, w_in.data(), w_in.size()));
         H_TRY(up_d(&h->d_w_out, w_out.data(), w_out.size()));
         H_TRY(up_d(&h->d_s_out, s_out.data(), s_out.size()));
@@ -564,8 +693,8 @@ int mio_cuda_graph_create(const mio_graph_desc* d, int device, mio_handle** out)
         H_TRY(dev_alloc(&h->d_y[b], R * N * n));
     }
     if (E > 0) {
-        H_TRY(dev_alloc(&h->d_fac, R * N * G));
-        H_TRY(dev_alloc(&h->d_aux, R * N * G * 4));
+        H_TRY(dev_alloc(&h->d_fac, R * N * W));
+        H_TRY(dev_alloc(&h->d_aux, R * N * W * 4));
         H_TRY(dev_alloc(&h->d_u, R * N * n));
         H_TRY(dev_alloc(&h->d_vis, R * N * 2 * n));
         H_TRY(dev_alloc(&h->d_run_flags, R));
@@ -578,12 +707,12 @@ int mio_cuda_graph_create(const mio_graph_desc* d, int device, mio_handle** out)
             destroy(h);
             return fail(MIO_INVALID_VALUE, "record_daily needs max_days >= 1");
         }
-        H_TRY(dev_alloc(&h->d_daily, R * N * (size_t)d->max_days * n));
+        H_TRY(dev_alloc(&h->d_daily, R * N * (size_t)d->max_days * n_ref));
     }
     if (d->traj_capacity > 0) {
         H_TRY(dev_alloc(&h->d_traj_npts, R * N));
         H_TRY(dev_alloc(&h->d_traj_times, R * N * (size_t)d->traj_capacity));
-        H_TRY(dev_alloc(&h->d_traj_values, R * N * (size_t)d->traj_capacity * n));
+        H_TRY(dev_alloc(&h->d_traj_values, R * N * (size_t)d->traj_capacity * n_ref));
     }
     H_TRY(cudaMemset(h->d_counters, 0, sizeof(int) * R * N * 4));
 #undef H_TRY
@@ -591,6 +720,7 @@ int mio_cuda_graph_create(const mio_graph_desc* d, int device, mio_handle** out)
     h->desc.edge_start = h->desc.edge_end = nullptr;
     h->desc.edge_coeff                    = nullptr;
     h->desc.node_pset = h->desc.node_ctable = nullptr;
+    h->desc.vacc_partial = h->desc.vacc_full = nullptr;
     *out = h;
     return MIO_OK;
 }
@@ -616,16 +746,18 @@ int mio_cuda_set_runs(mio_handle* h, int32_t slot0, int32_t count, const mio_run
     }
     CUDA_TRY(cudaSetDevice(h->device));
     const Geometry& geo = h->geo;
-    const int G = geo.G, N = geo.N, n = geo.n;
+    const int G = geo.G, N = geo.N, n = geo.n, n_ref = geo.n_ref;
     const int64_t psz = pset_size(h->desc.model, G);
     const int64_t csz = geo.ctable_stride;
-    const int64_t msz = geo.mob_max_pts > 0 ? mobtable_size(n, geo.mob_max_pts) : 0;
+    const int64_t msz     = geo.mob_max_pts > 0 ? mobtable_size(n, geo.mob_max_pts) : 0;     // device layout
+    const int64_t msz_ref = geo.mob_max_pts > 0 ? mobtable_size(n_ref, geo.mob_max_pts) : 0; // caller's layout
     // build the device run blocks: derived parameter sets | contact tables | mobility table
     std::vector<double> block((size_t)count * geo.block_stride, 0.0);
     for (int r = 0; r < count; ++r) {
         double* b = block.data() + (size_t)r * geo.block_stride;
         for (int p = 0; p < geo.num_psets; ++p) {
-            derive_pset(data->psets + ((size_t)r * geo.num_psets + p) * psz, G, b + p * geo.pset_stride);
+            derive_pset(h->desc.model, data->psets + ((size_t)r * geo.num_psets + p) * psz, G,
+                        b + p * geo.pset_stride);
         }
         std::memcpy(b + geo.ct_off, data->ctables + (size_t)r * geo.num_ctables * csz,
                     sizeof(double) * geo.num_ctables * csz);
@@ -642,9 +774,20 @@ int mio_cuda_set_runs(mio_handle* h, int32_t slot0, int32_t count, const mio_run
             }
         }
         if (msz > 0) {
-            std::memcpy(b + geo.mob_off, data->mobtables + (size_t)r * msz, sizeof(double) * msz);
-            if (b[geo.mob_off] < 0 || b[geo.mob_off] > geo.mob_max_pts) {
+            const double* mt = data->mobtables + (size_t)r * msz_ref;
+            if (mt[0] < 0 || mt[0] > geo.mob_max_pts) {
                 return fail(MIO_INVALID_VALUE, "mobility table: number of change points out of range");
+            }
+            if (geo.LAY == 1) {
+                std::memcpy(b + geo.mob_off, mt, sizeof(double) * msz);
+            }
+            else {
+                double* md = b + geo.mob_off;
+                std::memcpy(md, mt, sizeof(double) * (1 + geo.mob_max_pts));
+                for (int k = 0; k < geo.mob_max_pts; ++k) {
+                    to_device_layout(geo.LAY, G, geo.C_ref, mt + 1 + geo.mob_max_pts + (size_t)k * n_ref,
+                                     md + 1 + geo.mob_max_pts + (size_t)k * n);
+                }
             }
         }
     }
@@ -653,8 +796,22 @@ int mio_cuda_set_runs(mio_handle* h, int32_t slot0, int32_t count, const mio_run
                              cudaMemcpyHostToDevice, h->stream));
     CUDA_TRY(cudaMemcpyAsync(h->d_node_local + s0 * N * 2, data->node_local, sizeof(double) * (size_t)count * N * 2,
                              cudaMemcpyHostToDevice, h->stream));
-    CUDA_TRY(cudaMemcpyAsync(h->d_y[h->cur] + s0 * N * n, data->y0, sizeof(double) * (size_t)count * N * n,
-                             cudaMemcpyHostToDevice, h->stream));
+    if (geo.LAY == 1) {
+        CUDA_TRY(cudaMemcpyAsync(h->d_y[h->cur] + s0 * N * n, data->y0, sizeof(double) * (size_t)count * N * n,
+                                 cudaMemcpyHostToDevice, h->stream));
+    }
+    else {
+        // staged in a free state buffer (n >= n_ref), then permuted into the device's lane order
+        const int stage = free_buffer(h, h->cur, -1, -1);
+        if (stage < 0 || !h->d_y[stage]) {
+            return fail(MIO_UNKNOWN_ERROR, "internal: no free state buffer");
+        }
+        CUDA_TRY(cudaMemcpyAsync(h->d_y[stage], data->y0, sizeof(double) * (size_t)count * N * n_ref,
+                                 cudaMemcpyHostToDevice, h->stream));
+        CUDA_TRY(launch_permute_state(geo, h->d_y[stage], h->d_y[h->cur] + s0 * N * n, (size_t)count * N, 1,
+                                      h->stream));
+        ++h->launches;
+    }
     std::vector<double> tn((size_t)count * N, h->desc.t0), dtn((size_t)count * N, 0.1);
     if (data->dt0) {
         std::copy(data->dt0, data->dt0 + (size_t)count * N, dtn.begin());
@@ -673,8 +830,8 @@ int mio_cuda_set_runs(mio_handle* h, int32_t slot0, int32_t count, const mio_run
         // day 0 = initial value (interpolate_simulation_result, analyze_result.h:228-231)
         std::vector<double> tmp; // strided copy: slot day 0 of each (run,node)
         const size_t md = (size_t)h->desc.max_days;
-        CUDA_TRY(cudaMemcpy2DAsync(h->d_daily + s0 * N * md * n, sizeof(double) * md * n, data->y0,
-                                   sizeof(double) * n, sizeof(double) * n, (size_t)count * N,
+        CUDA_TRY(cudaMemcpy2DAsync(h->d_daily + s0 * N * md * n_ref, sizeof(double) * md * n_ref, data->y0,
+                                   sizeof(double) * n_ref, sizeof(double) * n_ref, (size_t)count * N,
                                    cudaMemcpyHostToDevice, h->stream));
         h->days_recorded = std::max(h->days_recorded, 1);
     }
@@ -685,8 +842,8 @@ int mio_cuda_set_runs(mio_handle* h, int32_t slot0, int32_t count, const mio_run
                                  cudaMemcpyHostToDevice, h->stream));
         CUDA_TRY(cudaMemcpy2DAsync(h->d_traj_times + s0 * N * cap, sizeof(double) * cap, tn.data(), sizeof(double),
                                    sizeof(double), (size_t)count * N, cudaMemcpyHostToDevice, h->stream));
-        CUDA_TRY(cudaMemcpy2DAsync(h->d_traj_values + s0 * N * cap * n, sizeof(double) * cap * n, data->y0,
-                                   sizeof(double) * n, sizeof(double) * n, (size_t)count * N,
+        CUDA_TRY(cudaMemcpy2DAsync(h->d_traj_values + s0 * N * cap * n_ref, sizeof(double) * cap * n_ref, data->y0,
+                                   sizeof(double) * n_ref, sizeof(double) * n_ref, (size_t)count * N,
                                    cudaMemcpyHostToDevice, h->stream));
     }
     if (h->ens) {
@@ -695,8 +852,8 @@ int mio_cuda_set_runs(mio_handle* h, int32_t slot0, int32_t count, const mio_run
         }
         ++h->launches;
         ++h->prof_launches[MIO_KC_ENSEMBLE];
-        CUDA_TRY(launch_record_ensemble(h->d_y[h->cur] + s0 * N * n, h->ens->d_data, N, G, NC, count, 0,
-                                        h->ens->num_days, h->ens->mode, h->ens_offset + slot0, h->ens->capacity,
+        CUDA_TRY(launch_record_ensemble(h->d_y[h->cur] + s0 * N * n, h->ens->d_data, N, G, geo.C_ref, geo.LAY, count,
+                                        0, h->ens->num_days, h->ens->mode, h->ens_offset + slot0, h->ens->capacity,
                                         h->stream));
         h->ens->num_runs = std::max(h->ens->num_runs, h->ens_offset + slot0 + count);
     }
@@ -855,9 +1012,9 @@ int mio_cuda_advance(mio_handle* h, double t_max)
                 const int slot = (int)day - h->day0;
                 if (h->ens && slot >= 0 && slot < h->ens->num_days) {
                     ScopedSpan sp(h, MIO_KC_ENSEMBLE);
-                    CUDA_TRY(launch_record_ensemble(h->d_y[h->cur], h->ens->d_data, geo.N, geo.G, NC, R, slot,
-                                                    h->ens->num_days, h->ens->mode, h->ens_offset, h->ens->capacity,
-                                                    h->stream));
+                    CUDA_TRY(launch_record_ensemble(h->d_y[h->cur], h->ens->d_data, geo.N, geo.G, geo.C_ref, geo.LAY, R,
+                                                    slot, h->ens->num_days, h->ens->mode, h->ens_offset,
+                                                    h->ens->capacity, h->stream));
                 }
                 if (h->d_daily && slot >= 0 && slot < h->desc.max_days) {
                     ScopedSpan sp(h, MIO_KC_RECORD);
@@ -900,8 +1057,23 @@ int mio_cuda_get_state(mio_handle* h, int32_t slot0, int32_t count, double* out)
     }
     CUDA_TRY(cudaSetDevice(h->device));
     const size_t per = (size_t)h->geo.N * h->geo.n;
-    CUDA_TRY(cudaMemcpy(out, h->d_y[h->cur] + (size_t)slot0 * per, sizeof(double) * per * count,
-                        cudaMemcpyDeviceToHost));
+    if (h->geo.LAY == 1) {
+        CUDA_TRY(cudaMemcpy(out, h->d_y[h->cur] + (size_t)slot0 * per, sizeof(double) * per * count,
+                            cudaMemcpyDeviceToHost));
+    }
+    else {
+        // permuted into the reference's element order in a free state buffer, then copied out
+        const int stage = free_buffer(h, h->cur, -1, -1);
+        if (stage < 0 || !h->d_y[stage]) {
+            return fail(MIO_UNKNOWN_ERROR, "internal: no free state buffer");
+        }
+        CUDA_TRY(launch_permute_state(h->geo, h->d_y[h->cur] + (size_t)slot0 * per, h->d_y[stage],
+                                      (size_t)count * h->geo.N, 0, h->stream));
+        ++h->launches;
+        CUDA_TRY(cudaMemcpyAsync(out, h->d_y[stage], sizeof(double) * (size_t)count * h->geo.N * h->geo.n_ref,
+                                 cudaMemcpyDeviceToHost, h->stream));
+        CUDA_TRY(cudaStreamSynchronize(h->stream));
+    }
     return MIO_OK;
 }
 
@@ -942,7 +1114,7 @@ int mio_cuda_get_daily(mio_handle* h, int32_t slot0, int32_t count, int32_t* num
         return fail(MIO_INVALID_VALUE, "graph was created without record_daily");
     }
     CUDA_TRY(cudaSetDevice(h->device));
-    const size_t nd = (size_t)h->days_recorded, md = (size_t)h->desc.max_days, n = (size_t)h->geo.n;
+    const size_t nd = (size_t)h->days_recorded, md = (size_t)h->desc.max_days, n = (size_t)h->geo.n_ref;
     const size_t rows = (size_t)count * h->geo.N;
     if ((int64_t)(rows * nd * n) > out_capacity) {
         return fail(MIO_OUT_OF_RANGE, "output buffer too small for the daily record");
@@ -963,7 +1135,7 @@ int mio_cuda_get_trajectory(mio_handle* h, int32_t slot0, int32_t count, int32_t
         return fail(MIO_INVALID_VALUE, "graph was created without traj_capacity, or null output");
     }
     CUDA_TRY(cudaSetDevice(h->device));
-    const size_t rows = (size_t)count * h->geo.N, cap = (size_t)h->desc.traj_capacity, n = (size_t)h->geo.n;
+    const size_t rows = (size_t)count * h->geo.N, cap = (size_t)h->desc.traj_capacity, n = (size_t)h->geo.n_ref;
     const size_t off = (size_t)slot0 * h->geo.N;
     CUDA_TRY(cudaMemcpy(npts, h->d_traj_npts + off, sizeof(int) * rows, cudaMemcpyDeviceToHost));
     CUDA_TRY(cudaMemcpy(times, h->d_traj_times + off * cap, sizeof(double) * rows * cap, cudaMemcpyDeviceToHost));
@@ -1044,7 +1216,7 @@ int mio_cuda_ensemble_create(int device, int32_t model, int32_t num_groups, int3
         return fail(MIO_INVALID_VALUE, "null argument");
     }
     *out = nullptr;
-    if (model != MIO_MODEL_OSECIR || num_groups < 1 || num_groups > MIO_MAX_GROUPS || num_nodes < 1 || num_days < 1 ||
+    if ((model != MIO_MODEL_OSECIR && model != MIO_MODEL_OSECIRVVS) || num_groups < 1 || num_groups > MIO_MAX_GROUPS || num_nodes < 1 || num_days < 1 ||
         capacity_runs < 1 || (mode != MIO_ENS_FULL && mode != MIO_ENS_AGE_SUM)) {
         return fail(MIO_INVALID_VALUE, "invalid ensemble record sizes");
     }
@@ -1059,13 +1231,14 @@ int mio_cuda_ensemble_create(int device, int32_t model, int32_t num_groups, int3
     auto* e        = new mio_ensemble();
     e->device      = device;
     e->G           = num_groups;
-    e->C           = NC;
+    e->C           = mio_num_compartments(model);
+    e->lay         = model == MIO_MODEL_OSECIRVVS ? VVS_LAY : 1;
     e->N           = num_nodes;
     e->num_days    = num_days;
     e->mode        = mode;
     e->capacity    = capacity_runs;
-    const int n    = num_groups * NC;
-    const int El   = mode == MIO_ENS_AGE_SUM ? NC : n;
+    const int n    = num_groups * e->C;
+    const int El   = mode == MIO_ENS_AGE_SUM ? e->C : n;
     e->num_columns = (long long)num_nodes * num_days * El + (long long)num_days * n;
     cudaError_t er = dev_alloc(&e->d_data, (size_t)e->num_columns * (size_t)capacity_runs);
     if (er != cudaSuccess) {
@@ -1091,7 +1264,7 @@ int mio_cuda_attach_ensemble(mio_handle* h, mio_ensemble* e, int64_t run_offset)
         return fail(MIO_INVALID_VALUE, "null handle");
     }
     if (e) {
-        if (e->device != h->device || e->G != h->geo.G || e->N != h->geo.N) {
+        if (e->device != h->device || e->G != h->geo.G || e->N != h->geo.N || e->C != h->geo.C_ref) {
             return fail(MIO_INVALID_VALUE, "ensemble record does not match the graph (device, groups or nodes)");
         }
         if (run_offset < 0 || run_offset >= e->capacity) {

@@ -1,8 +1,13 @@
 // device_common.cuh -- shared device helpers of the B200 Graph-ODE backend (sm_100a only).
 //
-// Lane mapping used by every kernel: a warp owns NPW = 32/G consecutive (run, node) pairs; the G lanes of a "group"
-// own one age group each and keep that age group's C compartments in registers. Everything that couples age groups
-// (force of infection, test-and-trace load, ICU occupancy, error norm) is a G-lane exchange via warp shuffles.
+// Lane mapping used by every kernel: a warp owns NPW = 32/W consecutive (run, node) pairs; the W = G*LAY lanes of a
+// "group" own one (immunity layer, age group) each and keep that lane's NC = 10 compartment slots in registers.
+// osecir: LAY = 1, the ten slots are the model's ten compartments. osecirvvs: LAY = 3 (naive, partial immunity,
+// improved immunity), every layer has the same nine compartments S,E,INS,INSC,ISy,ISyC,ISev,ICr,D, stored in the
+// osecir slot order with the Recovered slot unused (recoveries of all layers flow into S of the improved-immunity
+// layer, cpp/models/ode_secirvvs/model.h:40-88); the device state of a node is [LAY][G][NC] and is permuted to and
+// from the reference's age*27+compartment order at the C-ABI. Everything that couples lanes (force of infection,
+// test-and-trace load, ICU occupancy, recoveries, error norm) is an exchange via warp shuffles.
 #pragma once
 
 #include <cfloat>
@@ -12,7 +17,9 @@
 namespace miocu
 {
 
-constexpr int NC      = 10; // osecir compartments, cpp/models/ode_secir/infection_state.h:33-47
+constexpr int NC      = 10; // compartment slots per lane = osecir compartments, ode_secir/infection_state.h:33-47
+constexpr int VVS_NC  = 27; // osecirvvs compartments per age group, ode_secirvvs/infection_state.h:36-67
+constexpr int VVS_LAY = 3;
 constexpr int AGE_REC = 20; // derived per-age record (doubles), see host_params.cpp
 constexpr int PHDR    = 8;  // derived parameter-set header
 
@@ -52,7 +59,9 @@ enum : int
     rMAXRISK,      // MaxRiskOfInfectionFromSymptomatic
     rCRIT,         // CriticalPerSevere
     rT_ISEV,       // TimeInfectedSevere
-    rDPS           // DeathsPerSevere
+    rDPS,          // DeathsPerSevere
+    rREDEXP,       // osecirvvs: ReducExposed{Partial,Improved}Immunity of the lane's layer (1 for naive / osecir)
+    rINFNV         // osecirvvs: InfectiousnessNewVariant
 };
 // header slots
 enum : int
@@ -62,12 +71,38 @@ enum : int
     hTNT_MAX_RISK,
     hNONDETECTION,
     hSTART_DETECTION,
-    hEND_DETECTION
+    hEND_DETECTION,
+    hTNT_MAX_RISK_NOSYMP, // osecirvvs: TestAndTraceCapacityMaxRiskNoSymptoms (slot 2 holds ...MaxRiskSymptoms)
+    hSTART_DAY_NEW_VARIANT
 };
+
+// osecirvvs: reference compartment index of (layer, slot), -1 for the unused Recovered slot
+// (ode_secirvvs/infection_state.h:36-67)
+__host__ __device__ inline int vvs_ref_comp(int layer, int slot)
+{
+    constexpr int tab[VVS_LAY][NC] = {{0, 2, 5, 8, 11, 14, 17, 20, -1, 24},
+                                      {1, 3, 6, 9, 12, 15, 18, 21, -1, 25},
+                                      {23, 4, 7, 10, 13, 16, 19, 22, -1, 26}};
+    return tab[layer][slot];
+}
+// device index (inside one node's [LAY][G][NC] block) of reference element (age, comp); LAY = 1: identity
+__host__ __device__ inline int dev_index_of_ref(int lay, int G, int age, int comp)
+{
+    if (lay == 1) {
+        return age * NC + comp;
+    }
+    constexpr int layer_of[VVS_NC] = {0, 1, 0, 1, 2, 0, 1, 2, 0, 1, 2, 0, 1, 2, 0, 1, 2, 0, 1, 2, 0, 1, 2, 2, 0, 1, 2};
+    constexpr int slot_of[VVS_NC]  = {0, 0, 1, 1, 1, 2, 2, 2, 3, 3, 3, 4, 4, 4, 5, 5, 5, 6, 6, 6, 7, 7, 7, 0, 9, 9, 9};
+    return (layer_of[comp] * G + age) * NC + slot_of[comp];
+}
 
 // problem geometry shared by all kernels (passed by value)
 struct Geometry {
-    int G, N, E, n;          // groups, nodes, edges, n = G*NC
+    int G, N, E, n;          // age groups, nodes, edges, n = W*NC doubles of one node's device state
+    int LAY, W;              // immunity layers (1 osecir, 3 osecirvvs), lanes per node W = G*LAY
+    int C_ref, n_ref;        // the reference's compartments per age group and state size G*C_ref
+    int sim_kind;            // MIO_SIM_BASE / MIO_SIM_MODEL (osecirvvs: vaccination, variant, ADL mobility hooks)
+    int vacc_days;           // osecirvvs: length of the cumulative vaccination arrays
     int num_psets, num_ctables;
     int ct_max_loc, ct_max_pts, mob_max_pts;
     int pset_stride;         // doubles per derived parameter set
@@ -85,6 +120,8 @@ struct DeviceState {
     double* t_node;            // [R][N] node-local simulation time (result.get_last_time())
     double* dt_node;           // [R][N] SimulationBase::m_dt
     int* counters;             // [R][N][4]
+    const double* vacc_partial; // [N][G][vacc_days] cumulative DailyPartialVaccinations (osecirvvs), run-invariant
+    const double* vacc_full;    // [N][G][vacc_days] cumulative DailyFullVaccinations
 };
 
 __device__ __forceinline__ double shfl(double v, int src)
@@ -92,51 +129,60 @@ __device__ __forceinline__ double shfl(double v, int src)
     return __shfl_sync(0xffffffffu, v, src);
 }
 
-// G-lane group helpers. Lanes >= NPW*G form no group and idle.
-template <int G>
+// W-lane group helpers, W = G*LAY; group lane gl = layer*G + age. Lanes >= NPW*W form no group and idle.
+template <int G, int LAY = 1>
 struct Group {
-    static constexpr int NPW = 32 / G;
-    int lane, gl, gbase;
+    static constexpr int W   = G * LAY;
+    static constexpr int NPW = 32 / W;
+    static_assert(W <= 32, "a node must fit into one warp");
+    int lane, gl, gbase, age, layer;
     __device__ __forceinline__ Group()
     {
         lane  = threadIdx.x & 31;
-        gl    = lane % G;
+        gl    = lane % W;
         gbase = lane - gl;
-        if (lane >= NPW * G) { // spare lanes talk to themselves
+        if (lane >= NPW * W) { // spare lanes talk to themselves
             gl    = 0;
             gbase = lane;
         }
+        layer = LAY == 1 ? 0 : gl / G;
+        age   = LAY == 1 ? gl : gl - layer * G;
     }
     __device__ __forceinline__ bool spare() const
     {
-        return lane >= NPW * G;
+        return lane >= NPW * W;
     }
-    // value of group lane j
+    // value of group lane l (0 <= l < W)
+    __device__ __forceinline__ double get_lane(double v, int l) const
+    {
+        return shfl(v, spare() ? lane : gbase + l);
+    }
+    // value of the lane of age group j in this lane's own layer
     __device__ __forceinline__ double get(double v, int j) const
     {
-        int src = spare() ? lane : gbase + j;
-        return shfl(v, src);
+        return shfl(v, spare() ? lane : gbase + layer * G + j);
     }
-    // all-reduce sum over the group (pairwise tree where G allows, otherwise sequential gather)
-    __device__ __forceinline__ double sum(double v) const
+    // all-reduce sum over the G age lanes of this lane's layer (pairwise tree where G allows)
+    __device__ __forceinline__ double sum_ages(double v) const
     {
+        const int abase = gbase + layer * G;
         if constexpr (G == 1) {
             return v;
         }
         else if constexpr (G == 2 || G == 4 || G == 8) {
 #pragma unroll
             for (int o = 1; o < G; o <<= 1) {
-                v += shfl(v, spare() ? lane : (gbase + (gl ^ o)));
+                v += shfl(v, spare() ? lane : (abase + (age ^ o)));
             }
             return v;
         }
         else if constexpr (G == 6) {
-            // pairs (gbase is even for G=6), then the two other pair sums
-            v += shfl(v, spare() ? lane : (lane ^ 1));
-            int s1   = gl + 2 >= G ? gl + 2 - G : gl + 2;
-            int s2   = gl + 4 >= G ? gl + 4 - G : gl + 4;
-            double a = shfl(v, spare() ? lane : gbase + s1);
-            double b = shfl(v, spare() ? lane : gbase + s2);
+            // pairs, then the two other pair sums
+            v += shfl(v, spare() ? lane : (abase + (age ^ 1)));
+            int s1   = age + 2 >= G ? age + 2 - G : age + 2;
+            int s2   = age + 4 >= G ? age + 4 - G : age + 4;
+            double a = shfl(v, spare() ? lane : abase + s1);
+            double b = shfl(v, spare() ? lane : abase + s2);
             return v + a + b;
         }
         else {
@@ -148,17 +194,51 @@ struct Group {
             return s;
         }
     }
+    // all-reduce sum over the LAY layer lanes of this lane's age group
+    __device__ __forceinline__ double sum_layers(double v) const
+    {
+        if constexpr (LAY == 1) {
+            return v;
+        }
+        else {
+            double s = v;
+#pragma unroll
+            for (int k = 1; k < LAY; ++k) {
+                int l = gl + k * G;
+                l     = l >= W ? l - W : l;
+                s += shfl(v, spare() ? lane : gbase + l);
+            }
+            return s;
+        }
+    }
+    // all-reduce sum over the whole group
+    __device__ __forceinline__ double sum(double v) const
+    {
+        return sum_layers(sum_ages(v));
+    }
     __device__ __forceinline__ double max(double v) const
     {
-        if constexpr (G == 1) {
+        if constexpr (W == 1) {
             return v;
         }
         else {
             double m = v;
+            if constexpr (G > 1) {
+                const int abase = gbase + layer * G;
 #pragma unroll
-            for (int j = 1; j < G; ++j) {
-                int s = gl + j >= G ? gl + j - G : gl + j;
-                m     = fmax(m, shfl(v, spare() ? lane : gbase + s));
+                for (int j = 1; j < G; ++j) {
+                    int s = age + j >= G ? age + j - G : age + j;
+                    m     = fmax(m, shfl(v, spare() ? lane : abase + s));
+                }
+            }
+            if constexpr (LAY > 1) {
+                const double mm = m;
+#pragma unroll
+                for (int k = 1; k < LAY; ++k) {
+                    int l = gl + k * G;
+                    l     = l >= W ? l - W : l;
+                    m     = fmax(m, shfl(mm, spare() ? lane : gbase + l));
+                }
             }
             return m;
         }
@@ -166,7 +246,7 @@ struct Group {
     __device__ __forceinline__ bool any(bool p) const
     {
         unsigned b    = __ballot_sync(0xffffffffu, p);
-        unsigned mask = spare() ? (1u << lane) : (((1u << G) - 1u) << gbase);
+        unsigned mask = spare() ? (1u << lane) : (((1u << W) - 1u) << gbase);
         return (b & mask) != 0u;
     }
 };
@@ -323,7 +403,7 @@ __device__ __forceinline__ void stage_run_block(double* smem_dst, const double* 
 // osecir per-lane coefficients kept in registers
 struct LaneCoef {
     double rE_INS, rINS_ISy, rINS_R, rISy_ISev, rISy_R, rISev_ICr0, rISev_R, rISev_D0, rICr_D, rICr_R, rTNT, rP,
-        rREL, rRISK, rMAXRISK;
+        rREL, rRISK, rMAXRISK, rREDEXP;
     __device__ __forceinline__ void load(const double* a)
     {
         rE_INS     = a[miocu::rE_INS];
@@ -341,6 +421,7 @@ struct LaneCoef {
         rREL       = a[miocu::rREL];
         rRISK      = a[miocu::rRISK];
         rMAXRISK   = a[miocu::rMAXRISK];
+        rREDEXP    = a[miocu::rREDEXP];
     }
 };
 
@@ -361,5 +442,155 @@ __device__ __forceinline__ void flows_to_dydt(double fSE, double fE_INS, double 
     k[cR]    = ((((fINS_R + fINSC_R) + fISy_R) + fISyC_R) + fISev_R) + fICr_R;
     k[cD]    = fISev_D + fICr_D;
 }
+
+// osecirvvs: the recoveries of every layer flow into SusceptibleImprovedImmunity (ode_secirvvs/model.h:40-88), i.e.
+// into the S slot of the layer-2 lane of the same age group; the Recovered slot itself stays empty.
+template <int G, int LAY>
+__device__ __forceinline__ void route_recoveries(const Group<G, LAY>& g, double (&k)[NC])
+{
+    if constexpr (LAY > 1) {
+        const double rec = g.sum_layers(k[cR]);
+        k[cR]            = 0.0;
+        if (g.layer == LAY - 1) {
+            k[cS] += rec;
+        }
+    }
+}
+
+// ---------------------------------------------------------------------------------------------------------------
+// Right-hand side of one node as seen by one lane: cpp/models/ode_secir/model.h:82-214 (LAY = 1),
+// cpp/models/ode_secirvvs/model.h:111-520 (LAY = 3) + cpp/memilio/compartments/flow_model.h:112-144.
+template <int G, int LAY>
+struct NodeRhs {
+    // LAY == 1: the whole row i of C(t); LAY > 1: the layer lanes of an age group split the row, lane (layer, i) keeps
+    // the entries j = q*LAY + layer
+    static constexpr int Q = LAY == 1 ? G : (G + LAY - 1) / LAY;
+    LaneCoef c;
+    const double* age_rec; // shared memory, for the rarely used slots
+    const double* ctable;  // shared memory
+    double start_day, seasonality;
+    double p_eff; // TransmissionProbabilityOnContact in effect (osecirvvs apply_variant changes it during advance)
+    double tnt_cap, tnt_cap_hi, tnt_cap_hi_ns, icu_lo, icu_cap;
+    double crow[Q];
+    double valid_lo, valid_hi;
+    int ct_max_loc, ct_max_pts;
+
+    __device__ __forceinline__ double season_at(double ts) const
+    {
+        // model.h:128-130
+        if (seasonality == 0.0) {
+            return 1.0;
+        }
+        return 1 + seasonality * sin(3.141592653589793238462643383279502884 * ((start_day + ts) / 182.5 + 0.5));
+    }
+
+    __device__ __forceinline__ void contact_row(const Group<G, LAY>& g, double ts)
+    {
+        if (!(ts >= valid_lo && ts <= valid_hi)) {
+            if constexpr (LAY == 1) {
+                contact_row_eval<G>(ctable, ct_max_loc, ct_max_pts, g.age, ts, crow, valid_lo, valid_hi);
+            }
+            else {
+                double row[G];
+                contact_row_eval<G>(ctable, ct_max_loc, ct_max_pts, g.age, ts, row, valid_lo, valid_hi);
+#pragma unroll
+                for (int q = 0; q < Q; ++q) {
+                    const int j = q * LAY + g.layer;
+                    crow[q]     = j < G ? row[j] : 0.0;
+                }
+            }
+        }
+    }
+
+    // sum_j C(t)(i,j) * divN_j * (infectious weight of age group j) with pop = y:
+    // osecir  model.h:120-145 (risk and relative transmission are those of the infectious group j),
+    // osecirvvs model.h:229-260 (both risk factors are those of the susceptible group i)
+    __device__ __forceinline__ double infection_pressure(const Group<G, LAY>& g, const double (&y)[NC], double tnt) const
+    {
+        if constexpr (LAY == 1) {
+            const double Nj   = y[cS] + y[cE] + y[cINS] + y[cISy] + y[cISev] + y[cICr] + y[cR];
+            const double divN = (Nj < 1e-12) ? 0.0 : 1.0 / Nj;
+            const double risk = smoother_cosine(tnt, tnt_cap, tnt_cap_hi, c.rRISK, c.rMAXRISK);
+            const double w    = divN * (c.rREL * y[cINS] + risk * y[cISy]);
+            double lam        = 0.0;
+#pragma unroll
+            for (int j = 0; j < G; ++j) {
+                lam += crow[j] * g.get(w, j);
+            }
+            return lam;
+        }
+        else {
+            // N_j counts every living compartment of the three layers, the *Confirmed ones included (model.h:244-248)
+            const double npart =
+                y[cS] + y[cE] + y[cINS] + y[cISy] + y[cISev] + y[cICr] + y[cINSC] + y[cISyC];
+            const double Nj    = g.sum_layers(npart);
+            const double INSj  = g.sum_layers(y[cINS]);
+            const double ISyj  = g.sum_layers(y[cISy]);
+            const double divN  = (Nj < 1e-12) ? 0.0 : 1.0 / Nj;
+            const double w_ins = divN * INSj, w_isy = divN * ISyj;
+            const double r_sy  = smoother_cosine(tnt, tnt_cap, tnt_cap_hi, c.rRISK, c.rMAXRISK);
+            const double r_ns  = smoother_cosine(tnt, tnt_cap, tnt_cap_hi_ns, c.rREL, 1.0);
+            double part        = 0.0;
+#pragma unroll
+            for (int q = 0; q < Q; ++q) {
+                const int j  = q * LAY + g.layer;
+                const int jj = j < G ? j : 0;
+                part += crow[q] * (r_ns * g.get(w_ins, jj) + r_sy * g.get(w_isy, jj));
+            }
+            return g.sum_layers(part);
+        }
+    }
+
+    // test_and_trace_required and icu_occupancy of pop = y (osecir model.h:90-97, osecirvvs model.h:199-206)
+    __device__ __forceinline__ void node_loads(const Group<G, LAY>& g, const double (&y)[NC], double& tnt,
+                                               double& icu) const
+    {
+        if constexpr (LAY == 1) {
+            tnt = g.sum(c.rTNT * y[cINS]);
+        }
+        else {
+            tnt = g.sum(c.rTNT * (y[cINS] + y[cINSC]));
+        }
+        icu = g.sum(y[cICr]);
+    }
+
+    // ICU capacity shortage (model.h:148-153): InfectedSevere -> InfectedCritical / Dead rates
+    __device__ __forceinline__ void icu_rates(double icu, double& rISev_ICr, double& rISev_D) const
+    {
+        rISev_ICr = c.rISev_ICr0;
+        rISev_D   = c.rISev_D0;
+        if (icu > icu_lo) {
+            const double crit = age_rec[rCRIT];
+            const double adj  = smoother_cosine(icu, icu_lo, icu_cap, crit, 0.0);
+            const double dadj = crit - adj;
+            rISev_ICr         = adj / age_rec[rT_ISEV];
+            rISev_D           = (age_rec[rDPS] + dadj) / age_rec[rT_ISEV];
+        }
+    }
+
+    // dydt = f(y, ts) with pop == y; `season` is the seasonality factor at ts
+    __device__ __forceinline__ void eval(const Group<G, LAY>& g, const double (&y)[NC], double ts, double season,
+                                         double (&k)[NC])
+    {
+        contact_row(g, ts);
+        double tnt, icu;
+        node_loads(g, y, tnt, icu);
+        const double lam = infection_pressure(g, y, tnt);
+        double fSE;
+        if constexpr (LAY == 1) {
+            fSE = y[cS] * (season * p_eff) * lam;
+        }
+        else {
+            fSE = (y[cS] * c.rREDEXP) * ((season * p_eff) * lam);
+        }
+        double rISev_ICr, rISev_D;
+        icu_rates(icu, rISev_ICr, rISev_D);
+        flows_to_dydt(fSE, c.rE_INS * y[cE], c.rINS_ISy * y[cINS], c.rINS_R * y[cINS], c.rINS_ISy * y[cINSC],
+                      c.rINS_R * y[cINSC], c.rISy_ISev * y[cISy], c.rISy_R * y[cISy], c.rISy_ISev * y[cISyC],
+                      c.rISy_R * y[cISyC], rISev_ICr * y[cISev], c.rISev_R * y[cISev], rISev_D * y[cISev],
+                      c.rICr_D * y[cICr], c.rICr_R * y[cICr], k);
+        route_recoveries(g, k);
+    }
+};
 
 } // namespace miocu

@@ -20,11 +20,11 @@
 namespace miocu
 {
 
-constexpr int AUX = 4; // per (run,node,age): season*p_i*lambda_i, rISev_ICr, rISev_D, pad
+constexpr int AUX = 4; // per (run,node,lane): season*p_i*lambda_i (*ReducExposed), rISev_ICr, rISev_D, pad
 
-template <int G>
+template <int G, int LAY>
 struct EdgeLane {
-    Group<G> g;
+    Group<G, LAY> g;
     int run, node;
     bool valid;
     size_t rn;
@@ -85,32 +85,35 @@ __device__ __forceinline__ bool mobile_at_departure(const double* coeff_e, const
 
 // y1 = m + dt * f(pop = v0(dest), y = m): explicit Euler step of the destination's model on the traveler vector.
 // slam = season*p_i*lambda_i(dest); the linear rates are the destination's.
-__device__ __forceinline__ void euler_return(const LaneCoef& c, double slam, double rISev_ICr, double rISev_D,
-                                             double dt, double (&m)[NC])
+template <int G, int LAY>
+__device__ __forceinline__ void euler_return(const Group<G, LAY>& g, const LaneCoef& c, double slam, double rISev_ICr,
+                                             double rISev_D, double dt, double (&m)[NC])
 {
     double k[NC];
     flows_to_dydt(m[cS] * slam, c.rE_INS * m[cE], c.rINS_ISy * m[cINS], c.rINS_R * m[cINS], c.rINS_ISy * m[cINSC],
                   c.rINS_R * m[cINSC], c.rISy_ISev * m[cISy], c.rISy_R * m[cISy], c.rISy_ISev * m[cISyC],
                   c.rISy_R * m[cISyC], rISev_ICr * m[cISev], c.rISev_R * m[cISev], rISev_D * m[cISev],
                   c.rICr_D * m[cICr], c.rICr_R * m[cICr], k);
+    route_recoveries<G, LAY>(g, k);
 #pragma unroll
     for (int i = 0; i < NC; ++i) {
         m[i] = m[i] + dt * k[i];
     }
 }
 
-template <int G>
-__device__ __forceinline__ void edge_lane_setup(const Geometry& geo, const int* order, int num_runs, EdgeLane<G>& L,
-                                                bool& cta_active)
+template <int G, int LAY>
+__device__ __forceinline__ void edge_lane_setup(const Geometry& geo, const int* order, int num_runs,
+                                                EdgeLane<G, LAY>& L, bool& cta_active)
 {
-    constexpr int NPW   = 32 / G;
+    constexpr int W     = G * LAY;
+    constexpr int NPW   = 32 / W;
     constexpr int WARPS = EDGE_THREADS / 32;
     const int chunks    = (geo.N + NPW * WARPS - 1) / (NPW * WARPS);
     L.run               = blockIdx.x / chunks;
     const int chunk     = blockIdx.x - L.run * chunks;
     cta_active          = L.run < num_runs;
     const int warp      = threadIdx.x >> 5;
-    const int item      = (chunk * WARPS + warp) * NPW + L.g.lane / G;
+    const int item      = (chunk * WARPS + warp) * NPW + L.g.lane / W;
     L.valid             = cta_active && !L.g.spare() && item < geo.N;
     L.node              = L.valid ? order[item] : 0;
     L.rn                = (size_t)(cta_active ? L.run : 0) * geo.N + L.node;
@@ -126,7 +129,7 @@ __device__ __forceinline__ int warp_max(int v)
 }
 
 // V += coeff_e * u_src over the incoming edges [beg, beg+cnt) of this lane's node (SpMV row, edge order)
-template <bool FACT, int G>
+template <bool FACT, int W>
 __device__ __forceinline__ void gather_visitors(const EdgeArgs& a, const Geometry& geo, int run, int gl, int beg,
                                                 int cnt, int max_cnt, double (&V)[NC])
 {
@@ -137,7 +140,7 @@ __device__ __forceinline__ void gather_visitors(const EdgeArgs& a, const Geometr
         double us[NC];
         load10(a.u + ((size_t)run * geo.N + src) * geo.n + gl * NC, us);
         if (FACT) {
-            const double w = act ? a.csr.w_in[(size_t)pos * G + gl] : 0.0;
+            const double w = act ? a.csr.w_in[(size_t)pos * W + gl] : 0.0;
 #pragma unroll
             for (int i = 0; i < NC; ++i) {
                 V[i] += w * us[i];
@@ -164,26 +167,30 @@ __device__ __forceinline__ void gather_visitors(const EdgeArgs& a, const Geometr
 // Then the return coefficients of k as a destination (lambda_i, ICU adjusted rates) from v0 = y_out at time t.
 // Everything of the departure after the visitor gather: test_commuters bookkeeping, the in-place node update in the
 // reference's block order, and the return coefficients of the node as a destination.
-template <int G>
-__device__ __forceinline__ void depart_node_update(const EdgeArgs& a, const Geometry& geo, const EdgeLane<G>& L,
+template <int G, int LAY>
+__device__ __forceinline__ void depart_node_update(const EdgeArgs& a, const Geometry& geo, const EdgeLane<G, LAY>& L,
                                                    const double* smem, const double (&V1)[NC], const double (&V3)[NC])
 {
-    const Group<G>& g  = L.g;
-    const int ps_own   = a.st.node_pset ? a.st.node_pset[L.node] : 0;
-    const double* pset = smem + ps_own * geo.pset_stride;
+    constexpr int W        = G * LAY;
+    const Group<G, LAY>& g = L.g;
+    const int ps_own       = a.st.node_pset ? a.st.node_pset[L.node] : 0;
+    const double* pset     = smem + ps_own * geo.pset_stride;
+    // a plain mio::Simulation<osecirvvs::Model> node has no test_commuters hook (instant.h:537-541)
+    const bool hooks = !(LAY == VVS_LAY && geo.sim_kind != 1);
     double y[NC], uk[NC], so[NC];
     load10(a.y_in + L.rn * geo.n + g.gl * NC, y);
     load10(a.u + L.rn * geo.n + g.gl * NC, uk);
     load10(a.csr.s_out + (size_t)L.node * geo.n + g.gl * NC, so);
-    // test_commuters (ode_secir/model.h:717-742): detected commuters stay, in the *Confirmed compartments
-    const double nd = nondetection_at(pset, a.t);
+    // test_commuters (ode_secir/model.h:717-742, ode_secirvvs/model.h:887-940): detected commuters stay, in the
+    // *Confirmed compartments (of their own immunity layer)
+    const double nd = hooks ? nondetection_at(pset, a.t) : 1.0;
     if (nd != 1.0) {
         // u holds the tested (travelling) population; the untested one is rebuilt from the snapshot (= y here)
         const double* mob = geo.mob_max_pts > 0 ? smem + geo.mob_off : nullptr;
         double damp[NC];
         mobility_damping_eval((mob != nullptr && mob[0] > 0.0) ? mob : nullptr, geo.mob_max_pts, geo.n, g.gl, a.t,
                               damp);
-        const double fk       = a.fac[L.rn * G + g.gl];
+        const double fk       = a.fac[L.rn * W + g.gl];
         const double lost_ins = so[cINS] * (y[cINS] * (1.0 - damp[cINS]) * a.csr.umask[g.gl * NC + cINS]);
         const double lost_isy = so[cISy] * (y[cISy] * (1.0 - damp[cISy]) * fk * a.csr.umask[g.gl * NC + cISy]);
         y[cINS] -= lost_ins * (1 - nd);
@@ -200,65 +207,58 @@ __device__ __forceinline__ void depart_node_update(const EdgeArgs& a, const Geom
         store10(a.vis + (L.rn * 2 + 0) * geo.n + g.gl * NC, V1);
         store10(a.vis + (L.rn * 2 + 1) * geo.n + g.gl * NC, V3);
     }
-    // return coefficients of this node as destination: get_flows with pop = v0 (ode_secir/model.h:90-153)
+    // return coefficients of this node as destination: get_flows with pop = v0 (ode_secir/model.h:90-153,
+    // ode_secirvvs/model.h:199-264)
     {
-        LaneCoef c;
-        const double* age_rec = pset + PHDR + g.gl * AGE_REC;
-        c.load(age_rec);
-        const int ci         = a.st.node_ctable ? a.st.node_ctable[L.node] : 0;
-        const double icu_cap = a.st.node_local[L.rn * 2 + 0];
-        const double tnt_cap = a.st.node_local[L.rn * 2 + 1];
-        double crow[G], lo, hi;
-        contact_row_eval<G>(smem + geo.ct_off + ci * geo.ctable_stride, geo.ct_max_loc, geo.ct_max_pts, g.gl, a.t,
-                            crow, lo, hi);
-        const double seasonality = pset[hSEASONALITY];
-        const double season =
-            seasonality == 0.0
-                ? 1.0
-                : 1 + seasonality *
-                          sin(3.141592653589793238462643383279502884 * ((pset[hSTART_DAY] + a.t) / 182.5 + 0.5));
-        const double tnt  = g.sum(c.rTNT * y[cINS]);
-        const double icu  = g.sum(y[cICr]);
-        const double Nj   = y[cS] + y[cE] + y[cINS] + y[cISy] + y[cISev] + y[cICr] + y[cR];
-        const double divN = (Nj < 1e-12) ? 0.0 : 1.0 / Nj;
-        const double risk = smoother_cosine(tnt, tnt_cap, tnt_cap * pset[hTNT_MAX_RISK], c.rRISK, c.rMAXRISK);
-        const double w    = divN * (c.rREL * y[cINS] + risk * y[cISy]);
-        double lam        = 0.0;
-#pragma unroll
-        for (int j = 0; j < G; ++j) {
-            lam += crow[j] * g.get(w, j);
-        }
-        double rISev_ICr = c.rISev_ICr0, rISev_D = c.rISev_D0;
-        const double icu_lo = 0.90 * icu_cap;
-        if (icu > icu_lo) {
-            const double crit = age_rec[rCRIT];
-            const double adj  = smoother_cosine(icu, icu_lo, icu_cap, crit, 0.0);
-            rISev_ICr         = adj / age_rec[rT_ISEV];
-            rISev_D           = (age_rec[rDPS] + (crit - adj)) / age_rec[rT_ISEV];
-        }
+        NodeRhs<G, LAY> rhs;
+        rhs.age_rec = pset + PHDR + g.gl * AGE_REC;
+        rhs.c.load(rhs.age_rec);
+        rhs.p_eff         = rhs.c.rP;
+        const int ci      = a.st.node_ctable ? a.st.node_ctable[L.node] : 0;
+        rhs.ctable        = smem + geo.ct_off + ci * geo.ctable_stride;
+        rhs.start_day     = pset[hSTART_DAY];
+        rhs.seasonality   = pset[hSEASONALITY];
+        rhs.icu_cap       = a.st.node_local[L.rn * 2 + 0];
+        rhs.tnt_cap       = a.st.node_local[L.rn * 2 + 1];
+        rhs.tnt_cap_hi    = rhs.tnt_cap * pset[hTNT_MAX_RISK];
+        rhs.tnt_cap_hi_ns = rhs.tnt_cap * pset[hTNT_MAX_RISK_NOSYMP];
+        rhs.icu_lo        = 0.90 * rhs.icu_cap;
+        rhs.valid_lo      = DBL_MAX;
+        rhs.valid_hi      = -DBL_MAX;
+        rhs.ct_max_loc    = geo.ct_max_loc;
+        rhs.ct_max_pts    = geo.ct_max_pts;
+        rhs.contact_row(g, a.t);
+        const double season = rhs.season_at(a.t);
+        double tnt, icu;
+        rhs.node_loads(g, y, tnt, icu);
+        const double lam = rhs.infection_pressure(g, y, tnt);
+        double rISev_ICr, rISev_D;
+        rhs.icu_rates(icu, rISev_ICr, rISev_D);
+        const double slam = LAY == 1 ? (season * rhs.c.rP) * lam : rhs.c.rREDEXP * ((season * rhs.c.rP) * lam);
         if (L.valid) {
-            double* ax = a.aux + (L.rn * G + g.gl) * AUX;
-            reinterpret_cast<double2*>(ax)[0] = make_double2((season * c.rP) * lam, rISev_ICr);
+            double* ax = a.aux + (L.rn * W + g.gl) * AUX;
+            reinterpret_cast<double2*>(ax)[0] = make_double2(slam, rISev_ICr);
             reinterpret_cast<double2*>(ax)[1] = make_double2(rISev_D, 0.0);
         }
     }
 }
 
-template <int G, bool FACT>
+template <int G, int LAY, bool FACT>
 __global__ void __launch_bounds__(EDGE_THREADS, MIO_DEPART_MINBLOCKS) depart_kernel(EdgeArgs a)
 {
     extern __shared__ __align__(16) double smem[];
     __shared__ __align__(8) uint64_t mbar;
+    constexpr int W     = G * LAY;
     const Geometry& geo = a.geo;
-    EdgeLane<G> L;
+    EdgeLane<G, LAY> L;
     bool cta_active;
-    edge_lane_setup<G>(geo, a.csr.order_in, a.num_runs, L, cta_active);
+    edge_lane_setup<G, LAY>(geo, a.csr.order_in, a.num_runs, L, cta_active);
     if (!cta_active) {
         return;
     }
     stage_run_block(smem, a.st.run_block + (size_t)L.run * geo.block_stride, geo.block_stride * 8, &mbar);
-    const Group<G>& g = L.g;
-    const int beg     = L.valid ? a.csr.in_ptr[L.node] : 0;
+    const Group<G, LAY>& g = L.g;
+    const int beg          = L.valid ? a.csr.in_ptr[L.node] : 0;
     const int cnt     = L.valid ? a.csr.in_ptr[L.node + 1] - beg : 0;
     const int split   = L.valid ? a.csr.in_split[L.node] : 0;
     double V1[NC], V3[NC];
@@ -267,9 +267,9 @@ __global__ void __launch_bounds__(EDGE_THREADS, MIO_DEPART_MINBLOCKS) depart_ker
         V1[i] = 0.0;
         V3[i] = 0.0;
     }
-    gather_visitors<FACT, G>(a, geo, L.run, g.gl, beg, split, warp_max(split), V1);
-    gather_visitors<FACT, G>(a, geo, L.run, g.gl, beg + split, cnt - split, warp_max(cnt - split), V3);
-    depart_node_update<G>(a, geo, L, smem, V1, V3);
+    gather_visitors<FACT, W>(a, geo, L.run, g.gl, beg, split, warp_max(split), V1);
+    gather_visitors<FACT, W>(a, geo, L.run, g.gl, beg + split, cnt - split, warp_max(cnt - split), V3);
+    depart_node_update<G, LAY>(a, geo, L, smem, V1, V3);
 }
 
 // ---------------------------------------------------------------------------------------------------------------
@@ -279,13 +279,14 @@ __global__ void __launch_bounds__(EDGE_THREADS, MIO_DEPART_MINBLOCKS) depart_ker
 // 400-county graph) into shared memory once, and every incoming edge is then a shared-memory read.
 constexpr int DEPART_SMEM_THREADS = 256;
 
-template <int G, int M>
+template <int G, int LAY, int M>
 __global__ void __launch_bounds__(DEPART_SMEM_THREADS, 2) depart_smem_kernel(EdgeArgs a)
 {
     extern __shared__ __align__(16) double smem[];
     __shared__ __align__(8) uint64_t mbar;
     const Geometry& geo = a.geo;
-    constexpr int NPW   = 32 / G;
+    constexpr int W     = G * LAY;
+    constexpr int NPW   = 32 / W;
     constexpr int WARPS = DEPART_SMEM_THREADS / 32;
     const int run       = blockIdx.x;
     if (run >= a.num_runs) {
@@ -296,7 +297,7 @@ __global__ void __launch_bounds__(DEPART_SMEM_THREADS, 2) depart_smem_kernel(Edg
     {
         // one (node, age) record of 10 doubles per thread and iteration: five 16-byte loads in flight per thread
         const double2* ug = reinterpret_cast<const double2*>(a.u + (size_t)run * geo.N * geo.n);
-        const int total   = geo.N * G;
+        const int total   = geo.N * W;
         for (int rec = threadIdx.x; rec < total; rec += DEPART_SMEM_THREADS) {
             double v[NC];
 #pragma unroll
@@ -318,12 +319,12 @@ __global__ void __launch_bounds__(DEPART_SMEM_THREADS, 2) depart_smem_kernel(Edg
         }
     }
     __syncthreads();
-    EdgeLane<G> L;
+    EdgeLane<G, LAY> L;
     L.run            = run;
     const int warp   = threadIdx.x >> 5;
     const int passes = (geo.N + NPW * WARPS - 1) / (NPW * WARPS);
     for (int pass = 0; pass < passes; ++pass) {
-        const int item = (pass * WARPS + warp) * NPW + L.g.lane / G;
+        const int item = (pass * WARPS + warp) * NPW + L.g.lane / W;
         L.valid        = !L.g.spare() && item < geo.N;
         L.node         = L.valid ? a.csr.order_in[item] : 0;
         L.rn           = (size_t)run * geo.N + L.node;
@@ -349,11 +350,11 @@ __global__ void __launch_bounds__(DEPART_SMEM_THREADS, 2) depart_smem_kernel(Edg
                 const bool act = it0 + j < cnt;
                 const int pos  = beg + (act ? it0 + j : 0);
                 src[j]         = __ldg(a.csr.in_src + pos);
-                w[j]           = act ? __ldg(a.csr.w_in + (size_t)pos * G + gl) : 0.0;
+                w[j]           = act ? __ldg(a.csr.w_in + (size_t)pos * W + gl) : 0.0;
             }
 #pragma unroll
             for (int j = 0; j < BATCH; ++j) {
-                const double* p  = us + (src[j] * G + gl) * M;
+                const double* p  = us + (src[j] * W + gl) * M;
                 const bool first = it0 + j < split;
                 const double w1 = first ? w[j] : 0.0, w3 = first ? 0.0 : w[j];
 #pragma unroll
@@ -381,7 +382,7 @@ __global__ void __launch_bounds__(DEPART_SMEM_THREADS, 2) depart_smem_kernel(Edg
                 }
             }
         }
-        depart_node_update<G>(a, geo, L, smem, V1, V3);
+        depart_node_update<G, LAY>(a, geo, L, smem, V1, V3);
     }
 }
 
@@ -396,28 +397,29 @@ __global__ void __launch_bounds__(DEPART_SMEM_THREADS, 2) depart_smem_kernel(Edg
 // the running value decreases monotonically along the incoming edges (returning visitor vectors are non-negative as
 // long as dt*rate <= 1, checked), so it is enough to test it after the first and after the last block. Flagged runs
 // are replayed literally by return_exact_kernel.
-template <int G, bool FACT>
+template <int G, int LAY, bool FACT>
 __global__ void __launch_bounds__(EDGE_THREADS, MIO_RETURN_MINBLOCKS < 2 ? 2 : MIO_RETURN_MINBLOCKS)
     return_kernel(EdgeArgs a)
 {
     extern __shared__ __align__(16) double smem[];
     __shared__ __align__(8) uint64_t mbar;
+    constexpr int W     = G * LAY;
     const Geometry& geo = a.geo;
-    EdgeLane<G> L;
+    EdgeLane<G, LAY> L;
     bool cta_active;
-    edge_lane_setup<G>(geo, a.csr.order_out, a.num_runs, L, cta_active);
+    edge_lane_setup<G, LAY>(geo, a.csr.order_out, a.num_runs, L, cta_active);
     if (!cta_active) {
         return;
     }
     stage_run_block(smem, a.st.run_block + (size_t)L.run * geo.block_stride, geo.block_stride * 8, &mbar);
-    const Group<G>& g  = L.g;
-    const int ps_own   = a.st.node_pset ? a.st.node_pset[L.node] : 0;
-    const double* pset = smem + ps_own * geo.pset_stride;
+    const Group<G, LAY>& g = L.g;
+    const int ps_own       = a.st.node_pset ? a.st.node_pset[L.node] : 0;
+    const double* pset     = smem + ps_own * geo.pset_stride;
     LaneCoef c_own;
     c_own.load(pset + PHDR + g.gl * AGE_REC);
     double slam_own, ricr_own, rd_own;
     {
-        const double2* ax = reinterpret_cast<const double2*>(a.aux + (L.rn * G + g.gl) * AUX);
+        const double2* ax = reinterpret_cast<const double2*>(a.aux + (L.rn * W + g.gl) * AUX);
         double2 a0 = ax[0], a1 = ax[1];
         slam_own = a0.x;
         ricr_own = a0.y;
@@ -435,7 +437,7 @@ __global__ void __launch_bounds__(EDGE_THREADS, MIO_RETURN_MINBLOCKS < 2 ? 2 : M
     }
     // visitors from sources < k
     load10(a.vis + (L.rn * 2 + 0) * geo.n + g.gl * NC, V);
-    euler_return(c_own, slam_own, ricr_own, rd_own, a.dt, V);
+    euler_return<G, LAY>(g, c_own, slam_own, ricr_own, rd_own, a.dt, V);
 #pragma unroll
     for (int i = 0; i < NC; ++i) {
         y[i] -= V[i];
@@ -460,7 +462,7 @@ __global__ void __launch_bounds__(EDGE_THREADS, MIO_RETURN_MINBLOCKS < 2 ? 2 : M
                     const bool act = it0 + j < cnt;
                     const int e    = beg + (act ? it0 + j : 0);
                     dst[j]         = __ldg(a.csr.out_dst + e);
-                    w[j] = __ldg(reinterpret_cast<const double2*>(a.csr.w_out) + (size_t)e * G + g.gl);
+                    w[j] = __ldg(reinterpret_cast<const double2*>(a.csr.w_out) + (size_t)e * W + g.gl);
                     if (!act) {
                         w[j] = make_double2(0.0, 0.0);
                     }
@@ -468,7 +470,7 @@ __global__ void __launch_bounds__(EDGE_THREADS, MIO_RETURN_MINBLOCKS < 2 ? 2 : M
 #pragma unroll
                 for (int j = 0; j < BATCH; ++j) {
                     const double2* ax =
-                        reinterpret_cast<const double2*>(a.aux + (((size_t)L.run * geo.N + dst[j]) * G + g.gl) * AUX);
+                        reinterpret_cast<const double2*>(a.aux + (((size_t)L.run * geo.N + dst[j]) * W + g.gl) * AUX);
                     a0[j] = ax[0];
                     a1[j] = ax[1];
                 }
@@ -489,6 +491,7 @@ __global__ void __launch_bounds__(EDGE_THREADS, MIO_RETURN_MINBLOCKS < 2 ? 2 : M
                           c.rINS_ISy * q[cINSC], c.rINS_R * q[cINSC], c.rISy_ISev * q[cISy], c.rISy_R * q[cISy],
                           c.rISy_ISev * q[cISyC], c.rISy_R * q[cISyC], a_icr * uk[cISev], c.rISev_R * q[cISev],
                           a_d * uk[cISev], c.rICr_D * q[cICr], c.rICr_R * q[cICr], k);
+            route_recoveries<G, LAY>(g, k);
 #pragma unroll
             for (int i = 0; i < NC; ++i) {
                 y[i] += q[i] + a.dt * k[i];
@@ -509,9 +512,9 @@ __global__ void __launch_bounds__(EDGE_THREADS, MIO_RETURN_MINBLOCKS < 2 ? 2 : M
                 LaneCoef c_o;
                 c_o.load(smem + a.st.node_pset[dst] * geo.pset_stride + PHDR + g.gl * AGE_REC);
                 const double2* ax =
-                    reinterpret_cast<const double2*>(a.aux + (((size_t)L.run * geo.N + dst) * G + g.gl) * AUX);
+                    reinterpret_cast<const double2*>(a.aux + (((size_t)L.run * geo.N + dst) * W + g.gl) * AUX);
                 const double2 a0 = ax[0], a1 = ax[1];
-                euler_return(c_o, a0.x, a0.y, a1.x, a.dt, m);
+                euler_return<G, LAY>(g, c_o, a0.x, a0.y, a1.x, a.dt, m);
                 if (act) {
 #pragma unroll
                     for (int i = 0; i < NC; ++i) {
@@ -523,7 +526,7 @@ __global__ void __launch_bounds__(EDGE_THREADS, MIO_RETURN_MINBLOCKS < 2 ? 2 : M
     }
     // visitors from sources > k
     load10(a.vis + (L.rn * 2 + 1) * geo.n + g.gl * NC, V);
-    euler_return(c_own, slam_own, ricr_own, rd_own, a.dt, V);
+    euler_return<G, LAY>(g, c_own, slam_own, ricr_own, rd_own, a.dt, V);
 #pragma unroll
     for (int i = 0; i < NC; ++i) {
         y[i] -= V[i];
@@ -540,11 +543,12 @@ __global__ void __launch_bounds__(EDGE_THREADS, MIO_RETURN_MINBLOCKS < 2 ? 2 : M
 // ---------------------------------------------------------------------------------------------------------------
 // Literal sequential replay of the return phase for flagged runs: one warp per run, lane = age group, edges in
 // reference order, both end nodes updated in place in y_out (which is first reset to y_in).
-template <int G>
+template <int G, int LAY>
 __global__ void __launch_bounds__(32) return_exact_kernel(EdgeArgs a)
 {
     extern __shared__ __align__(16) double smem[];
     __shared__ __align__(8) uint64_t mbar;
+    constexpr int W     = G * LAY;
     const Geometry& geo = a.geo;
     const int run       = blockIdx.x;
     if (run >= a.num_runs || a.run_flags[run] == 0) {
@@ -562,15 +566,17 @@ __global__ void __launch_bounds__(32) return_exact_kernel(EdgeArgs a)
         a.run_flags[run] = 0;
         atomicAdd((unsigned long long*)a.stats, 1ull);
     }
-    if (lane >= G) {
-        return;
-    }
-    const int gl      = lane;
+    // the first group of the warp does the work; the lanes of the other groups shadow it (same loads, no stores) so
+    // that the warp stays convergent for the shuffles of the layer exchange
+    Group<G, LAY> g;
+    const bool act    = lane < W;
+    const int gl      = g.gl;
+    const bool hooks  = !(LAY == VVS_LAY && geo.sim_kind != 1);
     const double* mob = geo.mob_max_pts > 0 ? smem + geo.mob_off : nullptr;
     const bool damped = mob != nullptr && mob[0] > 0.0;
     double damp[NC];
     mobility_damping_eval(damped ? mob : nullptr, geo.mob_max_pts, geo.n, gl, a.t_dep, damp);
-    const unsigned gmask = (1u << G) - 1u;
+    const unsigned gmask = (1u << W) - 1u;
     for (int e = 0; e < geo.E; ++e) {
         const int from   = a.csr.edge_start[e];
         const int to     = a.csr.edge_end[e];
@@ -578,49 +584,100 @@ __global__ void __launch_bounds__(32) return_exact_kernel(EdgeArgs a)
         const size_t rt  = (size_t)run * geo.N + to;
         const int ps_f   = a.st.node_pset ? a.st.node_pset[from] : 0;
         const int ps_t   = a.st.node_pset ? a.st.node_pset[to] : 0;
-        const double nd  = nondetection_at(smem + ps_f * geo.pset_stride, a.t_dep);
+        const double nd  = hooks ? nondetection_at(smem + ps_f * geo.pset_stride, a.t_dep) : 1.0;
         double sf[NC], m[NC], mu[2];
         load10(a.snap + rf * geo.n + gl * NC, sf);
-        const double ff = a.fac[rf * G + gl];
+        const double ff = a.fac[rf * W + gl];
         const bool pos =
             damped ? mobile_at_departure<true>(a.csr.coeff + (size_t)e * geo.n + gl * NC, damp, sf, ff, nd, m, mu)
                    : mobile_at_departure<false>(a.csr.coeff + (size_t)e * geo.n + gl * NC, damp, sf, ff, nd, m, mu);
-        const bool any = (__ballot_sync(gmask, pos) & gmask) != 0u;
+        const bool any = (__ballot_sync(0xffffffffu, pos) & gmask) != 0u;
         if (!any) {
             continue;
         }
         LaneCoef c_t;
         c_t.load(smem + ps_t * geo.pset_stride + PHDR + gl * AGE_REC);
-        const double2* ax = reinterpret_cast<const double2*>(a.aux + (rt * G + gl) * AUX);
+        const double2* ax = reinterpret_cast<const double2*>(a.aux + (rt * W + gl) * AUX);
         double2 a0 = ax[0], a1 = ax[1];
-        euler_return(c_t, a0.x, a0.y, a1.x, a.dt, m);
+        euler_return<G, LAY>(g, c_t, a0.x, a0.y, a1.x, a.dt, m);
         double yt[NC], yf[NC], rem[NC];
         load10(a.y_out + rt * geo.n + gl * NC, yt);
         load10(a.y_out + rf * geo.n + gl * NC, yf);
-        // underflow fix-up, instant.h:579-596 (per age group: j runs over this lane's compartments in order)
+        // underflow fix-up, instant.h:579-596: per age group, the supernumerous returns are taken from the biggest
+        // remaining compartment of that age group (first maximum in the reference's compartment order)
         int fixes = 0;
 #pragma unroll
         for (int i = 0; i < NC; ++i) {
             rem[i] = yt[i] - m[i];
         }
-        int max_index = 0;
+        int max_index = 0; // slot of the lane's own maximum, ties: lowest reference index
+        if constexpr (LAY == 1) {
 #pragma unroll
-        for (int i = 1; i < NC; ++i) {
-            if (rem[i] > rem[max_index]) {
-                max_index = i;
+            for (int i = 1; i < NC; ++i) {
+                if (rem[i] > rem[max_index]) {
+                    max_index = i;
+                }
             }
         }
+        else {
+#pragma unroll
+            for (int i = 1; i < NC; ++i) {
+                if (i != cR && (rem[i] > rem[max_index] ||
+                                (rem[i] == rem[max_index] &&
+                                 vvs_ref_comp(g.layer, i) < vvs_ref_comp(g.layer, max_index)))) {
+                    max_index = i;
+                }
+            }
+        }
+        double neg = 0.0; // sum of the negative remainders of this lane
 #pragma unroll
         for (int j = 0; j < NC; ++j) {
             if (rem[j] < 0) {
+                if constexpr (LAY == 1) {
 #pragma unroll
-                for (int q = 0; q < NC; ++q) { // register array: select instead of dynamic index
-                    if (q == max_index) {
-                        m[q] -= rem[j];
+                    for (int q = 0; q < NC; ++q) { // register array: select instead of dynamic index
+                        if (q == max_index) {
+                            m[q] -= rem[j];
+                        }
                     }
+                }
+                else {
+                    neg += rem[j];
                 }
                 m[j] += rem[j];
                 ++fixes;
+            }
+        }
+        if constexpr (LAY > 1) {
+            // the age group's maximum over the layers; the owning lane gives up the summed deficit of the age group
+            double best = 0.0;
+#pragma unroll
+            for (int q = 0; q < NC; ++q) {
+                if (q == max_index) {
+                    best = rem[q];
+                }
+            }
+            int best_ref = vvs_ref_comp(g.layer, max_index);
+            bool owner   = true;
+#pragma unroll
+            for (int k = 1; k < LAY; ++k) {
+                int l = gl + k * G;
+                l     = l >= W ? l - W : l;
+                const int src      = g.spare() ? lane : g.gbase + l;
+                const double ov    = __shfl_sync(0xffffffffu, best, src);
+                const int oref     = __shfl_sync(0xffffffffu, best_ref, src);
+                if (ov > best || (ov == best && oref < best_ref)) {
+                    owner = false;
+                }
+            }
+            const double deficit = g.sum_layers(neg);
+            if (owner && deficit != 0.0) {
+#pragma unroll
+                for (int q = 0; q < NC; ++q) {
+                    if (q == max_index) {
+                        m[q] -= deficit;
+                    }
+                }
             }
         }
 #pragma unroll
@@ -628,10 +685,12 @@ __global__ void __launch_bounds__(32) return_exact_kernel(EdgeArgs a)
             yf[i] += m[i];
             yt[i] -= m[i];
         }
-        store10(a.y_out + rf * geo.n + gl * NC, yf);
-        store10(a.y_out + rt * geo.n + gl * NC, yt);
-        if (fixes) {
-            atomicAdd(a.st.counters + rt * 4 + 3, fixes);
+        if (act) {
+            store10(a.y_out + rf * geo.n + gl * NC, yf);
+            store10(a.y_out + rt * geo.n + gl * NC, yt);
+            if (fixes) {
+                atomicAdd(a.st.counters + rt * 4 + 3, fixes);
+            }
         }
     }
 }
@@ -650,10 +709,11 @@ __global__ void record_daily_kernel(int N, int n, const double* __restrict__ y, 
     }
 }
 
-template <int G>
+template <int G, int LAY>
 static cudaError_t launch_edges_g(const EdgeArgs& a, int which, cudaStream_t stream)
 {
-    constexpr int NPW   = 32 / G;
+    constexpr int W     = G * LAY;
+    constexpr int NPW   = 32 / W;
     constexpr int WARPS = EDGE_THREADS / 32;
     const int chunks    = (a.geo.N + NPW * WARPS - 1) / (NPW * WARPS);
     const size_t grid   = (size_t)chunks * a.num_runs;
@@ -668,64 +728,70 @@ static cudaError_t launch_edges_g(const EdgeArgs& a, int which, cudaStream_t str
     } while (0)
     if (which == 0) {
         const int M          = a.csr.num_mob <= 5 ? 5 : NC;
-        const size_t shmem_u = shmem + sizeof(double) * (size_t)a.geo.N * G * M;
+        const size_t shmem_u = shmem + sizeof(double) * (size_t)a.geo.N * W * M;
         if (a.csr.factorized && a.csr.num_mob > 0 && shmem_u <= 110 * 1024) {
             // two CTAs per SM keep both the FP64 tail and the shared-memory gather busy
             if (M == 5) {
-                auto kern = depart_smem_kernel<G, 5>;
+                auto kern = depart_smem_kernel<G, LAY, 5>;
                 cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)shmem_u);
                 kern<<<(unsigned)a.num_runs, DEPART_SMEM_THREADS, shmem_u, stream>>>(a);
             }
             else {
-                auto kern = depart_smem_kernel<G, NC>;
+                auto kern = depart_smem_kernel<G, LAY, NC>;
                 cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)shmem_u);
                 kern<<<(unsigned)a.num_runs, DEPART_SMEM_THREADS, shmem_u, stream>>>(a);
             }
         }
         else if (a.csr.factorized) {
-            MIO_EDGE_LAUNCH((depart_kernel<G, true>), grid, EDGE_THREADS);
+            MIO_EDGE_LAUNCH((depart_kernel<G, LAY, true>), grid, EDGE_THREADS);
         }
         else {
-            MIO_EDGE_LAUNCH((depart_kernel<G, false>), grid, EDGE_THREADS);
+            MIO_EDGE_LAUNCH((depart_kernel<G, LAY, false>), grid, EDGE_THREADS);
         }
     }
     else if (which == 1) {
         if (a.csr.factorized) {
-            MIO_EDGE_LAUNCH((return_kernel<G, true>), grid, EDGE_THREADS);
+            MIO_EDGE_LAUNCH((return_kernel<G, LAY, true>), grid, EDGE_THREADS);
         }
         else {
-            MIO_EDGE_LAUNCH((return_kernel<G, false>), grid, EDGE_THREADS);
+            MIO_EDGE_LAUNCH((return_kernel<G, LAY, false>), grid, EDGE_THREADS);
         }
     }
     else {
-        MIO_EDGE_LAUNCH((return_exact_kernel<G>), a.num_runs, 32);
+        MIO_EDGE_LAUNCH((return_exact_kernel<G, LAY>), a.num_runs, 32);
     }
 #undef MIO_EDGE_LAUNCH
     return cudaGetLastError();
 }
 
-static cudaError_t launch_edges(const EdgeArgs& a, int which, cudaStream_t stream)
+template <int LAY>
+static cudaError_t launch_edges_lay(const EdgeArgs& a, int which, cudaStream_t stream)
 {
     switch (a.geo.G) {
     case 1:
-        return launch_edges_g<1>(a, which, stream);
+        return launch_edges_g<1, LAY>(a, which, stream);
     case 2:
-        return launch_edges_g<2>(a, which, stream);
+        return launch_edges_g<2, LAY>(a, which, stream);
     case 3:
-        return launch_edges_g<3>(a, which, stream);
+        return launch_edges_g<3, LAY>(a, which, stream);
     case 4:
-        return launch_edges_g<4>(a, which, stream);
+        return launch_edges_g<4, LAY>(a, which, stream);
     case 5:
-        return launch_edges_g<5>(a, which, stream);
+        return launch_edges_g<5, LAY>(a, which, stream);
     case 6:
-        return launch_edges_g<6>(a, which, stream);
+        return launch_edges_g<6, LAY>(a, which, stream);
     case 7:
-        return launch_edges_g<7>(a, which, stream);
+        return launch_edges_g<7, LAY>(a, which, stream);
     case 8:
-        return launch_edges_g<8>(a, which, stream);
+        return launch_edges_g<8, LAY>(a, which, stream);
     default:
         return cudaErrorInvalidValue;
     }
+}
+
+static cudaError_t launch_edges(const EdgeArgs& a, int which, cudaStream_t stream)
+{
+    return a.geo.LAY == VVS_LAY ? launch_edges_lay<VVS_LAY>(a, which, stream) : launch_edges_lay<1>(a, which, stream);
 }
 
 cudaError_t launch_depart(const EdgeArgs& a, cudaStream_t stream)
@@ -741,13 +807,73 @@ cudaError_t launch_return_exact(const EdgeArgs& a, cudaStream_t stream)
     return launch_edges(a, 2, stream);
 }
 
+// same copy for a layered model: device order [LAY][G][NC] -> reference order age*C + compartment
+__global__ void record_daily_ref_kernel(int N, int G, int lay, int n_dev, int C_ref, const double* __restrict__ y,
+                                        double* __restrict__ daily, int day_index, int max_days, size_t total)
+{
+    const size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
+    const int n_ref = G * C_ref;
+    if (i < total) {
+        const size_t rn = i / n_ref;
+        const int j     = (int)(i - rn * n_ref);
+        const int age   = j / C_ref;
+        daily[(rn * max_days + day_index) * n_ref + j] = y[rn * n_dev + dev_index_of_ref(lay, G, age, j - age * C_ref)];
+    }
+}
+
 cudaError_t launch_record_daily(const Geometry& geo, const double* y, double* daily, int day_index, int max_days,
                                 int num_runs, cudaStream_t stream)
 {
-    const size_t total = (size_t)num_runs * geo.N * (geo.n / 2);
+    const int threads = 256;
+    if (geo.LAY == 1) {
+        const size_t total = (size_t)num_runs * geo.N * (geo.n / 2);
+        const size_t grid  = (total + threads - 1) / threads;
+        record_daily_kernel<<<(unsigned)grid, threads, 0, stream>>>(geo.N, geo.n, y, daily, day_index, max_days,
+                                                                    total);
+    }
+    else {
+        const size_t total = (size_t)num_runs * geo.N * geo.n_ref;
+        const size_t grid  = (total + threads - 1) / threads;
+        record_daily_ref_kernel<<<(unsigned)grid, threads, 0, stream>>>(geo.N, geo.G, geo.LAY, geo.n, geo.C_ref, y,
+                                                                        daily, day_index, max_days, total);
+    }
+    return cudaGetLastError();
+}
+
+// state buffers <-> reference element order (C-ABI side of a layered model); dst and src must not overlap
+__global__ void permute_state_kernel(int G, int lay, int n_dev, int C_ref, const double* __restrict__ src,
+                                     double* __restrict__ dst, size_t total, int to_device)
+{
+    const size_t i  = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
+    const int n_ref = G * C_ref;
+    if (i < total) {
+        if (to_device) { // i runs over device elements; the unused Recovered slots are zeroed
+            const size_t rn = i / n_dev;
+            const int d     = (int)(i - rn * n_dev);
+            const int gl = d / NC, slot = d - gl * NC;
+            const int layer = gl / G, age = gl - layer * G;
+            const int comp  = vvs_ref_comp(layer, slot);
+            dst[i]          = comp < 0 ? 0.0 : src[rn * n_ref + age * C_ref + comp];
+        }
+        else { // i runs over reference elements
+            const size_t rn = i / n_ref;
+            const int j     = (int)(i - rn * n_ref);
+            const int age   = j / C_ref;
+            dst[i]          = src[rn * n_dev + dev_index_of_ref(lay, G, age, j - age * C_ref)];
+        }
+    }
+}
+
+cudaError_t launch_permute_state(const Geometry& geo, const double* src, double* dst, size_t num_run_nodes,
+                                 int to_device, cudaStream_t stream)
+{
+    const size_t total = num_run_nodes * (to_device ? geo.n : geo.n_ref);
     const int threads  = 256;
     const size_t grid  = (total + threads - 1) / threads;
-    record_daily_kernel<<<(unsigned)grid, threads, 0, stream>>>(geo.N, geo.n, y, daily, day_index, max_days, total);
+    if (grid > 0) {
+        permute_state_kernel<<<(unsigned)grid, threads, 0, stream>>>(geo.G, geo.LAY, geo.n, geo.C_ref, src, dst, total,
+                                                                     to_device);
+    }
     return cudaGetLastError();
 }
 

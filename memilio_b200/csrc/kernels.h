@@ -38,7 +38,7 @@ struct IntegrateArgs {
     const double* y_in;
     double* y_out;
     // written only by the node phase that precedes a departure (null otherwise):
-    double* fac_out; // [R][N][G] get_mobility_factors of the new snapshot (InfectedSymptoms entry; the others are 1)
+    double* fac_out; // [R][N][W] get_mobility_factors of the new snapshot (InfectedSymptoms entry; the others are 1)
     double* u_out;   // [R][N][n] emigration base vector: snapshot * (1 - mobility damping) * factor * nondetection,
                      //           masked to the mobile compartments; mobile population of edge e = coeff_e * u_from
     const double* umask; // [n]
@@ -100,6 +100,10 @@ cudaError_t launch_return_exact(const EdgeArgs& a, cudaStream_t stream);
 cudaError_t launch_record_daily(const Geometry& geo, const double* y, double* daily, int day_index, int max_days,
                                 int num_runs, cudaStream_t stream);
 
+// layered models (osecirvvs): device state order [LAY][G][NC] <-> reference order age*C + compartment
+cudaError_t launch_permute_state(const Geometry& geo, const double* src, double* dst, size_t num_run_nodes,
+                                 int to_device, cudaStream_t stream);
+
 // ---- ensemble reduction (reduce.cu) -------------------------------------------------------------------------------
 constexpr int SEL_MAX_P    = 8;
 constexpr int SEL_MAX_SEG  = 8;
@@ -122,7 +126,8 @@ struct SelectArgs {
 
 
 // y[R][N][n] of the current integer day -> columns of the ensemble matrix (per-node part and node-summed part)
-cudaError_t launch_record_ensemble(const double* y, double* ens, int N, int G, int C, int num_runs, int day,
+// G, C: the reference's age groups and compartments per age group; lay: 1 (device order == reference order) or 3
+cudaError_t launch_record_ensemble(const double* y, double* ens, int N, int G, int C, int lay, int num_runs, int day,
                                    int num_days, int age_sum, long long run_offset, long long stride,
                                    cudaStream_t stream);
 cudaError_t launch_select(const SelectArgs& a, cudaStream_t stream);

@@ -19,17 +19,28 @@ namespace miocu
 // ---------------------------------------------------------------------------------------------------------------
 // y[R][N][n] at an integer day -> ens[col][run_offset + r]
 __global__ void __launch_bounds__(256) record_ensemble_kernel(const double* __restrict__ y, double* __restrict__ ens,
-                                                              int N, int G, int C, int num_runs, int day, int num_days,
-                                                              int age_sum, long long run_offset, long long stride)
+                                                              int N, int G, int C, int lay, int num_runs, int day,
+                                                              int num_days, int age_sum, long long run_offset,
+                                                              long long stride)
 {
-    extern __shared__ double tile[]; // [32][n + 1]
-    const int n    = G * C;
-    const int node = blockIdx.y;
-    const int r0   = blockIdx.x * 32;
-    const int rows = min(32, num_runs - r0);
-    for (int idx = threadIdx.x; idx < rows * n; idx += blockDim.x) {
-        const int rr = idx / n, e = idx - rr * n;
-        tile[rr * (n + 1) + e] = y[((size_t)(r0 + rr) * N + node) * n + e];
+    extern __shared__ double tile[]; // [32][n + 1], reference element order
+    const int n     = G * C;
+    const int n_dev = G * lay * NC;
+    const int node  = blockIdx.y;
+    const int r0    = blockIdx.x * 32;
+    const int rows  = min(32, num_runs - r0);
+    for (int idx = threadIdx.x; idx < rows * n_dev; idx += blockDim.x) {
+        const int rr = idx / n_dev, d = idx - rr * n_dev;
+        int e        = d;
+        if (lay != 1) {
+            const int gl = d / NC, slot = d - gl * NC;
+            const int layer = gl / G, age = gl - layer * G;
+            const int comp  = vvs_ref_comp(layer, slot);
+            e               = comp < 0 ? -1 : age * C + comp;
+        }
+        if (e >= 0) {
+            tile[rr * (n + 1) + e] = y[((size_t)(r0 + rr) * N + node) * n_dev + d];
+        }
     }
     __syncthreads();
     const int El   = age_sum ? C : n;
@@ -52,19 +63,23 @@ __global__ void __launch_bounds__(256) record_ensemble_kernel(const double* __re
 }
 
 // sum_nodes: ens[base + day*n + j][run] = sum_k y[run][k][j], nodes added in index order
-__global__ void __launch_bounds__(128) record_node_sum_kernel(const double* __restrict__ y, double* __restrict__ ens,
-                                                              int N, int n, int num_runs, int day, long long base_col,
-                                                              long long run_offset, long long stride)
+__global__ void __launch_bounds__(256) record_node_sum_kernel(const double* __restrict__ y, double* __restrict__ ens,
+                                                              int N, int G, int C, int lay, int num_runs, int day,
+                                                              long long base_col, long long run_offset,
+                                                              long long stride)
 {
-    const int run = blockIdx.x;
-    const int j   = threadIdx.x;
+    const int run   = blockIdx.x;
+    const int j     = threadIdx.x;
+    const int n     = G * C;
+    const int n_dev = G * lay * NC;
     if (run >= num_runs || j >= n) {
         return;
     }
-    const double* p = y + (size_t)run * N * n + j;
+    const int age   = j / C;
+    const double* p = y + (size_t)run * N * n_dev + dev_index_of_ref(lay, G, age, j - age * C);
     double s        = 0.0;
     for (int k = 0; k < N; ++k) {
-        s += p[(size_t)k * n];
+        s += p[(size_t)k * n_dev];
     }
     ens[(size_t)(base_col + (long long)day * n + j) * stride + run_offset + run] = s;
 }
@@ -198,17 +213,21 @@ __global__ void __launch_bounds__(SEL_THREADS) select_percentiles_kernel(SelectA
     }
 }
 
-cudaError_t launch_record_ensemble(const double* y, double* ens, int N, int G, int C, int num_runs, int day,
+cudaError_t launch_record_ensemble(const double* y, double* ens, int N, int G, int C, int lay, int num_runs, int day,
                                    int num_days, int age_sum, long long run_offset, long long stride,
                                    cudaStream_t stream)
 {
     const int n = G * C;
     dim3 grid((num_runs + 31) / 32, N);
-    record_ensemble_kernel<<<grid, 256, sizeof(double) * 32 * (n + 1), stream>>>(y, ens, N, G, C, num_runs, day,
-                                                                                 num_days, age_sum, run_offset, stride);
+    const size_t shmem = sizeof(double) * 32 * (n + 1);
+    if (shmem > 48 * 1024) {
+        cudaFuncSetAttribute(record_ensemble_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)shmem);
+    }
+    record_ensemble_kernel<<<grid, 256, shmem, stream>>>(y, ens, N, G, C, lay, num_runs, day, num_days, age_sum,
+                                                         run_offset, stride);
     const long long base = (long long)N * num_days * (age_sum ? C : n);
-    record_node_sum_kernel<<<num_runs, ((n + 31) / 32) * 32, 0, stream>>>(y, ens, N, n, num_runs, day, base, run_offset,
-                                                                         stride);
+    record_node_sum_kernel<<<num_runs, ((n + 31) / 32) * 32, 0, stream>>>(y, ens, N, G, C, lay, num_runs, day, base,
+                                                                         run_offset, stride);
     return cudaGetLastError();
 }
 

@@ -134,7 +134,8 @@ class GraphProblem:
 
 
 def single_node_problem(G, pset, local, ctable, y0, *, ct_max_loc, ct_max_pts, integrator=None, t0=0.0, dt0=0.1,
-                        dt_graph=float("inf"), model=flat.MODEL_OSECIR) -> GraphProblem:
+                        dt_graph=float("inf"), model=flat.MODEL_OSECIR, sim_kind=flat.SIM_MODEL, vacc_partial=None,
+                        vacc_full=None) -> GraphProblem:
     """A 1-node, 0-edge graph: `mio::simulate` expressed as a graph run (make_no_mobility_sim, instant.h:700-712)."""
     n = G * flat.num_compartments(model)
     return GraphProblem(model=model, num_groups=G, num_nodes=1, edge_start=np.zeros(0, np.int32),
@@ -145,4 +146,4 @@ def single_node_problem(G, pset, local, ctable, y0, *, ct_max_loc, ct_max_pts, i
                         y0=np.asarray(y0, dtype=np.float64).reshape(1, 1, n), ct_max_loc=ct_max_loc,
                         ct_max_pts=ct_max_pts, dt0=np.full((1, 1), dt0),
                         integrator=integrator if integrator is not None else cdefs.integrator_desc(), t0=t0,
-                        dt_graph=dt_graph)
+                        dt_graph=dt_graph, sim_kind=sim_kind, vacc_partial=vacc_partial, vacc_full=vacc_full)

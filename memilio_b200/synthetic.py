@@ -121,6 +121,86 @@ def county_problem(N: int = 400, runs: int = 1, seed: int = 20261017, G: int = 6
                         t0=0.0, dt_graph=dt_graph)
 
 
+# pycode/memilio-simulation/memilio/simulation/bindings/models/osecirvvs.cpp:220-231
+VVS_MOBILE_COMPARTMENTS = (flat.V_SN, flat.V_EN, flat.V_INSN, flat.V_ISYN, flat.V_SII, flat.V_SPI, flat.V_EPI,
+                           flat.V_INSPI, flat.V_ISYPI, flat.V_EII, flat.V_INSII, flat.V_ISYII)
+VVS_INFECTED = (flat.V_EN, flat.V_EPI, flat.V_EII, flat.V_INSN, flat.V_INSNC, flat.V_INSPI, flat.V_INSPIC,
+                flat.V_INSII, flat.V_INSIIC, flat.V_ISYN, flat.V_ISYNC, flat.V_ISYPI, flat.V_ISYPIC, flat.V_ISYII,
+                flat.V_ISYIIC, flat.V_ISEVN, flat.V_ISEVII, flat.V_ISEVPI, flat.V_ICRN, flat.V_ICRPI, flat.V_ICRII)
+
+
+def benchmark_vvs_pset(G: int = 6) -> np.ndarray:
+    """Parameters of cpp/benchmarks/graph_simulation.cpp:31-112 (create_model)."""
+    return flat.osecirvvs_pset(
+        G, Seasonality=0.2, TimeExposed=3.33, TimeInfectedNoSymptoms=1.87, TimeInfectedSymptoms=7.0,
+        TimeInfectedSevere=6.0, TimeInfectedCritical=7.0, TransmissionProbabilityOnContact=0.15,
+        RelativeTransmissionNoSymptoms=0.5, RiskOfInfectionFromSymptomatic=0.0, MaxRiskOfInfectionFromSymptomatic=0.4,
+        RecoveredPerInfectedNoSymptoms=0.2, SeverePerInfectedSymptoms=0.1, CriticalPerSevere=0.1,
+        DeathsPerCritical=0.1, ReducExposedPartialImmunity=0.8, ReducExposedImprovedImmunity=0.331,
+        ReducInfectedSymptomsPartialImmunity=0.65, ReducInfectedSymptomsImprovedImmunity=0.243,
+        ReducInfectedSevereCriticalDeadPartialImmunity=0.1, ReducInfectedSevereCriticalDeadImprovedImmunity=0.091,
+        ReducTimeInfectedMild=0.9)
+
+
+def county_problem_vvs(N: int = 400, runs: int = 1, seed: int = 20261017, G: int = 6, max_out_degree: int = 25,
+                       days: int = 100, sim_kind: int = flat.SIM_MODEL, perturb: float = 0.0,
+                       damping_day: float = 5.0, daily_vaccinations: float = 5.0, init_per_10k: float = 20.0,
+                       icu_per_10k: float = 100.0 / 6, start_day_new_variant: Optional[float] = None,
+                       integrator: Optional[cdefs.IntegratorDesc] = None, dt_graph: float = 0.5) -> GraphProblem:
+    """BASELINE config 5 shaped inputs: the synthetic county graph with ODE-SECIRVVS nodes carrying the parameters and
+    the initial-value pattern of the reference's graph benchmark (cpp/benchmarks/graph_simulation.cpp:31-112), scaled
+    from its 10 000 people per age group to the county's age groups; cumulative vaccination arrays 5*(d+1)
+    (SURVEY.md 8d config 5). sim_kind SIM_MODEL = osecirvvs::Simulation nodes, SIM_BASE = the plain mio::Simulation
+    the reference benchmark instantiates."""
+    pop, es, ee, coeff10 = county_graph(N, seed, max_out_degree, G)
+    C = flat.OSECIRVVS_NCOMP
+    n = G * C
+    coeff = np.zeros((es.size, G, C))
+    w_age = coeff10.reshape(es.size, G, 10)[:, :, flat.S]
+    for c in VVS_MOBILE_COMPARTMENTS:
+        coeff[:, :, c] = w_age
+    y0 = np.zeros((N, G, C))
+    scale = pop / 10000.0
+    for c in VVS_INFECTED:
+        y0[:, :, c] = init_per_10k * scale
+    y0[:, :, flat.V_SII] = pop / 3
+    y0[:, :, flat.V_SPI] = pop / 3
+    y0[:, :, flat.V_SN] = pop - y0.sum(axis=2)
+    local = np.zeros((N, 2))
+    local[:, 0] = icu_per_10k * pop.sum(axis=1) / 10000.0
+    local[:, 1] = 0.0143 * pop.sum(axis=1) / 10000.0
+    kw = {} if start_day_new_variant is None else dict(StartDayNewVariant=start_day_new_variant,
+                                                        InfectiousnessNewVariant=1.4)
+    pset = benchmark_vvs_pset(G)
+    if kw:
+        pset[flat.PHV["StartDayNewVariant"]] = kw["StartDayNewVariant"]
+        pset[flat.PSET_HEADER:].reshape(G, flat.OSECIRVVS_AGE_STRIDE)[:, flat.PV["InfectiousnessNewVariant"]] = 1.4
+    base = np.full((G, G), 0.5)
+    np.fill_diagonal(base, 5.0)
+    ct = flat.contact_table(G, [ContactLocation(base, None, [damping_day], [np.full((G, G), 0.3)])], 1, 2)
+    psets = np.broadcast_to(pset, (runs, 1, pset.size)).copy()
+    ctables = np.broadcast_to(ct, (runs, 1, ct.size)).copy()
+    locals_ = np.broadcast_to(local, (runs, N, 2)).copy()
+    y0s = np.broadcast_to(y0.reshape(N, n), (runs, N, n)).copy()
+    if perturb > 0.0:
+        prng = np.random.default_rng(seed + 2)
+        rec = psets[:, 0, flat.PSET_HEADER:].reshape(runs, G, flat.OSECIRVVS_AGE_STRIDE)
+        rec[:, :, :21] *= prng.uniform(1 - perturb, 1 + perturb, (runs, G, 21))
+        psets[:, 0, flat.PHV["Seasonality"]] = prng.uniform(0.1, 0.3, runs)
+        locals_ *= prng.uniform(0.8, 1.2, (runs, N, 2))
+        y0s *= prng.uniform(0.9, 1.1, (runs, N, n))
+        for r in range(runs):
+            flat.osecirvvs_apply_constraints(psets[r, 0], G)
+    vacc_days = days + 2
+    vacc = np.broadcast_to(daily_vaccinations * (np.arange(vacc_days) + 1.0), (N, G, vacc_days)).copy()
+    vacc *= scale[:, :, None]
+    return GraphProblem(model=flat.MODEL_OSECIRVVS, num_groups=G, num_nodes=N, edge_start=es, edge_end=ee,
+                        edge_coeff=coeff.reshape(es.size, n), psets=psets, ctables=ctables, node_local=locals_, y0=y0s,
+                        ct_max_loc=1, ct_max_pts=2,
+                        integrator=integrator if integrator is not None else cdefs.integrator_desc(), t0=0.0,
+                        dt_graph=dt_graph, sim_kind=sim_kind, vacc_partial=vacc, vacc_full=vacc.copy())
+
+
 # uniform ranges of set_covid_parameters, cpp/examples/ode_secir_parameter_study_graph.cpp:91-159
 COVID_UNIFORM = dict(
     TimeExposed=(2.67, 4.0), TimeInfectedNoSymptoms=(1.2, 2.53),
