@@ -34,17 +34,21 @@ def build(force: bool = False, verbose: bool = False, defines=(), out: str = LIB
     if out == LIB and not force and not needs_build():
         return LIB
     os.makedirs(objdir, exist_ok=True)
-    objs = []
-    logs = []
-    for src in CU_SOURCES + CXX_SOURCES:
+    from concurrent.futures import ThreadPoolExecutor
+
+    def compile_one(src):
         obj = os.path.join(objdir, os.path.splitext(src)[0] + ".o")
         cmd = [_nvcc()] + NVCC_FLAGS + ["-D" + d for d in defines] + ["-c", os.path.join(CSRC, src), "-o", obj]
         r = subprocess.run(cmd, capture_output=True, text=True)
-        logs.append(r.stderr)
         if r.returncode != 0:
             sys.stderr.write(r.stdout + r.stderr)
             raise RuntimeError("nvcc failed for " + src)
-        objs.append(obj)
+        return obj, r.stderr
+
+    with ThreadPoolExecutor(max_workers=min(8, os.cpu_count() or 1)) as pool:
+        results = list(pool.map(compile_one, CU_SOURCES + CXX_SOURCES))
+    objs = [o for o, _ in results]
+    logs = [l for _, l in results]
     cmd = [_nvcc(), "-shared", "-o", out] + objs + ["-gencode", "arch=compute_100a,code=sm_100a"]
     r = subprocess.run(cmd, capture_output=True, text=True)
     if r.returncode != 0:

@@ -8,9 +8,11 @@ sys.path.insert(0, ROOT)
 from memilio_b200 import build as b  # noqa: E402
 
 VARIANTS = {
-    "i128x3": ["MIO_INTEGRATE_THREADS=128", "MIO_INTEGRATE_MINBLOCKS=3"],
-    "i128x4": ["MIO_INTEGRATE_THREADS=128", "MIO_INTEGRATE_MINBLOCKS=4"],
-    "i256x2": ["MIO_INTEGRATE_MINBLOCKS=2"],
+    "i128x2": ["MIO_TUNE_ONLY_G6", "MIO_INTEGRATE_THREADS=128", "MIO_INTEGRATE_MINBLOCKS=2"],
+    "i128x3": ["MIO_TUNE_ONLY_G6", "MIO_INTEGRATE_THREADS=128", "MIO_INTEGRATE_MINBLOCKS=3"],
+    "i128x4": ["MIO_TUNE_ONLY_G6", "MIO_INTEGRATE_THREADS=128", "MIO_INTEGRATE_MINBLOCKS=4"],
+    "i64x4": ["MIO_TUNE_ONLY_G6", "MIO_INTEGRATE_THREADS=64", "MIO_INTEGRATE_MINBLOCKS=4"],
+    "i64x6": ["MIO_TUNE_ONLY_G6", "MIO_INTEGRATE_THREADS=64", "MIO_INTEGRATE_MINBLOCKS=6"],
     "e256x2": ["MIO_DEPART_MINBLOCKS=2", "MIO_RETURN_MINBLOCKS=3"],
     "e256x4": ["MIO_DEPART_MINBLOCKS=4", "MIO_RETURN_MINBLOCKS=4"],
     "e128x6": ["MIO_EDGE_THREADS=128", "MIO_DEPART_MINBLOCKS=6", "MIO_RETURN_MINBLOCKS=8"],
