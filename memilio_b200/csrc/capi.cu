@@ -94,6 +94,7 @@ struct mio_handle {
     // statistics
     long long launches = 0;
     long long* d_stats = nullptr; // [0] exact replays of return steps
+    int* d_work = nullptr;        // work item counter of the persistent node-phase kernel
     // optional per-kernel-class device timing (CUDA events on the launching stream)
     bool profiling = false;
     struct Span {
@@ -282,7 +283,7 @@ void destroy(mio_handle* h)
                     h->d_run_block,  h->d_node_local,  h->d_t_node,     h->d_dt_node,   h->d_counters,
                     h->d_y[0],       h->d_y[1],        h->d_y[2],       h->d_y[3],      h->d_fac,
                     h->d_aux,        h->d_run_flags,   h->d_daily,      h->d_traj_npts, h->d_traj_times,
-                    h->d_traj_values, h->d_stats,      h->d_vacc_partial, h->d_vacc_full};
+                    h->d_traj_values, h->d_stats,      h->d_vacc_partial, h->d_vacc_full, h->d_work};
     for (void* p : ptrs) {
         if (p) {
             cudaFree(p);
@@ -688,6 +689,7 @@ int mio_cuda_graph_create(const mio_graph_desc* d, int device, mio_handle** out)
     H_TRY(dev_alloc(&h->d_t_node, R * N));
     H_TRY(dev_alloc(&h->d_dt_node, R * N));
     H_TRY(dev_alloc(&h->d_counters, R * N * 4));
+    H_TRY(dev_alloc(&h->d_work, (size_t)4));
     const int nbuf = E > 0 ? 4 : 2;
     for (int b = 0; b < nbuf; ++b) {
         H_TRY(dev_alloc(&h->d_y[b], R * N * n));
@@ -931,6 +933,7 @@ int mio_cuda_advance(mio_handle* h, double t_max)
         ia.dt_max     = h->desc.integrator.dt_max;
         ia.traj       = TrajectoryBuffers{h->desc.traj_capacity, h->d_traj_npts, h->d_traj_times, h->d_traj_values};
         ia.num_runs   = R;
+        ia.work_counter = h->d_work;
         {
             ScopedSpan sp(h, MIO_KC_INTEGRATE);
             CUDA_TRY(launch_integrate(ia, h->stream));

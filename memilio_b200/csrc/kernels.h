@@ -8,10 +8,10 @@ namespace miocu
 
 // launch shapes (tunable at build time; see tools/build_variants.py and profiles/ for the measurements behind them)
 #ifndef MIO_INTEGRATE_THREADS
-#define MIO_INTEGRATE_THREADS 256
+#define MIO_INTEGRATE_THREADS 128
 #endif
 #ifndef MIO_INTEGRATE_MINBLOCKS
-#define MIO_INTEGRATE_MINBLOCKS 1
+#define MIO_INTEGRATE_MINBLOCKS 2
 #endif
 #ifndef MIO_EDGE_THREADS
 #define MIO_EDGE_THREADS 256
@@ -47,6 +47,7 @@ struct IntegrateArgs {
     double abs_tol, rel_tol, dt_min, dt_max;
     TrajectoryBuffers traj;
     int num_runs;
+    int* work_counter; // [1] device scratch: the persistent node-phase kernel hands out its work items through it
 };
 
 // Graph in the two forms the edge phase uses.

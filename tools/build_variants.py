@@ -11,6 +11,9 @@ VARIANTS = {
     "i128x2": ["MIO_TUNE_ONLY_G6", "MIO_INTEGRATE_THREADS=128", "MIO_INTEGRATE_MINBLOCKS=2"],
     "i128x3": ["MIO_TUNE_ONLY_G6", "MIO_INTEGRATE_THREADS=128", "MIO_INTEGRATE_MINBLOCKS=3"],
     "i128x4": ["MIO_TUNE_ONLY_G6", "MIO_INTEGRATE_THREADS=128", "MIO_INTEGRATE_MINBLOCKS=4"],
+    "i256x1": ["MIO_TUNE_ONLY_G6", "MIO_INTEGRATE_THREADS=256", "MIO_INTEGRATE_MINBLOCKS=1"],
+    "i160x3": ["MIO_TUNE_ONLY_G6", "MIO_INTEGRATE_THREADS=160", "MIO_INTEGRATE_MINBLOCKS=3"],
+    "i192x2": ["MIO_TUNE_ONLY_G6", "MIO_INTEGRATE_THREADS=192", "MIO_INTEGRATE_MINBLOCKS=2"],
     "i64x4": ["MIO_TUNE_ONLY_G6", "MIO_INTEGRATE_THREADS=64", "MIO_INTEGRATE_MINBLOCKS=4"],
     "i64x6": ["MIO_TUNE_ONLY_G6", "MIO_INTEGRATE_THREADS=64", "MIO_INTEGRATE_MINBLOCKS=6"],
     "e256x2": ["MIO_DEPART_MINBLOCKS=2", "MIO_RETURN_MINBLOCKS=3"],

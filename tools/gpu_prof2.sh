@@ -2,7 +2,7 @@
 # ncu full capture of one kernel for several library variants; CSV pages exported on the box
 set -u
 mkdir -p gpurun_out
-ARGS="${BENCH_ARGS:---runs 2000 --days 5 --steps 1 --warmup 1 --no-cpu-baseline}"
+ARGS="${BENCH_ARGS:---runs 10000 --days 5 --steps 1 --warmup 1 --no-cpu-baseline}"
 k=${KERNEL:-integrate_nodes}
 for v in "$@"; do
   if [ "$v" = default ]; then unset MIO_CUDA_LIB; else export MIO_CUDA_LIB=$PWD/memilio_b200/csrc/variants/libmio_cuda_$v.so; fi
