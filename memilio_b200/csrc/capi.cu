@@ -94,7 +94,8 @@ struct mio_handle {
     // statistics
     long long launches = 0;
     long long* d_stats = nullptr; // [0] exact replays of return steps
-    int* d_work = nullptr;        // work item counter of the persistent node-phase kernel
+    int* d_work = nullptr;        // [0] work item counter of the persistent node-phase kernel, [1] run list length
+    int* d_run_list = nullptr;    // [R] runs flagged for the exact replay of a return step
     // optional per-kernel-class device timing (CUDA events on the launching stream)
     bool profiling = false;
     struct Span {
@@ -283,7 +284,7 @@ void destroy(mio_handle* h)
                     h->d_run_block,  h->d_node_local,  h->d_t_node,     h->d_dt_node,   h->d_counters,
                     h->d_y[0],       h->d_y[1],        h->d_y[2],       h->d_y[3],      h->d_fac,
                     h->d_aux,        h->d_run_flags,   h->d_daily,      h->d_traj_npts, h->d_traj_times,
-                    h->d_traj_values, h->d_stats,      h->d_vacc_partial, h->d_vacc_full, h->d_work};
+                    h->d_traj_values, h->d_stats,      h->d_vacc_partial, h->d_vacc_full, h->d_work, h->d_run_list};
     for (void* p : ptrs) {
         if (p) {
             cudaFree(p);
@@ -700,6 +701,7 @@ int mio_cuda_graph_create(const mio_graph_desc* d, int device, mio_handle** out)
         H_TRY(dev_alloc(&h->d_u, R * N * n));
         H_TRY(dev_alloc(&h->d_vis, R * N * 2 * n));
         H_TRY(dev_alloc(&h->d_run_flags, R));
+        H_TRY(dev_alloc(&h->d_run_list, R));
         H_TRY(cudaMemset(h->d_run_flags, 0, sizeof(int) * R));
         H_TRY(dev_alloc(&h->d_stats, (size_t)4));
         H_TRY(cudaMemset(h->d_stats, 0, sizeof(long long) * 4));
@@ -956,6 +958,8 @@ int mio_cuda_advance(mio_handle* h, double t_max)
             ea.aux            = h->d_aux;
             ea.run_flags      = h->d_run_flags;
             ea.stats          = h->d_stats;
+            ea.run_list       = h->d_run_list;
+            ea.list_count     = h->d_work + 1;
             ea.num_runs       = R;
             ea.dt             = dt;
             ea.t              = h->t;

@@ -541,75 +541,168 @@ __global__ void __launch_bounds__(EDGE_THREADS, MIO_RETURN_MINBLOCKS < 2 ? 2 : M
 }
 
 // ---------------------------------------------------------------------------------------------------------------
-// Literal sequential replay of the return phase for flagged runs: one warp per run, lane = age group, edges in
-// reference order, both end nodes updated in place in y_out (which is first reset to y_in).
-template <int G, int LAY>
-__global__ void __launch_bounds__(32) return_exact_kernel(EdgeArgs a)
+// Literal sequential replay of the return phase for flagged runs, two kernels:
+//  collect_flagged_kernel  one CTA per run; a flagged run is appended to the run list, its flag cleared and its live
+//                          state reset to the state before the return phase (y_out[run] = y_in[run]).
+//  return_exact_kernel     one warp per NPW listed runs (group of W lanes = one run, lane = age group); the edges are
+//                          walked in reference order and both end nodes are updated in place in y_out. The walk is a
+//                          dependent chain per run, so it is software pipelined: edge indices are fetched two edges
+//                          ahead, the edge's read-only operands (coefficients, destination coefficients) one edge
+//                          ahead, and the source node's snapshot and running state stay in registers while consecutive
+//                          edges share the source (edges are sorted by source).
+template <int THREADS>
+__global__ void __launch_bounds__(THREADS) collect_flagged_kernel(EdgeArgs a, int* __restrict__ run_list,
+                                                                   int* __restrict__ list_count)
 {
-    extern __shared__ __align__(16) double smem[];
-    __shared__ __align__(8) uint64_t mbar;
-    constexpr int W     = G * LAY;
-    const Geometry& geo = a.geo;
-    const int run       = blockIdx.x;
+    const int run = blockIdx.x;
     if (run >= a.num_runs || a.run_flags[run] == 0) {
         return;
     }
-    stage_run_block(smem, a.st.run_block + (size_t)run * geo.block_stride, geo.block_stride * 8, &mbar);
-    const int lane     = threadIdx.x;
-    const size_t base  = (size_t)run * geo.N * geo.n;
-    const size_t total = (size_t)geo.N * geo.n;
-    for (size_t i = lane; i < total; i += 32) {
-        a.y_out[base + i] = a.y_in[base + i];
+    const size_t total = (size_t)a.geo.N * a.geo.n / 2; // n is even
+    const double2* src = reinterpret_cast<const double2*>(a.y_in + (size_t)run * a.geo.N * a.geo.n);
+    double2* dst       = reinterpret_cast<double2*>(a.y_out + (size_t)run * a.geo.N * a.geo.n);
+    for (size_t i = threadIdx.x; i < total; i += THREADS) {
+        dst[i] = src[i];
     }
-    __syncwarp();
-    if (lane == 0) {
-        a.run_flags[run] = 0;
+    __syncthreads(); // every thread has read the flag
+    if (threadIdx.x == 0) {
+        a.run_flags[run]                 = 0;
+        run_list[atomicAdd(list_count, 1)] = run;
         atomicAdd((unsigned long long*)a.stats, 1ull);
     }
-    // the first group of the warp does the work; the lanes of the other groups shadow it (same loads, no stores) so
-    // that the warp stays convergent for the shuffles of the layer exchange
+}
+
+template <int G, int LAY>
+struct ExactEdge {
+    int from, to;
+    double c[NC];   // coefficient vector of the edge for this lane
+    double2 a0, a1; // return coefficients of the destination (aux)
+};
+
+template <int G, int LAY>
+__device__ __forceinline__ void exact_edge_load(const EdgeArgs& a, const Geometry& geo, int run, int gl, int e,
+                                                int from, int to, ExactEdge<G, LAY>& d)
+{
+    constexpr int W = G * LAY;
+    d.from          = from;
+    d.to            = to;
+    const double2* cp = reinterpret_cast<const double2*>(a.csr.coeff + (size_t)e * geo.n + gl * NC);
+#pragma unroll
+    for (int i = 0; i < NC / 2; ++i) {
+        const double2 v = __ldg(cp + i);
+        d.c[2 * i]      = v.x;
+        d.c[2 * i + 1]  = v.y;
+    }
+    const double2* ax = reinterpret_cast<const double2*>(a.aux + (((size_t)run * geo.N + to) * W + gl) * AUX);
+    d.a0              = ax[0];
+    d.a1              = ax[1];
+}
+
+template <int G, int LAY>
+__global__ void __launch_bounds__(32, 14) return_exact_kernel(EdgeArgs a, const int* __restrict__ run_list,
+                                                          const int* __restrict__ list_count)
+{
+    constexpr int W     = G * LAY;
+    constexpr int NPW   = 32 / W;
+    const Geometry& geo = a.geo;
+    const int count     = *list_count;
+    const int base      = blockIdx.x * NPW;
+    if (base >= count) {
+        return;
+    }
     Group<G, LAY> g;
-    const bool act    = lane < W;
-    const int gl      = g.gl;
-    const bool hooks  = !(LAY == VVS_LAY && geo.sim_kind != 1);
-    const double* mob = geo.mob_max_pts > 0 ? smem + geo.mob_off : nullptr;
+    const int lane   = threadIdx.x;
+    const int slot   = base + lane / W;
+    const bool act   = !g.spare() && slot < count;
+    const int run    = run_list[act ? slot : base];
+    const int gl     = g.gl;
+    const bool hooks = !(LAY == VVS_LAY && geo.sim_kind != 1);
+    // the run's parameter block is read from global memory (L2): mobility damping at the departure time, and the
+    // rate coefficients of the destination's parameter set (kept in registers when the run has only one set)
+    const double* blk = a.st.run_block + (size_t)run * geo.block_stride;
+    const double* mob = geo.mob_max_pts > 0 ? blk + geo.mob_off : nullptr;
     const bool damped = mob != nullptr && mob[0] > 0.0;
     double damp[NC];
     mobility_damping_eval(damped ? mob : nullptr, geo.mob_max_pts, geo.n, gl, a.t_dep, damp);
-    const unsigned gmask = (1u << W) - 1u;
-    for (int e = 0; e < geo.E; ++e) {
-        const int from   = a.csr.edge_start[e];
-        const int to     = a.csr.edge_end[e];
-        const size_t rf  = (size_t)run * geo.N + from;
-        const size_t rt  = (size_t)run * geo.N + to;
-        const int ps_f   = a.st.node_pset ? a.st.node_pset[from] : 0;
-        const int ps_t   = a.st.node_pset ? a.st.node_pset[to] : 0;
-        const double nd  = hooks ? nondetection_at(smem + ps_f * geo.pset_stride, a.t_dep) : 1.0;
-        double sf[NC], m[NC], mu[2];
-        load10(a.snap + rf * geo.n + gl * NC, sf);
-        const double ff = a.fac[rf * W + gl];
-        const bool pos =
-            damped ? mobile_at_departure<true>(a.csr.coeff + (size_t)e * geo.n + gl * NC, damp, sf, ff, nd, m, mu)
-                   : mobile_at_departure<false>(a.csr.coeff + (size_t)e * geo.n + gl * NC, damp, sf, ff, nd, m, mu);
-        const bool any = (__ballot_sync(0xffffffffu, pos) & gmask) != 0u;
-        if (!any) {
-            continue;
+    LaneCoef c_t;
+    c_t.load(blk + PHDR + gl * AGE_REC);
+    const bool one_pset = geo.num_psets == 1;
+    const size_t rbase  = (size_t)run * geo.N;
+
+    const int E = geo.E;
+    if (E == 0) {
+        return;
+    }
+    // pipeline: indices of edge e+1, operands of edge e
+    int f_next = E > 1 ? __ldg(a.csr.edge_start + 1) : 0;
+    int t_next = E > 1 ? __ldg(a.csr.edge_end + 1) : 0;
+    ExactEdge<G, LAY> cur;
+    exact_edge_load<G, LAY>(a, geo, run, gl, 0, __ldg(a.csr.edge_start), __ldg(a.csr.edge_end), cur);
+    // source node state held in registers while the source stays the same; it and the destination's running state
+    // are fetched at the end of the previous edge's iteration (after that edge's stores, so that the loads see them)
+    double sf[NC], yf[NC], ytn[NC], ff, nd;
+    {
+        const int from0 = cur.from;
+        const int ps_f  = a.st.node_pset ? a.st.node_pset[from0] : 0;
+        nd              = hooks ? nondetection_at(blk + ps_f * geo.pset_stride, a.t_dep) : 1.0;
+        load10(a.snap + (rbase + from0) * geo.n + gl * NC, sf);
+        ff = a.fac[(rbase + from0) * W + gl];
+        load10(a.y_out + (rbase + from0) * geo.n + gl * NC, yf);
+        load10(a.y_out + (rbase + cur.to) * geo.n + gl * NC, ytn);
+    }
+    for (int e = 0; e < E; ++e) {
+        // fetch ahead: indices of e+2, operands of e+1
+        const int f_next2 = e + 2 < E ? __ldg(a.csr.edge_start + e + 2) : 0;
+        const int t_next2 = e + 2 < E ? __ldg(a.csr.edge_end + e + 2) : 0;
+        ExactEdge<G, LAY> nxt;
+        if (e + 1 < E) {
+            exact_edge_load<G, LAY>(a, geo, run, gl, e + 1, f_next, t_next, nxt);
         }
-        LaneCoef c_t;
-        c_t.load(smem + ps_t * geo.pset_stride + PHDR + gl * AGE_REC);
-        const double2* ax = reinterpret_cast<const double2*>(a.aux + (rt * W + gl) * AUX);
-        double2 a0 = ax[0], a1 = ax[1];
-        euler_return<G, LAY>(g, c_t, a0.x, a0.y, a1.x, a.dt, m);
-        double yt[NC], yf[NC], rem[NC];
-        load10(a.y_out + rt * geo.n + gl * NC, yt);
-        load10(a.y_out + rf * geo.n + gl * NC, yf);
+        const int from  = cur.from;
+        const int to    = cur.to;
+        const size_t rt = rbase + to;
+        double yt[NC];
+#pragma unroll
+        for (int i = 0; i < NC; ++i) {
+            yt[i] = ytn[i];
+        }
+        if (!one_pset) {
+            const int ps_t = a.st.node_pset ? a.st.node_pset[to] : 0;
+            c_t.load(blk + ps_t * geo.pset_stride + PHDR + gl * AGE_REC);
+        }
+        // mobile population of the edge at departure (instant.h:608-615)
+        double m[NC];
+        bool pos = false;
+#pragma unroll
+        for (int i = 0; i < NC; ++i) {
+            double c = cur.c[i];
+            if (damped) {
+                c = __dsub_rn(c, __dmul_rn(damp[i], c));
+            }
+            pos  = pos || (c > 0.0);
+            m[i] = sf[i] * c;
+        }
+        m[cISy] *= ff;
+        if (nd != 1.0) {
+            m[cISy] *= nd;
+            m[cINS] *= nd;
+        }
+        const bool any = g.any(pos); // the reference skips edges without a positive coefficient
+        euler_return<G, LAY>(g, c_t, cur.a0.x, cur.a0.y, cur.a1.x, a.dt, m);
         // underflow fix-up, instant.h:579-596: per age group, the supernumerous returns are taken from the biggest
         // remaining compartment of that age group (first maximum in the reference's compartment order)
+        double rem[NC];
         int fixes = 0;
 #pragma unroll
         for (int i = 0; i < NC; ++i) {
             rem[i] = yt[i] - m[i];
         }
+        bool neg_any = false;
+#pragma unroll
+        for (int i = 0; i < NC; ++i) {
+            neg_any = neg_any || (rem[i] < 0);
+        }
+        if (__any_sync(0xffffffffu, neg_any)) { // uniform over the warp; no lane underflows on most edges
         int max_index = 0; // slot of the lane's own maximum, ties: lowest reference index
         if constexpr (LAY == 1) {
 #pragma unroll
@@ -663,9 +756,9 @@ __global__ void __launch_bounds__(32) return_exact_kernel(EdgeArgs a)
             for (int k = 1; k < LAY; ++k) {
                 int l = gl + k * G;
                 l     = l >= W ? l - W : l;
-                const int src      = g.spare() ? lane : g.gbase + l;
-                const double ov    = __shfl_sync(0xffffffffu, best, src);
-                const int oref     = __shfl_sync(0xffffffffu, best_ref, src);
+                const int src   = g.spare() ? lane : g.gbase + l;
+                const double ov = __shfl_sync(0xffffffffu, best, src);
+                const int oref  = __shfl_sync(0xffffffffu, best_ref, src);
                 if (ov > best || (ov == best && oref < best_ref)) {
                     owner = false;
                 }
@@ -680,18 +773,40 @@ __global__ void __launch_bounds__(32) return_exact_kernel(EdgeArgs a)
                 }
             }
         }
-#pragma unroll
-        for (int i = 0; i < NC; ++i) {
-            yf[i] += m[i];
-            yt[i] -= m[i];
         }
-        if (act) {
-            store10(a.y_out + rf * geo.n + gl * NC, yf);
-            store10(a.y_out + rt * geo.n + gl * NC, yt);
-            if (fixes) {
-                atomicAdd(a.st.counters + rt * 4 + 3, fixes);
+        if (any) {
+#pragma unroll
+            for (int i = 0; i < NC; ++i) {
+                yf[i] += m[i];
+                yt[i] -= m[i];
+            }
+            if (act) {
+                store10(a.y_out + rt * geo.n + gl * NC, yt);
+                if (fixes) {
+                    atomicAdd(a.st.counters + rt * 4 + 3, fixes);
+                }
             }
         }
+        if (e + 1 < E) {
+            if (nxt.from != from) { // uniform over the warp: the next edge starts a new source node
+                if (act) {
+                    store10(a.y_out + (rbase + from) * geo.n + gl * NC, yf);
+                }
+                const int ps_f = a.st.node_pset ? a.st.node_pset[nxt.from] : 0;
+                nd             = hooks ? nondetection_at(blk + ps_f * geo.pset_stride, a.t_dep) : 1.0;
+                load10(a.snap + (rbase + nxt.from) * geo.n + gl * NC, sf);
+                ff = a.fac[(rbase + nxt.from) * W + gl];
+                load10(a.y_out + (rbase + nxt.from) * geo.n + gl * NC, yf);
+            }
+            // (an edge from a node to itself is not supported: its destination state would be the held source state)
+            load10(a.y_out + (rbase + nxt.to) * geo.n + gl * NC, ytn);
+            cur = nxt;
+        }
+        f_next = f_next2;
+        t_next = t_next2;
+    }
+    if (act) {
+        store10(a.y_out + (rbase + cur.from) * geo.n + gl * NC, yf);
     }
 }
 
@@ -758,7 +873,11 @@ static cudaError_t launch_edges_g(const EdgeArgs& a, int which, cudaStream_t str
         }
     }
     else {
-        MIO_EDGE_LAUNCH((return_exact_kernel<G, LAY>), a.num_runs, 32);
+        // a.run_list: [R] run indices, a.list_count: [1]
+        cudaMemsetAsync(a.list_count, 0, sizeof(int), stream);
+        collect_flagged_kernel<256><<<(unsigned)a.num_runs, 256, 0, stream>>>(a, a.run_list, a.list_count);
+        return_exact_kernel<G, LAY><<<(unsigned)((a.num_runs + NPW - 1) / NPW), 32, 0, stream>>>(a, a.run_list,
+                                                                                                 a.list_count);
     }
 #undef MIO_EDGE_LAUNCH
     return cudaGetLastError();

@@ -86,6 +86,8 @@ struct EdgeArgs {
     double* aux;         // [R][N][G][4] return coefficients of a node as destination (written at departure)
     int* run_flags;      // [R] return: set to 1 when an underflow fix-up is needed (exact replay required)
     long long* stats;    // [0] += number of (run, step) replays done by the exact kernel
+    int* run_list;       // [R] scratch: the runs flagged for the exact replay of this step
+    int* list_count;     // [1] scratch: length of run_list
     double t;            // time of this edge phase (m_t after the node phase)
     double t_dep;        // return only: departure time of the returning commuters
     double dt;           // dt of this graph step
