@@ -96,36 +96,58 @@ __device__ __forceinline__ double key_to_double(unsigned long long k)
     return __longlong_as_double((long long)b);
 }
 
-// One CTA per column. Pass over the digits from the most significant; every percentile keeps its own prefix.
+// One CTA per column; exact radix select of all requested order statistics in the same passes over the digits, from
+// the most significant. Percentiles whose prefixes agree so far share one histogram, so an element contributes to at
+// most one histogram per pass, and equal (histogram, digit) pairs are aggregated inside the warp before the shared
+// memory atomic (columns whose runs agree -- empty compartments -- would otherwise serialise on one counter).
+// STAGED: the column's keys are first copied to shared memory (one pass over HBM, which also yields the mean) and the
+// digit passes (8 bits each, stopping as soon as every order statistic is alone in its bin) read shared memory.
+// Otherwise (columns too long for shared memory) the digit passes (11/10 bits) read the column from global memory.
+template <bool STAGED>
 __global__ void __launch_bounds__(SEL_THREADS) select_percentiles_kernel(SelectArgs a)
 {
-    extern __shared__ unsigned int hist_dyn[]; // [num_p][SEL_BINS]
-    unsigned int(*hist)[SEL_BINS] = reinterpret_cast<unsigned int(*)[SEL_BINS]>(hist_dyn);
-    __shared__ unsigned long long prefix[SEL_MAX_P];
+    constexpr int BITS = STAGED ? 8 : SEL_BITS;
+    constexpr int BINS = 1 << BITS;
+    extern __shared__ __align__(16) unsigned char sel_smem[];
+    unsigned int(*hist)[BINS] = reinterpret_cast<unsigned int(*)[BINS]>(sel_smem);               // [num_p][BINS]
+    unsigned long long* keys  = reinterpret_cast<unsigned long long*>(sel_smem + sizeof(unsigned int) * BINS * SEL_MAX_P);
+    __shared__ unsigned long long prefix[SEL_MAX_P]; // of percentile q
     __shared__ long long remaining[SEL_MAX_P];
+    __shared__ unsigned int bin_count[SEL_MAX_P];    // size of the bin percentile q fell into in the last pass
+    __shared__ int hist_of[SEL_MAX_P];               // histogram used by percentile q (first q with the same prefix)
     __shared__ double red[SEL_THREADS];
     const long long col = blockIdx.x;
     const int tid       = threadIdx.x;
-    if (a.out_mean != nullptr) {
-        // ensemble_mean: sum of value / num_runs (fixed summation tree => deterministic)
+    const int lane      = tid & 31;
+    const int total     = (int)a.total;
+    // ensemble_mean: sum of value / num_runs (fixed summation tree => deterministic); staging pass
+    if (a.out_mean != nullptr || STAGED) {
         double s           = 0.0;
         const double denom = (double)a.total;
+        long long base     = 0;
         for (int sg = 0; sg < a.num_segments; ++sg) {
             const double* p = a.seg_ptr[sg] + (size_t)col * a.seg_stride[sg];
             for (long long i = tid; i < a.seg_count[sg]; i += SEL_THREADS) {
-                s += p[i] / denom;
+                const double v = p[i];
+                s += v / denom;
+                if (STAGED) {
+                    keys[base + i] = ordered_key(v);
+                }
             }
+            base += a.seg_count[sg];
         }
-        red[tid] = s;
-        __syncthreads();
-        for (int o = SEL_THREADS / 2; o > 0; o >>= 1) {
-            if (tid < o) {
-                red[tid] += red[tid + o];
-            }
+        if (a.out_mean != nullptr) {
+            red[tid] = s;
             __syncthreads();
-        }
-        if (tid == 0) {
-            a.out_mean[col] = red[0];
+            for (int o = SEL_THREADS / 2; o > 0; o >>= 1) {
+                if (tid < o) {
+                    red[tid] += red[tid + o];
+                }
+                __syncthreads();
+            }
+            if (tid == 0) {
+                a.out_mean[col] = red[0];
+            }
         }
     }
     if (a.out_select == nullptr || a.num_p == 0) {
@@ -134,47 +156,83 @@ __global__ void __launch_bounds__(SEL_THREADS) select_percentiles_kernel(SelectA
     if (tid < a.num_p) {
         prefix[tid]    = 0ull;
         remaining[tid] = a.rank[tid];
+        bin_count[tid] = 0xffffffffu;
+        hist_of[tid]   = 0;
     }
-    int shift = 64;
+    __syncthreads();
+    const int num_p = a.num_p;
+    int shift       = 64;
     while (shift > 0) {
-        const int bits = shift >= 20 + SEL_BITS ? SEL_BITS : (shift > 10 ? 10 : shift); // 11,11,11,11,10,10
+        int bits;
+        if (STAGED) {
+            bits = BITS;
+        }
+        else {
+            bits = shift >= 20 + SEL_BITS ? SEL_BITS : (shift > 10 ? 10 : shift); // 11,11,11,11,10,10
+        }
         shift -= bits;
         const unsigned int nb = 1u << bits;
-        for (int i = tid; i < a.num_p * SEL_BINS; i += SEL_THREADS) {
+        for (int i = tid; i < num_p * BINS; i += SEL_THREADS) {
             (&hist[0][0])[i] = 0u;
         }
         __syncthreads();
+        // distinct prefixes of this pass (registers): histogram u belongs to the first percentile with that prefix
+        unsigned long long upre[SEL_MAX_P];
+        int nu = 0;
+#pragma unroll
+        for (int q = 0; q < SEL_MAX_P; ++q) {
+            if (q < num_p && hist_of[q] == q) {
+                upre[nu++] = prefix[q];
+            }
+        }
         const bool first = (shift + bits) == 64;
-        for (int sg = 0; sg < a.num_segments; ++sg) {
-            const double* p = a.seg_ptr[sg] + (size_t)col * a.seg_stride[sg];
-            for (long long i = tid; i < a.seg_count[sg]; i += SEL_THREADS) {
-                const unsigned long long k = ordered_key(p[i]);
-                const unsigned int digit   = (unsigned int)(k >> shift) & (nb - 1u);
-                if (first) {
-                    // all percentiles share the empty prefix. The leading digit (sign + exponent bits) is the same
-                    // for most runs of a column: aggregate equal digits inside the warp before touching shared memory
-                    const unsigned int act  = __activemask();
-                    const unsigned int same = __match_any_sync(act, digit);
-                    if ((int)(threadIdx.x & 31) == __ffs(same) - 1) {
-                        atomicAdd(&hist[0][digit], (unsigned int)__popc(same));
+        auto visit = [&](unsigned long long k) {
+            const unsigned int digit = (unsigned int)(k >> shift) & (nb - 1u);
+            int u = -1;
+            if (first) {
+                u = 0;
+            }
+            else {
+                const unsigned long long hi = k >> (shift + bits);
+#pragma unroll
+                for (int j = 0; j < SEL_MAX_P; ++j) {
+                    if (j < nu && hi == upre[j]) {
+                        u = j;
                     }
                 }
-                else {
-                    const unsigned long long hi = k >> (shift + bits);
-                    for (int q = 0; q < a.num_p; ++q) {
-                        if (hi == prefix[q]) {
-                            atomicAdd(&hist[q][digit], 1u);
-                        }
-                    }
+            }
+            // warp aggregation of equal (histogram, digit) pairs
+            const unsigned int code = u < 0 ? 0xffffffffu : ((unsigned int)u << 16) | digit;
+            const unsigned int act  = __activemask();
+            const unsigned int same = __match_any_sync(act, code);
+            if (u >= 0 && lane == __ffs(same) - 1) {
+                atomicAdd(&hist[u][digit], (unsigned int)__popc(same));
+            }
+        };
+        if (STAGED) {
+            for (int i = tid; i < total; i += SEL_THREADS) {
+                visit(keys[i]);
+            }
+        }
+        else {
+            for (int sg = 0; sg < a.num_segments; ++sg) {
+                const double* p = a.seg_ptr[sg] + (size_t)col * a.seg_stride[sg];
+                for (long long i = tid; i < a.seg_count[sg]; i += SEL_THREADS) {
+                    visit(ordered_key(p[i]));
                 }
             }
         }
         __syncthreads();
-        // warp q locates the digit of percentile q: per-lane partial sums, warp scan, then a short in-lane search
+        // warp q locates the digit of percentile q: per-lane partial sums, warp scan, then a short in-lane search.
+        // histogram index of q: position of hist_of[q] among the distinct ones
         {
-            const int wq = tid >> 5, lane = tid & 31;
-            if (wq < a.num_p) {
-                const unsigned int* h = first ? hist[0] : hist[wq];
+            const int wq = tid >> 5;
+            if (wq < num_p) {
+                int u = 0;
+                for (int q = 0; q < hist_of[wq]; ++q) {
+                    u += (hist_of[q] == q) ? 1 : 0;
+                }
+                const unsigned int* h = hist[u];
                 const int per         = (int)(nb / 32u);
                 unsigned int sum      = 0;
                 for (int i = 0; i < per; ++i) {
@@ -194,19 +252,53 @@ __global__ void __launch_bounds__(SEL_THREADS) select_percentiles_kernel(SelectA
                 if (who != 0u && lane == __ffs(who) - 1) {
                     long long r    = rem - exc;
                     unsigned int d = lane * per;
+                    unsigned int c = 0;
                     for (;; ++d) {
-                        const unsigned int c = h[d];
+                        c = h[d];
                         if (r < (long long)c) {
                             break;
                         }
                         r -= c;
                     }
                     remaining[wq] = r;
+                    bin_count[wq] = c;
                     prefix[wq]    = (prefix[wq] << bits) | (unsigned long long)d;
                 }
             }
         }
         __syncthreads();
+        if (tid == 0) {
+            for (int q = 0; q < num_p; ++q) {
+                int hq = q;
+                for (int j = 0; j < q; ++j) {
+                    if (prefix[j] == prefix[q]) {
+                        hq = j;
+                        break;
+                    }
+                }
+                hist_of[q] = hq;
+            }
+        }
+        __syncthreads();
+        if (STAGED && shift > 0) {
+            // every order statistic alone in its bin: its key is the one element with that prefix
+            bool alone = true;
+            for (int q = 0; q < num_p; ++q) {
+                alone = alone && bin_count[q] == 1u;
+            }
+            if (alone) { // uniform over the CTA
+                for (int i = tid; i < total; i += SEL_THREADS) {
+                    const unsigned long long k  = keys[i];
+                    const unsigned long long hi = k >> shift;
+                    for (int q = 0; q < num_p; ++q) {
+                        if (hi == prefix[q]) {
+                            a.out_select[(size_t)q * a.num_columns + col] = key_to_double(k);
+                        }
+                    }
+                }
+                return;
+            }
+        }
     }
     if (tid < a.num_p) {
         a.out_select[(size_t)tid * a.num_columns + col] = key_to_double(prefix[tid]);
@@ -236,11 +328,18 @@ cudaError_t launch_select(const SelectArgs& a, cudaStream_t stream)
     if (a.num_columns == 0) {
         return cudaSuccess;
     }
-    const int shmem = (int)sizeof(unsigned int) * SEL_BINS * (a.num_p > 0 ? a.num_p : 1);
-    // static shared (prefixes, reduction scratch) comes on top: always raise the dynamic limit to the maximum used
-    cudaFuncSetAttribute(select_percentiles_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize,
-                         (int)sizeof(unsigned int) * SEL_BINS * SEL_MAX_P);
-    select_percentiles_kernel<<<(unsigned)a.num_columns, SEL_THREADS, shmem, stream>>>(a);
+    // columns that fit into shared memory (two CTAs per SM) are staged there: one pass over HBM
+    const size_t hist_staged = sizeof(unsigned int) * 256 * SEL_MAX_P;
+    const size_t staged      = hist_staged + sizeof(unsigned long long) * (size_t)a.total;
+    if (staged <= 110 * 1024) {
+        cudaFuncSetAttribute(select_percentiles_kernel<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)staged);
+        select_percentiles_kernel<true><<<(unsigned)a.num_columns, SEL_THREADS, staged, stream>>>(a);
+    }
+    else {
+        const int shmem = (int)sizeof(unsigned int) * SEL_BINS * SEL_MAX_P;
+        cudaFuncSetAttribute(select_percentiles_kernel<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, shmem);
+        select_percentiles_kernel<false><<<(unsigned)a.num_columns, SEL_THREADS, shmem, stream>>>(a);
+    }
     return cudaGetLastError();
 }
 
