@@ -119,6 +119,21 @@ __device__ __forceinline__ void edge_lane_setup(const Geometry& geo, const int* 
     L.rn                = (size_t)(cta_active ? L.run : 0) * geo.N + L.node;
 }
 
+__device__ __forceinline__ void wait_mbar(uint64_t* mbar, uint32_t parity)
+{
+    uint32_t done = 0;
+    while (!done) {
+        asm volatile("{\n"
+                     ".reg .pred p;\n"
+                     "mbarrier.try_wait.parity.shared::cta.b64 p, [%1], %2;\n"
+                     "selp.u32 %0, 1, 0, p;\n"
+                     "}\n"
+                     : "=r"(done)
+                     : "r"(smem_u32(mbar)), "r"(parity)
+                     : "memory");
+    }
+}
+
 __device__ __forceinline__ int warp_max(int v)
 {
 #pragma unroll
@@ -541,6 +556,222 @@ __global__ void __launch_bounds__(EDGE_THREADS, MIO_RETURN_MINBLOCKS < 2 ? 2 : M
 }
 
 // ---------------------------------------------------------------------------------------------------------------
+// Return with the node records moved by TMA (one parameter set per run, i.e. the ensemble case). A lane's record is
+// 80 contiguous bytes, so a warp-wide 16 byte load touches 30 different sectors and return_kernel is bound by the
+// load/store unit, not by HBM. Here every warp owns a tile in shared memory: one elected lane issues a bulk copy per
+// (node, array) -- 480 contiguous bytes each -- for the NPW nodes of the pass (state, both visitor vectors, emigration
+// base vector); the lanes then read their records with conflict-free 16 byte shared-memory loads, and the new state
+// leaves through bulk stores. Same arithmetic and order as return_kernel.
+constexpr int RETURN_TMA_THREADS = 256;
+constexpr int RETURN_TMA_ARRAYS  = 4; // y, V1, V3, u
+
+__device__ __forceinline__ void lds10(const double* p, double (&v)[NC])
+{
+    const double2* s = reinterpret_cast<const double2*>(p);
+#pragma unroll
+    for (int i = 0; i < NC / 2; ++i) {
+        const double2 x = s[i];
+        v[2 * i]        = x.x;
+        v[2 * i + 1]    = x.y;
+    }
+}
+
+template <int G, int LAY>
+__global__ void __launch_bounds__(RETURN_TMA_THREADS, 2) return_tma_kernel(EdgeArgs a)
+{
+    extern __shared__ __align__(16) double smem[];
+    constexpr int WARPS = RETURN_TMA_THREADS / 32;
+    __shared__ __align__(8) uint64_t mbar;         // parameter block
+    __shared__ __align__(8) uint64_t wbar[WARPS];  // one per warp tile
+    const Geometry& geo = a.geo;
+    constexpr int W     = G * LAY;
+    constexpr int NPW   = 32 / W;
+    const int run       = blockIdx.x;
+    if (run >= a.num_runs) {
+        return;
+    }
+    const int warp = threadIdx.x >> 5;
+    const int lane = threadIdx.x & 31;
+    if (threadIdx.x == 0) {
+        asm volatile("mbarrier.init.shared::cta.b64 [%0], 1;" ::"r"(smem_u32(&mbar)));
+        for (int w = 0; w < WARPS; ++w) {
+            asm volatile("mbarrier.init.shared::cta.b64 [%0], 1;" ::"r"(smem_u32(&wbar[w])));
+        }
+        asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+    }
+    __syncthreads();
+    if (threadIdx.x == 0) {
+        const int blk_bytes = geo.block_stride * 8;
+        asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(smem_u32(&mbar)), "r"(blk_bytes)
+                     : "memory");
+        asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];" ::"r"(
+                         smem_u32(smem)),
+                     "l"(a.st.run_block + (size_t)run * geo.block_stride), "r"(blk_bytes), "r"(smem_u32(&mbar))
+                     : "memory");
+    }
+    const int rec_bytes = geo.n * 8;                  // one node record
+    const int tile_dbl  = NPW * geo.n;                // doubles of one array's tile
+    double* tile        = smem + geo.block_stride + (size_t)warp * RETURN_TMA_ARRAYS * tile_dbl;
+    const double* src[RETURN_TMA_ARRAYS] = {a.y_in, a.vis, a.vis + geo.n, a.u};
+    const int src_stride[RETURN_TMA_ARRAYS] = {1, 2, 2, 1}; // records per node in the source array
+    const int passes = (geo.N + NPW * WARPS - 1) / (NPW * WARPS);
+    EdgeLane<G, LAY> L;
+    L.run                  = run;
+    const Group<G, LAY>& g = L.g;
+    bool underflow_any     = false;
+    bool have_params       = false;
+    LaneCoef c_own;
+    for (int pass = 0; pass < passes; ++pass) {
+        const int item0 = (pass * WARPS + warp) * NPW;
+        if (item0 >= geo.N) { // uniform over the warp
+            break;
+        }
+        const int cnt_nodes = min(NPW, geo.N - item0);
+        if (lane == 0) {
+            // the bulk stores of the previous pass have read the tile
+            asm volatile("cp.async.bulk.wait_group.read 0;" ::: "memory");
+            asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(smem_u32(&wbar[warp])),
+                         "r"(cnt_nodes * RETURN_TMA_ARRAYS * rec_bytes)
+                         : "memory");
+            for (int j = 0; j < cnt_nodes; ++j) {
+                const size_t rn = (size_t)run * geo.N + a.csr.order_out[item0 + j];
+#pragma unroll
+                for (int q = 0; q < RETURN_TMA_ARRAYS; ++q) {
+                    asm volatile(
+                        "cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];" ::"r"(
+                            smem_u32(tile + q * tile_dbl + j * geo.n)),
+                        "l"(src[q] + rn * src_stride[q] * geo.n), "r"(rec_bytes), "r"(smem_u32(&wbar[warp]))
+                        : "memory");
+                }
+            }
+        }
+        const int item = item0 + g.lane / W;
+        L.valid        = !g.spare() && item < geo.N;
+        L.node         = L.valid ? a.csr.order_out[item] : 0;
+        L.rn           = (size_t)run * geo.N + L.node;
+        if (!have_params) {
+            wait_mbar(&mbar, 0);
+            c_own.load(smem + PHDR + g.gl * AGE_REC); // one parameter set per run
+            have_params = true;
+        }
+        double slam_own, ricr_own, rd_own, so[NC];
+        {
+            const double2* ax = reinterpret_cast<const double2*>(a.aux + (L.rn * W + g.gl) * AUX);
+            const double2 a0 = ax[0], a1 = ax[1];
+            slam_own = a0.x;
+            ricr_own = a0.y;
+            rd_own   = a1.x;
+        }
+        load10(a.csr.s_out + (size_t)L.node * geo.n + g.gl * NC, so);
+        // own commuters: destination dependent flows gathered over the outgoing edges (L2)
+        double a_slam = 0.0, a_icr = 0.0, a_d = 0.0;
+        {
+            const int beg = L.valid ? a.csr.out_ptr[L.node] : 0;
+            const int cnt = L.valid ? a.csr.out_ptr[L.node + 1] - beg : 0;
+            const int mx  = warp_max(cnt);
+            constexpr int BATCH = 4;
+            for (int it0 = 0; it0 < mx; it0 += BATCH) {
+                int dst[BATCH];
+                double2 w[BATCH], a0[BATCH], a1[BATCH];
+#pragma unroll
+                for (int j = 0; j < BATCH; ++j) {
+                    const bool act = it0 + j < cnt;
+                    const int e    = beg + (act ? it0 + j : 0);
+                    dst[j]         = __ldg(a.csr.out_dst + e);
+                    w[j]           = __ldg(reinterpret_cast<const double2*>(a.csr.w_out) + (size_t)e * W + g.gl);
+                    if (!act) {
+                        w[j] = make_double2(0.0, 0.0);
+                    }
+                }
+#pragma unroll
+                for (int j = 0; j < BATCH; ++j) {
+                    const double2* ax =
+                        reinterpret_cast<const double2*>(a.aux + (((size_t)run * geo.N + dst[j]) * W + g.gl) * AUX);
+                    a0[j] = ax[0];
+                    a1[j] = ax[1];
+                }
+#pragma unroll
+                for (int j = 0; j < BATCH; ++j) {
+                    a_slam += w[j].x * a0[j].x;
+                    a_icr += w[j].y * a0[j].y;
+                    a_d += w[j].y * a1[j].x;
+                }
+            }
+        }
+        // the tile has arrived
+        wait_mbar(&wbar[warp], pass & 1);
+        const int slot_off = (g.spare() ? 0 : (g.lane / W)) * geo.n + g.gl * NC;
+        double y[NC], V[NC], V3[NC], uk[NC];
+        lds10(tile + 0 * tile_dbl + slot_off, y);
+        lds10(tile + 1 * tile_dbl + slot_off, V);
+        lds10(tile + 2 * tile_dbl + slot_off, V3);
+        lds10(tile + 3 * tile_dbl + slot_off, uk);
+        bool underflow = false;
+        // monotonicity guard: returning visitor vectors stay non-negative iff dt * (outflow rate) <= 1
+        {
+            const double rmax = fmax(fmax(fmax(slam_own, c_own.rE_INS), fmax(c_own.rINS_ISy + c_own.rINS_R,
+                                                                             c_own.rISy_ISev + c_own.rISy_R)),
+                                     fmax(ricr_own + c_own.rISev_R + rd_own, c_own.rICr_D + c_own.rICr_R));
+            underflow = !(a.dt * rmax <= 1.0);
+        }
+        // visitors from sources < k
+        euler_return<G, LAY>(g, c_own, slam_own, ricr_own, rd_own, a.dt, V);
+#pragma unroll
+        for (int i = 0; i < NC; ++i) {
+            y[i] -= V[i];
+            underflow = underflow || (y[i] < 0.0);
+        }
+        // own commuters
+        {
+            double q[NC], k[NC];
+#pragma unroll
+            for (int i = 0; i < NC; ++i) {
+                q[i] = so[i] * uk[i];
+            }
+            const LaneCoef& c = c_own;
+            flows_to_dydt(a_slam * uk[cS], c.rE_INS * q[cE], c.rINS_ISy * q[cINS], c.rINS_R * q[cINS],
+                          c.rINS_ISy * q[cINSC], c.rINS_R * q[cINSC], c.rISy_ISev * q[cISy], c.rISy_R * q[cISy],
+                          c.rISy_ISev * q[cISyC], c.rISy_R * q[cISyC], a_icr * uk[cISev], c.rISev_R * q[cISev],
+                          a_d * uk[cISev], c.rICr_D * q[cICr], c.rICr_R * q[cICr], k);
+            route_recoveries<G, LAY>(g, k);
+#pragma unroll
+            for (int i = 0; i < NC; ++i) {
+                y[i] += q[i] + a.dt * k[i];
+            }
+        }
+        // visitors from sources > k
+        euler_return<G, LAY>(g, c_own, slam_own, ricr_own, rd_own, a.dt, V3);
+#pragma unroll
+        for (int i = 0; i < NC; ++i) {
+            y[i] -= V3[i];
+            underflow = underflow || (y[i] < 0.0);
+        }
+        if (L.valid) {
+            store10(tile + slot_off, y); // shared memory: the state's tile is reused for the result
+            underflow_any = underflow_any || underflow;
+        }
+        asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
+        __syncwarp();
+        if (lane == 0) {
+            for (int j = 0; j < cnt_nodes; ++j) {
+                const size_t rn = (size_t)run * geo.N + a.csr.order_out[item0 + j];
+                asm volatile("cp.async.bulk.global.shared::cta.bulk_group [%0], [%1], %2;" ::"l"(a.y_out + rn * geo.n),
+                             "r"(smem_u32(tile + j * geo.n)), "r"(rec_bytes)
+                             : "memory");
+            }
+            asm volatile("cp.async.bulk.commit_group;" ::: "memory");
+        }
+        __syncwarp();
+    }
+    if (lane == 0) {
+        asm volatile("cp.async.bulk.wait_group 0;" ::: "memory");
+    }
+    if (underflow_any) {
+        a.run_flags[run] = 1;
+    }
+}
+
+// ---------------------------------------------------------------------------------------------------------------
 // Literal sequential replay of the return phase for flagged runs, two kernels:
 //  collect_flagged_kernel  one CTA per run; a flagged run is appended to the run list, its flag cleared and its live
 //                          state reset to the state before the return phase (y_out[run] = y_in[run]).
@@ -865,7 +1096,14 @@ static cudaError_t launch_edges_g(const EdgeArgs& a, int which, cudaStream_t str
         }
     }
     else if (which == 1) {
-        if (a.csr.factorized) {
+        const size_t shmem_t =
+            shmem + sizeof(double) * (size_t)(RETURN_TMA_THREADS / 32) * RETURN_TMA_ARRAYS * NPW * a.geo.n;
+        if (a.csr.factorized && a.geo.num_psets == 1 && shmem_t <= 110 * 1024) {
+            auto kern = return_tma_kernel<G, LAY>;
+            cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)shmem_t);
+            kern<<<(unsigned)a.num_runs, RETURN_TMA_THREADS, shmem_t, stream>>>(a);
+        }
+        else if (a.csr.factorized) {
             MIO_EDGE_LAUNCH((return_kernel<G, LAY, true>), grid, EDGE_THREADS);
         }
         else {

@@ -19,6 +19,8 @@
 #include <random>
 #include <string>
 #include <tuple>
+#include <cstdlib>
+#include <thread>
 #include <vector>
 
 int mio_set_last_error(int code, const std::string& msg); // capi.cu
@@ -352,12 +354,12 @@ void write_cache(const DampingCache& c, int max_pts, size_t sz, double* times_ou
     (void)max_pts;
 }
 
-int sample_one_run(mio_study* s, uint64_t counter, double* pset, double* ctables, double* node_local, double* y0,
+int sample_one_run(const mio_study* s, uint64_t counter, double* pset, double* ctables, double* node_local, double* y0,
                    double* mobtable, uint64_t* draws)
 {
     const mio_study_desc& d = s->d;
     const int G = d.num_groups, N = d.num_nodes, L = d.num_locations, n = G * NC_OSECIR;
-    Engine& rng = s->rng;
+    Engine rng  = s->rng; // private copy: runs are sampled concurrently
     rng.counter = counter;
 
     // working copies: every run starts from the study's distributions (the example copies the graph per run,
@@ -659,14 +661,45 @@ int mio_study_sample_runs(mio_study* s, int64_t run0, int32_t count, double* pse
     const int64_t psz = MIO_PSET_HEADER + int64_t(MIO_OSECIR_AGE_STRIDE) * G;
     const int64_t csz = ctable_size(G, d.num_locations, d.ct_max_pts) * s->num_ctables;
     const int64_t msz = d.mob_max_pts > 0 ? 1 + d.mob_max_pts + int64_t(d.mob_max_pts) * n : 0;
-    for (int32_t r = 0; r < count; ++r) {
-        // parameter_studies.h:310-313: counter = m_rng.counter + rng_totalsequence_counter(run_idx, 0)
-        const uint64_t counter = d.rng_counter + (uint64_t(run0 + r) << 32);
-        int rc = sample_one_run(s, counter, psets + r * psz, ctables + r * csz, node_local + size_t(r) * N * 2,
-                                y0 + size_t(r) * N * n, (mobtables && msz) ? mobtables + r * msz : nullptr,
-                                draws ? draws + r : nullptr);
+    // parameter_studies.h:310-313: counter = m_rng.counter + rng_totalsequence_counter(run_idx, 0). Every run has its
+    // own counter subsequence and its own output slices, so the runs are sampled by several host threads; the values
+    // are the same bit for bit as in the reference's serial loop.
+    auto sample_range = [&](int32_t r0, int32_t r1) -> int {
+        for (int32_t r = r0; r < r1; ++r) {
+            const uint64_t counter = d.rng_counter + (uint64_t(run0 + r) << 32);
+            int rc = sample_one_run(s, counter, psets + r * psz, ctables + r * csz, node_local + size_t(r) * N * 2,
+                                    y0 + size_t(r) * N * n, (mobtables && msz) ? mobtables + r * msz : nullptr,
+                                    draws ? draws + r : nullptr);
+            if (rc != MIO_OK) {
+                return rc;
+            }
+        }
+        return MIO_OK;
+    };
+    int num_threads = 1;
+    if (const char* env = std::getenv("MIO_SAMPLE_THREADS")) {
+        num_threads = std::max(1, std::atoi(env));
+    }
+    else {
+        num_threads = (int)std::min<unsigned>(16u, std::max(1u, std::thread::hardware_concurrency()));
+    }
+    num_threads = std::min<int>(num_threads, std::max<int32_t>(1, count / 16));
+    if (num_threads <= 1) {
+        return sample_range(0, count);
+    }
+    std::vector<int> rcs(num_threads, MIO_OK);
+    std::vector<std::thread> workers;
+    for (int t = 0; t < num_threads; ++t) {
+        const int32_t r0 = (int32_t)((int64_t)count * t / num_threads);
+        const int32_t r1 = (int32_t)((int64_t)count * (t + 1) / num_threads);
+        workers.emplace_back([&, t, r0, r1] { rcs[t] = sample_range(r0, r1); });
+    }
+    for (auto& w : workers) {
+        w.join();
+    }
+    for (int rc : rcs) {
         if (rc != MIO_OK) {
-            return rc;
+            return mio_set_last_error(rc, "sampling failed in a worker thread (dampings exceed the table sizes?)");
         }
     }
     return MIO_OK;

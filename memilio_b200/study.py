@@ -276,19 +276,41 @@ class ParameterStudy:
         self.seeds = list(seeds)
         self._invalidate()
 
-    def sample(self, run0: int, count: int) -> GraphProblem:
-        """The sampled graphs of runs [run0, run0+count) as flat run data (what create_simulation would build)."""
+    def sample_buffers(self, count: int, pinned: bool = False):
+        """Host buffers for `sample(..., out=)`; pinned (page locked, via torch) when asked for and available."""
+        h = self._study()
+        g = self.graph
+        G, N, n = g.num_groups, g.num_nodes, g.n
+        nct = _lib().mio_study_num_ctables(h)
+        shapes = {"psets": (count, 1, flat.pset_size(g.model, G)),
+                  "ctables": (count, nct, flat.ctable_size(G, g.num_locations, self.ct_max_pts)),
+                  "node_local": (count, N, 2), "y0": (count, N, n)}
+        if self.mob_max_pts > 0:
+            shapes["mobtables"] = (count, flat.mobtable_size(n, self.mob_max_pts))
+        out = {}
+        for k, shp in shapes.items():
+            if pinned:
+                import torch
+                t = torch.zeros(shp, dtype=torch.float64, pin_memory=True)
+                out[k] = t.numpy()
+                out["_pin_" + k] = t  # keeps the page-locked allocation alive
+            else:
+                out[k] = np.zeros(shp)
+        return out
+
+    def sample(self, run0: int, count: int, out=None) -> GraphProblem:
+        """The sampled graphs of runs [run0, run0+count) as flat run data (what create_simulation would build).
+        `out`: buffers from sample_buffers (at least `count` runs) to sample into instead of fresh arrays."""
         h = self._study()
         g = self.graph
         G, N, n = g.num_groups, g.num_nodes, g.n
         nct = _lib().mio_study_num_ctables(h)
         node_ct = np.zeros(N, dtype=np.int32)
         _check(_lib().mio_study_node_ctable(h, cdefs.iptr(node_ct)))
-        psets = np.zeros((count, 1, flat.pset_size(g.model, G)))
-        ctables = np.zeros((count, nct, flat.ctable_size(G, g.num_locations, self.ct_max_pts)))
-        local = np.zeros((count, N, 2))
-        y0 = np.zeros((count, N, n))
-        mob = np.zeros((count, flat.mobtable_size(n, self.mob_max_pts))) if self.mob_max_pts > 0 else None
+        if out is None:
+            out = self.sample_buffers(count)
+        psets, ctables, local, y0 = (out[k][:count] for k in ("psets", "ctables", "node_local", "y0"))
+        mob = out["mobtables"][:count] if self.mob_max_pts > 0 else None
         draws = (C.c_uint64 * max(count, 1))()
         _check(_lib().mio_study_sample_runs(h, run0, count, cdefs.dptr(psets), cdefs.dptr(ctables), cdefs.dptr(local),
                                             cdefs.dptr(y0), cdefs.dptr(mob), draws))
@@ -332,7 +354,75 @@ class ParameterStudy:
         self._invalidate()
         return out
 
+    def run_ensemble(self, p: Optional[Sequence[float]] = None, mean: bool = True, num_batches: int = 4,
+                     device: int = 0, rank: int = 0, world: int = 1, mode: Optional[int] = None, pinned: bool = True):
+        """ParameterStudy::run with the ensemble post-processing of save_results done on the device
+        (parameter_studies.h:158-217 + data/analyze_result.h:289-343): this rank's block of runs (distribute_runs) is
+        sampled, uploaded and advanced in `num_batches` batches, the daily results are recorded on the GPU and reduced
+        to percentiles / mean at the end (exchange over torch.distributed when world > 1; result on rank 0).
+        Pipeline: a host thread samples batch b+1 (C library, several threads) and uploads it into the second of two
+        simulation handles while the GPU advances batch b. Returns (percentiles [len(p)][columns], mean [columns])."""
+        from concurrent.futures import ThreadPoolExecutor
+        from . import capi, ensemble
+        if p is None:
+            p = ensemble.DEFAULT_PERCENTILES
+        if mode is None:
+            mode = ensemble.ENS_AGE_SUM
+        run0, count = distribute_runs(self.num_runs, world, rank)
+        nb = max(1, min(num_batches, count))
+        bounds = [(i * count // nb, (i + 1) * count // nb) for i in range(nb)]
+        bmax = max(b - a for a, b in bounds)
+        days = int(np.floor(self.tmax + 1e-14) - np.ceil(self.t0 - 1e-14)) + 1
+        g = self.graph
+        key = (count, bmax, days, mode, device, pinned)
+        cache = getattr(self, "_ens", None)
+        if cache is None or cache["key"] != key:
+            self._drop_ensemble_cache()
+            bufs = [self.sample_buffers(bmax, pinned) for _ in range(2)]
+            first = self.sample(run0 + bounds[0][0], bounds[0][1] - bounds[0][0], out=bufs[0])
+            sims = [capi.GraphSimulation(first, device=device, max_runs=bmax, upload=False) for _ in range(2)]
+            rec = ensemble.EnsembleRecord(g.num_groups, g.num_nodes, days, capacity_runs=count, mode=mode, device=device,
+                                          model=g.model)
+            cache = self._ens = {"key": key, "bufs": bufs, "sims": sims, "rec": rec,
+                                 "pool": ThreadPoolExecutor(max_workers=1)}
+        bufs, sims, rec, pool = cache["bufs"], cache["sims"], cache["rec"], cache["pool"]
+        h2d = 0
+
+        def prepare(i):
+            a, b = bounds[i]
+            pb = self.sample(run0 + a, b - a, out=bufs[i % 2])
+            sim = sims[i % 2]
+            sim.reset()
+            sim.set_active_runs(b - a)
+            rec.attach(sim, a)
+            sim.set_runs(0, pb, 0, b - a)
+            return sim, sum(getattr(pb, k).nbytes for k in ("psets", "ctables", "node_local", "y0"))
+
+        fut = pool.submit(prepare, 0)
+        for i in range(nb):
+            sim, nbytes = fut.result()
+            h2d += nbytes
+            if i + 1 < nb:
+                fut = pool.submit(prepare, i + 1)
+            sim.advance(self.tmax)
+        self.last_h2d_bytes = h2d
+        pct, mn = ensemble.reduce_distributed(rec.as_torch(), count, rank, world, p, mean)
+        # parameter_studies.h:339: future calls of run() produce different parameters
+        self.rng_counter += self.num_runs << 32
+        self._invalidate()
+        return pct, mn
+
+    def _drop_ensemble_cache(self):
+        cache = getattr(self, "_ens", None)
+        if cache is not None:
+            cache["pool"].shutdown(wait=True)
+            for sim in cache["sims"]:
+                sim.close()
+            cache["rec"].close()
+            self._ens = None
+
     def close(self):
+        self._drop_ensemble_cache()
         self._invalidate()
 
     def __del__(self):

@@ -120,3 +120,27 @@ def test_parameter_study_run_matches_manual_batches():
     assert len(part) == 5
     for r in range(5):
         np.testing.assert_array_equal(part[r], daily[6 + r])
+
+
+def test_run_ensemble_matches_record_and_reduce():
+    # the pipelined public call (sampling thread, two handles, on-device reduction) against one handle + reduce
+    G, N, runs, T = 6, 12, 29, 5
+    g = synthetic.covid_study_graph(N=N, max_out_degree=4, n_seeded=3, damping_day=2.0)
+    ps = study.ParameterStudy(g, 0.0, float(T), 0.5, runs)
+    pct, mean = ps.run_ensemble(num_batches=3)
+    assert ps.rng_counter == runs << 32
+    ps2 = study.ParameterStudy(g, 0.0, float(T), 0.5, runs)
+    p = ps2.sample(0, runs)
+    rec = ensemble.EnsembleRecord(G, N, T + 1, capacity_runs=runs, mode=ensemble.ENS_AGE_SUM)
+    with capi.GraphSimulation(p, upload=False) as sim:
+        rec.attach(sim, 0)
+        sim.set_runs(0, p, 0, runs)
+        sim.advance(float(T))
+    pct2, mean2 = rec.reduce()
+    np.testing.assert_array_equal(pct, pct2)
+    np.testing.assert_array_equal(mean, mean2)
+    # a second call continues the random sequence and reuses the cached handles
+    pct3, _ = ps.run_ensemble(num_batches=3)
+    assert not np.array_equal(pct3, pct)
+    ps.close()
+    rec.close()
