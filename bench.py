@@ -121,8 +121,8 @@ def workload_config(args):
                 else "mio::Simulation<osecirvvs::Model> (as cpp/benchmarks/graph_simulation.cpp)",
                 "parallelism": f"runs sharded x{args.gpus}",
                 "l2_policy": "inputs larger than L2 (state 4 x %.2f GB per GPU)" % (args.runs * args.nodes * 1440 / 1e9),
-                "sampling": "parameters of cpp/benchmarks/graph_simulation.cpp, 32 distinct runs with +-10% uniform "
-                            "variation (numpy) tiled to the run count; no MEmilio sampler for osecirvvs yet",
+                "sampling": "osecirvvs::draw_sample(graph) semantics, threefry2x32 seeds {1..6}, uniform +-10% "
+                            "distributions around the parameters of cpp/benchmarks/graph_simulation.cpp",
                 "outputs": "per-node daily p05/p25/p50/p75/p95 + mean of age-summed compartments and of the "
                            "node-summed state"}
     return {"workload": f"ParameterStudy ensemble, synthetic {args.nodes}-county ODE-SECIR graph "
@@ -152,33 +152,6 @@ def cpu_baseline(problem, days, sample_runs, threads):
 METRIC = {"osecir": "graph_ode_secir_node_days_per_s", "osecirvvs": "graph_ode_secirvvs_node_days_per_s"}
 
 
-def vvs_problem(args, runs):
-    """osecirvvs county ensemble: 32 distinct runs (numpy +-10 % variation) tiled to `runs`."""
-    from memilio_b200 import flat, synthetic
-    distinct = min(32, runs)
-    base = synthetic.county_problem_vvs(N=args.nodes, runs=distinct, days=int(args.days) + 1, perturb=0.1,
-                                        sim_kind=flat.SIM_MODEL if args.sim_kind == "model" else flat.SIM_BASE)
-    reps = (runs + distinct - 1) // distinct
-    for name in ("psets", "ctables", "node_local", "y0"):
-        a = getattr(base, name)
-        setattr(base, name, np.ascontiguousarray(np.concatenate([a] * reps, axis=0)[:runs]))
-    return base
-
-
-class SlicedSampler:
-    """Stands in for ParameterStudy.sample where there is no sampler: hands out slices of pre-built runs."""
-
-    def __init__(self, problem):
-        self.problem = problem
-
-    def sample(self, run0, count):
-        import copy
-        q = copy.copy(self.problem)
-        for name in ("psets", "ctables", "node_local", "y0"):
-            setattr(q, name, getattr(self.problem, name)[run0:run0 + count])
-        return q
-
-
 def run_reference(args, rank, world):
     """--impl reference: the reference's own CPU implementation of the path (oracle port; the reference itself
     cannot be built here) on all host threads. Rank 0 only."""
@@ -189,10 +162,13 @@ def run_reference(args, rank, world):
     sample = args.cpu_sample_runs or 4 * cores
     from memilio_b200 import study
     if args.model == "osecirvvs":
-        problem = vvs_problem(args, max(sample, 1))
+        from memilio_b200 import flat
+        graph = synthetic.vvs_study_graph(N=args.nodes, days=int(args.days) + 1,
+                                          sim_kind=flat.SIM_MODEL if args.sim_kind == "model" else flat.SIM_BASE)
     else:
-        ps = study.ParameterStudy(synthetic.covid_study_graph(N=args.nodes), 0.0, args.days, 0.5, max(sample, 1))
-        problem = ps.sample(0, max(sample, 1))
+        graph = synthetic.covid_study_graph(N=args.nodes)
+    ps = study.ParameterStudy(graph, 0.0, args.days, 0.5, max(sample, 1))
+    problem = ps.sample(0, max(sample, 1))
     for _ in range(min(args.warmup, 1)):
         cpu_baseline(problem, min(args.days, 2.0), cores, cores)
     vals, secs = [], []
@@ -250,16 +226,14 @@ def main():
     assert count == R
     t_s = time.perf_counter()
     if args.model == "osecirvvs":
-        problem = vvs_problem(args, R)
-        ps = SlicedSampler(problem)
-        run0 = 0
-        num_groups = problem.num_groups
+        graph = synthetic.vvs_study_graph(N=N, days=int(T) + 1,
+                                          sim_kind=flat.SIM_MODEL if args.sim_kind == "model" else flat.SIM_BASE)
     else:
         graph = synthetic.covid_study_graph(N=N)
-        ps = study.ParameterStudy(graph, 0.0, T, 0.5, world * R)
-        problem = ps.sample(run0, R)
-        num_groups = graph.num_groups
-    host_sampling_s = time.perf_counter() - t_s if args.model == "osecir" else 0.0
+    ps = study.ParameterStudy(graph, 0.0, T, 0.5, world * R)
+    problem = ps.sample(run0, R)
+    num_groups = graph.num_groups
+    host_sampling_s = time.perf_counter() - t_s
     # pinned host staging
     pinned_names = [n_ for n_ in ("y0", "node_local", "psets", "ctables", "mobtables")
                     if getattr(problem, n_) is not None]
@@ -331,28 +305,13 @@ def main():
     nb = max(1, min(args.e2e_batches, R))
     bounds = [(i * R // nb, (i + 1) * R // nb) for i in range(nb)]
     bmax = max(b - a for a, b in bounds)
-    sim2 = capi.GraphSimulation(problem, device=local_rank, max_runs=bmax, upload=False) if args.model != "osecir" else None
-    pool = ThreadPoolExecutor(max_workers=1)
+    sim2 = None
 
     def step_e2e():
         t0 = time.perf_counter()
-        if args.model == "osecir":
-            # the public call: ParameterStudy.run_ensemble = sampling (host threads), H2D from pinned buffers, advance,
-            # on-device percentile reduction, D2H of the reduced result
-            out = ps.run_ensemble(num_batches=nb, device=local_rank, rank=rank, world=world)
-            torch.cuda.synchronize()
-            return (time.perf_counter() - t0) * 1e3, out
-        fut = pool.submit(ps.sample, run0 + bounds[0][0], bounds[0][1] - bounds[0][0])
-        for i, (a, b) in enumerate(bounds):
-            pb = fut.result()
-            if i + 1 < nb:
-                fut = pool.submit(ps.sample, run0 + bounds[i + 1][0], bounds[i + 1][1] - bounds[i + 1][0])
-            sim2.reset()
-            sim2.set_active_runs(b - a)
-            rec.attach(sim2, a)
-            sim2.set_runs(0, pb, 0, b - a)
-            sim2.advance(T)
-        out = reduce()
+        # the public call: ParameterStudy.run_ensemble = sampling (host threads), H2D from pinned buffers, advance,
+        # on-device percentile reduction, D2H of the reduced result
+        out = ps.run_ensemble(num_batches=nb, device=local_rank, rank=rank, world=world)
         torch.cuda.synchronize()
         return (time.perf_counter() - t0) * 1e3, out
 
@@ -415,8 +374,7 @@ def main():
             "e2e": {"value": e2e, "unit": "node-days/s",
                     "h2d_bytes_per_step": int(getattr(ps, "last_h2d_bytes", h2d)), "d2h_bytes_per_step": int(d2h),
                     "ms_per_step": tot_e2e_ms / args.steps, "batches": nb,
-                    "includes": ("ParameterStudy.run_ensemble: host sampling (C library threads, overlapped), "
-                                 if args.model == "osecir" else "") +
+                    "includes": "ParameterStudy.run_ensemble: host sampling (C library threads, overlapped), "
                                 "H2D of the runs' parameters and initial values from pinned memory, advance, "
                                 "percentile reduction, D2H"},
             "gpu_launches": int(agg[1].item()),

@@ -273,7 +273,7 @@ typedef struct {
 } mio_damping_sampling;
 
 typedef struct {
-    int32_t model;         /* MIO_MODEL_OSECIR */
+    int32_t model;         /* MIO_MODEL_OSECIR or MIO_MODEL_OSECIRVVS (ode_secirvvs/parameter_space.h:40-211) */
     int32_t num_groups;    /* G */
     int32_t num_nodes;     /* N */
     int32_t num_locations; /* L contact matrices of ContactPatterns */

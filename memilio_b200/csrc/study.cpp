@@ -345,6 +345,71 @@ void apply_constraints(double* pset, int G, double* local)
     }
 }
 
+// Parameters::apply_constraints, ode_secirvvs/parameters.h:710-938 on the flat layout (age stride 32)
+void apply_constraints_vvs(double* pset, int G, double* local)
+{
+    if (pset[MIO_PH_SEASONALITY] < 0.0 || pset[MIO_PH_SEASONALITY] > 0.5) {
+        pset[MIO_PH_SEASONALITY] = 0;
+    }
+    if (local[MIO_NL_ICU_CAPACITY] < 0.0) {
+        local[MIO_NL_ICU_CAPACITY] = 0;
+    }
+    if (local[MIO_NL_TNT_CAPACITY] < 0.0) {
+        local[MIO_NL_TNT_CAPACITY] = 0;
+    }
+    if (pset[MIO_PH_TNT_MAX_RISK] < 0.0) { // TestAndTraceCapacityMaxRiskSymptoms
+        pset[MIO_PH_TNT_MAX_RISK] = 0;
+    }
+    if (pset[MIO_PH_TNT_MAX_RISK_NOSYMP] < 0.0) {
+        pset[MIO_PH_TNT_MAX_RISK_NOSYMP] = 0;
+    }
+    const double tol_times = 1e-1;
+    for (int i = 0; i < G; ++i) {
+        double* a = pset + MIO_PSET_HEADER + i * MIO_OSECIRVVS_AGE_STRIDE;
+        for (int s : {MIO_PA_TIME_EXPOSED, MIO_PA_TIME_INS, MIO_PA_TIME_ISY, MIO_PA_TIME_ISEV, MIO_PA_TIME_ICR}) {
+            if (a[s] < tol_times) {
+                a[s] = tol_times;
+            }
+        }
+        if (a[MIO_PA_TRANS_PROB] < 0.0 || a[MIO_PA_TRANS_PROB] > 1.0) {
+            a[MIO_PA_TRANS_PROB] = 0.0;
+        }
+        if (a[MIO_PA_REL_TRANS_NOSYMP] < 0.0) {
+            a[MIO_PA_REL_TRANS_NOSYMP] = 0;
+        }
+        for (int s : {MIO_PA_REC_PER_INS, MIO_PA_RISK_SYMP, MIO_PA_SEV_PER_ISY, MIO_PA_CRIT_PER_SEV,
+                      MIO_PA_DEATHS_PER_SEV}) {
+            if (a[s] < 0.0 || a[s] > 1.0) {
+                a[s] = 0;
+            }
+        }
+        if (a[MIO_PA_CRIT_PER_SEV] + a[MIO_PA_DEATHS_PER_SEV] > 1.0) {
+            a[MIO_PA_DEATHS_PER_SEV] = 0;
+        }
+        if (a[MIO_PA_DEATHS_PER_CRIT] < 0.0 || a[MIO_PA_DEATHS_PER_CRIT] > 1.0) {
+            a[MIO_PA_DEATHS_PER_CRIT] = 0;
+        }
+        for (int s : {MIO_PV_DAYS_UNTIL_EFFECTIVE_PI, MIO_PV_DAYS_UNTIL_EFFECTIVE_II}) {
+            if (a[s] < 0.0) {
+                a[s] = 0;
+            }
+        }
+        for (int s : {MIO_PV_REDUC_EXPOSED_PI, MIO_PV_REDUC_EXPOSED_II, MIO_PV_REDUC_INF_SYMP_PI,
+                      MIO_PV_REDUC_INF_SYMP_II, MIO_PV_REDUC_SEV_CRIT_DEAD_PI, MIO_PV_REDUC_SEV_CRIT_DEAD_II,
+                      MIO_PV_REDUC_TIME_MILD}) {
+            if (a[s] <= 0.0 || a[s] > 1.0) {
+                a[s] = 1;
+            }
+        }
+        if (a[MIO_PV_INFECTIOUSNESS_NEW_VARIANT] < 0.0) {
+            a[MIO_PV_INFECTIOUSNESS_NEW_VARIANT] = 1.0;
+        }
+        if (a[MIO_PV_VACCINATION_GAP] < 0.0) {
+            a[MIO_PV_VACCINATION_GAP] = 0;
+        }
+    }
+}
+
 void write_cache(const DampingCache& c, int max_pts, size_t sz, double* times_out, double* mats_out)
 {
     for (size_t k = 0; k < c.times.size(); ++k) {
@@ -358,13 +423,16 @@ int sample_one_run(const mio_study* s, uint64_t counter, double* pset, double* c
                    double* mobtable, uint64_t* draws)
 {
     const mio_study_desc& d = s->d;
-    const int G = d.num_groups, N = d.num_nodes, L = d.num_locations, n = G * NC_OSECIR;
+    const bool vvs = d.model == MIO_MODEL_OSECIRVVS;
+    const int NCm  = vvs ? 27 : NC_OSECIR;                                    // compartments per age group
+    const int AS   = vvs ? MIO_OSECIRVVS_AGE_STRIDE : MIO_OSECIR_AGE_STRIDE;  // age record stride
+    const int G = d.num_groups, N = d.num_nodes, L = d.num_locations, n = G * NCm;
     Engine rng  = s->rng; // private copy: runs are sampled concurrently
     rng.counter = counter;
 
     // working copies: every run starts from the study's distributions (the example copies the graph per run,
     // cpp/examples/ode_secir_parameter_study_graph.cpp:278-282)
-    std::vector<Uncertain> header(MIO_PSET_HEADER), age(size_t(G) * MIO_OSECIR_AGE_STRIDE);
+    std::vector<Uncertain> header(MIO_PSET_HEADER), age(size_t(G) * AS);
     for (int k = 0; k < MIO_PSET_HEADER; ++k) {
         header[k].d = s->header[k];
     }
@@ -372,30 +440,58 @@ int sample_one_run(const mio_study* s, uint64_t counter, double* pset, double* c
         age[k].d = s->age[k];
     }
     auto A = [&](int i, int slot) -> Uncertain& {
-        return age[size_t(i) * MIO_OSECIR_AGE_STRIDE + slot];
+        return age[size_t(i) * AS + slot];
     };
 
-    // draw_sample_infection, parameter_space.h:155-191
-    header[MIO_PH_SEASONALITY].draw(rng);
-    A(0, MIO_PA_TIME_EXPOSED).draw(rng);
-    A(0, MIO_PA_TIME_INS).draw(rng);
-    A(0, MIO_PA_TIME_ISY).draw(rng);
-    A(0, MIO_PA_REL_TRANS_NOSYMP).draw(rng);
-    A(0, MIO_PA_RISK_SYMP).draw(rng);
-    A(0, MIO_PA_MAX_RISK_SYMP).draw(rng);
-    for (int i = 0; i < G; ++i) {
-        for (int slot : {MIO_PA_TIME_EXPOSED, MIO_PA_TIME_INS, MIO_PA_REL_TRANS_NOSYMP, MIO_PA_RISK_SYMP,
-                         MIO_PA_MAX_RISK_SYMP}) {
-            A(i, slot) = A(0, slot);
+    if (!vvs) {
+        // draw_sample_infection, ode_secir/parameter_space.h:155-191
+        header[MIO_PH_SEASONALITY].draw(rng);
+        A(0, MIO_PA_TIME_EXPOSED).draw(rng);
+        A(0, MIO_PA_TIME_INS).draw(rng);
+        A(0, MIO_PA_TIME_ISY).draw(rng);
+        A(0, MIO_PA_REL_TRANS_NOSYMP).draw(rng);
+        A(0, MIO_PA_RISK_SYMP).draw(rng);
+        A(0, MIO_PA_MAX_RISK_SYMP).draw(rng);
+        for (int i = 0; i < G; ++i) {
+            for (int slot : {MIO_PA_TIME_EXPOSED, MIO_PA_TIME_INS, MIO_PA_REL_TRANS_NOSYMP, MIO_PA_RISK_SYMP,
+                             MIO_PA_MAX_RISK_SYMP}) {
+                A(i, slot) = A(0, slot);
+            }
+            A(i, MIO_PA_TIME_ISY).draw(rng);
+            A(i, MIO_PA_TIME_ISEV).draw(rng);
+            A(i, MIO_PA_TIME_ICR).draw(rng);
+            A(i, MIO_PA_TRANS_PROB).draw(rng);
+            A(i, MIO_PA_REC_PER_INS).draw(rng);
+            A(i, MIO_PA_DEATHS_PER_CRIT).draw(rng);
+            A(i, MIO_PA_SEV_PER_ISY).draw(rng);
+            A(i, MIO_PA_CRIT_PER_SEV).draw(rng);
         }
-        A(i, MIO_PA_TIME_ISY).draw(rng);
-        A(i, MIO_PA_TIME_ISEV).draw(rng);
-        A(i, MIO_PA_TIME_ICR).draw(rng);
-        A(i, MIO_PA_TRANS_PROB).draw(rng);
-        A(i, MIO_PA_REC_PER_INS).draw(rng);
-        A(i, MIO_PA_DEATHS_PER_CRIT).draw(rng);
-        A(i, MIO_PA_SEV_PER_ISY).draw(rng);
-        A(i, MIO_PA_CRIT_PER_SEV).draw(rng);
+    }
+    else {
+        // draw_sample_infection, ode_secirvvs/parameter_space.h:86-141
+        static const int shared_slots[] = {MIO_PA_TIME_EXPOSED,           MIO_PA_TIME_INS,
+                                           MIO_PA_REL_TRANS_NOSYMP,       MIO_PA_RISK_SYMP,
+                                           MIO_PA_MAX_RISK_SYMP,          MIO_PV_REDUC_EXPOSED_PI,
+                                           MIO_PV_REDUC_EXPOSED_II,       MIO_PV_REDUC_INF_SYMP_PI,
+                                           MIO_PV_REDUC_INF_SYMP_II,      MIO_PV_REDUC_SEV_CRIT_DEAD_PI,
+                                           MIO_PV_REDUC_SEV_CRIT_DEAD_II, MIO_PV_REDUC_TIME_MILD};
+        header[MIO_PH_SEASONALITY].draw(rng);
+        for (int slot : shared_slots) {
+            A(0, slot).draw(rng);
+        }
+        for (int i = 0; i < G; ++i) {
+            for (int slot : shared_slots) {
+                A(i, slot) = A(0, slot);
+            }
+            A(i, MIO_PA_TIME_ISY).draw(rng);
+            A(i, MIO_PA_TIME_ISEV).draw(rng);
+            A(i, MIO_PA_TIME_ICR).draw(rng);
+            A(i, MIO_PA_TRANS_PROB).draw(rng);
+            A(i, MIO_PA_REC_PER_INS).draw(rng);
+            A(i, MIO_PA_DEATHS_PER_CRIT).draw(rng);
+            A(i, MIO_PA_SEV_PER_ISY).draw(rng);
+            A(i, MIO_PA_CRIT_PER_SEV).draw(rng);
+        }
     }
     // shared_contacts.draw_sample_dampings(), uncertain_matrix.h:165-171
     std::vector<double> dvalue(s->dampings.size());
@@ -414,12 +510,12 @@ int sample_one_run(const mio_study* s, uint64_t counter, double* pset, double* c
         pset[k] = header[k].d.value;
     }
     for (int i = 0; i < G; ++i) {
-        for (int slot = 0; slot < MIO_OSECIR_AGE_STRIDE; ++slot) {
-            pset[MIO_PSET_HEADER + i * MIO_OSECIR_AGE_STRIDE + slot] = A(i, slot).d.value;
+        for (int slot = 0; slot < AS; ++slot) {
+            pset[MIO_PSET_HEADER + i * AS + slot] = A(i, slot).d.value;
         }
     }
 
-    // per node: draw_sample_demographics, parameter_space.h:125-148
+    // per node: draw_sample_demographics (ode_secir/parameter_space.h:125-148, ode_secirvvs/parameter_space.h:40-78)
     for (int k = 0; k < N; ++k) {
         Uncertain icu{s->local[size_t(k) * 2 + MIO_NL_ICU_CAPACITY]}, tnt{s->local[size_t(k) * 2 + MIO_NL_TNT_CAPACITY]};
         double* loc              = node_local + size_t(k) * 2;
@@ -432,27 +528,47 @@ int sample_one_run(const mio_study* s, uint64_t counter, double* pset, double* c
         }
         auto group_total = [&](int i) { // Populations::get_group_total, populations.h:136-142
             double acc = 0.0;
-            for (int c = 0; c < NC_OSECIR; ++c) {
-                acc = acc + y[i * NC_OSECIR + c];
+            for (int c = 0; c < NCm; ++c) {
+                acc = acc + y[i * NCm + c];
             }
             return acc;
         };
         auto set_difference = [&](int i, int comp, double total) { // populations.h:194-205
             double current = group_total(i);
-            current -= y[i * NC_OSECIR + comp];
-            y[i * NC_OSECIR + comp] = total - current;
+            current -= y[i * NCm + comp];
+            y[i * NCm + comp] = total - current;
         };
         for (int i = 0; i < G; ++i) {
             const double total = group_total(i);
-            for (int c : {cE, cINS, cISy, cISev, cICr, cR}) {
-                Uncertain u{pk[i * NC_OSECIR + c]};
-                y[i * NC_OSECIR + c] = u.draw(rng);
+            if (!vvs) {
+                for (int c : {cE, cINS, cISy, cISev, cICr, cR}) {
+                    Uncertain u{pk[i * NCm + c]};
+                    y[i * NCm + c] = u.draw(rng);
+                }
+                set_difference(i, cS, total);
+                set_difference(i, cS, group_total(i));
             }
-            set_difference(i, cS, total);
-            set_difference(i, cS, group_total(i));
+            else {
+                // every compartment but SusceptibleNaive (0) and the three Dead ones (24, 25, 26)
+                for (int c = 1; c < 24; ++c) {
+                    Uncertain u{pk[i * NCm + c]};
+                    y[i * NCm + c] = u.draw(rng);
+                }
+                y[i * NCm + 0]    = 0;
+                const double diff = group_total(i) - total;
+                if (diff > 0) {
+                    y[i * NCm + 23] -= diff; // SusceptibleImprovedImmunity
+                }
+                set_difference(i, 0, total);
+            }
         }
         // apply_constraints of the node model: parameters (shared set + this node's capacities), populations
-        apply_constraints(pset, G, loc);
+        if (vvs) {
+            apply_constraints_vvs(pset, G, loc);
+        }
+        else {
+            apply_constraints(pset, G, loc);
+        }
         for (int j = 0; j < n; ++j) {
             if (y[j] < 0.0) {
                 y[j] = 0.0;
@@ -515,7 +631,12 @@ int sample_one_run(const mio_study* s, uint64_t counter, double* pset, double* c
 
     // edges: apply_dampings(mobility coefficients, shared dampings, make_mobility_damping_vector),
     // parameter_space.h:241-248
-    if (d.mob_max_pts > 0 && mobtable != nullptr) {
+    if (d.mob_max_pts > 0 && mobtable != nullptr && vvs) {
+        // ode_secirvvs draw_sample copies the edges unchanged (parameter_space.h:205-211): no mobility dampings
+        const int64_t msz0 = 1 + d.mob_max_pts + int64_t(d.mob_max_pts) * n;
+        std::fill(mobtable, mobtable + msz0, 0.0);
+    }
+    else if (d.mob_max_pts > 0 && mobtable != nullptr) {
         const int64_t msz = 1 + d.mob_max_pts + int64_t(d.mob_max_pts) * n;
         std::fill(mobtable, mobtable + msz, 0.0);
         DampingCache cache;
@@ -527,7 +648,7 @@ int sample_one_run(const mio_study* s, uint64_t counter, double* pset, double* c
                 continue;
             }
             for (int j = 0; j < n; ++j) {
-                vec[j] = dvalue[k] * ds.group_weights[j / NC_OSECIR];
+                vec[j] = dvalue[k] * ds.group_weights[j / NCm];
             }
             cache.add({ds.time, ds.level, ds.type, vec});
         }
@@ -554,8 +675,8 @@ int mio_study_create(const mio_study_desc* d, mio_study** out)
         return mio_set_last_error(MIO_INVALID_VALUE, "null argument");
     }
     *out = nullptr;
-    if (d->model != MIO_MODEL_OSECIR) {
-        return mio_set_last_error(MIO_INVALID_VALUE, "study sampling: model kind not supported (osecir only)");
+    if (d->model != MIO_MODEL_OSECIR && d->model != MIO_MODEL_OSECIRVVS) {
+        return mio_set_last_error(MIO_INVALID_VALUE, "study sampling: unknown model kind");
     }
     if (d->num_groups < 1 || d->num_groups > MIO_MAX_GROUPS || d->num_nodes < 1 || d->num_locations < 1 ||
         d->num_locations > 64 || d->num_dampings < 0 || d->num_holiday_sets < 0 || d->ct_max_pts < 0 ||
@@ -568,11 +689,13 @@ int mio_study_create(const mio_study_desc* d, mio_study** out)
         (d->num_holiday_sets > 0 && (!d->holiday_ptr || !d->holiday_periods || !d->node_holiday_set))) {
         return mio_set_last_error(MIO_INVALID_VALUE, "study descriptor: missing array");
     }
-    const int G = d->num_groups, N = d->num_nodes, L = d->num_locations, n = G * NC_OSECIR;
+    const bool vvs = d->model == MIO_MODEL_OSECIRVVS;
+    const int G = d->num_groups, N = d->num_nodes, L = d->num_locations, n = G * (vvs ? 27 : NC_OSECIR);
     auto* s = new mio_study();
     s->d    = *d;
     s->header.assign(d->header, d->header + MIO_PSET_HEADER);
-    s->age.assign(d->age_params, d->age_params + size_t(G) * MIO_OSECIR_AGE_STRIDE);
+    s->age.assign(d->age_params,
+                  d->age_params + size_t(G) * (vvs ? MIO_OSECIRVVS_AGE_STRIDE : MIO_OSECIR_AGE_STRIDE));
     s->local.assign(d->node_local, d->node_local + size_t(N) * 2);
     s->pop.assign(d->populations, d->populations + size_t(N) * n);
     s->baseline.assign(d->baseline, d->baseline + size_t(L) * G * G);
@@ -657,8 +780,9 @@ int mio_study_sample_runs(mio_study* s, int64_t run0, int32_t count, double* pse
         return mio_set_last_error(MIO_OUT_OF_RANGE, "run index exceeds the 32 bit subsequence index");
     }
     const mio_study_desc& d = s->d;
-    const int G = d.num_groups, N = d.num_nodes, n = G * NC_OSECIR;
-    const int64_t psz = MIO_PSET_HEADER + int64_t(MIO_OSECIR_AGE_STRIDE) * G;
+    const bool vvs    = d.model == MIO_MODEL_OSECIRVVS;
+    const int G = d.num_groups, N = d.num_nodes, n = G * (vvs ? 27 : NC_OSECIR);
+    const int64_t psz = MIO_PSET_HEADER + int64_t(vvs ? MIO_OSECIRVVS_AGE_STRIDE : MIO_OSECIR_AGE_STRIDE) * G;
     const int64_t csz = ctable_size(G, d.num_locations, d.ct_max_pts) * s->num_ctables;
     const int64_t msz = d.mob_max_pts > 0 ? 1 + d.mob_max_pts + int64_t(d.mob_max_pts) * n : 0;
     // parameter_studies.h:310-313: counter = m_rng.counter + rng_totalsequence_counter(run_idx, 0). Every run has its

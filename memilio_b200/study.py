@@ -107,6 +107,10 @@ class StudyGraph:
     mobility_location: int = 0
     damp_mobility: bool = True
     model: int = flat.MODEL_OSECIR
+    # osecirvvs: node type and the run-invariant cumulative vaccination arrays [N][G][days]
+    sim_kind: int = flat.SIM_MODEL
+    vacc_partial: Optional[np.ndarray] = None
+    vacc_full: Optional[np.ndarray] = None
 
     @property
     def n(self):
@@ -179,7 +183,7 @@ def build_desc(g: StudyGraph, seeds: Sequence[int], rng_counter: int, ct_max_pts
         return a.ctypes.data_as(C.POINTER(UncertainValue))
 
     d.header = uvp(g.header, (flat.PSET_HEADER,))
-    d.age_params = uvp(g.age_params, (G, flat.OSECIR_AGE_STRIDE))
+    d.age_params = uvp(g.age_params, (G, flat.age_stride(g.model)))
     d.node_local = uvp(g.node_local, (N, 2))
     d.populations = uvp(g.populations, (N, g.n))
     base = np.ascontiguousarray(g.baseline, dtype=np.float64).reshape(g.num_locations, G, G)
@@ -252,7 +256,9 @@ class ParameterStudy:
         self.rng_counter = 0
         self.ct_max_pts = ct_max_pts
         if mob_max_pts is None:
-            mob_max_pts = ct_max_pts if (graph.damp_mobility and graph.dampings) else 0
+            # the osecirvvs draw_sample(graph) copies the edges unchanged (ode_secirvvs/parameter_space.h:205-211)
+            mob_max_pts = ct_max_pts if (graph.damp_mobility and graph.dampings and
+                                         graph.model == flat.MODEL_OSECIR) else 0
         self.mob_max_pts = mob_max_pts
         self.integrator = integrator if integrator is not None else cdefs.integrator_desc()
         self._h = None
@@ -319,7 +325,8 @@ class ParameterStudy:
                             edge_coeff=g.edge_coeff, psets=psets, ctables=ctables, node_local=local, y0=y0,
                             ct_max_loc=g.num_locations, ct_max_pts=self.ct_max_pts,
                             node_ctable=node_ct if nct > 1 else None, mobtables=mob, mob_max_pts=self.mob_max_pts,
-                            integrator=self.integrator, t0=self.t0, dt_graph=self.dt)
+                            integrator=self.integrator, t0=self.t0, dt_graph=self.dt, sim_kind=g.sim_kind,
+                            vacc_partial=g.vacc_partial, vacc_full=g.vacc_full)
 
     # -- run ----------------------------------------------------------------------------------------------------
     def run(self, process_result: Optional[Callable] = None, batch: int = 1024, device: int = 0, rank: int = 0,

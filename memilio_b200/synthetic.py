@@ -267,3 +267,64 @@ def covid_study_graph(N: int = 400, seed: int = 20261017, G: int = 6, max_out_de
     return st.StudyGraph(num_groups=G, num_nodes=N, header=header, age_params=age, node_local=local,
                          populations=pops, baseline=np.full((1, G, G), cont_freq / G), minimum=None, edge_start=es,
                          edge_end=ee, edge_coeff=coeff, dampings=dampings)
+
+
+def vvs_study_graph(N: int = 400, seed: int = 20261017, G: int = 6, max_out_degree: int = 25, days: int = 100,
+                    sim_kind: int = flat.SIM_MODEL, rel: float = 0.1, damping_day: Optional[float] = 5.0,
+                    daily_vaccinations: float = 5.0, init_per_10k: float = 20.0, icu_per_10k: float = 100.0 / 6):
+    """Config 5 (SURVEY 8d) as a *parameter graph* for `osecirvvs::draw_sample(graph)`
+    (cpp/models/ode_secirvvs/parameter_space.h:166-214): the county graph of county_problem_vvs with the reference
+    benchmark's parameters (cpp/benchmarks/graph_simulation.cpp:31-112) as the centres of uniform distributions of
+    relative half-width `rel` on every sampled parameter, Seasonality U(0.1, 0.3), +-10 % on the initially infected
+    compartments and 0.8-1.2 on the test-and-trace capacity, and one sampled contact damping U(0.2, 0.4)."""
+    from . import study as st
+    base = county_problem_vvs(N=N, runs=1, seed=seed, G=G, max_out_degree=max_out_degree, days=days, sim_kind=sim_kind,
+                              perturb=0.0, daily_vaccinations=daily_vaccinations, init_per_10k=init_per_10k,
+                              icu_per_10k=icu_per_10k)
+    C = flat.OSECIRVVS_NCOMP
+    n = G * C
+    pset = base.psets[0, 0]
+    header = st.uv_array(flat.PSET_HEADER)
+    header["value"] = pset[:flat.PSET_HEADER]
+    st.set_uniform(header, flat.PHV["Seasonality"], 0.1, 0.3)
+    age = st.uv_array((G, flat.OSECIRVVS_AGE_STRIDE))
+    age["value"] = pset[flat.PSET_HEADER:].reshape(G, flat.OSECIRVVS_AGE_STRIDE)
+    sampled = ["TimeExposed", "TimeInfectedNoSymptoms", "TimeInfectedSymptoms", "TimeInfectedSevere",
+               "TimeInfectedCritical", "TransmissionProbabilityOnContact", "RelativeTransmissionNoSymptoms",
+               "RecoveredPerInfectedNoSymptoms", "MaxRiskOfInfectionFromSymptomatic", "SeverePerInfectedSymptoms",
+               "CriticalPerSevere", "DeathsPerCritical", "ReducExposedPartialImmunity", "ReducExposedImprovedImmunity",
+               "ReducInfectedSymptomsPartialImmunity", "ReducInfectedSymptomsImprovedImmunity",
+               "ReducInfectedSevereCriticalDeadPartialImmunity", "ReducInfectedSevereCriticalDeadImprovedImmunity",
+               "ReducTimeInfectedMild"]
+    for name in sampled:
+        slot = flat.PV[name]
+        for i in range(G):
+            v = float(age[i, slot]["value"])
+            if v > 0:
+                st.set_uniform(age, (i, slot), (1 - rel) * v, (1 + rel) * v)
+    pops = st.uv_array((N, n))
+    pops["value"] = base.y0[0]
+    y0 = base.y0[0].reshape(N, G, C)
+    for k in range(N):
+        for i in range(G):
+            for c in VVS_INFECTED:
+                v = y0[k, i, c]
+                if v > 0:
+                    st.set_uniform(pops, (k, i * C + c), 0.9 * v, 1.1 * v)
+    local = st.uv_array((N, 2))
+    local["value"] = base.node_local[0]
+    for k in range(N):
+        t = float(base.node_local[0, k, 1])
+        st.set_uniform(local, (k, 1), 0.8 * t, 1.2 * t)
+    baseline = np.full((1, G, G), 0.5)
+    for i in range(G):
+        baseline[0, i, i] = 5.0
+    dampings = []
+    if damping_day is not None:
+        v = st.uv_array(1)
+        st.set_uniform(v, 0, 0.2, 0.4)
+        dampings.append(st.Damping(value=v, time=damping_day, level=0, type=0, matrices=(0,)))
+    return st.StudyGraph(num_groups=G, num_nodes=N, header=header, age_params=age, node_local=local, populations=pops,
+                         baseline=baseline, minimum=None, edge_start=base.edge_start, edge_end=base.edge_end,
+                         edge_coeff=base.edge_coeff, dampings=dampings, model=flat.MODEL_OSECIRVVS, sim_kind=sim_kind,
+                         vacc_partial=base.vacc_partial, vacc_full=base.vacc_full)

@@ -260,9 +260,12 @@ struct DampingSampling {
 
 // osecir::Parameters restricted to what is sampled, as UncertainValues per age group
 struct SecirParamsU {
-    int G = 0;
+    int G     = 0;
+    int model = 0; // 0: osecir::Parameters, 1: osecirvvs::Parameters
     UncertainValue StartDay, Seasonality, TestAndTraceCapacityMaxRisk, commuter_nondetection, start_commuter_detection,
         end_commuter_detection;
+    // osecirvvs: TestAndTraceCapacityMaxRisk above is ...MaxRiskSymptoms
+    UncertainValue TestAndTraceCapacityMaxRiskNoSymptoms, StartDayNewVariant;
     UncertainValue ICUCapacity, TestAndTraceCapacity;
     // [tag][age], tag order = MIO_PA_*
     std::vector<std::vector<UncertainValue>> age;
@@ -276,7 +279,8 @@ struct SecirParamsU {
 
 struct NodeModelU {
     SecirParamsU parameters;
-    std::vector<UncertainValue> populations; // [G*10]
+    std::vector<UncertainValue> populations; // [G*C]
+    int C = 10;                              // compartments per age group: 10 (osecir), 27 (osecirvvs)
 };
 
 enum Tag
@@ -295,7 +299,20 @@ enum Tag
     CriticalPerSevere,
     DeathsPerSevere,
     DeathsPerCritical,
-    NumTags
+    NumTags,
+    // osecirvvs only (ode_secirvvs/parameters.h:422-625), same order as MIO_PV_*
+    ReducExposedPartialImmunity = NumTags,
+    ReducExposedImprovedImmunity,
+    ReducInfectedSymptomsPartialImmunity,
+    ReducInfectedSymptomsImprovedImmunity,
+    ReducInfectedSevereCriticalDeadPartialImmunity,
+    ReducInfectedSevereCriticalDeadImprovedImmunity,
+    ReducTimeInfectedMild,
+    InfectiousnessNewVariant,
+    VaccinationGap,
+    DaysUntilEffectivePartialImmunity,
+    DaysUntilEffectiveImprovedImmunity,
+    NumTagsVvs
 };
 
 // parameter_space.h:155-191
@@ -329,8 +346,8 @@ inline void draw_sample_infection(NodeModelU& model, RandomNumberGenerator& rng)
 inline double get_group_total(const NodeModelU& m, int i)
 {
     double acc = 0.0;
-    for (int c = 0; c < 10; ++c) {
-        acc = acc + m.populations[size_t(i) * 10 + c].value;
+    for (int c = 0; c < m.C; ++c) {
+        acc = acc + m.populations[size_t(i) * m.C + c].value;
     }
     return acc;
 }
@@ -338,7 +355,7 @@ inline double get_group_total(const NodeModelU& m, int i)
 inline void set_difference_from_group_total(NodeModelU& m, int i, int comp, double total_group_population)
 {
     double current_population = get_group_total(m, i);
-    size_t idx                = size_t(i) * 10 + comp;
+    size_t idx                = size_t(i) * m.C + comp;
     current_population -= m.populations[idx].value;
     m.populations[idx].value = total_group_population - current_population;
 }
@@ -355,6 +372,80 @@ inline void draw_sample_demographics(NodeModelU& model, RandomNumberGenerator& r
         }
         set_difference_from_group_total(model, i, 0, group_total);
         set_difference_from_group_total(model, i, 0, get_group_total(model, i));
+    }
+}
+
+// ode_secirvvs/parameter_space.h:86-141
+inline void draw_sample_infection_vvs(NodeModelU& model, RandomNumberGenerator& rng)
+{
+    auto& p = model.parameters;
+    p.Seasonality.draw_sample(rng);
+    // not age dependent
+    p.age[TimeExposed][0].draw_sample(rng);
+    p.age[TimeInfectedNoSymptoms][0].draw_sample(rng);
+    p.age[RelativeTransmissionNoSymptoms][0].draw_sample(rng);
+    p.age[RiskOfInfectionFromSymptomatic][0].draw_sample(rng);
+    p.age[MaxRiskOfInfectionFromSymptomatic][0].draw_sample(rng);
+    p.age[ReducExposedPartialImmunity][0].draw_sample(rng);
+    p.age[ReducExposedImprovedImmunity][0].draw_sample(rng);
+    p.age[ReducInfectedSymptomsPartialImmunity][0].draw_sample(rng);
+    p.age[ReducInfectedSymptomsImprovedImmunity][0].draw_sample(rng);
+    p.age[ReducInfectedSevereCriticalDeadPartialImmunity][0].draw_sample(rng);
+    p.age[ReducInfectedSevereCriticalDeadImprovedImmunity][0].draw_sample(rng);
+    p.age[ReducTimeInfectedMild][0].draw_sample(rng);
+    for (int i = 0; i < p.G; i++) {
+        p.age[TimeExposed][i]                                     = p.age[TimeExposed][0];
+        p.age[TimeInfectedNoSymptoms][i]                          = p.age[TimeInfectedNoSymptoms][0];
+        p.age[RelativeTransmissionNoSymptoms][i]                  = p.age[RelativeTransmissionNoSymptoms][0];
+        p.age[RiskOfInfectionFromSymptomatic][i]                  = p.age[RiskOfInfectionFromSymptomatic][0];
+        p.age[MaxRiskOfInfectionFromSymptomatic][i]               = p.age[MaxRiskOfInfectionFromSymptomatic][0];
+        p.age[ReducExposedPartialImmunity][i]                     = p.age[ReducExposedPartialImmunity][0];
+        p.age[ReducExposedImprovedImmunity][i]                    = p.age[ReducExposedImprovedImmunity][0];
+        p.age[ReducInfectedSymptomsPartialImmunity][i]            = p.age[ReducInfectedSymptomsPartialImmunity][0];
+        p.age[ReducInfectedSymptomsImprovedImmunity][i]           = p.age[ReducInfectedSymptomsImprovedImmunity][0];
+        p.age[ReducInfectedSevereCriticalDeadPartialImmunity][i]  = p.age[ReducInfectedSevereCriticalDeadPartialImmunity][0];
+        p.age[ReducInfectedSevereCriticalDeadImprovedImmunity][i] = p.age[ReducInfectedSevereCriticalDeadImprovedImmunity][0];
+        p.age[ReducTimeInfectedMild][i]                           = p.age[ReducTimeInfectedMild][0];
+        // age dependent
+        p.age[TimeInfectedSymptoms][i].draw_sample(rng);
+        p.age[TimeInfectedSevere][i].draw_sample(rng);
+        p.age[TimeInfectedCritical][i].draw_sample(rng);
+        p.age[TransmissionProbabilityOnContact][i].draw_sample(rng);
+        p.age[RecoveredPerInfectedNoSymptoms][i].draw_sample(rng);
+        p.age[DeathsPerCritical][i].draw_sample(rng);
+        p.age[SeverePerInfectedSymptoms][i].draw_sample(rng);
+        p.age[CriticalPerSevere][i].draw_sample(rng);
+    }
+}
+
+// ode_secirvvs/parameter_space.h:40-78; InfectionState order ode_secirvvs/infection_state.h:36-67
+inline void draw_sample_demographics_vvs(NodeModelU& model, RandomNumberGenerator& rng)
+{
+    enum
+    {
+        SusceptibleNaive            = 0,
+        SusceptibleImprovedImmunity = 23,
+        DeadNaive                   = 24,
+        DeadPartialImmunity         = 25,
+        DeadImprovedImmunity        = 26,
+        Count                       = 27
+    };
+    model.parameters.ICUCapacity.draw_sample(rng);
+    model.parameters.TestAndTraceCapacity.draw_sample(rng);
+    for (int i = 0; i < model.parameters.G; i++) {
+        double group_total = get_group_total(model, i);
+        for (int inf_state = 0; inf_state < Count; ++inf_state) {
+            if (inf_state != SusceptibleNaive && inf_state != DeadNaive && inf_state != DeadPartialImmunity &&
+                inf_state != DeadImprovedImmunity) {
+                model.populations[size_t(i) * Count + inf_state].draw_sample(rng);
+            }
+        }
+        model.populations[size_t(i) * Count + SusceptibleNaive].value = 0;
+        double diff = get_group_total(model, i) - group_total;
+        if (diff > 0) {
+            model.populations[size_t(i) * Count + SusceptibleImprovedImmunity].value -= diff;
+        }
+        set_difference_from_group_total(model, i, SusceptibleNaive, group_total);
     }
 }
 
@@ -434,6 +525,54 @@ inline void apply_constraints(SecirParamsU& p)
     }
 }
 
+// ode_secirvvs/parameters.h:710-938 (values only)
+inline void apply_constraints_vvs(SecirParamsU& p)
+{
+    auto set_if = [](UncertainValue& v, bool bad, double to) {
+        if (bad) {
+            v.value = to;
+        }
+    };
+    set_if(p.Seasonality, p.Seasonality.value < 0.0 || p.Seasonality.value > 0.5, 0);
+    set_if(p.ICUCapacity, p.ICUCapacity.value < 0.0, 0);
+    set_if(p.TestAndTraceCapacity, p.TestAndTraceCapacity.value < 0.0, 0);
+    set_if(p.TestAndTraceCapacityMaxRisk, p.TestAndTraceCapacityMaxRisk.value < 0.0, 0);
+    set_if(p.TestAndTraceCapacityMaxRiskNoSymptoms, p.TestAndTraceCapacityMaxRiskNoSymptoms.value < 0.0, 0);
+    const double tol_times = 1e-1;
+    for (int i = 0; i < p.G; ++i) {
+        auto v = [&](int tag) -> UncertainValue& {
+            return p.age[tag][i];
+        };
+        set_if(v(TimeExposed), v(TimeExposed).value < tol_times, tol_times);
+        set_if(v(TimeInfectedNoSymptoms), v(TimeInfectedNoSymptoms).value < tol_times, tol_times);
+        set_if(v(TimeInfectedSymptoms), v(TimeInfectedSymptoms).value < tol_times, tol_times);
+        set_if(v(TimeInfectedSevere), v(TimeInfectedSevere).value < tol_times, tol_times);
+        set_if(v(TimeInfectedCritical), v(TimeInfectedCritical).value < tol_times, tol_times);
+        set_if(v(TransmissionProbabilityOnContact),
+               v(TransmissionProbabilityOnContact).value < 0.0 || v(TransmissionProbabilityOnContact).value > 1.0, 0.0);
+        set_if(v(RelativeTransmissionNoSymptoms), v(RelativeTransmissionNoSymptoms).value < 0.0, 0);
+        set_if(v(RecoveredPerInfectedNoSymptoms),
+               v(RecoveredPerInfectedNoSymptoms).value < 0.0 || v(RecoveredPerInfectedNoSymptoms).value > 1.0, 0);
+        set_if(v(RiskOfInfectionFromSymptomatic),
+               v(RiskOfInfectionFromSymptomatic).value < 0.0 || v(RiskOfInfectionFromSymptomatic).value > 1.0, 0);
+        set_if(v(SeverePerInfectedSymptoms),
+               v(SeverePerInfectedSymptoms).value < 0.0 || v(SeverePerInfectedSymptoms).value > 1.0, 0);
+        set_if(v(CriticalPerSevere), v(CriticalPerSevere).value < 0.0 || v(CriticalPerSevere).value > 1.0, 0);
+        set_if(v(DeathsPerSevere), v(DeathsPerSevere).value < 0.0 || v(DeathsPerSevere).value > 1.0, 0);
+        set_if(v(DeathsPerSevere), v(CriticalPerSevere).value + v(DeathsPerSevere).value > 1.0, 0);
+        set_if(v(DeathsPerCritical), v(DeathsPerCritical).value < 0.0 || v(DeathsPerCritical).value > 1.0, 0);
+        set_if(v(DaysUntilEffectivePartialImmunity), v(DaysUntilEffectivePartialImmunity).value < 0.0, 0);
+        set_if(v(DaysUntilEffectiveImprovedImmunity), v(DaysUntilEffectiveImprovedImmunity).value < 0.0, 0);
+        for (int tag : {ReducExposedPartialImmunity, ReducExposedImprovedImmunity, ReducInfectedSymptomsPartialImmunity,
+                        ReducInfectedSymptomsImprovedImmunity, ReducInfectedSevereCriticalDeadPartialImmunity,
+                        ReducInfectedSevereCriticalDeadImprovedImmunity, ReducTimeInfectedMild}) {
+            set_if(v(tag), v(tag).value <= 0.0 || v(tag).value > 1.0, 1);
+        }
+        set_if(v(InfectiousnessNewVariant), v(InfectiousnessNewVariant).value < 0.0, 1.0);
+        set_if(v(VaccinationGap), v(VaccinationGap).value < 0.0, 0);
+    }
+}
+
 struct EdgeU {
     int start, end;
     Dampings coeff_dampings; // of the MobilityCoefficients member that carries the baseline
@@ -451,7 +590,13 @@ inline std::pair<std::vector<NodeModelU>, Dampings> draw_sample(GraphU& graph, R
 {
     std::vector<NodeModelU> sampled;
     auto& shared_params_model = graph.nodes[0];
-    draw_sample_infection(shared_params_model, rng);
+    const bool vvs            = shared_params_model.parameters.model == 1;
+    if (vvs) {
+        draw_sample_infection_vvs(shared_params_model, rng);
+    }
+    else {
+        draw_sample_infection(shared_params_model, rng);
+    }
     auto& shared_contacts = shared_params_model.parameters;
     for (auto& d : shared_contacts.dampings) { // draw_sample_dampings
         d.value.draw_sample(rng);
@@ -461,7 +606,12 @@ inline std::pair<std::vector<NodeModelU>, Dampings> draw_sample(GraphU& graph, R
 
     for (size_t k = 0; k < graph.nodes.size(); ++k) {
         auto& node_model = graph.nodes[k];
-        draw_sample_demographics(node_model, rng);
+        if (vvs) {
+            draw_sample_demographics_vvs(node_model, rng);
+        }
+        else {
+            draw_sample_demographics(node_model, rng);
+        }
         auto local_icu_capacity = node_model.parameters.ICUCapacity;
         auto local_tnt_capacity = node_model.parameters.TestAndTraceCapacity;
         auto local_holidays     = node_model.parameters.school_holidays;
@@ -472,7 +622,12 @@ inline std::pair<std::vector<NodeModelU>, Dampings> draw_sample(GraphU& graph, R
         node_model.parameters.TestAndTraceCapacity = local_tnt_capacity;
         node_model.parameters.school_holidays      = local_holidays;
         make_matrix(node_model.parameters);
-        apply_constraints(node_model.parameters);
+        if (vvs) {
+            apply_constraints_vvs(node_model.parameters);
+        }
+        else {
+            apply_constraints(node_model.parameters);
+        }
         for (auto& v : node_model.populations) { // Populations::apply_constraints
             if (v.value < 0.0) {
                 v.value = 0.0;
@@ -480,9 +635,13 @@ inline std::pair<std::vector<NodeModelU>, Dampings> draw_sample(GraphU& graph, R
         }
         sampled.push_back(node_model);
     }
-    // edges: apply_dampings(coefficients, shared dampings, make_mobility_damping_vector)
+    // edges: apply_dampings(coefficients, shared dampings, make_mobility_damping_vector); the osecirvvs draw_sample
+    // copies the edges unchanged (ode_secirvvs/parameter_space.h:205-211)
     Dampings mob(graph.n, 1);
     for (auto& d : shared_contacts.dampings) {
+        if (vvs) {
+            break;
+        }
         for (size_t i : d.matrices) {
             if (int(i) != graph.mobility_location) {
                 continue; // other group members have a zero baseline (set_edges, graph.h:420-440)

@@ -481,23 +481,30 @@ int orc_study_sample_runs(const mio_study_desc* d, int64_t run0, int count, doub
                           double* node_local, double* y0, double* mobtables, uint64_t* draws)
 {
     namespace sp = orc::sampling;
-    const int G = d->num_groups, N = d->num_nodes, L = d->num_locations, n = G * 10;
+    const bool vvs   = d->model == MIO_MODEL_OSECIRVVS;
+    const int Cm     = vvs ? 27 : 10;
+    const int AS     = vvs ? MIO_OSECIRVVS_AGE_STRIDE : MIO_OSECIR_AGE_STRIDE;
+    const int ntags  = vvs ? int(sp::NumTagsVvs) : int(sp::NumTags);
+    const int G = d->num_groups, N = d->num_nodes, L = d->num_locations, n = G * Cm;
     // the parameter graph: every node carries node 0's parameter distributions (only node 0's are ever used)
     sp::GraphU graph;
     graph.n                 = n;
     graph.mobility_location = d->mobility_location;
     sp::SecirParamsU p0;
     p0.G                            = G;
+    p0.model                        = vvs ? 1 : 0;
+    p0.TestAndTraceCapacityMaxRiskNoSymptoms = uv_from(d->header[MIO_PH_TNT_MAX_RISK_NOSYMP]);
+    p0.StartDayNewVariant                    = uv_from(d->header[MIO_PH_START_DAY_NEW_VARIANT]);
     p0.StartDay                     = uv_from(d->header[MIO_PH_START_DAY]);
     p0.Seasonality                  = uv_from(d->header[MIO_PH_SEASONALITY]);
     p0.TestAndTraceCapacityMaxRisk  = uv_from(d->header[MIO_PH_TNT_MAX_RISK]);
     p0.commuter_nondetection        = uv_from(d->header[MIO_PH_COMMUTER_NONDETECTION]);
     p0.start_commuter_detection     = uv_from(d->header[MIO_PH_START_COMMUTER_DETECTION]);
     p0.end_commuter_detection       = uv_from(d->header[MIO_PH_END_COMMUTER_DETECTION]);
-    p0.age.assign(sp::NumTags, std::vector<sp::UncertainValue>(G));
+    p0.age.assign(ntags, std::vector<sp::UncertainValue>(G));
     for (int i = 0; i < G; ++i) {
-        for (int tag = 0; tag < sp::NumTags; ++tag) {
-            p0.age[tag][i] = uv_from(d->age_params[i * MIO_OSECIR_AGE_STRIDE + tag]);
+        for (int tag = 0; tag < ntags; ++tag) {
+            p0.age[tag][i] = uv_from(d->age_params[i * AS + tag]);
         }
     }
     for (int l = 0; l < L; ++l) {
@@ -528,6 +535,7 @@ int orc_study_sample_runs(const mio_study_desc* d, int64_t run0, int count, doub
     }
     for (int k = 0; k < N; ++k) {
         sp::NodeModelU node;
+        node.C                               = Cm;
         node.parameters                      = p0;
         node.parameters.ICUCapacity          = uv_from(d->node_local[k * 2 + MIO_NL_ICU_CAPACITY]);
         node.parameters.TestAndTraceCapacity = uv_from(d->node_local[k * 2 + MIO_NL_TNT_CAPACITY]);
@@ -544,7 +552,7 @@ int orc_study_sample_runs(const mio_study_desc* d, int64_t run0, int count, doub
     }
     sp::RandomNumberGenerator rng;
     rng.seed(std::vector<uint32_t>(d->seeds, d->seeds + d->num_seeds));
-    const int64_t psz = pset_size(MIO_MODEL_OSECIR, G);
+    const int64_t psz = pset_size(d->model, G);
     const int64_t csz = ctable_size(G, L, d->ct_max_pts);
     const int64_t msz = d->mob_max_pts > 0 ? 1 + d->mob_max_pts + int64_t(d->mob_max_pts) * n : 0;
     const int64_t lstr = d->ct_max_pts + int64_t(2 + d->ct_max_pts) * G * G;
@@ -566,14 +574,15 @@ int orc_study_sample_runs(const mio_study_desc* d, int64_t run0, int count, doub
         ps[MIO_PH_COMMUTER_NONDETECTION]  = q.commuter_nondetection.value;
         ps[MIO_PH_START_COMMUTER_DETECTION] = q.start_commuter_detection.value;
         ps[MIO_PH_END_COMMUTER_DETECTION] = q.end_commuter_detection.value;
-        ps[MIO_PH_RESERVED6]              = d->header[MIO_PH_RESERVED6].value;
-        ps[MIO_PH_RESERVED7]              = d->header[MIO_PH_RESERVED7].value;
+        ps[MIO_PH_RESERVED6]              = vvs ? q.TestAndTraceCapacityMaxRiskNoSymptoms.value
+                                                : d->header[MIO_PH_RESERVED6].value;
+        ps[MIO_PH_RESERVED7]              = vvs ? q.StartDayNewVariant.value : d->header[MIO_PH_RESERVED7].value;
         for (int i = 0; i < G; ++i) {
-            for (int tag = 0; tag < sp::NumTags; ++tag) {
-                ps[MIO_PSET_HEADER + i * MIO_OSECIR_AGE_STRIDE + tag] = q.age[tag][i].value;
+            for (int tag = 0; tag < ntags; ++tag) {
+                ps[MIO_PSET_HEADER + i * AS + tag] = q.age[tag][i].value;
             }
-            for (int tag = sp::NumTags; tag < MIO_OSECIR_AGE_STRIDE; ++tag) {
-                ps[MIO_PSET_HEADER + i * MIO_OSECIR_AGE_STRIDE + tag] = d->age_params[i * MIO_OSECIR_AGE_STRIDE + tag].value;
+            for (int tag = ntags; tag < AS; ++tag) {
+                ps[MIO_PSET_HEADER + i * AS + tag] = d->age_params[i * AS + tag].value;
             }
         }
         for (int k = 0; k < N; ++k) {

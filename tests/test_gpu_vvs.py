@@ -123,3 +123,20 @@ def test_vvs_graph_variants_match_oracle(name):
         assert abs(int(cnt[r][:, 3].sum()) - int(ref["counters"][:, 3].sum())) <= max(
             2, 0.02 * ref["counters"][:, 3].sum())
     print(name, "underflow fix-ups", fix, "replays", st["exact_replays"])
+
+
+def test_vvs_parameter_study_sample_matches_oracle():
+    # osecirvvs::draw_sample(graph) samples (library) -> CUDA graph simulation vs the CPU oracle on the same samples
+    from memilio_b200 import study
+    g = synthetic.vvs_study_graph(N=8, max_out_degree=3, days=5, damping_day=2.0)
+    ps = study.ParameterStudy(g, 0.0, 4.0, 0.5, 5)
+    p = ps.sample(0, 5)
+    assert p.model == flat.MODEL_OSECIRVVS and p.vacc_partial is not None
+    with capi.GraphSimulation(p) as sim:
+        sim.advance(4.0)
+        state = sim.state()
+        cnt = sim.counters()
+    for r in range(5):
+        ref = oracle_lib.graph_simulate(p, r, 4.0)
+        np.testing.assert_allclose(state[r], ref["state"], rtol=1e-8, atol=1e-9)
+        np.testing.assert_array_equal(cnt[r][:, :3], ref["counters"][:, :3])
