@@ -10,6 +10,10 @@
 #include <limits>
 #include <numeric>
 #include <string>
+#include <chrono>
+#include <mutex>
+#include <cstdio>
+#include <cstdlib>
 #include <vector>
 
 using namespace miocu;
@@ -1340,31 +1344,74 @@ int mio_cuda_select_percentiles(int device, int32_t num_segments, const void* co
         a.rank[q] = (long long)(size_t)((double)a.total * p[q]);
     }
     a.num_columns = num_columns;
+    // timing of the phases to stderr when MIO_CUDA_TRACE is set (allocation, wait for the record kernels, selection,
+    // copy back)
+    const bool trace = std::getenv("MIO_CUDA_TRACE") != nullptr;
+    auto now         = [] { return std::chrono::steady_clock::now(); };
+    auto ms          = [](std::chrono::steady_clock::time_point a0, std::chrono::steady_clock::time_point a1) {
+        return std::chrono::duration<double, std::milli>(a1 - a0).count();
+    };
+    const auto t0 = now();
+    // result buffers are kept per device between calls (grow only): cudaMalloc / cudaFree of a process that holds tens
+    // of GB cost up to hundreds of milliseconds each
+    static std::mutex scratch_mutex;
+    static struct {
+        double* p[2]  = {nullptr, nullptr};
+        size_t cap[2] = {0, 0};
+    } scratch[64];
+    if (device < 0 || device >= 64) {
+        return fail(MIO_INVALID_VALUE, "device index out of range");
+    }
+    std::lock_guard<std::mutex> guard(scratch_mutex);
+    auto reserve = [&](int which, size_t count) -> double* {
+        auto& sc = scratch[device];
+        if (sc.cap[which] < count) {
+            cudaFree(sc.p[which]);
+            sc.p[which]   = nullptr;
+            sc.cap[which] = 0;
+            if (cudaMalloc(&sc.p[which], sizeof(double) * count) != cudaSuccess) {
+                return nullptr;
+            }
+            sc.cap[which] = count;
+        }
+        return sc.p[which];
+    };
     double *d_sel = nullptr, *d_mean = nullptr;
     if (num_p > 0) {
-        CUDA_TRY(dev_alloc(&d_sel, (size_t)num_p * num_columns));
+        d_sel = reserve(0, (size_t)num_p * num_columns);
+        if (!d_sel) {
+            return fail(MIO_UNKNOWN_ERROR, "select_percentiles: out of device memory");
+        }
     }
     if (mean) {
-        cudaError_t er = dev_alloc(&d_mean, (size_t)num_columns);
-        if (er != cudaSuccess) {
-            cudaFree(d_sel);
-            return fail(MIO_UNKNOWN_ERROR, cudaGetErrorString(er));
+        d_mean = reserve(1, (size_t)num_columns);
+        if (!d_mean) {
+            return fail(MIO_UNKNOWN_ERROR, "select_percentiles: out of device memory");
         }
     }
     a.out_select   = d_sel;
     a.out_mean     = d_mean;
+    const auto t1  = now();
     cudaError_t er = cudaDeviceSynchronize(); // the record kernels run on the handles' streams
+    const auto t2  = now();
     if (er == cudaSuccess) {
         er = launch_select(a, nullptr);
     }
+    if (er == cudaSuccess && trace) {
+        er = cudaDeviceSynchronize();
+    }
+    const auto t3 = now();
     if (er == cudaSuccess && d_sel) {
         er = cudaMemcpy(percentiles, d_sel, sizeof(double) * (size_t)num_p * num_columns, cudaMemcpyDeviceToHost);
     }
     if (er == cudaSuccess && d_mean) {
         er = cudaMemcpy(mean, d_mean, sizeof(double) * (size_t)num_columns, cudaMemcpyDeviceToHost);
     }
-    cudaFree(d_sel);
-    cudaFree(d_mean);
+    const auto t4 = now();
+    if (trace) {
+        std::fprintf(stderr, "[mio_cuda] select: alloc %.2f ms, wait %.2f ms, kernel %.2f ms, copy back %.2f ms, free %.2f ms\n",
+                     ms(t0, t1), ms(t1, t2), ms(t2, t3), ms(t3, t4), ms(t4, now()));
+    }
     if (er != cudaSuccess) {
         return fail(MIO_UNKNOWN_ERROR, std::string("select_percentiles: ") + cudaGetErrorString(er));
     }

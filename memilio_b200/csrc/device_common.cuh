@@ -251,7 +251,14 @@ struct Group {
     }
 };
 
-// cpp/memilio/math/smoother.h:32-55
+// cpp/memilio/math/smoother.h:32-55. The cosine ramp is taken only while a capacity threshold is being crossed; it is
+// kept out of line so that the many inlined copies of the right-hand side stay small (instruction cache).
+static __device__ __noinline__ double smoother_cosine_ramp(double x, double xleft, double xright, double yleft,
+                                                           double yright)
+{
+    return 0.5 * (yleft - yright) * cos(3.141592653589793238462643383279502884 / (xright - xleft) * (x - xleft)) +
+           0.5 * (yleft + yright);
+}
 __device__ __forceinline__ double smoother_cosine(double x, double xleft, double xright, double yleft, double yright)
 {
     if (x <= xleft) {
@@ -260,8 +267,7 @@ __device__ __forceinline__ double smoother_cosine(double x, double xleft, double
     if (x >= xright) {
         return yright;
     }
-    return 0.5 * (yleft - yright) * cos(3.141592653589793238462643383279502884 / (xright - xleft) * (x - xleft)) +
-           0.5 * (yleft + yright);
+    return smoother_cosine_ramp(x, xleft, xright, yleft, yright);
 }
 
 // ---------------------------------------------------------------------------------------------------------------
@@ -326,6 +332,69 @@ __device__ __noinline__ void contact_row_eval(const double* ct, int max_loc, int
             const double e = __dsub_rn(B[j], __dmul_rn(d, __dsub_rn(B[j], M[j])));
             row[j]         = __dadd_rn(row[j], e);
         }
+    }
+    valid_lo = lo;
+    valid_hi = hi;
+}
+
+// C(t) of one contact table by the lanes of a warp, entry e = i*G + j per lane (contact_matrix.h:392-400, :190-194;
+// damping.h:381-396): written to cm[G*G]; returns the closed interval of times for which it stays the same (empty,
+// lo > hi, while any location is inside a cosine ramp: then cm is not written and the lanes evaluate their row at
+// every stage time, see contact_row_slow). Same arithmetic as the reference, no FMA contraction.
+template <int G>
+__device__ __forceinline__ void warp_contact_matrix(const double* ct, int max_loc, int max_pts, double t, double* cm,
+                                                    double& valid_lo, double& valid_hi)
+{
+    const int lane   = threadIdx.x & 31;
+    const int L      = (int)ct[0];
+    const int stride = max_pts + (2 + max_pts) * G * G;
+    double lo = -DBL_MAX, hi = DBL_MAX;
+    bool ramp = false;
+    for (int l = 0; l < L; ++l) {
+        const int K         = (int)ct[1 + l];
+        const double* times = ct + 1 + max_loc + l * stride;
+        int k               = 0;
+        while (k < K && !(t < times[k])) {
+            ++k;
+        }
+        const double xr = k < K ? times[k] : DBL_MAX;
+        const double xl = xr - 1.0;
+        if ((t > xl) && (t < xr)) {
+            ramp = true;
+        }
+        else {
+            if (k > 0) {
+                lo = fmax(lo, times[k - 1]);
+            }
+            hi = fmin(hi, xl);
+        }
+    }
+    if (ramp) {
+        valid_lo = DBL_MAX;
+        valid_hi = -DBL_MAX;
+        return;
+    }
+    for (int e = lane; e < G * G; e += 32) {
+        double acc = 0.0;
+        for (int l = 0; l < L; ++l) {
+            const int K         = (int)ct[1 + l];
+            const double* p     = ct + 1 + max_loc + l * stride;
+            const double* times = p;
+            int k               = 0;
+            while (k < K && !(t < times[k])) {
+                ++k;
+            }
+            const double* D = p + max_pts + 2 * G * G;
+            const double xr = k < K ? times[k] : DBL_MAX;
+            const double xl = xr - 1.0;
+            const double yl = k > 0 ? D[(k - 1) * G * G + e] : 0.0;
+            const double yr = k < K ? D[k * G * G + e] : yl;
+            const double d  = (t <= xl) ? yl : yr;
+            const double B  = p[max_pts + e];
+            const double M  = p[max_pts + G * G + e];
+            acc             = __dadd_rn(acc, __dsub_rn(B, __dmul_rn(d, __dsub_rn(B, M))));
+        }
+        cm[e] = acc;
     }
     valid_lo = lo;
     valid_hi = hi;

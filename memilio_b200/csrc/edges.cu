@@ -184,7 +184,8 @@ __device__ __forceinline__ void gather_visitors(const EdgeArgs& a, const Geometr
 // reference's block order, and the return coefficients of the node as a destination.
 template <int G, int LAY>
 __device__ __forceinline__ void depart_node_update(const EdgeArgs& a, const Geometry& geo, const EdgeLane<G, LAY>& L,
-                                                   const double* smem, const double (&V1)[NC], const double (&V3)[NC])
+                                                   const double* smem, const double (&V1)[NC], const double (&V3)[NC],
+                                                   const double* cm = nullptr)
 {
     constexpr int W        = G * LAY;
     const Group<G, LAY>& g = L.g;
@@ -242,6 +243,16 @@ __device__ __forceinline__ void depart_node_update(const EdgeArgs& a, const Geom
         rhs.valid_hi      = -DBL_MAX;
         rhs.ct_max_loc    = geo.ct_max_loc;
         rhs.ct_max_pts    = geo.ct_max_pts;
+        if (cm != nullptr) {
+            // C(t) of the run's contact table was evaluated once for the CTA (cm[G*G], shared memory)
+#pragma unroll
+            for (int q = 0; q < NodeRhs<G, LAY>::Q; ++q) {
+                const int j = LAY == 1 ? q : q * LAY + g.layer;
+                rhs.crow[q] = j < G ? cm[g.age * G + j] : 0.0;
+            }
+            rhs.valid_lo = a.t;
+            rhs.valid_hi = a.t;
+        }
         rhs.contact_row(g, a.t);
         const double season = rhs.season_at(a.t);
         double tnt, icu;
@@ -333,7 +344,20 @@ __global__ void __launch_bounds__(DEPART_SMEM_THREADS, 2) depart_smem_kernel(Edg
             }
         }
     }
+    // one contact table per run: C(t) is evaluated once for the CTA by its first warp (one entry per lane)
+    __shared__ double cm_s[(G * G + 1) & ~1];
+    __shared__ int cm_ok;
+    if (threadIdx.x < 32) {
+        double lo = 1.0, hi = 0.0;
+        if (geo.num_ctables == 1) {
+            warp_contact_matrix<G>(smem + geo.ct_off, geo.ct_max_loc, geo.ct_max_pts, a.t, cm_s, lo, hi);
+        }
+        if (threadIdx.x == 0) {
+            cm_ok = lo <= hi ? 1 : 0;
+        }
+    }
     __syncthreads();
+    const double* cm = cm_ok ? cm_s : nullptr;
     EdgeLane<G, LAY> L;
     L.run            = run;
     const int warp   = threadIdx.x >> 5;
@@ -353,30 +377,48 @@ __global__ void __launch_bounds__(DEPART_SMEM_THREADS, 2) depart_smem_kernel(Edg
             v1[m] = 0.0;
             v3[m] = 0.0;
         }
-        // the edge list and weights come from global memory (L2): fetch a batch of BATCH edges first, then do the
-        // shared-memory reads and FMAs, so that BATCH independent loads are in flight per lane
+        // the edge list and weights come from global memory (L2): the batch of BATCH edges after the current one is
+        // fetched before the current batch's shared-memory reads and FMAs (software pipeline), so that the index ->
+        // value dependency is not exposed once per batch
         constexpr int BATCH = 8;
         const int mx        = warp_max(cnt);
-        for (int it0 = 0; it0 < mx; it0 += BATCH) {
-            int src[BATCH];
-            double w[BATCH];
+        int src[BATCH], src_n[BATCH];
+        double w[BATCH], w_n[BATCH];
+        auto fetch = [&](int it0, int(&sr)[BATCH], double(&ww)[BATCH]) {
 #pragma unroll
             for (int j = 0; j < BATCH; ++j) {
                 const bool act = it0 + j < cnt;
                 const int pos  = beg + (act ? it0 + j : 0);
-                src[j]         = __ldg(a.csr.in_src + pos);
-                w[j]           = act ? __ldg(a.csr.w_in + (size_t)pos * W + gl) : 0.0;
+                sr[j]          = __ldg(a.csr.in_src + pos);
+                ww[j]          = act ? __ldg(a.csr.w_in + (size_t)pos * W + gl) : 0.0;
+            }
+        };
+        if (mx > 0) {
+            fetch(0, src_n, w_n);
+        }
+        for (int it0 = 0; it0 < mx; it0 += BATCH) {
+#pragma unroll
+            for (int j = 0; j < BATCH; ++j) {
+                src[j] = src_n[j];
+                w[j]   = w_n[j];
+            }
+            if (it0 + BATCH < mx) {
+                fetch(it0 + BATCH, src_n, w_n);
             }
 #pragma unroll
             for (int j = 0; j < BATCH; ++j) {
-                const double* p  = us + (src[j] * W + gl) * M;
-                const bool first = it0 + j < split;
-                const double w1 = first ? w[j] : 0.0, w3 = first ? 0.0 : w[j];
+                // age groups that do not travel on this edge (weight 0: the sum would only gain +0.0) issue no
+                // shared-memory reads
+                if (w[j] != 0.0) {
+                    const double* p  = us + (src[j] * W + gl) * M;
+                    const bool first = it0 + j < split;
+                    const double w1 = first ? w[j] : 0.0, w3 = first ? 0.0 : w[j];
 #pragma unroll
-                for (int m = 0; m < M; ++m) {
-                    const double x = p[m];
-                    v1[m] += w1 * x;
-                    v3[m] += w3 * x;
+                    for (int m = 0; m < M; ++m) {
+                        const double x = p[m];
+                        v1[m] += w1 * x;
+                        v3[m] += w3 * x;
+                    }
                 }
             }
         }
@@ -397,7 +439,7 @@ __global__ void __launch_bounds__(DEPART_SMEM_THREADS, 2) depart_smem_kernel(Edg
                 }
             }
         }
-        depart_node_update<G, LAY>(a, geo, L, smem, V1, V3);
+        depart_node_update<G, LAY>(a, geo, L, smem, V1, V3, cm);
     }
 }
 
@@ -685,10 +727,15 @@ __global__ void __launch_bounds__(RETURN_TMA_THREADS, 2) return_tma_kernel(EdgeA
                 }
 #pragma unroll
                 for (int j = 0; j < BATCH; ++j) {
-                    const double2* ax =
-                        reinterpret_cast<const double2*>(a.aux + (((size_t)run * geo.N + dst[j]) * W + g.gl) * AUX);
-                    a0[j] = ax[0];
-                    a1[j] = ax[1];
+                    // lanes whose age group does not travel on this edge (both weights 0) issue no loads
+                    a0[j] = make_double2(0.0, 0.0);
+                    a1[j] = make_double2(0.0, 0.0);
+                    if (w[j].x != 0.0 || w[j].y != 0.0) {
+                        const double2* ax = reinterpret_cast<const double2*>(
+                            a.aux + (((size_t)run * geo.N + dst[j]) * W + g.gl) * AUX);
+                        a0[j] = ax[0];
+                        a1[j] = ax[1];
+                    }
                 }
 #pragma unroll
                 for (int j = 0; j < BATCH; ++j) {
