@@ -51,7 +51,7 @@ def parse():
     ap.add_argument("--nodes", type=int, default=400)
     ap.add_argument("--cpu-sample-runs", type=int, default=0, help="runs of the CPU baseline sample (0 = one per core)")
     ap.add_argument("--no-cpu-baseline", action="store_true")
-    ap.add_argument("--e2e-batches", type=int, default=4, help="batches of the end-to-end leg (sampling overlaps GPU)")
+    ap.add_argument("--e2e-batches", type=int, default=2, help="batches of the end-to-end leg (sampling overlaps GPU)")
     ap.add_argument("--model", default="osecir", choices=["osecir", "osecirvvs"],
                     help="osecir = BASELINE configs[3] (the default bench line); osecirvvs = configs[4]'s model on one GPU")
     ap.add_argument("--sim-kind", default="model", choices=["model", "base"],

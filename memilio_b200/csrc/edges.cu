@@ -877,7 +877,7 @@ __device__ __forceinline__ void exact_edge_load(const EdgeArgs& a, const Geometr
 }
 
 template <int G, int LAY>
-__global__ void __launch_bounds__(32, 14) return_exact_kernel(EdgeArgs a, const int* __restrict__ run_list,
+__global__ void __launch_bounds__(32, MIO_EXACT_MINBLOCKS) return_exact_kernel(EdgeArgs a, const int* __restrict__ run_list,
                                                           const int* __restrict__ list_count)
 {
     constexpr int W     = G * LAY;

@@ -22,6 +22,9 @@ namespace miocu
 #ifndef MIO_RETURN_MINBLOCKS
 #define MIO_RETURN_MINBLOCKS 1
 #endif
+#ifndef MIO_EXACT_MINBLOCKS
+#define MIO_EXACT_MINBLOCKS 14
+#endif
 constexpr int INTEGRATE_THREADS = MIO_INTEGRATE_THREADS;
 constexpr int EDGE_THREADS      = MIO_EDGE_THREADS;
 

@@ -361,14 +361,15 @@ class ParameterStudy:
         self._invalidate()
         return out
 
-    def run_ensemble(self, p: Optional[Sequence[float]] = None, mean: bool = True, num_batches: int = 4,
+    def run_ensemble(self, p: Optional[Sequence[float]] = None, mean: bool = True, num_batches: int = 2,
                      device: int = 0, rank: int = 0, world: int = 1, mode: Optional[int] = None, pinned: bool = True):
         """ParameterStudy::run with the ensemble post-processing of save_results done on the device
         (parameter_studies.h:158-217 + data/analyze_result.h:289-343): this rank's block of runs (distribute_runs) is
         sampled, uploaded and advanced in `num_batches` batches, the daily results are recorded on the GPU and reduced
         to percentiles / mean at the end (exchange over torch.distributed when world > 1; result on rank 0).
-        Pipeline: a host thread samples batch b+1 (C library, several threads) and uploads it into the second of two
-        simulation handles while the GPU advances batch b. Returns (percentiles [len(p)][columns], mean [columns])."""
+        Pipeline: two host threads, each with its own simulation handle and CUDA stream, sample (C library, several
+        threads), upload and advance alternate batches, so that uploads and the latency bound kernels of one batch
+        overlap the other batch's work on the GPU. Returns (percentiles [len(p)][columns], mean [columns])."""
         from concurrent.futures import ThreadPoolExecutor
         from . import capi, ensemble
         if p is None:
@@ -391,7 +392,7 @@ class ParameterStudy:
             rec = ensemble.EnsembleRecord(g.num_groups, g.num_nodes, days, capacity_runs=count, mode=mode, device=device,
                                           model=g.model)
             cache = self._ens = {"key": key, "bufs": bufs, "sims": sims, "rec": rec,
-                                 "pool": ThreadPoolExecutor(max_workers=1)}
+                                 "pool": ThreadPoolExecutor(max_workers=2)}
         bufs, sims, rec, pool = cache["bufs"], cache["sims"], cache["rec"], cache["pool"]
         h2d = 0
 
@@ -405,15 +406,33 @@ class ParameterStudy:
             sim.set_runs(0, pb, 0, b - a)
             return sim, sum(getattr(pb, k).nbytes for k in ("psets", "ctables", "node_local", "y0"))
 
-        fut = pool.submit(prepare, 0)
-        for i in range(nb):
-            sim, nbytes = fut.result()
-            h2d += nbytes
-            if i + 1 < nb:
-                fut = pool.submit(prepare, i + 1)
-            sim.advance(self.tmax)
+        import os
+        import time
+        trace = os.environ.get("MIO_CUDA_TRACE") is not None
+        t_start = time.perf_counter()
+
+        # two host threads, one per simulation handle (own CUDA stream): each samples, uploads and advances its
+        # batches; the kernels of the two streams overlap on the GPU (the order dependent replay of early return
+        # steps is latency bound and leaves most of the GPU idle on its own)
+        def lane(w):
+            total = 0
+            for i in range(w, nb, 2):
+                sim, nbytes = prepare(i)
+                total += nbytes
+                sim.advance(self.tmax)
+            return total
+
+        futs = [pool.submit(lane, w) for w in range(min(2, nb))]
+        h2d = sum(f.result() for f in futs)
+        t_wait, t_adv = 0.0, time.perf_counter() - t_start
         self.last_h2d_bytes = h2d
+        t2 = time.perf_counter()
         pct, mn = ensemble.reduce_distributed(rec.as_torch(), count, rank, world, p, mean)
+        if trace:
+            import sys
+            print(f"[run_ensemble] waiting for sampling+upload {1e3 * t_wait:.1f} ms, advance {1e3 * t_adv:.1f} ms, "
+                  f"reduce {1e3 * (time.perf_counter() - t2):.1f} ms, total {1e3 * (time.perf_counter() - t_start):.1f} ms",
+                  file=sys.stderr)
         # parameter_studies.h:339: future calls of run() produce different parameters
         self.rng_counter += self.num_runs << 32
         self._invalidate()

@@ -14,6 +14,9 @@ VARIANTS = {
     "i256x1": ["MIO_TUNE_ONLY_G6", "MIO_INTEGRATE_THREADS=256", "MIO_INTEGRATE_MINBLOCKS=1"],
     "i160x3": ["MIO_TUNE_ONLY_G6", "MIO_INTEGRATE_THREADS=160", "MIO_INTEGRATE_MINBLOCKS=3"],
     "i192x2": ["MIO_TUNE_ONLY_G6", "MIO_INTEGRATE_THREADS=192", "MIO_INTEGRATE_MINBLOCKS=2"],
+    "x8": ["MIO_TUNE_ONLY_G6", "MIO_EXACT_MINBLOCKS=8"],
+    "x10": ["MIO_TUNE_ONLY_G6", "MIO_EXACT_MINBLOCKS=10"],
+    "x12": ["MIO_TUNE_ONLY_G6", "MIO_EXACT_MINBLOCKS=12"],
     "i64x4": ["MIO_TUNE_ONLY_G6", "MIO_INTEGRATE_THREADS=64", "MIO_INTEGRATE_MINBLOCKS=4"],
     "i64x6": ["MIO_TUNE_ONLY_G6", "MIO_INTEGRATE_THREADS=64", "MIO_INTEGRATE_MINBLOCKS=6"],
     "e256x2": ["MIO_DEPART_MINBLOCKS=2", "MIO_RETURN_MINBLOCKS=3"],
