@@ -75,6 +75,7 @@ struct mio_handle {
     int *d_order_in = nullptr, *d_order_out = nullptr, *d_in_ptr = nullptr, *d_in_split = nullptr, *d_in_src = nullptr,
         *d_out_ptr = nullptr, *d_out_dst = nullptr, *d_edge_start = nullptr, *d_edge_end = nullptr;
     double *d_coeff = nullptr, *d_w_in = nullptr, *d_w_out = nullptr, *d_s_out = nullptr, *d_umask = nullptr;
+    double* d_w_edge = nullptr; // factorized graphs: [E][W] weight per (edge, lane) in reference edge order
     int factorized = 0;
     int num_mob = 0;
     int mob_comp[NC] = {0, 0, 0, 0, 0, 0, 0, 0, 0, 0};
@@ -288,7 +289,7 @@ void destroy(mio_handle* h)
                     h->d_run_block,  h->d_node_local,  h->d_t_node,     h->d_dt_node,   h->d_counters,
                     h->d_y[0],       h->d_y[1],        h->d_y[2],       h->d_y[3],      h->d_fac,
                     h->d_aux,        h->d_run_flags,   h->d_daily,      h->d_traj_npts, h->d_traj_times,
-                    h->d_traj_values, h->d_stats,      h->d_vacc_partial, h->d_vacc_full, h->d_work, h->d_run_list};
+                    h->d_traj_values, h->d_stats,      h->d_vacc_partial, h->d_vacc_full, h->d_work, h->d_run_list, h->d_w_edge};
     for (void* p : ptrs) {
         if (p) {
             cudaFree(p);
@@ -684,6 +685,9 @@ int mio_cuda_graph_create(const mio_graph_desc* d, int device, mio_handle** out)
         H_TRY(up_d(&h->d_coeff, edge_coeff, (size_t)E * n));
         H_TRY(up_d(&h->d_w_in, w_in.data(), w_in.size()));
         H_TRY(up_d(&h->d_w_out, w_out.data(), w_out.size()));
+        if (fact) {
+            H_TRY(up_d(&h->d_w_edge, w_age.data(), w_age.size()));
+        }
         H_TRY(up_d(&h->d_s_out, s_out.data(), s_out.size()));
         H_TRY(up_d(&h->d_umask, umask.data(), umask.size()));
     }
@@ -964,6 +968,7 @@ int mio_cuda_advance(mio_handle* h, double t_max)
             ea.stats          = h->d_stats;
             ea.run_list       = h->d_run_list;
             ea.list_count     = h->d_work + 1;
+            ea.csr.w_edge     = h->d_w_edge;
             ea.num_runs       = R;
             ea.dt             = dt;
             ea.t              = h->t;

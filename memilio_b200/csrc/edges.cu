@@ -850,39 +850,51 @@ __global__ void __launch_bounds__(THREADS) collect_flagged_kernel(EdgeArgs a, in
     }
 }
 
-template <int G, int LAY>
+// FACT: the graph's coefficients factorize exactly (coeff[e][l][c] == w[e][l] * mask[l][c], mask 0/1): one weight per
+// (edge, lane) is fetched instead of ten coefficients
+template <int G, int LAY, bool FACT>
 struct ExactEdge {
     int from, to;
-    double c[NC];   // coefficient vector of the edge for this lane
-    double2 a0, a1; // return coefficients of the destination (aux)
+    double c[FACT ? 1 : NC]; // coefficient vector of the edge for this lane (FACT: the weight)
+    double2 a0, a1;          // return coefficients of the destination (aux)
 };
 
-template <int G, int LAY>
+template <int G, int LAY, bool FACT>
 __device__ __forceinline__ void exact_edge_load(const EdgeArgs& a, const Geometry& geo, int run, int gl, int e,
-                                                int from, int to, ExactEdge<G, LAY>& d)
+                                                int from, int to, ExactEdge<G, LAY, FACT>& d)
 {
     constexpr int W = G * LAY;
     d.from          = from;
     d.to            = to;
-    const double2* cp = reinterpret_cast<const double2*>(a.csr.coeff + (size_t)e * geo.n + gl * NC);
+    if constexpr (FACT) {
+        d.c[0] = __ldg(a.csr.w_edge + (size_t)e * W + gl);
+    }
+    else {
+        const double2* cp = reinterpret_cast<const double2*>(a.csr.coeff + (size_t)e * geo.n + gl * NC);
 #pragma unroll
-    for (int i = 0; i < NC / 2; ++i) {
-        const double2 v = __ldg(cp + i);
-        d.c[2 * i]      = v.x;
-        d.c[2 * i + 1]  = v.y;
+        for (int i = 0; i < NC / 2; ++i) {
+            const double2 v = __ldg(cp + i);
+            d.c[2 * i]      = v.x;
+            d.c[2 * i + 1]  = v.y;
+        }
     }
     const double2* ax = reinterpret_cast<const double2*>(a.aux + (((size_t)run * geo.N + to) * W + gl) * AUX);
     d.a0              = ax[0];
     d.a1              = ax[1];
 }
 
-template <int G, int LAY>
-__global__ void __launch_bounds__(32, MIO_EXACT_MINBLOCKS) return_exact_kernel(EdgeArgs a, const int* __restrict__ run_list,
+template <int G, int LAY, bool FACT>
+__global__ void __launch_bounds__(32, FACT ? MIO_EXACT_MINBLOCKS_FACT : MIO_EXACT_MINBLOCKS) return_exact_kernel(EdgeArgs a, const int* __restrict__ run_list,
                                                           const int* __restrict__ list_count)
 {
     constexpr int W     = G * LAY;
     constexpr int NPW   = 32 / W;
     const Geometry& geo = a.geo;
+    // lane constants live in shared memory ([k][32], conflict free) rather than in registers: destination rate
+    // coefficients (one parameter set per run), mobility damping, the held source node's snapshot
+    __shared__ double ct_s[16 * 32];
+    __shared__ double damp_s[NC * 32];
+    __shared__ double sf_s[NC * 32];
     const int count     = *list_count;
     const int base      = blockIdx.x * NPW;
     if (base >= count) {
@@ -900,12 +912,27 @@ __global__ void __launch_bounds__(32, MIO_EXACT_MINBLOCKS) return_exact_kernel(E
     const double* blk = a.st.run_block + (size_t)run * geo.block_stride;
     const double* mob = geo.mob_max_pts > 0 ? blk + geo.mob_off : nullptr;
     const bool damped = mob != nullptr && mob[0] > 0.0;
-    double damp[NC];
-    mobility_damping_eval(damped ? mob : nullptr, geo.mob_max_pts, geo.n, gl, a.t_dep, damp);
-    LaneCoef c_t;
-    c_t.load(blk + PHDR + gl * AGE_REC);
+    {
+        double damp[NC];
+        mobility_damping_eval(damped ? mob : nullptr, geo.mob_max_pts, geo.n, gl, a.t_dep, damp);
+#pragma unroll
+        for (int i = 0; i < NC; ++i) {
+            damp_s[i * 32 + lane] = damp[i];
+        }
+        const double* rec = blk + PHDR + gl * AGE_REC;
+#pragma unroll
+        for (int i = 0; i < 16; ++i) {
+            ct_s[i * 32 + lane] = rec[i];
+        }
+    }
     const bool one_pset = geo.num_psets == 1;
     const size_t rbase  = (size_t)run * geo.N;
+    unsigned maskbits   = 0u; // mobile compartments of this lane
+    if constexpr (FACT) {
+        for (int i = 0; i < NC; ++i) {
+            maskbits |= (a.csr.umask[gl * NC + i] != 0.0 ? 1u : 0u) << i;
+        }
+    }
 
     const int E = geo.E;
     if (E == 0) {
@@ -914,16 +941,24 @@ __global__ void __launch_bounds__(32, MIO_EXACT_MINBLOCKS) return_exact_kernel(E
     // pipeline: indices of edge e+1, operands of edge e
     int f_next = E > 1 ? __ldg(a.csr.edge_start + 1) : 0;
     int t_next = E > 1 ? __ldg(a.csr.edge_end + 1) : 0;
-    ExactEdge<G, LAY> cur;
-    exact_edge_load<G, LAY>(a, geo, run, gl, 0, __ldg(a.csr.edge_start), __ldg(a.csr.edge_end), cur);
+    ExactEdge<G, LAY, FACT> cur;
+    exact_edge_load<G, LAY, FACT>(a, geo, run, gl, 0, __ldg(a.csr.edge_start), __ldg(a.csr.edge_end), cur);
     // source node state held in registers while the source stays the same; it and the destination's running state
     // are fetched at the end of the previous edge's iteration (after that edge's stores, so that the loads see them)
-    double sf[NC], yf[NC], ytn[NC], ff, nd;
+    double yf[NC], ytn[NC], ff, nd;
+    auto hold_source = [&](int node) {
+        double sf[NC];
+        load10(a.snap + (rbase + node) * geo.n + gl * NC, sf);
+#pragma unroll
+        for (int i = 0; i < NC; ++i) {
+            sf_s[i * 32 + lane] = sf[i];
+        }
+    };
     {
         const int from0 = cur.from;
         const int ps_f  = a.st.node_pset ? a.st.node_pset[from0] : 0;
         nd              = hooks ? nondetection_at(blk + ps_f * geo.pset_stride, a.t_dep) : 1.0;
-        load10(a.snap + (rbase + from0) * geo.n + gl * NC, sf);
+        hold_source(from0);
         ff = a.fac[(rbase + from0) * W + gl];
         load10(a.y_out + (rbase + from0) * geo.n + gl * NC, yf);
         load10(a.y_out + (rbase + cur.to) * geo.n + gl * NC, ytn);
@@ -932,9 +967,9 @@ __global__ void __launch_bounds__(32, MIO_EXACT_MINBLOCKS) return_exact_kernel(E
         // fetch ahead: indices of e+2, operands of e+1
         const int f_next2 = e + 2 < E ? __ldg(a.csr.edge_start + e + 2) : 0;
         const int t_next2 = e + 2 < E ? __ldg(a.csr.edge_end + e + 2) : 0;
-        ExactEdge<G, LAY> nxt;
+        ExactEdge<G, LAY, FACT> nxt;
         if (e + 1 < E) {
-            exact_edge_load<G, LAY>(a, geo, run, gl, e + 1, f_next, t_next, nxt);
+            exact_edge_load<G, LAY, FACT>(a, geo, run, gl, e + 1, f_next, t_next, nxt);
         }
         const int from  = cur.from;
         const int to    = cur.to;
@@ -944,21 +979,31 @@ __global__ void __launch_bounds__(32, MIO_EXACT_MINBLOCKS) return_exact_kernel(E
         for (int i = 0; i < NC; ++i) {
             yt[i] = ytn[i];
         }
+        LaneCoef c_t;
         if (!one_pset) {
             const int ps_t = a.st.node_pset ? a.st.node_pset[to] : 0;
             c_t.load(blk + ps_t * geo.pset_stride + PHDR + gl * AGE_REC);
+        }
+        else {
+            double rec[16];
+#pragma unroll
+            for (int i = 0; i < 16; ++i) {
+                rec[i] = ct_s[i * 32 + lane];
+            }
+            c_t.load(rec);
         }
         // mobile population of the edge at departure (instant.h:608-615)
         double m[NC];
         bool pos = false;
 #pragma unroll
         for (int i = 0; i < NC; ++i) {
-            double c = cur.c[i];
+            // FACT: w * mask with a 0/1 mask is the stored coefficient, bit for bit
+            double c = FACT ? (((maskbits >> i) & 1u) ? cur.c[0] : 0.0) : cur.c[i];
             if (damped) {
-                c = __dsub_rn(c, __dmul_rn(damp[i], c));
+                c = __dsub_rn(c, __dmul_rn(damp_s[i * 32 + lane], c));
             }
             pos  = pos || (c > 0.0);
-            m[i] = sf[i] * c;
+            m[i] = sf_s[i * 32 + lane] * c;
         }
         m[cISy] *= ff;
         if (nd != 1.0) {
@@ -1072,7 +1117,7 @@ __global__ void __launch_bounds__(32, MIO_EXACT_MINBLOCKS) return_exact_kernel(E
                 }
                 const int ps_f = a.st.node_pset ? a.st.node_pset[nxt.from] : 0;
                 nd             = hooks ? nondetection_at(blk + ps_f * geo.pset_stride, a.t_dep) : 1.0;
-                load10(a.snap + (rbase + nxt.from) * geo.n + gl * NC, sf);
+                hold_source(nxt.from);
                 ff = a.fac[(rbase + nxt.from) * W + gl];
                 load10(a.y_out + (rbase + nxt.from) * geo.n + gl * NC, yf);
             }
@@ -1161,8 +1206,13 @@ static cudaError_t launch_edges_g(const EdgeArgs& a, int which, cudaStream_t str
         // a.run_list: [R] run indices, a.list_count: [1]
         cudaMemsetAsync(a.list_count, 0, sizeof(int), stream);
         collect_flagged_kernel<256><<<(unsigned)a.num_runs, 256, 0, stream>>>(a, a.run_list, a.list_count);
-        return_exact_kernel<G, LAY><<<(unsigned)((a.num_runs + NPW - 1) / NPW), 32, 0, stream>>>(a, a.run_list,
-                                                                                                 a.list_count);
+        const unsigned warps = (unsigned)((a.num_runs + NPW - 1) / NPW);
+        if (a.csr.factorized && a.csr.w_edge != nullptr) {
+            return_exact_kernel<G, LAY, true><<<warps, 32, 0, stream>>>(a, a.run_list, a.list_count);
+        }
+        else {
+            return_exact_kernel<G, LAY, false><<<warps, 32, 0, stream>>>(a, a.run_list, a.list_count);
+        }
     }
 #undef MIO_EDGE_LAUNCH
     return cudaGetLastError();

@@ -22,8 +22,14 @@ namespace miocu
 #ifndef MIO_RETURN_MINBLOCKS
 #define MIO_RETURN_MINBLOCKS 1
 #endif
+#ifndef MIO_INTEGRATE_ITEM_PASSES
+#define MIO_INTEGRATE_ITEM_PASSES 20
+#endif
+#ifndef MIO_EXACT_MINBLOCKS_FACT
+#define MIO_EXACT_MINBLOCKS_FACT 16
+#endif
 #ifndef MIO_EXACT_MINBLOCKS
-#define MIO_EXACT_MINBLOCKS 14
+#define MIO_EXACT_MINBLOCKS 8
 #endif
 constexpr int INTEGRATE_THREADS = MIO_INTEGRATE_THREADS;
 constexpr int EDGE_THREADS      = MIO_EDGE_THREADS;
@@ -74,6 +80,7 @@ struct GraphCsr {
     const int* edge_start; // [E]
     const int* edge_end;   // [E]
     const double* coeff;   // [E][n]
+    const double* w_edge;  // factorized graphs: [E][W] weight per (edge, lane), coeff[e][l][c] == w_edge[e][l] * umask[l][c]
 };
 
 struct EdgeArgs {

@@ -14,6 +14,11 @@ VARIANTS = {
     "i256x1": ["MIO_TUNE_ONLY_G6", "MIO_INTEGRATE_THREADS=256", "MIO_INTEGRATE_MINBLOCKS=1"],
     "i160x3": ["MIO_TUNE_ONLY_G6", "MIO_INTEGRATE_THREADS=160", "MIO_INTEGRATE_MINBLOCKS=3"],
     "i192x2": ["MIO_TUNE_ONLY_G6", "MIO_INTEGRATE_THREADS=192", "MIO_INTEGRATE_MINBLOCKS=2"],
+    "p10": ["MIO_TUNE_ONLY_G6", "MIO_INTEGRATE_ITEM_PASSES=10"],
+    "p20": ["MIO_TUNE_ONLY_G6", "MIO_INTEGRATE_ITEM_PASSES=20"],
+    "p2": ["MIO_TUNE_ONLY_G6", "MIO_INTEGRATE_ITEM_PASSES=2"],
+    "xf8": ["MIO_TUNE_ONLY_G6", "MIO_EXACT_MINBLOCKS_FACT=8"],
+    "xf12": ["MIO_TUNE_ONLY_G6", "MIO_EXACT_MINBLOCKS_FACT=12"],
     "x8": ["MIO_TUNE_ONLY_G6", "MIO_EXACT_MINBLOCKS=8"],
     "x10": ["MIO_TUNE_ONLY_G6", "MIO_EXACT_MINBLOCKS=10"],
     "x12": ["MIO_TUNE_ONLY_G6", "MIO_EXACT_MINBLOCKS=12"],
