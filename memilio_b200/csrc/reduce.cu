@@ -186,6 +186,7 @@ __global__ void __launch_bounds__(SEL_THREADS) select_percentiles_kernel(SelectA
             }
         }
         const bool first = (shift + bits) == 64;
+        const unsigned long long pre_lo = nu > 0 ? upre[0] : 0ull, pre_hi = nu > 0 ? upre[nu - 1] : 0ull;
         auto visit = [&](unsigned long long k) {
             const unsigned int digit = (unsigned int)(k >> shift) & (nb - 1u);
             int u = -1;
@@ -193,20 +194,26 @@ __global__ void __launch_bounds__(SEL_THREADS) select_percentiles_kernel(SelectA
                 u = 0;
             }
             else {
+                // the distinct prefixes ascend with the percentiles: most keys fall outside [first, last] after the
+                // leading digits and are rejected with two comparisons
                 const unsigned long long hi = k >> (shift + bits);
+                if (hi >= pre_lo && hi <= pre_hi) {
 #pragma unroll
-                for (int j = 0; j < SEL_MAX_P; ++j) {
-                    if (j < nu && hi == upre[j]) {
-                        u = j;
+                    for (int j = 0; j < SEL_MAX_P; ++j) {
+                        if (j < nu && hi == upre[j]) {
+                            u = j;
+                        }
                     }
                 }
             }
-            // warp aggregation of equal (histogram, digit) pairs
-            const unsigned int code = u < 0 ? 0xffffffffu : ((unsigned int)u << 16) | digit;
-            const unsigned int act  = __activemask();
-            const unsigned int same = __match_any_sync(act, code);
-            if (u >= 0 && lane == __ffs(same) - 1) {
-                atomicAdd(&hist[u][digit], (unsigned int)__popc(same));
+            // warp aggregation of equal (histogram, digit) pairs among the lanes that count
+            if (u >= 0) {
+                const unsigned int code = ((unsigned int)u << 16) | digit;
+                const unsigned int act  = __activemask();
+                const unsigned int same = __match_any_sync(act, code);
+                if (lane == __ffs(same) - 1) {
+                    atomicAdd(&hist[u][digit], (unsigned int)__popc(same));
+                }
             }
         };
         if (STAGED) {
