@@ -8,10 +8,10 @@ namespace miocu
 
 // launch shapes (tunable at build time; see tools/build_variants.py and profiles/ for the measurements behind them)
 #ifndef MIO_INTEGRATE_THREADS
-#define MIO_INTEGRATE_THREADS 128
+#define MIO_INTEGRATE_THREADS 256
 #endif
 #ifndef MIO_INTEGRATE_MINBLOCKS
-#define MIO_INTEGRATE_MINBLOCKS 2
+#define MIO_INTEGRATE_MINBLOCKS 1
 #endif
 #ifndef MIO_EDGE_THREADS
 #define MIO_EDGE_THREADS 256
