@@ -707,7 +707,7 @@ int mio_cuda_graph_create(const mio_graph_desc* d, int device, mio_handle** out)
         H_TRY(dev_alloc(&h->d_fac, R * N * W));
         H_TRY(dev_alloc(&h->d_aux, R * N * W * 4));
         H_TRY(dev_alloc(&h->d_u, R * N * n));
-        H_TRY(dev_alloc(&h->d_vis, R * N * 2 * n));
+        H_TRY(dev_alloc(&h->d_vis, R * N * n));
         H_TRY(dev_alloc(&h->d_run_flags, R));
         H_TRY(dev_alloc(&h->d_run_list, R));
         H_TRY(cudaMemset(h->d_run_flags, 0, sizeof(int) * R));

@@ -177,14 +177,14 @@ __device__ __forceinline__ void gather_visitors(const EdgeArgs& a, const Geometr
 // ---------------------------------------------------------------------------------------------------------------
 // Departure (all edges, one launch). With m_e = coeff_e * u_from (the mobile population of edge e) the in-place edge
 // loop leaves node k at  y_k + sum_{e into k} m_e - sum_{e out of k} m_e. The visitors are gathered per destination
-// (SpMV over the incoming-edge CSR; V1: sources < k, V3: sources > k, i.e. before / after k's own outgoing edges in
-// the reference order) and kept for the return phase; the emigrants are s_out_k * u_k.
+// (SpMV over the incoming-edge CSR; one vector V per node, see the note on the order at return_kernel) and kept for
+// the return phase; the emigrants are s_out_k * u_k.
 // Then the return coefficients of k as a destination (lambda_i, ICU adjusted rates) from v0 = y_out at time t.
-// Everything of the departure after the visitor gather: test_commuters bookkeeping, the in-place node update in the
-// reference's block order, and the return coefficients of the node as a destination.
+// Everything of the departure after the visitor gather: test_commuters bookkeeping, the in-place node update, and the
+// return coefficients of the node as a destination.
 template <int G, int LAY>
 __device__ __forceinline__ void depart_node_update(const EdgeArgs& a, const Geometry& geo, const EdgeLane<G, LAY>& L,
-                                                   const double* smem, const double (&V1)[NC], const double (&V3)[NC],
+                                                   const double* smem, const double (&V)[NC],
                                                    const double* cm = nullptr)
 {
     constexpr int W        = G * LAY;
@@ -216,12 +216,11 @@ __device__ __forceinline__ void depart_node_update(const EdgeArgs& a, const Geom
     }
 #pragma unroll
     for (int i = 0; i < NC; ++i) {
-        y[i] = ((y[i] + V1[i]) - so[i] * uk[i]) + V3[i];
+        y[i] = (y[i] + V[i]) - so[i] * uk[i];
     }
     if (L.valid) {
         store10(a.y_out + L.rn * geo.n + g.gl * NC, y);
-        store10(a.vis + (L.rn * 2 + 0) * geo.n + g.gl * NC, V1);
-        store10(a.vis + (L.rn * 2 + 1) * geo.n + g.gl * NC, V3);
+        store10(a.vis + L.rn * geo.n + g.gl * NC, V);
     }
     // return coefficients of this node as destination: get_flows with pop = v0 (ode_secir/model.h:90-153,
     // ode_secirvvs/model.h:199-264)
@@ -286,16 +285,13 @@ __global__ void __launch_bounds__(EDGE_THREADS, MIO_DEPART_MINBLOCKS) depart_ker
     const Group<G, LAY>& g = L.g;
     const int beg          = L.valid ? a.csr.in_ptr[L.node] : 0;
     const int cnt     = L.valid ? a.csr.in_ptr[L.node + 1] - beg : 0;
-    const int split   = L.valid ? a.csr.in_split[L.node] : 0;
-    double V1[NC], V3[NC];
+    double V[NC];
 #pragma unroll
     for (int i = 0; i < NC; ++i) {
-        V1[i] = 0.0;
-        V3[i] = 0.0;
+        V[i] = 0.0;
     }
-    gather_visitors<FACT, W>(a, geo, L.run, g.gl, beg, split, warp_max(split), V1);
-    gather_visitors<FACT, W>(a, geo, L.run, g.gl, beg + split, cnt - split, warp_max(cnt - split), V3);
-    depart_node_update<G, LAY>(a, geo, L, smem, V1, V3);
+    gather_visitors<FACT, W>(a, geo, L.run, g.gl, beg, cnt, warp_max(cnt), V);
+    depart_node_update<G, LAY>(a, geo, L, smem, V);
 }
 
 // ---------------------------------------------------------------------------------------------------------------
@@ -370,12 +366,10 @@ __global__ void __launch_bounds__(DEPART_SMEM_THREADS, 2) depart_smem_kernel(Edg
         const int gl   = L.g.gl;
         const int beg   = L.valid ? a.csr.in_ptr[L.node] : 0;
         const int cnt   = L.valid ? a.csr.in_ptr[L.node + 1] - beg : 0;
-        const int split = L.valid ? a.csr.in_split[L.node] : 0;
-        double v1[M], v3[M];
+        double v[M];
 #pragma unroll
         for (int m = 0; m < M; ++m) {
-            v1[m] = 0.0;
-            v3[m] = 0.0;
+            v[m] = 0.0;
         }
         // the edge list and weights come from global memory (L2): the batch of BATCH edges after the current one is
         // fetched before the current batch's shared-memory reads and FMAs (software pipeline), so that the index ->
@@ -410,23 +404,18 @@ __global__ void __launch_bounds__(DEPART_SMEM_THREADS, 2) depart_smem_kernel(Edg
                 // age groups that do not travel on this edge (weight 0: the sum would only gain +0.0) issue no
                 // shared-memory reads
                 if (w[j] != 0.0) {
-                    const double* p  = us + (src[j] * W + gl) * M;
-                    const bool first = it0 + j < split;
-                    const double w1 = first ? w[j] : 0.0, w3 = first ? 0.0 : w[j];
+                    const double* p = us + (src[j] * W + gl) * M;
 #pragma unroll
                     for (int m = 0; m < M; ++m) {
-                        const double x = p[m];
-                        v1[m] += w1 * x;
-                        v3[m] += w3 * x;
+                        v[m] += w[j] * p[m];
                     }
                 }
             }
         }
-        double V1[NC], V3[NC];
+        double V[NC];
 #pragma unroll
         for (int i = 0; i < NC; ++i) {
-            V1[i] = 0.0;
-            V3[i] = 0.0;
+            V[i] = 0.0;
         }
 #pragma unroll
         for (int m = 0; m < M; ++m) {
@@ -434,26 +423,29 @@ __global__ void __launch_bounds__(DEPART_SMEM_THREADS, 2) depart_smem_kernel(Edg
 #pragma unroll
             for (int i = 0; i < NC; ++i) { // register arrays: select instead of a dynamic index
                 if (i == c) {
-                    V1[i] += v1[m];
-                    V3[i] += v3[m];
+                    V[i] += v[m];
                 }
             }
         }
-        depart_node_update<G, LAY>(a, geo, L, smem, V1, V3, cm);
+        depart_node_update<G, LAY>(a, geo, L, smem, V, cm);
     }
 }
 
 // ---------------------------------------------------------------------------------------------------------------
 // Return (all edges, one launch). calculate_mobility_returns is one explicit Euler step m + dt*A_dest*m of the
 // destination's model, linear in the traveler vector m, so the sums over edges commute with it:
-//   visitors leaving k :  (I + dt*A_k) V1  and  (I + dt*A_k) V3                   (V from the departure gather)
+//   visitors leaving k :  (I + dt*A_k) V                                            (V from the departure gather)
 //   own commuters back :  sum_e (I + dt*A_dst(e)) coeff_e*u_k = (I + dt*A0)(s_out*u_k) + dt*(destination dependent
 //                         flows: S->E with sum_e coeff_e[S]*lambda_dst, ISev->ICr/D with the ICU adjusted rates)
-// Order kept from the reference: visitors from sources < k, then own commuters, then visitors from sources > k.
+// Order: the reference subtracts the visitors from sources < k, adds k's own commuters, then subtracts the visitors
+// from sources > k. Without a fix-up the three blocks commute up to rounding, so all visitors of a node are kept as
+// ONE vector V (half the traffic of two) and the node becomes (y - V') + own.
 // The underflow fix-up (instant.h:579-596) triggers iff the node's running value goes negative at an incoming edge;
-// the running value decreases monotonically along the incoming edges (returning visitor vectors are non-negative as
-// long as dt*rate <= 1, checked), so it is enough to test it after the first and after the last block. Flagged runs
-// are replayed literally by return_exact_kernel.
+// the running value decreases along the incoming edges (returning visitor vectors are non-negative as long as
+// dt*rate <= 1, checked) and the own commuters only add, so y - V' >= 0 implies that no fix-up happens anywhere in
+// the sequence. The test y - V' < 0 is conservative (the own commuters might have covered the deficit before the
+// later visitors left): such runs are merely replayed without need. Flagged runs are replayed literally by
+// return_exact_kernel.
 template <int G, int LAY, bool FACT>
 __global__ void __launch_bounds__(EDGE_THREADS, MIO_RETURN_MINBLOCKS < 2 ? 2 : MIO_RETURN_MINBLOCKS)
     return_kernel(EdgeArgs a)
@@ -492,8 +484,8 @@ __global__ void __launch_bounds__(EDGE_THREADS, MIO_RETURN_MINBLOCKS < 2 ? 2 : M
                                  fmax(ricr_own + c_own.rISev_R + rd_own, c_own.rICr_D + c_own.rICr_R));
         underflow = !(a.dt * rmax <= 1.0);
     }
-    // visitors from sources < k
-    load10(a.vis + (L.rn * 2 + 0) * geo.n + g.gl * NC, V);
+    // the node's visitors return home (all of them: see the note on the order above)
+    load10(a.vis + L.rn * geo.n + g.gl * NC, V);
     euler_return<G, LAY>(g, c_own, slam_own, ricr_own, rd_own, a.dt, V);
 #pragma unroll
     for (int i = 0; i < NC; ++i) {
@@ -581,14 +573,6 @@ __global__ void __launch_bounds__(EDGE_THREADS, MIO_RETURN_MINBLOCKS < 2 ? 2 : M
             }
         }
     }
-    // visitors from sources > k
-    load10(a.vis + (L.rn * 2 + 1) * geo.n + g.gl * NC, V);
-    euler_return<G, LAY>(g, c_own, slam_own, ricr_own, rd_own, a.dt, V);
-#pragma unroll
-    for (int i = 0; i < NC; ++i) {
-        y[i] -= V[i];
-        underflow = underflow || (y[i] < 0.0);
-    }
     if (L.valid) {
         store10(a.y_out + L.rn * geo.n + g.gl * NC, y);
         if (underflow) {
@@ -605,7 +589,7 @@ __global__ void __launch_bounds__(EDGE_THREADS, MIO_RETURN_MINBLOCKS < 2 ? 2 : M
 // base vector); the lanes then read their records with conflict-free 16 byte shared-memory loads, and the new state
 // leaves through bulk stores. Same arithmetic and order as return_kernel.
 constexpr int RETURN_TMA_THREADS = 256;
-constexpr int RETURN_TMA_ARRAYS  = 4; // y, V1, V3, u
+constexpr int RETURN_TMA_ARRAYS  = 3; // y, V, u
 
 __device__ __forceinline__ void lds10(const double* p, double (&v)[NC])
 {
@@ -654,8 +638,7 @@ __global__ void __launch_bounds__(RETURN_TMA_THREADS, 2) return_tma_kernel(EdgeA
     const int rec_bytes = geo.n * 8;                  // one node record
     const int tile_dbl  = NPW * geo.n;                // doubles of one array's tile
     double* tile        = smem + geo.block_stride + (size_t)warp * RETURN_TMA_ARRAYS * tile_dbl;
-    const double* src[RETURN_TMA_ARRAYS] = {a.y_in, a.vis, a.vis + geo.n, a.u};
-    const int src_stride[RETURN_TMA_ARRAYS] = {1, 2, 2, 1}; // records per node in the source array
+    const double* src[RETURN_TMA_ARRAYS] = {a.y_in, a.vis, a.u};
     const int passes = (geo.N + NPW * WARPS - 1) / (NPW * WARPS);
     EdgeLane<G, LAY> L;
     L.run                  = run;
@@ -682,7 +665,7 @@ __global__ void __launch_bounds__(RETURN_TMA_THREADS, 2) return_tma_kernel(EdgeA
                     asm volatile(
                         "cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];" ::"r"(
                             smem_u32(tile + q * tile_dbl + j * geo.n)),
-                        "l"(src[q] + rn * src_stride[q] * geo.n), "r"(rec_bytes), "r"(smem_u32(&wbar[warp]))
+                        "l"(src[q] + rn * geo.n), "r"(rec_bytes), "r"(smem_u32(&wbar[warp]))
                         : "memory");
                 }
             }
@@ -748,11 +731,10 @@ __global__ void __launch_bounds__(RETURN_TMA_THREADS, 2) return_tma_kernel(EdgeA
         // the tile has arrived
         wait_mbar(&wbar[warp], pass & 1);
         const int slot_off = (g.spare() ? 0 : (g.lane / W)) * geo.n + g.gl * NC;
-        double y[NC], V[NC], V3[NC], uk[NC];
+        double y[NC], V[NC], uk[NC];
         lds10(tile + 0 * tile_dbl + slot_off, y);
         lds10(tile + 1 * tile_dbl + slot_off, V);
-        lds10(tile + 2 * tile_dbl + slot_off, V3);
-        lds10(tile + 3 * tile_dbl + slot_off, uk);
+        lds10(tile + 2 * tile_dbl + slot_off, uk);
         bool underflow = false;
         // monotonicity guard: returning visitor vectors stay non-negative iff dt * (outflow rate) <= 1
         {
@@ -761,7 +743,7 @@ __global__ void __launch_bounds__(RETURN_TMA_THREADS, 2) return_tma_kernel(EdgeA
                                      fmax(ricr_own + c_own.rISev_R + rd_own, c_own.rICr_D + c_own.rICr_R));
             underflow = !(a.dt * rmax <= 1.0);
         }
-        // visitors from sources < k
+        // the node's visitors return home
         euler_return<G, LAY>(g, c_own, slam_own, ricr_own, rd_own, a.dt, V);
 #pragma unroll
         for (int i = 0; i < NC; ++i) {
@@ -785,13 +767,6 @@ __global__ void __launch_bounds__(RETURN_TMA_THREADS, 2) return_tma_kernel(EdgeA
             for (int i = 0; i < NC; ++i) {
                 y[i] += q[i] + a.dt * k[i];
             }
-        }
-        // visitors from sources > k
-        euler_return<G, LAY>(g, c_own, slam_own, ricr_own, rd_own, a.dt, V3);
-#pragma unroll
-        for (int i = 0; i < NC; ++i) {
-            y[i] -= V3[i];
-            underflow = underflow || (y[i] < 0.0);
         }
         if (L.valid) {
             store10(tile + slot_off, y); // shared memory: the state's tile is reused for the result

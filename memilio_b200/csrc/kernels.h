@@ -92,7 +92,7 @@ struct EdgeArgs {
     const double* u;     // [R][N][n] emigration base vectors of the departure step
     const double* y_in;  // [R][N][n] live state before this edge phase
     double* y_out;       // [R][N][n] live state after this edge phase
-    double* vis;         // [R][N][2][n] visitors held by a node between departure and return: V1 (from src < dst), V3
+    double* vis;         // [R][N][n] visitors held by a node between departure and return (sum over its incoming edges)
     double* aux;         // [R][N][G][4] return coefficients of a node as destination (written at departure)
     int* run_flags;      // [R] return: set to 1 when an underflow fix-up is needed (exact replay required)
     long long* stats;    // [0] += number of (run, step) replays done by the exact kernel
