@@ -144,3 +144,40 @@ def test_run_ensemble_matches_record_and_reduce():
     assert not np.array_equal(pct3, pct)
     ps.close()
     rec.close()
+
+
+def test_full_size_ensemble_properties():
+    # BASELINE config 4 shape (10 000 runs x 400 counties, 20 of its 100 days): size independent properties
+    import oracle_lib
+    R, N, T = 10000, 400, 20.0
+    g = synthetic.covid_study_graph(N=N)
+    ps = study.ParameterStudy(g, 0.0, T, 0.5, R)
+    p = ps.sample(0, R)
+    total0 = p.y0.sum(axis=(1, 2))
+    with capi.GraphSimulation(p) as sim:
+        sim.advance(T)
+        state = sim.state()
+        cnt = sim.counters()
+    # the population of a run is conserved by every flow and by the commuter exchange (Dead included)
+    np.testing.assert_allclose(state.sum(axis=(1, 2)), total0, rtol=1e-11)
+    assert np.isfinite(state).all() and state.min() >= -1e-9
+    # every node took at least the 40 graph steps; nothing had to be forced
+    assert cnt[:, :, 0].min() >= 40 and cnt[:, :, 2].sum() == 0
+    # a run does not depend on the ensemble it is computed in: the same runs alone, bit for bit
+    pick = [0, 4999, 9999]
+    import copy
+    q = copy.copy(p)
+    for name in ("psets", "ctables", "node_local", "y0", "mobtables"):
+        a = getattr(p, name)
+        if a is not None:
+            setattr(q, name, np.ascontiguousarray(a[pick]))
+    with capi.GraphSimulation(q) as sim:
+        sim.advance(T)
+        alone = sim.state()
+        cnt_alone = sim.counters()
+    np.testing.assert_array_equal(alone, state[pick])
+    np.testing.assert_array_equal(cnt_alone, cnt[pick])
+    # and one of them against the CPU oracle
+    ref = oracle_lib.graph_simulate(q, 1, T)
+    np.testing.assert_allclose(alone[1], ref["state"], rtol=1e-8, atol=1e-9)
+    np.testing.assert_array_equal(cnt_alone[1][:, :3], ref["counters"][:, :3])
