@@ -148,20 +148,41 @@ template <bool FACT, int W>
 __device__ __forceinline__ void gather_visitors(const EdgeArgs& a, const Geometry& geo, int run, int gl, int beg,
                                                 int cnt, int max_cnt, double (&V)[NC])
 {
-    for (int it = 0; it < max_cnt; ++it) {
-        const bool act = it < cnt;
-        const int pos  = beg + (act ? it : 0);
-        const int src  = a.csr.in_src[pos];
-        double us[NC];
-        load10(a.u + ((size_t)run * geo.N + src) * geo.n + gl * NC, us);
-        if (FACT) {
-            const double w = act ? a.csr.w_in[(size_t)pos * W + gl] : 0.0;
+    if constexpr (FACT) {
+        // batches of edges: the source indices and weights first, then the sources' records, so that the
+        // index -> record dependency is paid once per batch and BATCH records are in flight per lane
+        constexpr int BATCH = 4;
+        for (int it0 = 0; it0 < max_cnt; it0 += BATCH) {
+            int src[BATCH];
+            double w[BATCH];
 #pragma unroll
-            for (int i = 0; i < NC; ++i) {
-                V[i] += w * us[i];
+            for (int j = 0; j < BATCH; ++j) {
+                const bool act = it0 + j < cnt;
+                const int pos  = beg + (act ? it0 + j : 0);
+                src[j]         = __ldg(a.csr.in_src + pos);
+                w[j]           = act ? __ldg(a.csr.w_in + (size_t)pos * W + gl) : 0.0;
+            }
+            double us[BATCH][NC];
+#pragma unroll
+            for (int j = 0; j < BATCH; ++j) {
+                load10(a.u + ((size_t)run * geo.N + src[j]) * geo.n + gl * NC, us[j]);
+            }
+#pragma unroll
+            for (int j = 0; j < BATCH; ++j) {
+#pragma unroll
+                for (int i = 0; i < NC; ++i) {
+                    V[i] += w[j] * us[j][i];
+                }
             }
         }
-        else {
+    }
+    else {
+        for (int it = 0; it < max_cnt; ++it) {
+            const bool act = it < cnt;
+            const int pos  = beg + (act ? it : 0);
+            const int src  = a.csr.in_src[pos];
+            double us[NC];
+            load10(a.u + ((size_t)run * geo.N + src) * geo.n + gl * NC, us);
             double w[NC];
             load10(a.csr.w_in + (size_t)pos * geo.n + gl * NC, w);
             if (act) {
