@@ -127,14 +127,28 @@ __global__ void __launch_bounds__(SEL_THREADS) select_percentiles_kernel(SelectA
         long long base     = 0;
         for (int sg = 0; sg < a.num_segments; ++sg) {
             const double* p = a.seg_ptr[sg] + (size_t)col * a.seg_stride[sg];
-            for (long long i = tid; i < a.seg_count[sg]; i += SEL_THREADS) {
-                const double v = p[i];
-                s += v / denom;
-                if (STAGED) {
-                    keys[base + i] = ordered_key(v);
+            // eight independent loads in flight per thread (the column streams in from HBM once)
+            constexpr int UNROLL = 8;
+            const long long cnt  = a.seg_count[sg];
+            for (long long i0 = tid; i0 < cnt; i0 += (long long)UNROLL * SEL_THREADS) {
+                double v[UNROLL];
+#pragma unroll
+                for (int j = 0; j < UNROLL; ++j) {
+                    const long long i = i0 + (long long)j * SEL_THREADS;
+                    v[j]              = i < cnt ? p[i] : 0.0;
+                }
+#pragma unroll
+                for (int j = 0; j < UNROLL; ++j) {
+                    const long long i = i0 + (long long)j * SEL_THREADS;
+                    if (i < cnt) {
+                        s += v[j] / denom;
+                        if (STAGED) {
+                            keys[base + i] = ordered_key(v[j]);
+                        }
+                    }
                 }
             }
-            base += a.seg_count[sg];
+            base += cnt;
         }
         if (a.out_mean != nullptr) {
             red[tid] = s;
@@ -208,11 +222,19 @@ __global__ void __launch_bounds__(SEL_THREADS) select_percentiles_kernel(SelectA
             }
             // warp aggregation of equal (histogram, digit) pairs among the lanes that count
             if (u >= 0) {
-                const unsigned int code = ((unsigned int)u << 16) | digit;
-                const unsigned int act  = __activemask();
-                const unsigned int same = __match_any_sync(act, code);
-                if (lane == __ffs(same) - 1) {
-                    atomicAdd(&hist[u][digit], (unsigned int)__popc(same));
+                // columns whose runs agree (empty compartments) would serialise on one counter: when every counting
+                // lane of the warp has the same (histogram, digit) one lane adds the count, else plain atomics
+                const unsigned int code   = ((unsigned int)u << 16) | digit;
+                const unsigned int act    = __activemask();
+                const int leader          = __ffs(act) - 1;
+                const unsigned int code0  = __shfl_sync(act, code, leader);
+                if (__all_sync(act, code == code0)) {
+                    if (lane == leader) {
+                        atomicAdd(&hist[u][digit], (unsigned int)__popc(act));
+                    }
+                }
+                else {
+                    atomicAdd(&hist[u][digit], 1u);
                 }
             }
         };
