@@ -180,17 +180,32 @@ def run_reference(args, rank, world):
     cfg = workload_config(args)
     cfg["edges"] = problem.num_edges
     sample_txt = f"{sample} runs x {args.nodes} counties x {args.days:g} days per step over {cores} threads"
-    print(json.dumps({
+    emit({
         "impl": "reference", "metric": METRIC[args.model], "value": value, "unit": "node-days/s",
         "n_gpus": args.gpus, "steps": args.steps, "warmup": args.warmup, "ms_per_step": 1e3 * float(np.mean(secs)),
         "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "f64", "data": "synthetic",
         "config": cfg,
         "cpu_baseline": {"value": value, "unit": "node-days/s", "cores": cores, "kind": "port", "sample": sample_txt},
         "e2e": {"value": value, "unit": "node-days/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
-        "gpu_launches": 0}))
+        "gpu_launches": 0})
+
+
+# the one JSON line goes to the real stdout; everything else that libraries print there (the NCCL version banner of
+# the first communicator, ...) is sent to stderr
+_REAL_STDOUT = None
+
+
+def emit(line: dict):
+    out = _REAL_STDOUT if _REAL_STDOUT is not None else sys.stdout
+    out.write(json.dumps(line) + "\n")
+    out.flush()
 
 
 def main():
+    global _REAL_STDOUT
+    sys.stdout.flush()
+    _REAL_STDOUT = os.fdopen(os.dup(1), "w")
+    os.dup2(2, 1)
     args = parse()
     rank = int(os.environ.get("RANK", "0"))
     world = int(os.environ.get("WORLD_SIZE", "1"))
@@ -393,7 +408,7 @@ def main():
             line["cpu_baseline"] = {"value": v, "unit": "node-days/s", "cores": cores, "kind": "port",
                                     "sample": f"{sample} runs x {N} counties x {T:g} days over {cores} threads "
                                               f"({s:.1f} s)"}
-        print(json.dumps(line))
+        emit(line)
     sim.close()
     if sim2 is not None:
         sim2.close()

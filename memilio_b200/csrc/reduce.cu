@@ -246,8 +246,22 @@ __global__ void __launch_bounds__(SEL_THREADS) select_percentiles_kernel(SelectA
         else {
             for (int sg = 0; sg < a.num_segments; ++sg) {
                 const double* p = a.seg_ptr[sg] + (size_t)col * a.seg_stride[sg];
-                for (long long i = tid; i < a.seg_count[sg]; i += SEL_THREADS) {
-                    visit(ordered_key(p[i]));
+                // eight independent loads in flight per thread
+                constexpr int UNROLL = 8;
+                const long long cnt  = a.seg_count[sg];
+                for (long long i0 = tid; i0 < cnt; i0 += (long long)UNROLL * SEL_THREADS) {
+                    double v[UNROLL];
+#pragma unroll
+                    for (int j = 0; j < UNROLL; ++j) {
+                        const long long i = i0 + (long long)j * SEL_THREADS;
+                        v[j]              = i < cnt ? p[i] : 0.0;
+                    }
+#pragma unroll
+                    for (int j = 0; j < UNROLL; ++j) {
+                        if (i0 + (long long)j * SEL_THREADS < cnt) {
+                            visit(ordered_key(v[j]));
+                        }
+                    }
                 }
             }
         }
