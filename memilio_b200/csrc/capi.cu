@@ -99,6 +99,7 @@ struct mio_handle {
     // statistics
     long long launches = 0;
     long long* d_stats = nullptr; // [0] exact replays of return steps
+    bool aux_pending = false; // a departure happened and the next node phase has to write the return coefficients
     int* d_work = nullptr;        // [0] work item counter of the persistent node-phase kernel, [1] run list length
     int* d_run_list = nullptr;    // [R] runs flagged for the exact replay of a return step
     // optional per-kernel-class device timing (CUDA events on the launching stream)
@@ -944,6 +945,9 @@ int mio_cuda_advance(mio_handle* h, double t_max)
         ia.traj       = TrajectoryBuffers{h->desc.traj_capacity, h->d_traj_npts, h->d_traj_times, h->d_traj_values};
         ia.num_runs   = R;
         ia.work_counter = h->d_work;
+        // the node phase right after a departure also provides the return coefficients (see IntegrateArgs::aux_out)
+        ia.aux_out      = (geo.E > 0 && h->have_mobile && h->aux_pending) ? h->d_aux : nullptr;
+        h->aux_pending  = false;
         {
             ScopedSpan sp(h, MIO_KC_INTEGRATE);
             CUDA_TRY(launch_integrate(ia, h->stream));
@@ -964,6 +968,7 @@ int mio_cuda_advance(mio_handle* h, double t_max)
             ea.u              = h->d_u;
             ea.vis            = h->d_vis;
             ea.aux            = h->d_aux;
+            ea.aux_by_node_phase = 1;
             ea.run_flags      = h->d_run_flags;
             ea.stats          = h->d_stats;
             ea.run_list       = h->d_run_list;
@@ -1016,6 +1021,7 @@ int mio_cuda_advance(mio_handle* h, double t_max)
                 h->v0_idx      = dep_idx;
                 h->cur         = dep_idx;
                 h->have_mobile = true;
+                h->aux_pending = true;
                 h->t_dep       = h->t;
                 h->return_time = h->t + dt;
             }

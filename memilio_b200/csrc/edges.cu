@@ -244,8 +244,9 @@ __device__ __forceinline__ void depart_node_update(const EdgeArgs& a, const Geom
         store10(a.vis + L.rn * geo.n + g.gl * NC, V);
     }
     // return coefficients of this node as destination: get_flows with pop = v0 (ode_secir/model.h:90-153,
-    // ode_secirvvs/model.h:199-264)
-    {
+    // ode_secirvvs/model.h:199-264). The node phase that follows evaluates exactly this right-hand side (same state,
+    // same time) as its first stage and writes them then (aux_by_node_phase).
+    if (!a.aux_by_node_phase) {
         NodeRhs<G, LAY> rhs;
         rhs.age_rec = pset + PHDR + g.gl * AGE_REC;
         rhs.c.load(rhs.age_rec);

@@ -57,6 +57,8 @@ struct IntegrateArgs {
     TrajectoryBuffers traj;
     int num_runs;
     int* work_counter; // [1] device scratch: the persistent node-phase kernel hands out its work items through it
+    double* aux_out;   // [R][N][W][4] or null: the launch that follows a departure writes the return coefficients of
+                       // every node as a destination (by-product of its first right-hand side)
 };
 
 // Graph in the two forms the edge phase uses.
@@ -93,7 +95,9 @@ struct EdgeArgs {
     const double* y_in;  // [R][N][n] live state before this edge phase
     double* y_out;       // [R][N][n] live state after this edge phase
     double* vis;         // [R][N][n] visitors held by a node between departure and return (sum over its incoming edges)
-    double* aux;         // [R][N][G][4] return coefficients of a node as destination (written at departure)
+    double* aux;         // [R][N][G][4] return coefficients of a node as destination (written by the node phase that
+                         // follows the departure when aux_by_node_phase is set, else by the departure kernel)
+    int aux_by_node_phase;
     int* run_flags;      // [R] return: set to 1 when an underflow fix-up is needed (exact replay required)
     long long* stats;    // [0] += number of (run, step) replays done by the exact kernel
     int* run_list;       // [R] scratch: the runs flagged for the exact replay of this step
