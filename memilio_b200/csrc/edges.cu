@@ -339,26 +339,25 @@ __global__ void __launch_bounds__(DEPART_SMEM_THREADS, 2) depart_smem_kernel(Edg
     stage_run_block(smem, a.st.run_block + (size_t)run * geo.block_stride, geo.block_stride * 8, &mbar);
     double* us = smem + geo.block_stride;
     {
-        // one (node, age) record of 10 doubles per thread and iteration: five 16-byte loads in flight per thread
-        const double2* ug = reinterpret_cast<const double2*>(a.u + (size_t)run * geo.N * geo.n);
-        const int total   = geo.N * W;
-        for (int rec = threadIdx.x; rec < total; rec += DEPART_SMEM_THREADS) {
-            double v[NC];
+        // one (node, age) record per thread and iteration: only its M mobile compartments are read (M loads in
+        // flight per thread, no register shuffling of the other compartments)
+        const double* ug = a.u + (size_t)run * geo.N * geo.n;
+        const int total  = geo.N * W;
+        int comp[M];
 #pragma unroll
-            for (int i = 0; i < NC / 2; ++i) {
-                const double2 x = __ldg(ug + (size_t)rec * (NC / 2) + i);
-                v[2 * i]        = x.x;
-                v[2 * i + 1]    = x.y;
+        for (int m = 0; m < M; ++m) {
+            comp[m] = a.csr.mob_comp[m];
+        }
+#pragma unroll 2
+        for (int rec = threadIdx.x; rec < total; rec += DEPART_SMEM_THREADS) {
+            double x[M];
+#pragma unroll
+            for (int m = 0; m < M; ++m) {
+                x[m] = __ldg(ug + (size_t)rec * NC + comp[m]);
             }
 #pragma unroll
             for (int m = 0; m < M; ++m) {
-                const int c = a.csr.mob_comp[m];
-                double x    = 0.0;
-#pragma unroll
-                for (int i = 0; i < NC; ++i) {
-                    x = (i == c) ? v[i] : x;
-                }
-                us[rec * M + m] = x;
+                us[rec * M + m] = x[m];
             }
         }
     }
@@ -367,7 +366,7 @@ __global__ void __launch_bounds__(DEPART_SMEM_THREADS, 2) depart_smem_kernel(Edg
     __shared__ int cm_ok;
     if (threadIdx.x < 32) {
         double lo = 1.0, hi = 0.0;
-        if (geo.num_ctables == 1) {
+        if (geo.num_ctables == 1 && !a.aux_by_node_phase) { // only the right-hand side of the node update needs it
             warp_contact_matrix<G>(smem + geo.ct_off, geo.ct_max_loc, geo.ct_max_pts, a.t, cm_s, lo, hi);
         }
         if (threadIdx.x == 0) {
