@@ -38,7 +38,8 @@ def build(force: bool = False, verbose: bool = False, defines=(), out: str = LIB
 
     def compile_one(src):
         obj = os.path.join(objdir, os.path.splitext(src)[0] + ".o")
-        cmd = [_nvcc()] + NVCC_FLAGS + ["-D" + d for d in defines] + ["-c", os.path.join(CSRC, src), "-o", obj]
+        extra = os.environ.get("MIO_NVCC_EXTRA", "").split()  # tuning experiments only
+        cmd = [_nvcc()] + NVCC_FLAGS + extra + ["-D" + d for d in defines] + ["-c", os.path.join(CSRC, src), "-o", obj]
         r = subprocess.run(cmd, capture_output=True, text=True)
         if r.returncode != 0:
             sys.stderr.write(r.stdout + r.stderr)
