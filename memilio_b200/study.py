@@ -396,9 +396,13 @@ class ParameterStudy:
         bufs, sims, rec, pool = cache["bufs"], cache["sims"], cache["rec"], cache["pool"]
         h2d = 0
 
+        import threading
+        sample_lock = threading.Lock()  # one sampling call at a time: it uses all host cores itself
+
         def prepare(i):
             a, b = bounds[i]
-            pb = self.sample(run0 + a, b - a, out=bufs[i % 2])
+            with sample_lock:
+                pb = self.sample(run0 + a, b - a, out=bufs[i % 2])
             sim = sims[i % 2]
             sim.reset()
             sim.set_active_runs(b - a)
