@@ -12,6 +12,7 @@
 //   ParameterDistribution*       cpp/memilio/utils/parameter_distributions.h:159-350,439-490
 //   UncertainValue::draw_sample  cpp/memilio/utils/uncertain_value.h:181-188
 //   osecir::draw_sample(Graph&)  cpp/models/ode_secir/parameter_space.h:125-251
+//   osecirvvs::draw_sample(Graph&) cpp/models/ode_secirvvs/parameter_space.h:40-214, ode_secirvvs/parameters.h:710-938
 //   UncertainContactMatrix       cpp/memilio/epidemiology/uncertain_matrix.h:150-200
 //   damping_sampling.h:256-307, populations.h:136-205,264-281, ode_secir/parameters.h:465-615
 // PARITY UNPINNED by the reference's tests for sampled VALUES (only properties are tested there); this file and the
