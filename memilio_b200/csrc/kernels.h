@@ -126,7 +126,10 @@ constexpr int SEL_MAX_P    = 8;
 constexpr int SEL_MAX_SEG  = 8;
 constexpr int SEL_BITS     = 11;
 constexpr int SEL_BINS     = 1 << SEL_BITS;
-constexpr int SEL_THREADS  = 256;
+#ifndef MIO_SELECT_THREADS
+#define MIO_SELECT_THREADS 512
+#endif
+constexpr int SEL_THREADS  = MIO_SELECT_THREADS;
 
 struct SelectArgs {
     const double* seg_ptr[SEL_MAX_SEG]; // segment s holds rows [col][seg_stride[s]], seg_count[s] valid runs each

@@ -19,6 +19,8 @@ VARIANTS = {
     "p2": ["MIO_TUNE_ONLY_G6", "MIO_INTEGRATE_ITEM_PASSES=2"],
     "xf8": ["MIO_TUNE_ONLY_G6", "MIO_EXACT_MINBLOCKS_FACT=8"],
     "xf12": ["MIO_TUNE_ONLY_G6", "MIO_EXACT_MINBLOCKS_FACT=12"],
+    "s512": ["MIO_TUNE_ONLY_G6", "MIO_SELECT_THREADS=512"],
+    "s1024": ["MIO_TUNE_ONLY_G6", "MIO_SELECT_THREADS=1024"],
     "x8": ["MIO_TUNE_ONLY_G6", "MIO_EXACT_MINBLOCKS=8"],
     "x10": ["MIO_TUNE_ONLY_G6", "MIO_EXACT_MINBLOCKS=10"],
     "x12": ["MIO_TUNE_ONLY_G6", "MIO_EXACT_MINBLOCKS=12"],
