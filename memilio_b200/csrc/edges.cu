@@ -609,7 +609,13 @@ __global__ void __launch_bounds__(EDGE_THREADS, MIO_RETURN_MINBLOCKS < 2 ? 2 : M
 // (node, array) -- 480 contiguous bytes each -- for the NPW nodes of the pass (state, both visitor vectors, emigration
 // base vector); the lanes then read their records with conflict-free 16 byte shared-memory loads, and the new state
 // leaves through bulk stores. Same arithmetic and order as return_kernel.
-constexpr int RETURN_TMA_THREADS = 256;
+#ifndef MIO_RETURN_TMA_THREADS
+#define MIO_RETURN_TMA_THREADS 256
+#endif
+#ifndef MIO_RETURN_TMA_MINBLOCKS
+#define MIO_RETURN_TMA_MINBLOCKS 2
+#endif
+constexpr int RETURN_TMA_THREADS = MIO_RETURN_TMA_THREADS;
 constexpr int RETURN_TMA_ARRAYS  = 3; // y, V, u
 
 __device__ __forceinline__ void lds10(const double* p, double (&v)[NC])
@@ -624,7 +630,7 @@ __device__ __forceinline__ void lds10(const double* p, double (&v)[NC])
 }
 
 template <int G, int LAY>
-__global__ void __launch_bounds__(RETURN_TMA_THREADS, 2) return_tma_kernel(EdgeArgs a)
+__global__ void __launch_bounds__(RETURN_TMA_THREADS, MIO_RETURN_TMA_MINBLOCKS) return_tma_kernel(EdgeArgs a)
 {
     extern __shared__ __align__(16) double smem[];
     constexpr int WARPS = RETURN_TMA_THREADS / 32;

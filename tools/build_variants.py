@@ -21,6 +21,8 @@ VARIANTS = {
     "xf12": ["MIO_TUNE_ONLY_G6", "MIO_EXACT_MINBLOCKS_FACT=12"],
     "s512": ["MIO_TUNE_ONLY_G6", "MIO_SELECT_THREADS=512"],
     "s1024": ["MIO_TUNE_ONLY_G6", "MIO_SELECT_THREADS=1024"],
+    "r128x4": ["MIO_TUNE_ONLY_G6", "MIO_RETURN_TMA_THREADS=128", "MIO_RETURN_TMA_MINBLOCKS=4"],
+    "r512x1": ["MIO_TUNE_ONLY_G6", "MIO_RETURN_TMA_THREADS=512", "MIO_RETURN_TMA_MINBLOCKS=1"],
     "x8": ["MIO_TUNE_ONLY_G6", "MIO_EXACT_MINBLOCKS=8"],
     "x10": ["MIO_TUNE_ONLY_G6", "MIO_EXACT_MINBLOCKS=10"],
     "x12": ["MIO_TUNE_ONLY_G6", "MIO_EXACT_MINBLOCKS=12"],
