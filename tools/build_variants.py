@@ -19,6 +19,9 @@ VARIANTS = {
     "p2": ["MIO_TUNE_ONLY_G6", "MIO_INTEGRATE_ITEM_PASSES=2"],
     "xf8": ["MIO_TUNE_ONLY_G6", "MIO_EXACT_MINBLOCKS_FACT=8"],
     "xf12": ["MIO_TUNE_ONLY_G6", "MIO_EXACT_MINBLOCKS_FACT=12"],
+    "s384": ["MIO_TUNE_ONLY_G6", "MIO_SELECT_THREADS=384"],
+    "s640": ["MIO_TUNE_ONLY_G6", "MIO_SELECT_THREADS=640"],
+    "s768": ["MIO_TUNE_ONLY_G6", "MIO_SELECT_THREADS=768"],
     "s512": ["MIO_TUNE_ONLY_G6", "MIO_SELECT_THREADS=512"],
     "s1024": ["MIO_TUNE_ONLY_G6", "MIO_SELECT_THREADS=1024"],
     "r128x4": ["MIO_TUNE_ONLY_G6", "MIO_RETURN_TMA_THREADS=128", "MIO_RETURN_TMA_MINBLOCKS=4"],
