@@ -321,10 +321,16 @@ __global__ void __launch_bounds__(EDGE_THREADS, MIO_DEPART_MINBLOCKS) depart_ker
 // The gather of depart_kernel reads E*n doubles per run through L2 (48 GB per launch at R = 10^4) and is bound by L2
 // bandwidth; here one CTA owns one run, copies the M mobile compartments of u[run] (N*G*M doubles, 96 KB for the
 // 400-county graph) into shared memory once, and every incoming edge is then a shared-memory read.
-constexpr int DEPART_SMEM_THREADS = 256;
+#ifndef MIO_DEPART_SMEM_THREADS
+#define MIO_DEPART_SMEM_THREADS 512
+#endif
+#ifndef MIO_DEPART_SMEM_MINBLOCKS
+#define MIO_DEPART_SMEM_MINBLOCKS 1
+#endif
+constexpr int DEPART_SMEM_THREADS = MIO_DEPART_SMEM_THREADS;
 
 template <int G, int LAY, int M>
-__global__ void __launch_bounds__(DEPART_SMEM_THREADS, 2) depart_smem_kernel(EdgeArgs a)
+__global__ void __launch_bounds__(DEPART_SMEM_THREADS, MIO_DEPART_SMEM_MINBLOCKS) depart_smem_kernel(EdgeArgs a)
 {
     extern __shared__ __align__(16) double smem[];
     __shared__ __align__(8) uint64_t mbar;
