@@ -33,11 +33,26 @@ FLOP_PER_CK54_ATTEMPT = {"osecir": 7.7e3, "osecirvvs": 21.6e3}
 STATE_DOUBLES = {"osecir": 60, "osecirvvs": 162}
 
 
-def edge_bytes_per_run_day(model, N, E):
-    """SURVEY.md 8d, explicit traveler state: departure writes and return reads E*n*8 bytes, each phase reads two node
-    records and read-modify-writes a third: 2*E*n*8 + 2*N*3*n*8 (10.8 MB for osecir at N=400, E=10000)."""
+DEVICE_STATE_DOUBLES = {"osecir": 60, "osecirvvs": 180}  # W lanes x 10 slots (device_common.cuh)
+LANES = {"osecir": 6, "osecirvvs": 18}
+
+
+def edge_bytes_per_run_day_explicit(model, N, E):
+    """SURVEY.md 8d, explicit traveler state (what the reference moves): departure writes and return reads E*n*8 bytes,
+    each phase reads two node records and read-modify-writes a third: 2*E*n*8 + 2*N*3*n*8 (10.8 MB for osecir at
+    N=400, E=10000). Reported as a notional figure only: the kernels do not move these bytes."""
     n = STATE_DOUBLES[model]
     return 2.0 * E * n * 8 + 2.0 * N * 3 * n * 8
+
+
+def edge_bytes_per_run_day(model, N):
+    """Algorithmic bytes of the aggregated formulation the kernels implement, per run and day (one
+    departure + one return): departure reads u and y and writes y and the visitor vector (4 node records), return
+    reads y, the visitor vector and u and writes y (4 node records), and reads the return coefficients (32 B per
+    lane): 8*N*n*8 + N*W*32 (1.61 MB for osecir at N=400). The run-invariant graph (CSR, weights) is L2 resident and
+    not counted."""
+    n = DEVICE_STATE_DOUBLES[model]
+    return 8.0 * N * n * 8 + N * LANES[model] * 32.0
 
 
 def parse():
@@ -134,19 +149,61 @@ def workload_config(args):
             "outputs": "per-node daily p05/p25/p50/p75/p95 + mean of age-summed compartments and of the node-summed state"}
 
 
-def cpu_baseline(problem, days, sample_runs, threads):
-    """The reference's CPU path (oracle port) on the host cores: `sample_runs` runs partitioned over `threads`
-    workers like distribute_runs (parameter_studies.h:354-367). Returns (node-days/s, seconds)."""
-    sys.path.insert(0, os.path.join(ROOT, "tests"))
-    import oracle_lib
-    from concurrent.futures import ThreadPoolExecutor
-    oracle_lib.lib()
-    runs = [r % problem.num_runs for r in range(sample_runs)]
-    t0 = time.perf_counter()
-    with ThreadPoolExecutor(max_workers=threads) as ex:  # ctypes releases the GIL during the call
-        list(ex.map(lambda r: oracle_lib.graph_simulate(problem, r, days)["steps"], runs))
-    dt = time.perf_counter() - t0
-    return sample_runs * problem.num_nodes * days / dt, dt
+def cpu_baseline(args, sample_runs, workers, study_runs):
+    """The reference's CPU path (oracle port, built -O3) on the host cores: the first `sample_runs` runs of the study,
+    partitioned over `workers` PROCESSES like distribute_runs over MPI ranks (parameter_studies.h:163-213,354-367).
+    Every process times its own literal run_impl loop -- draw_sample(graph) + GraphSimulation::advance +
+    interpolate_simulation_result per run (oracle/cpu_arm_worker.py) -- after a common start; the arm's time is the
+    slowest process. Returns dict(value node-days/s, seconds, state[sample][N][n], counters[sample][N][4])."""
+    import tempfile
+    tmp = tempfile.mkdtemp(prefix="mio_cpu_arm_")
+    start = os.path.join(tmp, "start")
+    worker = os.path.join(ROOT, "oracle", "cpu_arm_worker.py")
+    procs, outs = [], []
+    for r in range(workers):
+        out = os.path.join(tmp, f"w{r}.npz")
+        outs.append(out)
+        procs.append(subprocess.Popen(
+            [sys.executable, worker, "--model", args.model, "--sim-kind", args.sim_kind, "--nodes", str(args.nodes),
+             "--days", str(args.days), "--sample-runs", str(sample_runs), "--study-runs", str(study_runs),
+             "--workers", str(workers), "--rank", str(r), "--out", out, "--start-file", start],
+            stdout=subprocess.DEVNULL, env=dict(os.environ, OMP_NUM_THREADS="1")))
+    # common start once every process has built its study (setup is not part of the reference's run() either)
+    deadline = time.time() + 600
+    while not all(os.path.exists(o + ".ready.npz") for o in outs):
+        if any(p.poll() not in (None, 0) for p in procs) or time.time() > deadline:
+            for p in procs:
+                p.kill()
+            raise RuntimeError("cpu_baseline: a worker failed during setup")
+        time.sleep(0.01)
+    open(start, "w").close()
+    for p in procs:
+        if p.wait() != 0:
+            raise RuntimeError("cpu_baseline: a worker failed")
+    res = [np.load(o) for o in outs]
+    secs = max(float(r["seconds"]) for r in res)
+    state = np.concatenate([r["state"] for r in res], axis=0)
+    counters = np.concatenate([r["counters"] for r in res], axis=0)
+    import shutil
+    shutil.rmtree(tmp, ignore_errors=True)
+    return dict(value=sample_runs * args.nodes * args.days / secs, seconds=secs, state=state, counters=counters)
+
+
+def parity_against_oracle(gpu_state, gpu_counters, cpu):
+    """The runs of the CPU sample are the first runs of the GPU ensemble (same study, same seeds): final states within
+    1e-8 relative (floor 1e-9 absolute: compartments that hold less than a billionth of a person), accepted / rejected
+    / forced step counts per node equal (north star). Mismatches are reported, not hidden."""
+    k = cpu["state"].shape[0]
+    gs, gc = gpu_state[:k], gpu_counters[:k]
+    denom = np.maximum(np.abs(cpu["state"]), 1e-1)  # 1e-9 absolute floor at 1e-8 relative
+    rel = np.abs(gs - cpu["state"]) / denom
+    mism = (gc[:, :, :3] != cpu["counters"][:, :, :3]).any(axis=2)
+    fix_gpu, fix_cpu = int(gc[:, :, 3].sum()), int(cpu["counters"][:, :, 3].sum())
+    return {"runs": int(k), "nodes_compared": int(mism.size), "max_rel_err": float(rel.max()) if rel.size else 0.0,
+            "tolerance": 1e-8, "within_tolerance": bool((rel <= 1e-8).all()),
+            "step_count_mismatches": int(mism.sum()),
+            "attempts_compared": int(cpu["counters"][:, :, 0].sum() + cpu["counters"][:, :, 1].sum()),
+            "underflow_fixups_gpu": fix_gpu, "underflow_fixups_oracle": fix_cpu}
 
 
 METRIC = {"osecir": "graph_ode_secir_node_days_per_s", "osecirvvs": "graph_ode_secirvvs_node_days_per_s"}
@@ -154,32 +211,27 @@ METRIC = {"osecir": "graph_ode_secir_node_days_per_s", "osecirvvs": "graph_ode_s
 
 def run_reference(args, rank, world):
     """--impl reference: the reference's own CPU implementation of the path (oracle port; the reference itself
-    cannot be built here) on all host threads. Rank 0 only."""
+    cannot be built here) on all host cores, one process per core. Rank 0 only."""
     if rank != 0:
         return
-    from memilio_b200 import synthetic
     cores = os.cpu_count() or 1
     sample = args.cpu_sample_runs or 4 * cores
-    from memilio_b200 import study
-    if args.model == "osecirvvs":
-        from memilio_b200 import flat
-        graph = synthetic.vvs_study_graph(N=args.nodes, days=int(args.days) + 1,
-                                          sim_kind=flat.SIM_MODEL if args.sim_kind == "model" else flat.SIM_BASE)
-    else:
-        graph = synthetic.covid_study_graph(N=args.nodes)
-    ps = study.ParameterStudy(graph, 0.0, args.days, 0.5, max(sample, 1))
-    problem = ps.sample(0, max(sample, 1))
+    study_runs = world * args.runs
     for _ in range(min(args.warmup, 1)):
-        cpu_baseline(problem, min(args.days, 2.0), cores, cores)
+        cpu_baseline(args, cores, cores, study_runs)
     vals, secs = [], []
     for _ in range(args.steps):
-        v, s = cpu_baseline(problem, args.days, sample, cores)
-        vals.append(v)
-        secs.append(s)
-    value = float(np.sum(sample * args.nodes * args.days * len(vals)) / np.sum(secs))
+        r = cpu_baseline(args, sample, cores, study_runs)
+        vals.append(r["value"])
+        secs.append(r["seconds"])
+    value = float(sample * args.nodes * args.days * len(vals) / np.sum(secs))
     cfg = workload_config(args)
-    cfg["edges"] = problem.num_edges
-    sample_txt = f"{sample} runs x {args.nodes} counties x {args.days:g} days per step over {cores} threads"
+    cfg["runs_timed_per_step"] = sample
+    cfg["extrapolated_from_runs"] = sample
+    cfg["note"] = ("the CPU arm times a bounded sample (the first %d runs of the same study) and reports node-days/s; "
+                   "throughput is linear in runs, so the figure compares with the GPU arm's at runs_per_gpu" % sample)
+    sample_txt = (f"{sample} runs x {args.nodes} counties x {args.days:g} days per step over {cores} processes "
+                  f"(oracle -O3; draw_sample + advance + interpolate per run; slowest process)")
     emit({
         "impl": "reference", "metric": METRIC[args.model], "value": value, "unit": "node-days/s",
         "n_gpus": args.gpus, "steps": args.steps, "warmup": args.warmup, "ms_per_step": 1e3 * float(np.mean(secs)),
@@ -285,13 +337,14 @@ def main():
         e0.record(stream)
         sim.advance(T)  # synchronises the handle's stream before it returns
         e1.record(stream)
-        reduce()        # synchronous: exchange (N>1), selection kernels, gather on rank 0
+        red = reduce()  # synchronous: exchange (N>1), selection kernels, gather on rank 0
         e2.record(stream)
         e2.synchronize()
-        return e0.elapsed_time(e2), e1.elapsed_time(e2)
+        return e0.elapsed_time(e2), e1.elapsed_time(e2), red
 
     for _ in range(args.warmup):
         step_device()
+    replays0 = sim.stats()["exact_replays"]
     # ---- timed: device leg (inputs resident in HBM) -----------------------------------------------------------------
     clocks = ClockSampler(local_rank)
     barrier()
@@ -300,8 +353,9 @@ def main():
     prof = None
     launches = 0
     attempts = 0
+    red_dev = None
     for k in range(args.steps):
-        a, b = step_device(profile=True)
+        a, b, red_dev = step_device(profile=True)
         ms_dev.append(a)
         ms_red.append(b)
         p = sim.profile()
@@ -311,8 +365,41 @@ def main():
         attempts += int(cnt[:, :, 0].sum() + cnt[:, :, 1].sum())
     barrier()
     clock_info = clocks.stop()
-    replays = sim.stats()["exact_replays"]
+    replays = (sim.stats()["exact_replays"] - replays0) / max(args.steps, 1)
     sim.set_profiling(False)
+    # the first runs of rank 0's block are the runs the CPU arm simulates: keep their GPU results for the parity check
+    cores = os.cpu_count() or 1
+    cpu_sample = min(args.cpu_sample_runs or 4 * cores, R)
+    gpu_state = gpu_cnt = None
+    want_cpu = rank == 0 and world == 1 and not args.no_cpu_baseline  # the CPU leg runs at N=1 only
+    if want_cpu:
+        gpu_state, gpu_cnt = sim.state(0, cpu_sample), sim.counters(0, cpu_sample)
+
+    # ---- N > 1: the sharded reduction (exchange + multi-segment select + gather) against directly gathered columns
+    multi_gpu_check = None
+    if world > 1:
+        gen = torch.Generator().manual_seed(1234)
+        ncheck = min(1000, ncol)
+        cols = torch.randperm(ncol, generator=gen)[:ncheck].sort().values.to(rec_t.device)
+        mine = rec_t[cols, :R].contiguous()
+        parts = [torch.empty_like(mine) for _ in range(world)] if rank == 0 else None
+        dist.gather(mine, parts, dst=0)
+        if rank == 0:
+            allruns = torch.cat(parts, dim=1)  # [ncheck][world*R], rank-major = run order
+            srt = torch.sort(allruns, dim=1).values
+            total = allruns.shape[1]
+            pct_dev = red_dev[0]
+            bad = 0
+            for i, q in enumerate(ensemble.DEFAULT_PERCENTILES):
+                want = srt[:, int(total * q)].cpu().numpy()
+                bad += int((pct_dev[i][cols.cpu().numpy()] != want).sum())
+            mean_ref = allruns.mean(dim=1).cpu().numpy()
+            mean_err = float(np.max(np.abs(red_dev[1][cols.cpu().numpy()] - mean_ref) /
+                                    np.maximum(np.abs(mean_ref), 1e-300)))
+            multi_gpu_check = {"columns": int(ncheck), "runs": int(total), "percentiles": len(ensemble.DEFAULT_PERCENTILES),
+                               "percentile_mismatches": bad, "mean_max_rel_err": mean_err,
+                               "method": "columns gathered from all ranks, torch.sort, index size_t(runs*p)"}
+            assert bad == 0, f"sharded percentiles differ from directly sorted columns in {bad} entries"
 
     # ---- timed: end-to-end leg: what a user of ParameterStudy.run pays, from distributions to percentiles ------------
     # host sampling (C library) of batch b+1 overlaps the GPU work of batch b; H2D of every batch and D2H of the
@@ -330,7 +417,17 @@ def main():
         torch.cuda.synchronize()
         return (time.perf_counter() - t0) * 1e3, out
 
-    step_e2e()
+    # the first (warm-up) call samples the study from RNG counter 0: the same runs as the device leg, so its result
+    # has to reproduce the device leg's bit for bit (sampling, batching, two handles, upload -- nothing may change a
+    # value); later calls continue the random sequence (parameter_studies.h:339)
+    _, first = step_e2e()
+    e2e_check = None
+    if rank == 0:
+        same_p = bool(np.array_equal(first[0], red_dev[0]))
+        same_m = bool(np.array_equal(first[1], red_dev[1]))
+        e2e_check = {"percentiles_bit_equal_to_device_leg": same_p, "mean_bit_equal_to_device_leg": same_m,
+                     "columns": int(ncol)}
+        assert same_p, "run_ensemble percentiles differ from the device-resident leg on the same runs"
     barrier()
     e2e_runs = [step_e2e() for _ in range(args.steps)]
     ms_e2e = [x[0] for x in e2e_runs]
@@ -363,7 +460,8 @@ def main():
         dominant = max(kernel_ms, key=kernel_ms.get)
         integ_s = prof["integrate"][0] * 1e-3
         flop_attempt = FLOP_PER_CK54_ATTEMPT[args.model]
-        edge_bytes = edge_bytes_per_run_day(args.model, N, problem.num_edges)
+        edge_bytes = edge_bytes_per_run_day(args.model, N)
+        edge_bytes_explicit = edge_bytes_per_run_day_explicit(args.model, N, problem.num_edges)
         fp64_achieved = attempts * flop_attempt / integ_s / 1e12 if integ_s > 0 else 0.0
         edge_s = (prof["depart"][0] + prof["return"][0] + prof["return_exact"][0]) * 1e-3
         edge_gbs = edge_bytes * R * T * args.steps / edge_s / 1e9 if edge_s > 0 else 0.0
@@ -375,12 +473,20 @@ def main():
                                     "MEASURED_PEAKS.json has no FP64 figure",
                      "attempts_per_launch": attempts / max(prof["integrate"][1], 1),
                      "flop_per_attempt": flop_attempt}
-        roof_edge = {"kernel": "depart_kernel+return_kernel(+return_exact)", "bound": "hbm", "achieved": edge_gbs,
+        edge_traffic = (traffic.get("depart", 0) + traffic.get("return", 0)) or None
+        edge_launches = max(prof["depart"][1] + prof["return"][1], 1)
+        alg_per_launch = edge_bytes * R * T * args.steps / edge_launches  # one departure or return of R runs
+        roof_edge = {"kernel": "depart + return (+ return_exact)", "bound": "hbm", "achieved": edge_gbs,
                      "peak": hbm_peak, "unit": "GB/s", "frac": edge_gbs / hbm_peak,
-                     "traffic": (traffic.get("depart", 0) + traffic.get("return", 0)) or None,
+                     "traffic": edge_traffic / 2 if edge_traffic else None,
+                     "traffic_over_algorithmic": (edge_traffic / 2) / alg_per_launch if edge_traffic else None,
                      "peak_source": hbm_src, "algorithmic_bytes_per_run_day": edge_bytes,
-                     "note": "algorithmic bytes are SURVEY 8d's explicit-traveler-state figure; the aggregated "
-                             "formulation moves fewer DRAM bytes (see traffic), so achieved can exceed DRAM throughput"}
+                     "algorithmic_bytes_per_launch": alg_per_launch,
+                     "explicit_traveler_bytes_per_run_day": edge_bytes_explicit,
+                     "note": "algorithmic bytes are those of the aggregated formulation the kernels implement "
+                             "(4 node records per phase + return coefficients); SURVEY 8d's explicit-traveler-state "
+                             "figure is listed for reference only, those bytes are never moved. time includes "
+                             "return_exact. traffic = measured DRAM bytes per launch (mean of depart and return)"}
         line = {
             "metric": METRIC[args.model], "value": value, "unit": "node-days/s", "n_gpus": world,
             "steps": args.steps, "warmup": args.warmup, "ms_per_step": tot_dev_ms / args.steps,
@@ -398,16 +504,20 @@ def main():
             "roofline_node_phase": roof_fp64, "roofline_edge_phase": roof_edge,
             "kernel_ms_per_step": kernel_ms, "dominant_kernel": dominant,
             "rk_attempts_per_node_day": float(agg[0].item()) / units,
-            "exact_return_replays": int(replays),
+            "exact_return_replays_per_step": float(replays),
             "host_sampling_s_per_step": samp_s,
+            "e2e_check": e2e_check,
         }
-        if not args.no_cpu_baseline:
-            cores = os.cpu_count() or 1
-            sample = args.cpu_sample_runs or 4 * cores
-            v, s = cpu_baseline(problem, T, sample, cores)
-            line["cpu_baseline"] = {"value": v, "unit": "node-days/s", "cores": cores, "kind": "port",
-                                    "sample": f"{sample} runs x {N} counties x {T:g} days over {cores} threads "
-                                              f"({s:.1f} s)"}
+        if multi_gpu_check is not None:
+            line["multi_gpu_check"] = multi_gpu_check
+        if want_cpu:
+            cpu = cpu_baseline(args, cpu_sample, cores, world * R)
+            line["cpu_baseline"] = {"value": cpu["value"], "unit": "node-days/s", "cores": cores, "kind": "port",
+                                    "sample": f"{cpu_sample} runs x {N} counties x {T:g} days over {cores} processes "
+                                              f"(oracle -O3; draw_sample + advance + interpolate per run; "
+                                              f"{cpu['seconds']:.1f} s)"}
+            # the same runs on both sides: the CPU arm's results are the parity vectors
+            line["parity_check"] = parity_against_oracle(gpu_state, gpu_cnt, cpu)
         emit(line)
     sim.close()
     if sim2 is not None:

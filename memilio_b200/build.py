@@ -55,7 +55,8 @@ def build(force: bool = False, verbose: bool = False, defines=(), out: str = LIB
     if r.returncode != 0:
         sys.stderr.write(r.stdout + r.stderr)
         raise RuntimeError("link failed")
-    with open(os.path.join(objdir, "ptxas.log"), "w") as f:
+    os.makedirs(os.path.join(objdir, "build"), exist_ok=True)
+    with open(os.path.join(objdir, "build", "ptxas.log"), "w") as f:
         f.write("\n".join(logs))
     if verbose:
         print("\n".join(logs))

@@ -4,6 +4,7 @@
 #include "kernels.h"
 
 #include <algorithm>
+#include <atomic>
 #include <cmath>
 #include <cstdio>
 #include <cstring>
@@ -58,7 +59,8 @@ int mio_set_last_error(int code, const std::string& msg)
 struct mio_ensemble {
     int device = 0;
     int G = 0, C = 0, N = 0, num_days = 0, mode = 0, lay = 1;
-    long long capacity = 0, num_runs = 0, num_columns = 0;
+    long long capacity = 0, num_columns = 0;
+    std::atomic<long long> num_runs{0}; // handles of several host threads record into one ensemble
     double* d_data = nullptr; // [num_columns][capacity]
 };
 
@@ -868,7 +870,12 @@ int mio_cuda_set_runs(mio_handle* h, int32_t slot0, int32_t count, const mio_run
         CUDA_TRY(launch_record_ensemble(h->d_y[h->cur] + s0 * N * n, h->ens->d_data, N, G, geo.C_ref, geo.LAY, count,
                                         0, h->ens->num_days, h->ens->mode, h->ens_offset + slot0, h->ens->capacity,
                                         h->stream));
-        h->ens->num_runs = std::max(h->ens->num_runs, h->ens_offset + slot0 + count);
+        {
+            const long long upto = h->ens_offset + slot0 + count;
+            long long seen       = h->ens->num_runs.load();
+            while (seen < upto && !h->ens->num_runs.compare_exchange_weak(seen, upto)) {
+            }
+        }
     }
     CUDA_TRY(cudaStreamSynchronize(h->stream));
     return MIO_OK;
@@ -1314,7 +1321,7 @@ int mio_cuda_ensemble_info(mio_ensemble* e, int64_t* num_columns, int64_t* strid
         *stride = e->capacity;
     }
     if (num_runs) {
-        *num_runs = e->num_runs;
+        *num_runs = e->num_runs.load();
     }
     if (device_ptr) {
         *device_ptr = e->d_data;
@@ -1435,7 +1442,7 @@ int mio_cuda_ensemble_reduce(mio_ensemble* e, int32_t num_p, const double* p, do
         return fail(MIO_INVALID_VALUE, "null argument");
     }
     const void* ptr      = e->d_data;
-    const int64_t stride = e->capacity, count = e->num_runs;
+    const int64_t stride = e->capacity, count = e->num_runs.load();
     return mio_cuda_select_percentiles(e->device, 1, &ptr, &stride, &count, e->num_columns, num_p, p, percentiles,
                                        mean);
 }

@@ -377,11 +377,23 @@ class ParameterStudy:
         if mode is None:
             mode = ensemble.ENS_AGE_SUM
         run0, count = distribute_runs(self.num_runs, world, rank)
+        days = int(np.floor(self.tmax + 1e-14) - np.ceil(self.t0 - 1e-14)) + 1
+        g = self.graph
+        if count == 0:
+            # more ranks than runs (distribute_runs gives this rank nothing): no sampling, no simulation, but the
+            # rank still takes part in the collectives of the reduction with an empty run segment
+            import torch
+            El = flat.num_compartments(g.model) if mode == ensemble.ENS_AGE_SUM else g.n
+            ncol = g.num_nodes * days * El + days * g.n
+            dev = torch.device("cuda", device) if torch.cuda.is_available() else torch.device("cpu")
+            out = ensemble.reduce_distributed(torch.empty((ncol, 0), dtype=torch.float64, device=dev), 0, rank, world,
+                                              p, mean)
+            self.rng_counter += self.num_runs << 32
+            self._invalidate()
+            return out
         nb = max(1, min(num_batches, count))
         bounds = [(i * count // nb, (i + 1) * count // nb) for i in range(nb)]
         bmax = max(b - a for a, b in bounds)
-        days = int(np.floor(self.tmax + 1e-14) - np.ceil(self.t0 - 1e-14)) + 1
-        g = self.graph
         key = (count, bmax, days, mode, device, pinned)
         cache = getattr(self, "_ens", None)
         if cache is None or cache["key"] != key:

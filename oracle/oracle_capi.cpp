@@ -4,6 +4,8 @@
 #include "mio_oracle.hpp"
 #include "mio_oracle_sampling.hpp"
 #include "mio_oracle_vvs.hpp"
+#include "mio_oracle_analyze.hpp"
+#include "mio_oracle_seir.hpp"
 #include "../include/mio_cuda.h"
 
 #include <cstring>
@@ -276,7 +278,9 @@ int orc_simulate_vvs(int sim_kind, int G, const double* pset, const double* loca
 template <class M, class MakeModel>
 static int graph_simulate_impl(const mio_graph_desc* desc, const mio_run_data* run, double t_max, double* out_state,
                                double* out_dt, int64_t* out_counters, double* out_halfsteps, int max_halfsteps,
-                               int ncomp, MakeModel&& make_model)
+                               int ncomp, MakeModel&& make_model,
+                               const std::function<void(GraphSim<M>&)>& on_done = nullptr,
+                               const std::vector<std::vector<size_t>>& save_indices = {})
 {
     const int G = desc->num_groups, N = desc->num_nodes, E = desc->num_edges;
     const int n = G * ncomp;
@@ -287,7 +291,7 @@ static int graph_simulate_impl(const mio_graph_desc* desc, const mio_run_data* r
     }
     for (int e = 0; e < E; ++e) {
         Vec c(desc->edge_coeff + int64_t(e) * n, desc->edge_coeff + int64_t(e + 1) * n);
-        MobilityEdge me(c);
+        MobilityEdge me(c, save_indices);
         if (run->mobtables && desc->mob_max_pts > 0) {
             const double* mt = run->mobtables;
             const int K      = int(mt[0]);
@@ -343,13 +347,20 @@ static int graph_simulate_impl(const mio_graph_desc* desc, const mio_run_data* r
             out_counters[e.end * 4 + 3] += e.property.stats.underflows;
         }
     }
+    if (on_done) {
+        on_done(g);
+    }
     return steps;
 }
 
-extern "C" {
+namespace
+{
 
-int orc_graph_simulate(const mio_graph_desc* desc, const mio_run_data* run, double t_max, double* out_state,
-                       double* out_dt, int64_t* out_counters, double* out_halfsteps, int max_halfsteps)
+// orc_graph_simulate for either model; on_done(GraphSim<M>&) sees the finished simulation (node time series, edges)
+template <class OnDone>
+int graph_simulate_dispatch(const mio_graph_desc* desc, const mio_run_data* run, double t_max, double* out_state,
+                            double* out_dt, int64_t* out_counters, double* out_halfsteps, int max_halfsteps,
+                            OnDone&& on_done, const std::vector<std::vector<size_t>>& save_indices = {})
 {
     const int G       = desc->num_groups;
     const int64_t psz = pset_size(desc->model, G);
@@ -363,10 +374,15 @@ int orc_graph_simulate(const mio_graph_desc* desc, const mio_run_data* run, doub
     };
     if (desc->model == MIO_MODEL_OSECIR) {
         return graph_simulate_impl<osecir::Model>(
-            desc, run, t_max, out_state, out_dt, out_counters, out_halfsteps, max_halfsteps, osecir::NC, [&](int k) {
+            desc, run, t_max, out_state, out_dt, out_counters, out_halfsteps, max_halfsteps, osecir::NC,
+            [&](int k) {
                 return osecir_from_flat(G, ps_of(k), run->node_local + int64_t(k) * MIO_NODE_LOCAL, ct_of(k),
                                         desc->ct_max_loc, desc->ct_max_pts, run->y0 + int64_t(k) * n);
-            });
+            },
+            [&](GraphSim<osecir::Model>& g) {
+                on_done(g);
+            },
+            save_indices);
     }
     if (desc->model == MIO_MODEL_OSECIRVVS) {
         return graph_simulate_impl<osecirvvs::Model>(
@@ -379,9 +395,140 @@ int orc_graph_simulate(const mio_graph_desc* desc, const mio_run_data* run, doub
                                              desc->vacc_full ? desc->vacc_full + vo : nullptr);
                 m.model_sim = desc->sim_kind == MIO_SIM_MODEL;
                 return m;
-            });
+            },
+            [&](GraphSim<osecirvvs::Model>& g) {
+                on_done(g);
+            },
+            save_indices);
     }
     return -1;
+}
+
+// interpolate_simulation_result(graph) (analyze_result.h:121-132) of a finished graph simulation into
+// out_daily[N][num_days][n]; returns false when a node does not yield exactly num_days integer days
+template <class GS>
+bool daily_from_graph(GS& g, int num_days, int n, double* out_daily)
+{
+    const int N = int(g.nodes.size());
+    for (int k = 0; k < N; ++k) {
+        const TimeSeries ts = interpolate_simulation_result(g.nodes[k].sim.result);
+        if (int(ts.n()) != num_days) {
+            return false;
+        }
+        for (int d = 0; d < num_days; ++d) {
+            std::copy(ts.values[d].begin(), ts.values[d].end(), out_daily + (int64_t(k) * num_days + d) * n);
+        }
+    }
+    return true;
+}
+
+} // namespace
+
+extern "C" {
+
+int orc_graph_simulate(const mio_graph_desc* desc, const mio_run_data* run, double t_max, double* out_state,
+                       double* out_dt, int64_t* out_counters, double* out_halfsteps, int max_halfsteps)
+{
+    return graph_simulate_dispatch(desc, run, t_max, out_state, out_dt, out_counters, out_halfsteps, max_halfsteps,
+                                   [](auto&) {});
+}
+
+// orc_graph_simulate + interpolate_simulation_result(graph): out_daily[N][num_days][n] (the per-node time series of
+// every adaptive step interpolated at the integer days, analyze_result.h:121-132,186-265). Returns the number of graph
+// steps, -2 when the number of days differs from num_days.
+int orc_graph_simulate_daily(const mio_graph_desc* desc, const mio_run_data* run, double t_max, int num_days,
+                             double* out_daily, double* out_state, int64_t* out_counters)
+{
+    const int n = desc->num_groups * ncomp_of(desc->model);
+    bool ok     = true;
+    std::vector<double> state(out_state ? 0 : size_t(desc->num_nodes) * n);
+    const int steps = graph_simulate_dispatch(desc, run, t_max, out_state ? out_state : state.data(), nullptr,
+                                              out_counters, nullptr, 0, [&](auto& g) {
+                                                  ok = daily_from_graph(g, num_days, n, out_daily);
+                                              });
+    return ok ? steps : -2;
+}
+
+// MobilityEdge::get_mobility_results (instant.h:421-445) of every edge: the edges are built with the same
+// saved_compartment_indices (num_groups index groups, group_ptr[num_groups+1] into group_idx). out_times[E][cap],
+// out_values[E][cap][num_groups+1], out_npts[E]. Returns the number of graph steps.
+int orc_graph_simulate_mobility(const mio_graph_desc* desc, const mio_run_data* run, double t_max, int num_save_groups,
+                                const int* group_ptr, const int* group_idx, int cap, int* out_npts, double* out_times,
+                                double* out_values, double* out_state)
+{
+    std::vector<std::vector<size_t>> save(num_save_groups);
+    for (int gI = 0; gI < num_save_groups; ++gI) {
+        save[gI].assign(group_idx + group_ptr[gI], group_idx + group_ptr[gI + 1]);
+    }
+    const int n = desc->num_groups * ncomp_of(desc->model);
+    std::vector<double> state(out_state ? 0 : size_t(desc->num_nodes) * n);
+    return graph_simulate_dispatch(
+        desc, run, t_max, out_state ? out_state : state.data(), nullptr, nullptr, nullptr, 0,
+        [&](auto& g) {
+            const int K = num_save_groups + 1;
+            for (size_t e = 0; e < g.edges.size(); ++e) {
+                const TimeSeries& mr = g.edges[e].property.mobility_results;
+                out_npts[e]          = int(mr.n());
+                for (int i = 0; i < int(mr.n()) && i < cap; ++i) {
+                    out_times[e * cap + i] = mr.times[i];
+                    std::copy(mr.values[i].begin(), mr.values[i].end(), out_values + (e * cap + i) * K);
+                }
+            }
+        },
+        save);
+}
+
+// analyze_result.h:186-265 on one time series: values[npts][n] at times[npts] -> integer days (abs_tol < 0: default)
+// or the given interpolation times. Returns the number of interpolated points (<= cap are stored).
+int orc_interpolate(const double* times, const double* values, int npts, int n, const double* tps, int ntps,
+                    double abs_tol, int cap, double* out_times, double* out_values)
+{
+    TimeSeries ts;
+    for (int i = 0; i < npts; ++i) {
+        ts.add(times[i], Vec(values + int64_t(i) * n, values + int64_t(i + 1) * n));
+    }
+    TimeSeries r = tps ? interpolate_simulation_result(ts, std::vector<double>(tps, tps + ntps))
+                       : (abs_tol < 0 ? interpolate_simulation_result(ts) : interpolate_simulation_result(ts, abs_tol));
+    for (int i = 0; i < int(r.n()) && i < cap; ++i) {
+        out_times[i] = r.times[i];
+        std::copy(r.values[i].begin(), r.values[i].end(), out_values + int64_t(i) * n);
+    }
+    return int(r.n());
+}
+
+// sum_nodes / ensemble_mean / ensemble_percentile (analyze_result.h:267-343) of data[runs][nodes][T][n]:
+// out_sum[runs][T][n] (nullable), out_mean[nodes][T][n] (nullable), out_pct[num_p][nodes][T][n]
+void orc_ensemble_reduce(const double* data, int runs, int nodes, int T, int n, int num_p, const double* p,
+                         double* out_sum, double* out_mean, double* out_pct)
+{
+    EnsembleResult ens(runs, std::vector<TimeSeries>(nodes));
+    for (int r = 0; r < runs; ++r) {
+        for (int k = 0; k < nodes; ++k) {
+            for (int t = 0; t < T; ++t) {
+                const double* v = data + ((int64_t(r) * nodes + k) * T + t) * n;
+                ens[r][k].add(double(t), Vec(v, v + n));
+            }
+        }
+    }
+    auto dump = [&](const std::vector<TimeSeries>& res, double* out) {
+        for (int k = 0; k < int(res.size()); ++k) {
+            for (int t = 0; t < T; ++t) {
+                std::copy(res[k].values[t].begin(), res[k].values[t].end(), out + (int64_t(k) * T + t) * n);
+            }
+        }
+    };
+    if (out_sum) {
+        auto s = sum_nodes(ens);
+        for (int r = 0; r < runs; ++r) {
+            dump(s[r], out_sum + int64_t(r) * T * n);
+        }
+    }
+    if (out_mean) {
+        dump(ensemble_mean(ens), out_mean);
+    }
+    for (int q = 0; q < num_p; ++q) {
+        dump(ensemble_percentile(ens, p[q]), out_pct + int64_t(q) * nodes * T * n);
+    }
 }
 
 // The call sequence of TestMobility.edgeApplyMobility (cpp/tests/test_mobility.cpp:154-215): two identical G=1 nodes,
@@ -640,6 +787,91 @@ int orc_study_sample_runs(const mio_study_desc* d, int64_t run0, int count, doub
         }
     }
     return 0;
+}
+
+// ParameterStudy::run_impl (parameter_studies.h:290-345) for runs [run0, run0+count) of this rank, literally per run:
+// copy + draw_sample of the parameter graph (RNG counter base + (run_idx << 32)), make_sampled_graph_simulation,
+// advance(t_max), then the process_result of the study example: interpolate_simulation_result(graph)
+// (cpp/examples/ode_secir_parameter_study_graph.cpp:292-301). Outputs (all nullable except checksum):
+//   out_daily[count][N][num_days][n], out_state[count][N][n], out_counters[count][N][4];
+//   checksum = sum of all interpolated values (keeps the interpolation alive when out_daily is null).
+// Returns 0, or a negative/positive error code.
+int orc_study_run_block(const mio_study_desc* sd, const mio_graph_desc* gd, int64_t run0, int count, double t_max,
+                        int num_days, double* out_daily, double* out_state, int64_t* out_counters, double* checksum)
+{
+    const int G = gd->num_groups, N = gd->num_nodes;
+    const int n = G * ncomp_of(gd->model);
+    const int64_t psz = pset_size(gd->model, G);
+    const int64_t csz = ctable_size(G, gd->ct_max_loc, gd->ct_max_pts);
+    const int64_t msz = gd->mob_max_pts > 0 ? 1 + gd->mob_max_pts + int64_t(gd->mob_max_pts) * n : 0;
+    std::vector<double> psets(psz * gd->num_psets), ctables(csz * gd->num_ctables), local(size_t(N) * 2),
+        y0(size_t(N) * n), mob(msz), daily(size_t(N) * num_days * n), state(size_t(N) * n);
+    double sum = 0.0;
+    for (int r = 0; r < count; ++r) {
+        int rc = orc_study_sample_runs(sd, run0 + r, 1, psets.data(), ctables.data(), local.data(), y0.data(),
+                                       msz > 0 ? mob.data() : nullptr, nullptr);
+        if (rc != 0) {
+            return rc;
+        }
+        mio_run_data rd{};
+        rd.psets      = psets.data();
+        rd.ctables    = ctables.data();
+        rd.node_local = local.data();
+        rd.y0         = y0.data();
+        rd.dt0        = nullptr;
+        rd.mobtables  = msz > 0 ? mob.data() : nullptr;
+        double* dly   = out_daily ? out_daily + int64_t(r) * N * num_days * n : daily.data();
+        rc = orc_graph_simulate_daily(gd, &rd, t_max, num_days, dly, out_state ? out_state + int64_t(r) * N * n : state.data(),
+                                      out_counters ? out_counters + int64_t(r) * N * 4 : nullptr);
+        if (rc < 0) {
+            return rc;
+        }
+        for (size_t i = 0; i < size_t(N) * num_days * n; ++i) {
+            sum += dly[i];
+        }
+    }
+    if (checksum) {
+        *checksum = sum;
+    }
+    return 0;
+}
+
+// The setup of TestGraphSimulation.consistencyFlowMobility (cpp/tests/test_graph_simulation.cpp:256-339): three
+// identical ODE-SEIR nodes, all six directed edges with coefficient 0.001 on every compartment, t0 = 0, tmax = 1,
+// dt = 0.001. Returns the number of time points of node 0's result; out_times[cap], out_values[cap][4].
+int orc_seir_graph_golden(int cap, double* out_times, double* out_values)
+{
+    oseir::Model model(1);
+    const double total_population = 10000;
+    model.populations[oseir::E]   = 100;
+    model.populations[oseir::I]   = 100;
+    model.populations[oseir::R]   = 100;
+    model.populations[oseir::S] =
+        total_population - model.populations[oseir::E] - model.populations[oseir::I] - model.populations[oseir::R];
+    model.TimeExposed[0]                      = 5.2;
+    model.TimeInfected[0]                     = 6;
+    model.TransmissionProbabilityOnContact[0] = 0.04;
+    Mat b(1, 1);
+    b.a[0] = 10;
+    model.ContactPatterns.m.emplace_back(b);
+    GraphSim<oseir::Model> g(0.0, 0.001);
+    for (int k = 0; k < 3; ++k) {
+        g.add_node(model, 0.0);
+    }
+    for (int i = 0; i < 3; ++i) {
+        for (int j = 0; j < 3; ++j) {
+            if (i != j) {
+                g.add_edge(i, j, MobilityEdge(Vec(4, 0.001)));
+            }
+        }
+    }
+    g.advance(1.0);
+    const TimeSeries& r = g.nodes[0].sim.result;
+    for (int i = 0; i < int(r.n()) && i < cap; ++i) {
+        out_times[i] = r.times[i];
+        std::copy(r.values[i].begin(), r.values[i].end(), out_values + int64_t(i) * 4);
+    }
+    return int(r.n());
 }
 
 } // extern "C"

@@ -127,3 +127,122 @@ def edge_apply_sequence(G, pset, local, ct, max_loc, max_pts, y0, coeff, t, dt):
                                   cdefs.dptr(args[3]), cdefs.dptr(args[4]), C.c_double(t), C.c_double(dt),
                                   cdefs.dptr(out))
     return out
+
+
+def graph_simulate_daily(p: GraphProblem, run: int, t_max: float, num_days: int):
+    """orc_graph_simulate + interpolate_simulation_result(graph): dict(daily[N][num_days][n], state, counters)."""
+    d = p.desc(max_runs=1)
+    rd = p.run_data(run, 1)
+    N, n = p.num_nodes, p.n
+    daily = np.zeros((N, num_days, n))
+    state = np.zeros((N, n))
+    cnt = np.zeros((N, 4), dtype=np.int64)
+    L = lib()
+    L.orc_graph_simulate_daily.restype = C.c_int
+    steps = L.orc_graph_simulate_daily(C.byref(d), C.byref(rd), C.c_double(t_max), C.c_int(num_days), cdefs.dptr(daily),
+                                       cdefs.dptr(state), cdefs.lptr(cnt))
+    assert steps >= 0, steps
+    return dict(daily=daily, state=state, counters=cnt, steps=steps)
+
+
+def graph_simulate_mobility(p: GraphProblem, run: int, t_max: float, save_groups, cap: int = 4096):
+    """get_mobility_results() of every edge (all edges built with saved_compartment_indices = save_groups).
+    Returns (npts[E], times[E][cap], values[E][cap][len(save_groups)+1], state[N][n])."""
+    d = p.desc(max_runs=1)
+    rd = p.run_data(run, 1)
+    E, K = p.num_edges, len(save_groups) + 1
+    ptr = np.zeros(len(save_groups) + 1, dtype=np.int32)
+    idx = []
+    for i, g in enumerate(save_groups):
+        idx += [int(x) for x in g]
+        ptr[i + 1] = len(idx)
+    idx = np.ascontiguousarray(idx, dtype=np.int32)
+    npts = np.zeros(E, dtype=np.int32)
+    times = np.zeros((E, cap))
+    values = np.zeros((E, cap, K))
+    state = np.zeros((p.num_nodes, p.n))
+    L = lib()
+    L.orc_graph_simulate_mobility.restype = C.c_int
+    steps = L.orc_graph_simulate_mobility(C.byref(d), C.byref(rd), C.c_double(t_max), C.c_int(len(save_groups)),
+                                          cdefs.iptr(ptr), cdefs.iptr(idx), C.c_int(cap), cdefs.iptr(npts),
+                                          cdefs.dptr(times), cdefs.dptr(values), cdefs.dptr(state))
+    assert steps >= 0
+    return npts, times, values, state
+
+
+def interpolate(times, values, tps=None, abs_tol: float = -1.0):
+    """interpolate_simulation_result (analyze_result.h:186-265) of one time series."""
+    times = np.ascontiguousarray(times, dtype=np.float64)
+    values = np.ascontiguousarray(values, dtype=np.float64).reshape(len(times), -1)
+    n = values.shape[1]
+    cap = (len(tps) if tps is not None else int(np.floor(times[-1]) - np.ceil(times[0])) + 3)
+    ot = np.zeros(cap)
+    ov = np.zeros((cap, n))
+    tp = None if tps is None else np.ascontiguousarray(tps, dtype=np.float64)
+    L = lib()
+    L.orc_interpolate.restype = C.c_int
+    k = L.orc_interpolate(cdefs.dptr(times), cdefs.dptr(values), len(times), n, cdefs.dptr(tp),
+                          0 if tp is None else len(tp), C.c_double(abs_tol), cap, cdefs.dptr(ot), cdefs.dptr(ov))
+    assert 0 <= k <= cap
+    return ot[:k].copy(), ov[:k].copy()
+
+
+def ensemble_reduce(data, p=(), want_sum=False, want_mean=False):
+    """sum_nodes / ensemble_mean / ensemble_percentile (analyze_result.h:267-343) of data[runs][nodes][T][n]."""
+    data = np.ascontiguousarray(data, dtype=np.float64)
+    runs, nodes, T, n = data.shape
+    pa = np.ascontiguousarray(p, dtype=np.float64)
+    out_sum = np.zeros((runs, T, n)) if want_sum else None
+    out_mean = np.zeros((nodes, T, n)) if want_mean else None
+    out_pct = np.zeros((max(len(pa), 1), nodes, T, n))
+    lib().orc_ensemble_reduce(cdefs.dptr(data), runs, nodes, T, n, len(pa), cdefs.dptr(pa), cdefs.dptr(out_sum),
+                              cdefs.dptr(out_mean), cdefs.dptr(out_pct))
+    return dict(sum=out_sum, mean=out_mean, percentile=out_pct[:len(pa)])
+
+
+def study_run_block(ps, problem: GraphProblem, run0: int, count: int, t_max: float, num_days: int,
+                    want_daily: bool = False):
+    """ParameterStudy::run_impl for runs [run0, run0+count) on the oracle: draw_sample + advance + interpolate per run.
+    `ps` is a memilio_b200.study.ParameterStudy (its distributions and seeds), `problem` any GraphProblem sampled from
+    it (graph topology and capacities). Returns dict(state[count][N][n], counters[count][N][4], checksum, daily?)."""
+    from memilio_b200 import study
+    sd, keep = study.build_desc(ps.graph, ps.seeds, ps.rng_counter, ps.ct_max_pts, ps.mob_max_pts)
+    gd = problem.desc(max_runs=1)
+    N, n = problem.num_nodes, problem.n
+    state = np.zeros((count, N, n))
+    cnt = np.zeros((count, N, 4), dtype=np.int64)
+    daily = np.zeros((count, N, num_days, n)) if want_daily else None
+    chk = C.c_double(0.0)
+    L = lib()
+    L.orc_study_run_block.restype = C.c_int
+    rc = L.orc_study_run_block(C.byref(sd), C.byref(gd), C.c_int64(run0), C.c_int(count), C.c_double(t_max),
+                               C.c_int(num_days), cdefs.dptr(daily), cdefs.dptr(state), cdefs.lptr(cnt), C.byref(chk))
+    assert rc == 0, rc
+    del keep
+    return dict(state=state, counters=cnt, checksum=chk.value, daily=daily)
+
+
+def sample_problem(ps, run0: int, count: int) -> GraphProblem:
+    """The runs [run0, run0+count) of the study `ps` sampled by the ORACLE's literal draw_sample(graph)
+    (oracle/mio_oracle_sampling.hpp), as a GraphProblem. Graphs without school holidays (one contact table)."""
+    from memilio_b200 import study
+    g = ps.graph
+    assert len(g.holiday_sets) == 0
+    d, keep = study.build_desc(g, ps.seeds, ps.rng_counter, ps.ct_max_pts, ps.mob_max_pts)
+    G, N, n = g.num_groups, g.num_nodes, g.n
+    psets = np.zeros((count, 1, flat.pset_size(g.model, G)))
+    ctables = np.zeros((count, 1, flat.ctable_size(G, g.num_locations, ps.ct_max_pts)))
+    local = np.zeros((count, N, 2))
+    y0 = np.zeros((count, N, n))
+    mob = np.zeros((count, flat.mobtable_size(n, ps.mob_max_pts))) if ps.mob_max_pts > 0 else None
+    L = lib()
+    L.orc_study_sample_runs.restype = C.c_int
+    rc = L.orc_study_sample_runs(C.byref(d), C.c_int64(run0), C.c_int(count), cdefs.dptr(psets), cdefs.dptr(ctables),
+                                 cdefs.dptr(local), cdefs.dptr(y0), cdefs.dptr(mob), None)
+    assert rc == 0
+    del keep
+    return GraphProblem(model=g.model, num_groups=G, num_nodes=N, edge_start=g.edge_start, edge_end=g.edge_end,
+                        edge_coeff=g.edge_coeff, psets=psets, ctables=ctables, node_local=local, y0=y0,
+                        ct_max_loc=g.num_locations, ct_max_pts=ps.ct_max_pts, mobtables=mob,
+                        mob_max_pts=ps.mob_max_pts, integrator=ps.integrator, t0=ps.t0, dt_graph=ps.dt,
+                        sim_kind=g.sim_kind, vacc_partial=g.vacc_partial, vacc_full=g.vacc_full)

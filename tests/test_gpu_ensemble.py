@@ -147,9 +147,10 @@ def test_run_ensemble_matches_record_and_reduce():
 
 
 def test_full_size_ensemble_properties():
-    # BASELINE config 4 shape (10 000 runs x 400 counties, 20 of its 100 days): size independent properties
+    # BASELINE config 4 at full size (10 000 runs x 400 counties x 100 days): size independent properties, and eight
+    # of the runs against the CPU oracle (states 1e-8, step counts equal)
     import oracle_lib
-    R, N, T = 10000, 400, 20.0
+    R, N, T = 10000, 400, 100.0
     g = synthetic.covid_study_graph(N=N)
     ps = study.ParameterStudy(g, 0.0, T, 0.5, R)
     p = ps.sample(0, R)
@@ -161,10 +162,10 @@ def test_full_size_ensemble_properties():
     # the population of a run is conserved by every flow and by the commuter exchange (Dead included)
     np.testing.assert_allclose(state.sum(axis=(1, 2)), total0, rtol=1e-11)
     assert np.isfinite(state).all() and state.min() >= -1e-9
-    # every node took at least the 40 graph steps; nothing had to be forced
-    assert cnt[:, :, 0].min() >= 40 and cnt[:, :, 2].sum() == 0
+    # every node took at least the 200 graph steps; nothing had to be forced
+    assert cnt[:, :, 0].min() >= 200 and cnt[:, :, 2].sum() == 0
     # a run does not depend on the ensemble it is computed in: the same runs alone, bit for bit
-    pick = [0, 4999, 9999]
+    pick = [0, 1, 2, 3, 4999, 5000, 9998, 9999]
     import copy
     q = copy.copy(p)
     for name in ("psets", "ctables", "node_local", "y0", "mobtables"):
@@ -177,7 +178,43 @@ def test_full_size_ensemble_properties():
         cnt_alone = sim.counters()
     np.testing.assert_array_equal(alone, state[pick])
     np.testing.assert_array_equal(cnt_alone, cnt[pick])
-    # and one of them against the CPU oracle
-    ref = oracle_lib.graph_simulate(q, 1, T)
-    np.testing.assert_allclose(alone[1], ref["state"], rtol=1e-8, atol=1e-9)
-    np.testing.assert_array_equal(cnt_alone[1][:, :3], ref["counters"][:, :3])
+    # and all eight against the CPU oracle over the full 100 days
+    from concurrent.futures import ThreadPoolExecutor
+    oracle_lib.lib()
+    with ThreadPoolExecutor(max_workers=8) as ex:  # ctypes releases the GIL
+        refs = list(ex.map(lambda r: oracle_lib.graph_simulate(q, r, T), range(len(pick))))
+    for r, ref in enumerate(refs):
+        np.testing.assert_allclose(alone[r], ref["state"], rtol=1e-8, atol=1e-9)
+        np.testing.assert_array_equal(cnt_alone[r][:, :3], ref["counters"][:, :3])
+
+
+def test_sharded_select_equals_single_gpu_reduce():
+    # the N-GPU reduction (runs -> columns exchange, then multi-segment selection per column block, gather) emulated on
+    # one device: the record of 3 "ranks" with uneven run counts, every rank's column block selected over the three run
+    # segments exactly as ensemble.reduce_distributed does after exchange_columns; bit-equal to the one-GPU reduce
+    import torch
+    G, N, runs, T = 6, 12, 41, 6
+    g = synthetic.covid_study_graph(N=N, max_out_degree=4, n_seeded=3, damping_day=2.0)
+    ps = study.ParameterStudy(g, 0.0, float(T), 0.5, runs)
+    p = ps.sample(0, runs)
+    rec = ensemble.EnsembleRecord(G, N, T + 1, capacity_runs=runs, mode=ensemble.ENS_AGE_SUM)
+    with capi.GraphSimulation(p, upload=False) as sim:
+        rec.attach(sim, 0)
+        sim.set_runs(0, p, 0, runs)
+        sim.advance(float(T))
+    pct1, mean1 = rec.reduce()
+    full = rec.as_torch()[:, :runs]
+    ncol = full.shape[0]
+    world = 3
+    blocks = [study.distribute_runs(runs, world, r) for r in range(world)]
+    local = [full[:, a:a + c].contiguous() for a, c in blocks]  # what each rank recorded
+    pct = np.zeros_like(pct1)
+    mean = np.zeros_like(mean1)
+    for rank, (c0, cn) in enumerate(ensemble.column_partition(ncol, world)):
+        segs = [local[s][c0:c0 + cn].contiguous() for s in range(world)]  # received from rank s
+        pr, mr = ensemble.select_cuda(segs, [c for _, c in blocks], ensemble.DEFAULT_PERCENTILES, True, 0)
+        pct[:, c0:c0 + cn] = pr
+        mean[c0:c0 + cn] = mr
+    np.testing.assert_array_equal(pct, pct1)
+    np.testing.assert_allclose(mean, mean1, rtol=1e-14, atol=1e-300)
+    rec.close()

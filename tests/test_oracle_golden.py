@@ -46,3 +46,25 @@ def test_vvs_oracle_reproduces_reference_golden_csv():
     np.testing.assert_allclose(y, ref[:, 1:], rtol=0, atol=1e-10)
     # the day chunks force a time point on every integer day (model.h:752)
     assert set(np.arange(1, 51)).issubset(set(np.round(t[np.abs(t - np.round(t)) < 1e-12]).astype(int)))
+
+
+def test_graph_mechanics_seir_golden():
+    # TestGraphSimulation.consistencyFlowMobility (cpp/tests/test_graph_simulation.cpp:276-339): node 0 of a fully
+    # connected 3-node ODE-SEIR graph, 1000 graph steps of dt 0.001 with commuter departure / return every other step,
+    # against cpp/tests/data/graphsimulation-compare.csv at the reference's 1e-10. Pins the oracle's GraphSim,
+    # SimulationNode, MobilityEdge::apply_mobility (incl. the Euler return step) and the default integrator on a graph.
+    import ctypes as C
+    import os
+    import numpy as np
+    import oracle_lib
+    from memilio_b200 import cdefs
+    ref = np.loadtxt(os.path.join(os.path.dirname(__file__), "golden", "graphsimulation-compare.csv"), skiprows=1)
+    cap = 2048
+    t = np.zeros(cap)
+    v = np.zeros((cap, 4))
+    L = oracle_lib.lib()
+    L.orc_seir_graph_golden.restype = C.c_int
+    n = L.orc_seir_graph_golden(cap, cdefs.dptr(t), cdefs.dptr(v))
+    assert n == ref.shape[0] == 1001
+    np.testing.assert_allclose(t[:n], ref[:, 0], rtol=0, atol=1e-10)
+    np.testing.assert_allclose(v[:n], ref[:, 1:5], rtol=0, atol=1e-10)
