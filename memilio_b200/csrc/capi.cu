@@ -82,7 +82,7 @@ struct mio_handle {
     int num_mob = 0;
     int mob_comp[NC] = {0, 0, 0, 0, 0, 0, 0, 0, 0, 0};
     // per run (device)
-    double *d_run_block = nullptr, *d_node_local = nullptr, *d_t_node = nullptr, *d_dt_node = nullptr;
+    double *d_run_block = nullptr, *d_node_local = nullptr, *d_node_ctl = nullptr;
     int* d_counters     = nullptr;
     double* d_y[4]      = {nullptr, nullptr, nullptr, nullptr};
     double *d_fac = nullptr, *d_aux = nullptr, *d_u = nullptr, *d_vis = nullptr;
@@ -289,7 +289,7 @@ void destroy(mio_handle* h)
                     h->d_in_split,   h->d_in_src,      h->d_out_ptr,    h->d_out_dst,   h->d_w_in,
                     h->d_w_out,      h->d_s_out,       h->d_umask,      h->d_u,         h->d_vis,
                     h->d_edge_start, h->d_edge_end,    h->d_coeff,
-                    h->d_run_block,  h->d_node_local,  h->d_t_node,     h->d_dt_node,   h->d_counters,
+                    h->d_run_block,  h->d_node_local,  h->d_node_ctl,   h->d_counters,
                     h->d_y[0],       h->d_y[1],        h->d_y[2],       h->d_y[3],      h->d_fac,
                     h->d_aux,        h->d_run_flags,   h->d_daily,      h->d_traj_npts, h->d_traj_times,
                     h->d_traj_values, h->d_stats,      h->d_vacc_partial, h->d_vacc_full, h->d_work, h->d_run_list, h->d_w_edge};
@@ -318,8 +318,7 @@ DeviceState device_state(const mio_handle* h)
     st.node_local  = h->d_node_local;
     st.node_pset   = h->d_node_pset;
     st.node_ctable = h->d_node_ctable;
-    st.t_node      = h->d_t_node;
-    st.dt_node     = h->d_dt_node;
+    st.node_ctl    = h->d_node_ctl;
     st.counters    = h->d_counters;
     st.vacc_partial = h->d_vacc_partial;
     st.vacc_full    = h->d_vacc_full;
@@ -698,8 +697,7 @@ int mio_cuda_graph_create(const mio_graph_desc* d, int device, mio_handle** out)
     const size_t R = (size_t)d->max_runs;
     H_TRY(dev_alloc(&h->d_run_block, R * geo.block_stride));
     H_TRY(dev_alloc(&h->d_node_local, R * N * 2));
-    H_TRY(dev_alloc(&h->d_t_node, R * N));
-    H_TRY(dev_alloc(&h->d_dt_node, R * N));
+    H_TRY(dev_alloc(&h->d_node_ctl, R * N * 4));
     H_TRY(dev_alloc(&h->d_counters, R * N * 4));
     H_TRY(dev_alloc(&h->d_work, (size_t)4));
     const int nbuf = E > 0 ? 4 : 2;
@@ -836,10 +834,16 @@ int mio_cuda_set_runs(mio_handle* h, int32_t slot0, int32_t count, const mio_run
             return fail(MIO_INVALID_VALUE, "initial integrator dt must be positive");
         }
     }
-    CUDA_TRY(cudaMemcpyAsync(h->d_t_node + s0 * N, tn.data(), sizeof(double) * tn.size(), cudaMemcpyHostToDevice,
-                             h->stream));
-    CUDA_TRY(cudaMemcpyAsync(h->d_dt_node + s0 * N, dtn.data(), sizeof(double) * dtn.size(), cudaMemcpyHostToDevice,
-                             h->stream));
+    // node clock records {t, dt, ICUCapacity, TestAndTraceCapacity}
+    std::vector<double> nctl((size_t)count * N * 4);
+    for (size_t i = 0; i < (size_t)count * N; ++i) {
+        nctl[i * 4 + 0] = tn[i];
+        nctl[i * 4 + 1] = dtn[i];
+        nctl[i * 4 + 2] = data->node_local[i * 2 + 0];
+        nctl[i * 4 + 3] = data->node_local[i * 2 + 1];
+    }
+    CUDA_TRY(cudaMemcpyAsync(h->d_node_ctl + s0 * N * 4, nctl.data(), sizeof(double) * nctl.size(),
+                             cudaMemcpyHostToDevice, h->stream));
     CUDA_TRY(cudaMemsetAsync(h->d_counters + s0 * N * 4, 0, sizeof(int) * (size_t)count * N * 4, h->stream));
     if (h->d_daily) {
         // day 0 = initial value (interpolate_simulation_result, analyze_result.h:228-231)
@@ -1112,8 +1116,8 @@ int mio_cuda_get_node_dt(mio_handle* h, int32_t slot0, int32_t count, double* ou
         return rc;
     }
     CUDA_TRY(cudaSetDevice(h->device));
-    CUDA_TRY(cudaMemcpy(out, h->d_dt_node + (size_t)slot0 * h->geo.N, sizeof(double) * (size_t)count * h->geo.N,
-                        cudaMemcpyDeviceToHost));
+    CUDA_TRY(cudaMemcpy2D(out, sizeof(double), h->d_node_ctl + (size_t)slot0 * h->geo.N * 4 + 1, sizeof(double) * 4,
+                          sizeof(double), (size_t)count * h->geo.N, cudaMemcpyDeviceToHost));
     return MIO_OK;
 }
 

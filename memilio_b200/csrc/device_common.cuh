@@ -20,7 +20,8 @@ namespace miocu
 constexpr int NC      = 10; // compartment slots per lane = osecir compartments, ode_secir/infection_state.h:33-47
 constexpr int VVS_NC  = 27; // osecirvvs compartments per age group, ode_secirvvs/infection_state.h:36-67
 constexpr int VVS_LAY = 3;
-constexpr int AGE_REC = 20; // derived per-age record (doubles), see host_params.cpp
+constexpr int AGE_REC = 22; // derived per-age record (doubles): 20 slots + 2 of padding, so that the 16-byte reads of
+                            // the six age groups of a node fall on different shared-memory banks
 constexpr int PHDR    = 8;  // derived parameter-set header
 
 // InfectionState order
@@ -117,8 +118,8 @@ struct DeviceState {
     const double* node_local;  // [R][N][2]
     const int* node_pset;      // [N]
     const int* node_ctable;    // [N]
-    double* t_node;            // [R][N] node-local simulation time (result.get_last_time())
-    double* dt_node;           // [R][N] SimulationBase::m_dt
+    double* node_ctl;          // [R][N][4] node clock record: result.get_last_time(), SimulationBase::m_dt, and a copy
+                               // of ICUCapacity, TestAndTraceCapacity (one 32-byte record per node: one bulk copy)
     int* counters;             // [R][N][4]
     const double* vacc_partial; // [N][G][vacc_days] cumulative DailyPartialVaccinations (osecirvvs), run-invariant
     const double* vacc_full;    // [N][G][vacc_days] cumulative DailyFullVaccinations

@@ -23,7 +23,7 @@ namespace miocu
 #define MIO_RETURN_MINBLOCKS 1
 #endif
 #ifndef MIO_INTEGRATE_ITEM_PASSES
-#define MIO_INTEGRATE_ITEM_PASSES 20
+#define MIO_INTEGRATE_ITEM_PASSES 1024 /* whole runs unless there are too few runs to keep every CTA busy */
 #endif
 #ifndef MIO_EXACT_MINBLOCKS_FACT
 #define MIO_EXACT_MINBLOCKS_FACT 16

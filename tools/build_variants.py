@@ -1,47 +1,30 @@
 #!/usr/bin/env python
-"""Build launch-shape variants of the library under memilio_b200/csrc/variants/ for A/B timing on the GPU box."""
+"""Build tuning variants of the CUDA library: tools/build_variants.py name=DEF1,DEF2=VAL ... -> memilio_b200/csrc/variants/<name>/libmio_cuda.so
+(select one at run time with MIO_CUDA_LIB=<path>). Variant builds compile the G = 6 kernels only."""
 import os
 import sys
+from concurrent.futures import ThreadPoolExecutor
 
 ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
 sys.path.insert(0, ROOT)
 from memilio_b200 import build as b  # noqa: E402
 
-VARIANTS = {
-    "i128x2": ["MIO_TUNE_ONLY_G6", "MIO_INTEGRATE_THREADS=128", "MIO_INTEGRATE_MINBLOCKS=2"],
-    "i128x3": ["MIO_TUNE_ONLY_G6", "MIO_INTEGRATE_THREADS=128", "MIO_INTEGRATE_MINBLOCKS=3"],
-    "i128x4": ["MIO_TUNE_ONLY_G6", "MIO_INTEGRATE_THREADS=128", "MIO_INTEGRATE_MINBLOCKS=4"],
-    "i256x1": ["MIO_TUNE_ONLY_G6", "MIO_INTEGRATE_THREADS=256", "MIO_INTEGRATE_MINBLOCKS=1"],
-    "i160x3": ["MIO_TUNE_ONLY_G6", "MIO_INTEGRATE_THREADS=160", "MIO_INTEGRATE_MINBLOCKS=3"],
-    "i192x2": ["MIO_TUNE_ONLY_G6", "MIO_INTEGRATE_THREADS=192", "MIO_INTEGRATE_MINBLOCKS=2"],
-    "p10": ["MIO_TUNE_ONLY_G6", "MIO_INTEGRATE_ITEM_PASSES=10"],
-    "p20": ["MIO_TUNE_ONLY_G6", "MIO_INTEGRATE_ITEM_PASSES=20"],
-    "p2": ["MIO_TUNE_ONLY_G6", "MIO_INTEGRATE_ITEM_PASSES=2"],
-    "xf8": ["MIO_TUNE_ONLY_G6", "MIO_EXACT_MINBLOCKS_FACT=8"],
-    "xf12": ["MIO_TUNE_ONLY_G6", "MIO_EXACT_MINBLOCKS_FACT=12"],
-    "s384": ["MIO_TUNE_ONLY_G6", "MIO_SELECT_THREADS=384"],
-    "s640": ["MIO_TUNE_ONLY_G6", "MIO_SELECT_THREADS=640"],
-    "s768": ["MIO_TUNE_ONLY_G6", "MIO_SELECT_THREADS=768"],
-    "d512x1": ["MIO_TUNE_ONLY_G6", "MIO_DEPART_SMEM_THREADS=512", "MIO_DEPART_SMEM_MINBLOCKS=1"],
-    "d128x2": ["MIO_TUNE_ONLY_G6", "MIO_DEPART_SMEM_THREADS=128", "MIO_DEPART_SMEM_MINBLOCKS=2"],
-    "s512": ["MIO_TUNE_ONLY_G6", "MIO_SELECT_THREADS=512"],
-    "s1024": ["MIO_TUNE_ONLY_G6", "MIO_SELECT_THREADS=1024"],
-    "r128x4": ["MIO_TUNE_ONLY_G6", "MIO_RETURN_TMA_THREADS=128", "MIO_RETURN_TMA_MINBLOCKS=4"],
-    "r512x1": ["MIO_TUNE_ONLY_G6", "MIO_RETURN_TMA_THREADS=512", "MIO_RETURN_TMA_MINBLOCKS=1"],
-    "x8": ["MIO_TUNE_ONLY_G6", "MIO_EXACT_MINBLOCKS=8"],
-    "x10": ["MIO_TUNE_ONLY_G6", "MIO_EXACT_MINBLOCKS=10"],
-    "x12": ["MIO_TUNE_ONLY_G6", "MIO_EXACT_MINBLOCKS=12"],
-    "i64x4": ["MIO_TUNE_ONLY_G6", "MIO_INTEGRATE_THREADS=64", "MIO_INTEGRATE_MINBLOCKS=4"],
-    "i64x6": ["MIO_TUNE_ONLY_G6", "MIO_INTEGRATE_THREADS=64", "MIO_INTEGRATE_MINBLOCKS=6"],
-    "e256x2": ["MIO_DEPART_MINBLOCKS=2", "MIO_RETURN_MINBLOCKS=3"],
-    "e256x4": ["MIO_DEPART_MINBLOCKS=4", "MIO_RETURN_MINBLOCKS=4"],
-    "e128x6": ["MIO_EDGE_THREADS=128", "MIO_DEPART_MINBLOCKS=6", "MIO_RETURN_MINBLOCKS=8"],
-}
+
+def one(spec):
+    name, _, defs = spec.partition("=")
+    defines = [d for d in defs.split(",") if d]
+    d = os.path.join(b.CSRC, "variants", name)
+    os.makedirs(d, exist_ok=True)
+    out = os.path.join(d, "libmio_cuda.so")
+    b.build(force=True, defines=defines, out=out, objdir=d)
+    log = open(os.path.join(d, "build", "ptxas.log")).read().splitlines()
+    for i, ln in enumerate(log):
+        if "integrate_nodes_kernelILi6ELi1ELi0" in ln and "Compiling" in ln:
+            print(name, "|", log[i + 2].strip(), "|", log[i + 3].strip()[:60])
+    return out
+
 
 if __name__ == "__main__":
-    names = sys.argv[1:] or list(VARIANTS)
-    for name in names:
-        d = os.path.join(b.CSRC, "variants", name)
-        out = os.path.join(b.CSRC, "variants", f"libmio_cuda_{name}.so")
-        b.build(force=True, defines=VARIANTS[name], out=out, objdir=d)
-        print(out)
+    with ThreadPoolExecutor(max_workers=2) as ex:
+        for o in ex.map(one, sys.argv[1:]):
+            print(os.path.relpath(o, ROOT))
