@@ -67,6 +67,9 @@ def parse():
     ap.add_argument("--cpu-sample-runs", type=int, default=0, help="runs of the CPU baseline sample (0 = one per core)")
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--e2e-batches", type=int, default=2, help="batches of the end-to-end leg (sampling overlaps GPU)")
+    ap.add_argument("--day-block", type=int, default=0,
+                    help="size the ensemble record for this many days and advance / reduce window by window "
+                         "(0 = one record for all days; needed when runs x columns does not fit the device)")
     ap.add_argument("--model", default="osecir", choices=["osecir", "osecirvvs"],
                     help="osecir = BASELINE configs[3] (the default bench line); osecirvvs = configs[4]'s model on one GPU")
     ap.add_argument("--sim-kind", default="model", choices=["model", "base"],
@@ -313,16 +316,18 @@ def main():
     h2d = sum(getattr(problem, n_).nbytes for n_ in pinned_names)
 
     sim = capi.GraphSimulation(problem, device=local_rank, max_runs=R, upload=False)
-    rec = ensemble.EnsembleRecord(num_groups, N, days, capacity_runs=R, mode=ensemble.ENS_AGE_SUM,
+    blk = args.day_block if args.day_block > 0 else days
+    rec = ensemble.EnsembleRecord(num_groups, N, min(blk, days), capacity_runs=R, mode=ensemble.ENS_AGE_SUM,
                                   device=local_rank, model=model)
     rec_t = rec.as_torch()
-    ncol = rec.info()["num_columns"]
+    ncol = N * days * rec.El + days * rec.n  # columns of the whole period
     d2h = (len(ensemble.DEFAULT_PERCENTILES) + 1) * ncol * 8
     stream = torch.cuda.ExternalStream(sim.stream_ptr(), device=torch.device("cuda", local_rank))
 
     def fresh():
         """rewind the handle to t0 and upload the runs (H2D) -- untimed for `value`"""
         sim.reset()
+        rec.set_window(0)
         rec.attach(sim, 0)
         sim.set_runs(0, problem, 0, R)
 
@@ -335,12 +340,28 @@ def main():
         torch.cuda.synchronize()
         e0, e1, e2 = (torch.cuda.Event(enable_timing=True) for _ in range(3))
         e0.record(stream)
-        sim.advance(T)  # synchronises the handle's stream before it returns
-        e1.record(stream)
-        red = reduce()  # synchronous: exchange (N>1), selection kernels, gather on rank 0
+        if blk >= days:
+            sim.advance(T)  # synchronises the handle's stream before it returns
+            e1.record(stream)
+            red = reduce()  # synchronous: exchange (N>1), selection kernels, gather on rank 0
+            e2.record(stream)
+            e2.synchronize()
+            return e0.elapsed_time(e2), e1.elapsed_time(e2), red
+        # windowed record: advance and reduce window by window (all calls are synchronous); the reduction time is the
+        # sum over the windows
+        marks = []
+
+        def timer(kind):
+            ev = torch.cuda.Event(enable_timing=True)
+            ev.record(stream)
+            marks.append((kind, ev))
+        full = ensemble.windowed_advance_reduce(sim, rec, rec_t, R, 0.0, T, days, blk, rank, world,
+                                                ensemble.DEFAULT_PERCENTILES, True, timer)
         e2.record(stream)
         e2.synchronize()
-        return e0.elapsed_time(e2), e1.elapsed_time(e2), red
+        ms_reduce = sum(a[1].elapsed_time(b[1]) for a, b in zip(marks[:-1], marks[1:]) if a[0] == "reduce")
+        red = (full[:-1], full[-1]) if full is not None else (None, None)
+        return e0.elapsed_time(e2), ms_reduce, red
 
     for _ in range(args.warmup):
         step_device()
@@ -378,9 +399,31 @@ def main():
     # ---- N > 1: the sharded reduction (exchange + multi-segment select + gather) against directly gathered columns
     multi_gpu_check = None
     if world > 1:
+        # the record holds the last window (all days when there is one window): columns of that window are compared
+        nblk = min(blk, days)
+        d0_last = ((days - 1) // nblk) * nblk
+        len_last = days - d0_last
+        ncol_rec = int(rec_t.shape[0])
         gen = torch.Generator().manual_seed(1234)
-        ncheck = min(1000, ncol)
-        cols = torch.randperm(ncol, generator=gen)[:ncheck].sort().values.to(rec_t.device)
+        cand = torch.randperm(ncol_rec, generator=gen)[:4000].sort().values.numpy()
+        El, nn = rec.El, rec.n
+        node_cols = N * nblk * El
+        full_idx, keep = [], []
+        for c in cand:
+            if c < node_cols:
+                k_, rem = divmod(int(c), nblk * El)
+                dd, e_ = divmod(rem, El)
+                if dd < len_last:
+                    full_idx.append((k_ * days + d0_last + dd) * El + e_)
+                    keep.append(int(c))
+            else:
+                dd, j_ = divmod(int(c) - node_cols, nn)
+                if dd < len_last:
+                    full_idx.append(N * days * El + (d0_last + dd) * nn + j_)
+                    keep.append(int(c))
+        keep, full_idx = keep[:1000], np.array(full_idx[:1000])
+        cols = torch.tensor(keep, device=rec_t.device)
+        ncheck = len(keep)
         mine = rec_t[cols, :R].contiguous()
         parts = [torch.empty_like(mine) for _ in range(world)] if rank == 0 else None
         dist.gather(mine, parts, dst=0)
@@ -392,12 +435,12 @@ def main():
             bad = 0
             for i, q in enumerate(ensemble.DEFAULT_PERCENTILES):
                 want = srt[:, int(total * q)].cpu().numpy()
-                bad += int((pct_dev[i][cols.cpu().numpy()] != want).sum())
+                bad += int((pct_dev[i][full_idx] != want).sum())
             mean_ref = allruns.mean(dim=1).cpu().numpy()
-            mean_err = float(np.max(np.abs(red_dev[1][cols.cpu().numpy()] - mean_ref) /
-                                    np.maximum(np.abs(mean_ref), 1e-300)))
+            mean_err = float(np.max(np.abs(red_dev[1][full_idx] - mean_ref) / np.maximum(np.abs(mean_ref), 1e-300)))
             multi_gpu_check = {"columns": int(ncheck), "runs": int(total), "percentiles": len(ensemble.DEFAULT_PERCENTILES),
                                "percentile_mismatches": bad, "mean_max_rel_err": mean_err,
+                               "days_checked": [int(d0_last), int(days - 1)],
                                "method": "columns gathered from all ranks, torch.sort, index size_t(runs*p)"}
             assert bad == 0, f"sharded percentiles differ from directly sorted columns in {bad} entries"
 
@@ -405,15 +448,21 @@ def main():
     # host sampling (C library) of batch b+1 overlaps the GPU work of batch b; H2D of every batch and D2H of the
     # reduced result are inside the timed region.
     nb = max(1, min(args.e2e_batches, R))
-    bounds = [(i * R // nb, (i + 1) * R // nb) for i in range(nb)]
-    bmax = max(b - a for a, b in bounds)
+    if blk < days:
+        nb = 1  # a windowed record keeps all runs of the rank resident
+        # the device leg's handle and record make room for the public call's own (same sizes)
+        sim.close()
+        rec.close()
+        del rec_t
+        torch.cuda.empty_cache()
     sim2 = None
 
     def step_e2e():
         t0 = time.perf_counter()
         # the public call: ParameterStudy.run_ensemble = sampling (host threads), H2D from pinned buffers, advance,
         # on-device percentile reduction, D2H of the reduced result
-        out = ps.run_ensemble(num_batches=nb, device=local_rank, rank=rank, world=world)
+        out = ps.run_ensemble(num_batches=nb, device=local_rank, rank=rank, world=world,
+                              day_block=args.day_block if args.day_block > 0 else None)
         torch.cuda.synchronize()
         return (time.perf_counter() - t0) * 1e3, out
 
@@ -519,9 +568,8 @@ def main():
             # the same runs on both sides: the CPU arm's results are the parity vectors
             line["parity_check"] = parity_against_oracle(gpu_state, gpu_cnt, cpu)
         emit(line)
+    ps.close()
     sim.close()
-    if sim2 is not None:
-        sim2.close()
     rec.close()
     if world > 1:
         dist.destroy_process_group()

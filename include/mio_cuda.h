@@ -342,6 +342,12 @@ MIO_API void mio_cuda_ensemble_destroy(mio_ensemble* e);
 MIO_API int mio_cuda_attach_ensemble(mio_handle* h, mio_ensemble* e, int64_t run_offset);
 MIO_API int mio_cuda_ensemble_info(mio_ensemble* e, int64_t* num_columns, int64_t* stride, int64_t* num_runs,
                                    void** device_ptr);
+/* Day window of the record: the days [first_day, first_day + num_days) since t0 are recorded into the slots
+ * [0, num_days), other days are skipped (default first_day = 0). A study whose full record does not fit device memory
+ * (ODE-SECIRVVS, 12 500 runs x 1.1 M columns = 110 GB) keeps all its runs resident, advances them one window at a
+ * time and reduces window by window: the record is sized for one window (interpolate_simulation_result +
+ * ensemble_percentile of cpp/memilio/data/analyze_result.h:186-343 are per day, so the result is the same). */
+MIO_API int mio_cuda_ensemble_set_window(mio_ensemble* e, int32_t first_day);
 /* ensemble_percentile (order statistic size_t(num_runs * p) per column, exact) and ensemble_mean over the recorded
  * runs. Host outputs percentiles[num_p][num_columns], mean[num_columns]; either may be NULL. num_p <= 8. */
 MIO_API int mio_cuda_ensemble_reduce(mio_ensemble* e, int32_t num_p, const double* p, double* percentiles,

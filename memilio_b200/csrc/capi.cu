@@ -59,6 +59,7 @@ int mio_set_last_error(int code, const std::string& msg)
 struct mio_ensemble {
     int device = 0;
     int G = 0, C = 0, N = 0, num_days = 0, mode = 0, lay = 1;
+    int first_day = 0; // day window [first_day, first_day + num_days) of the record
     long long capacity = 0, num_columns = 0;
     std::atomic<long long> num_runs{0}; // handles of several host threads record into one ensemble
     double* d_data = nullptr; // [num_columns][capacity]
@@ -869,11 +870,13 @@ int mio_cuda_set_runs(mio_handle* h, int32_t slot0, int32_t count, const mio_run
         if (h->ens_offset + slot0 + count > h->ens->capacity) {
             return fail(MIO_OUT_OF_RANGE, "ensemble record: run capacity exceeded");
         }
-        ++h->launches;
-        ++h->prof_launches[MIO_KC_ENSEMBLE];
-        CUDA_TRY(launch_record_ensemble(h->d_y[h->cur] + s0 * N * n, h->ens->d_data, N, G, geo.C_ref, geo.LAY, count,
-                                        0, h->ens->num_days, h->ens->mode, h->ens_offset + slot0, h->ens->capacity,
-                                        h->stream));
+        if (h->ens->first_day == 0) { // day 0 lies inside the record's window
+            ++h->launches;
+            ++h->prof_launches[MIO_KC_ENSEMBLE];
+            CUDA_TRY(launch_record_ensemble(h->d_y[h->cur] + s0 * N * n, h->ens->d_data, N, G, geo.C_ref, geo.LAY,
+                                            count, 0, h->ens->num_days, h->ens->mode, h->ens_offset + slot0,
+                                            h->ens->capacity, h->stream));
+        }
         {
             const long long upto = h->ens_offset + slot0 + count;
             long long seen       = h->ens->num_runs.load();
@@ -1043,10 +1046,11 @@ int mio_cuda_advance(mio_handle* h, double t_max)
             const double day = std::round(h->t);
             if (std::fabs(h->t - day) <= 1e-10 * std::max(1.0, std::fabs(day))) {
                 const int slot = (int)day - h->day0;
-                if (h->ens && slot >= 0 && slot < h->ens->num_days) {
+                const int wslot = h->ens ? slot - h->ens->first_day : -1; // slot inside the record's day window
+                if (h->ens && wslot >= 0 && wslot < h->ens->num_days) {
                     ScopedSpan sp(h, MIO_KC_ENSEMBLE);
                     CUDA_TRY(launch_record_ensemble(h->d_y[h->cur], h->ens->d_data, geo.N, geo.G, geo.C_ref, geo.LAY, R,
-                                                    slot, h->ens->num_days, h->ens->mode, h->ens_offset,
+                                                    wslot, h->ens->num_days, h->ens->mode, h->ens_offset,
                                                     h->ens->capacity, h->stream));
                 }
                 if (h->d_daily && slot >= 0 && slot < h->desc.max_days) {
@@ -1330,6 +1334,15 @@ int mio_cuda_ensemble_info(mio_ensemble* e, int64_t* num_columns, int64_t* strid
     if (device_ptr) {
         *device_ptr = e->d_data;
     }
+    return MIO_OK;
+}
+
+int mio_cuda_ensemble_set_window(mio_ensemble* e, int32_t first_day)
+{
+    if (!e || first_day < 0) {
+        return fail(MIO_INVALID_VALUE, "invalid ensemble day window");
+    }
+    e->first_day = first_day;
     return MIO_OK;
 }
 

@@ -26,6 +26,7 @@ def _lib():
         L.mio_cuda_attach_ensemble.argtypes = [C.c_void_p, C.c_void_p, C.c_int64]
         L.mio_cuda_ensemble_info.argtypes = [C.c_void_p, cdefs.c_int64_p, cdefs.c_int64_p, cdefs.c_int64_p,
                                              C.POINTER(C.c_void_p)]
+        L.mio_cuda_ensemble_set_window.argtypes = [C.c_void_p, C.c_int32]
         L.mio_cuda_ensemble_reduce.argtypes = [C.c_void_p, C.c_int32, cdefs.c_double_p, cdefs.c_double_p,
                                                cdefs.c_double_p]
         L.mio_cuda_select_percentiles.argtypes = [C.c_int, C.c_int32, C.POINTER(C.c_void_p), cdefs.c_int64_p,
@@ -55,6 +56,10 @@ class EnsembleRecord:
 
     def attach(self, sim, run_offset: int):
         _check(_lib().mio_cuda_attach_ensemble(sim._h, self._h, run_offset))
+
+    def set_window(self, first_day: int):
+        """Record the days [first_day, first_day + num_days) since t0 into the slots [0, num_days)."""
+        _check(_lib().mio_cuda_ensemble_set_window(self._h, int(first_day)))
 
     def detach(self, sim):
         _check(_lib().mio_cuda_attach_ensemble(sim._h, None, 0))
@@ -197,3 +202,38 @@ def reduce_distributed(local, count_local: int, rank: int, world: int, p: Sequen
     if full is None:
         return None, None
     return (full[:len(p)], full[len(p)] if mean else None)
+
+
+def windowed_advance_reduce(sim, rec, local, count: int, t0: float, tmax: float, num_days: int, day_block: int,
+                            rank: int, world: int, p: Sequence[float] = DEFAULT_PERCENTILES, mean: bool = True,
+                            timer: Optional[Callable] = None):
+    """Advance the resident runs of `sim` (None on a rank without runs) to tmax one window of `day_block` days at a
+    time and reduce every window (sharded when world > 1); `rec` is sized for one window. Returns the rows
+    [len(p) (+1 for the mean)][N*num_days*El + num_days*n] of the whole period on rank 0 (None elsewhere): the same
+    columns as a record of all days would give. `timer(kind)` is called before ("advance"/"reduce") phases."""
+    N, El, n = rec.N, rec.El, rec.n
+    blk = max(1, min(int(day_block), num_days))
+    k = len(p) + (1 if mean else 0)
+    full = np.zeros((k, N * num_days * El + num_days * n)) if rank == 0 else None
+    day0 = int(np.ceil(t0 - 1e-14))
+    for d0 in range(0, num_days, blk):
+        d1 = min(num_days, d0 + blk)  # window = days [d0, d1) since t0
+        if timer:
+            timer("advance")
+        if sim is not None:
+            rec.set_window(d0)
+            sim.advance(min(tmax, float(day0 + d1 - 1)))
+        if timer:
+            timer("reduce")
+        pct, mn = reduce_distributed(local, count, rank, world, p, mean)
+        if rank == 0:
+            rows = pct if mn is None else np.concatenate([pct, mn[None, :]], axis=0)
+            node_part = rows[:, :N * blk * El].reshape(k, N, blk, El)
+            sum_part = rows[:, N * blk * El:].reshape(k, blk, n)
+            full[:, :N * num_days * El].reshape(k, N, num_days, El)[:, :, d0:d1] = node_part[:, :, :d1 - d0]
+            full[:, N * num_days * El:].reshape(k, num_days, n)[:, d0:d1] = sum_part[:, :d1 - d0]
+    if sim is not None and tmax > sim.t:
+        sim.advance(tmax)
+    if timer:
+        timer("end")
+    return full

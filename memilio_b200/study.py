@@ -243,6 +243,13 @@ def damping_cache(rows, cols, times, levels, types, mats):
     return ot[:n.value].copy(), om[:n.value].reshape(n.value, rows, cols).copy()
 
 
+class _RecordShape:
+    """N, El, n of an ensemble record (a rank without runs has no record but takes part in the reduction)."""
+
+    def __init__(self, N, El, n):
+        self.N, self.El, self.n = N, El, n
+
+
 class ParameterStudy:
     """`mio::ParameterStudy(params_graph, t0, tmax, dt, num_runs)` (parameter_studies.h:84) for a Graph-ODE-SECIR
     study. `run` keeps the reference's semantics: run r is sampled with RNG counter `counter + (r << 32)`, advanced
@@ -362,20 +369,26 @@ class ParameterStudy:
         return out
 
     def run_ensemble(self, p: Optional[Sequence[float]] = None, mean: bool = True, num_batches: int = 2,
-                     device: int = 0, rank: int = 0, world: int = 1, mode: Optional[int] = None, pinned: bool = True):
+                     device: int = 0, rank: int = 0, world: int = 1, mode: Optional[int] = None, pinned: bool = True,
+                     day_block: Optional[int] = None):
         """ParameterStudy::run with the ensemble post-processing of save_results done on the device
         (parameter_studies.h:158-217 + data/analyze_result.h:289-343): this rank's block of runs (distribute_runs) is
         sampled, uploaded and advanced in `num_batches` batches, the daily results are recorded on the GPU and reduced
         to percentiles / mean at the end (exchange over torch.distributed when world > 1; result on rank 0).
         Pipeline: two host threads, each with its own simulation handle and CUDA stream, sample (C library, several
         threads), upload and advance alternate batches, so that uploads and the latency bound kernels of one batch
-        overlap the other batch's work on the GPU. Returns (percentiles [len(p)][columns], mean [columns])."""
+        overlap the other batch's work on the GPU. Returns (percentiles [len(p)][columns], mean [columns]).
+        `day_block`: the ensemble record is sized for that many days only; all runs of the rank stay resident (one
+        batch) and are advanced and reduced one day window at a time (studies whose full record does not fit the
+        device, e.g. ODE-SECIRVVS with 12 500 runs per GPU: 110 GB)."""
         from concurrent.futures import ThreadPoolExecutor
         from . import capi, ensemble
         if p is None:
             p = ensemble.DEFAULT_PERCENTILES
         if mode is None:
             mode = ensemble.ENS_AGE_SUM
+        if day_block is not None:
+            return self._run_ensemble_windows(p, mean, device, rank, world, mode, pinned, int(day_block))
         run0, count = distribute_runs(self.num_runs, world, rank)
         days = int(np.floor(self.tmax + 1e-14) - np.ceil(self.t0 - 1e-14)) + 1
         g = self.graph
@@ -454,10 +467,53 @@ class ParameterStudy:
         self._invalidate()
         return pct, mn
 
+    def _run_ensemble_windows(self, p, mean, device, rank, world, mode, pinned, day_block):
+        """run_ensemble with a windowed record: one batch, advance + reduce per window of `day_block` days."""
+        from . import capi, ensemble
+        run0, count = distribute_runs(self.num_runs, world, rank)
+        days = int(np.floor(self.tmax + 1e-14) - np.ceil(self.t0 - 1e-14)) + 1
+        g = self.graph
+        G, N, n = g.num_groups, g.num_nodes, g.n
+        El = flat.num_compartments(g.model) if mode == ensemble.ENS_AGE_SUM else n
+        blk = max(1, min(day_block, days))
+        key = ("windows", count, blk, days, mode, device, pinned)
+        cache = getattr(self, "_ens", None)
+        if count > 0 and (cache is None or cache["key"] != key):
+            self._drop_ensemble_cache()
+            bufs = [self.sample_buffers(count, pinned)]
+            first = self.sample(run0, count, out=bufs[0])
+            sims = [capi.GraphSimulation(first, device=device, max_runs=count, upload=False)]
+            rec = ensemble.EnsembleRecord(G, N, blk, capacity_runs=count, mode=mode, device=device, model=g.model)
+            cache = self._ens = {"key": key, "bufs": bufs, "sims": sims, "rec": rec, "pool": None, "sampled": True}
+        if count > 0:
+            sim, rec = cache["sims"][0], cache["rec"]
+            pb = first if cache.pop("sampled", False) else self.sample(run0, count, out=cache["bufs"][0])
+            sim.reset()
+            sim.set_active_runs(count)
+            rec.set_window(0)
+            rec.attach(sim, 0)
+            sim.set_runs(0, pb, 0, count)
+            self.last_h2d_bytes = sum(getattr(pb, kk).nbytes for kk in ("psets", "ctables", "node_local", "y0"))
+            local = rec.as_torch()
+        else:
+            import torch
+            sim = None
+            dev = torch.device("cuda", device) if torch.cuda.is_available() else torch.device("cpu")
+            rec = _RecordShape(N, El, n)
+            local = torch.empty((N * blk * El + blk * n, 0), dtype=torch.float64, device=dev)
+        full = ensemble.windowed_advance_reduce(sim, rec, local, count, self.t0, self.tmax, days, blk, rank, world, p,
+                                                mean)
+        self.rng_counter += self.num_runs << 32
+        self._invalidate()
+        if rank != 0:
+            return None, None
+        return full[:len(p)], (full[len(p)] if mean else None)
+
     def _drop_ensemble_cache(self):
         cache = getattr(self, "_ens", None)
         if cache is not None:
-            cache["pool"].shutdown(wait=True)
+            if cache["pool"] is not None:
+                cache["pool"].shutdown(wait=True)
             for sim in cache["sims"]:
                 sim.close()
             cache["rec"].close()

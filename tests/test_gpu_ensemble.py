@@ -218,3 +218,22 @@ def test_sharded_select_equals_single_gpu_reduce():
     np.testing.assert_array_equal(pct, pct1)
     np.testing.assert_allclose(mean, mean1, rtol=1e-14, atol=1e-300)
     rec.close()
+
+
+def test_windowed_record_equals_full_record():
+    # a record sized for 3 days, advanced and reduced window by window (what a study does whose full record does not
+    # fit the device), against the record of all days: every percentile and the mean, bit for bit
+    G, N, runs, T = 6, 12, 23, 7
+    g = synthetic.covid_study_graph(N=N, max_out_degree=4, n_seeded=3, damping_day=2.0)
+    ps = study.ParameterStudy(g, 0.0, float(T), 0.5, runs)
+    pct, mean = ps.run_ensemble(num_batches=2)
+    ps.close()
+    for blk in (3, 8, 1):
+        ps2 = study.ParameterStudy(g, 0.0, float(T), 0.5, runs)
+        pct2, mean2 = ps2.run_ensemble(day_block=blk)
+        np.testing.assert_array_equal(pct2, pct)
+        np.testing.assert_array_equal(mean2, mean)
+        # a second call reuses the handle and the record and continues the random sequence
+        pct3, _ = ps2.run_ensemble(day_block=blk)
+        assert not np.array_equal(pct3, pct)
+        ps2.close()
