@@ -224,8 +224,8 @@ public:
     {
         return m_parameters;
     }
-    // The per-edge traveler state is not materialised on the GPU: the condensed mobility results of
-    // add_mobility_result_time_point (instant.h:424-447) are not recorded by this backend; the series stays empty.
+    // add_mobility_result_time_point (instant.h:421-445): GraphSimulation::advance appends one time point per graph
+    // step when the edge was built with saved_compartment_indices (mio_cuda_enable_mobility_results)
     TimeSeries<FP>& get_mobility_results()
     {
         return m_mobility_results;
@@ -509,6 +509,38 @@ public:
             auto p = detail::pack_graph<FP>(m_graph);
             m_dev  = std::make_shared<detail::DeviceGraph>(p, m_dt, 1, int(p.psets.size()), int(p.ctables.size()), 0);
             m_dev->set_run(0, p, int(p.psets.size()), int(p.ctables.size()));
+            // MobilityEdge(coeffs, save_indices): the backend records one set of index groups for all edges
+            for (auto& e : m_graph.edges()) {
+                const auto& si = e.property.get_parameters().get_save_indices();
+                if (!si.empty()) {
+                    if (m_save.empty()) {
+                        m_save = si;
+                    }
+                    else if (m_save != si) {
+                        throw std::runtime_error("GraphSimulation: edges with different saved_compartment_indices are "
+                                                 "not supported by this backend");
+                    }
+                }
+            }
+            for (auto& e : m_graph.edges()) {
+                if (!m_save.empty() && e.property.get_parameters().get_save_indices().empty()) {
+                    throw std::runtime_error("GraphSimulation: either all edges or none must save mobility results");
+                }
+            }
+        }
+        if (!m_save.empty()) {
+            // room for the graph steps of this call
+            const int steps = int(std::ceil((t_max - m_t) / m_dt)) + 2;
+            std::vector<int32_t> ptr(1, 0), idx;
+            for (auto& grp : m_save) {
+                for (auto i : grp) {
+                    idx.push_back(int32_t(i));
+                }
+                ptr.push_back(int32_t(idx.size()));
+            }
+            m_mob_cap = m_mob_seen + steps;
+            cuda_check(mio_cuda_enable_mobility_results(m_dev->get(), int32_t(m_save.size()), ptr.data(), idx.data(),
+                                                        m_mob_cap));
         }
         const size_t total = size_t(m_dev->N()) * size_t(m_dev->n());
         std::vector<double> state(total);
@@ -521,6 +553,24 @@ public:
             cuda_check(mio_cuda_advance(m_dev->get(), m_t));
             cuda_check(mio_cuda_get_state(m_dev->get(), 0, 1, state.data()));
             append_time_point(m_t, state.data());
+        }
+        if (!m_save.empty()) {
+            const size_t E = m_graph.edges().size(), K1 = m_save.size() + 1, cap = size_t(m_mob_cap);
+            std::vector<int32_t> npts(E);
+            std::vector<double> times(cap), values(E * cap * K1);
+            cuda_check(mio_cuda_get_mobility_results(m_dev->get(), 0, 1, npts.data(), times.data(), values.data()));
+            int seen = m_mob_seen;
+            for (size_t e = 0; e < E; ++e) {
+                auto& ts = m_graph.edges()[e].property.get_mobility_results();
+                for (int i = m_mob_seen; i < npts[e]; ++i) {
+                    Eigen::VectorX<FP> v{Eigen::Index(K1)};
+                    std::copy(values.begin() + (e * cap + size_t(i)) * K1, values.begin() + (e * cap + size_t(i) + 1) * K1,
+                              v.data());
+                    ts.add_time_point(times[size_t(i)], v);
+                }
+                seen = std::max(seen, int(npts[e]));
+            }
+            m_mob_seen = seen;
         }
         const size_t Nn = size_t(m_dev->N());
         std::vector<double> dts(Nn);
@@ -568,6 +618,8 @@ private:
     GraphT m_graph;
     FP m_t, m_dt;
     std::shared_ptr<detail::DeviceGraph> m_dev;
+    std::vector<std::vector<size_t>> m_save; // saved_compartment_indices common to the edges
+    int m_mob_cap = 0, m_mob_seen = 0;
 };
 
 // make_mobility_sim, metapopulation_mobility_instant.h:656-678

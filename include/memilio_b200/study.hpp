@@ -15,52 +15,83 @@ namespace mio
 
 namespace osecir
 {
-// draw_sample(Graph<Model, MobilityParameters>&), parameter_space.h:207-251
+namespace detail
+{
+// what stays a node's own when the shared draw is laid over it: the capacities drawn with the node's demographics and
+// its school holidays (parameter_space.h:224-236)
+template <class FP>
+struct NodeOwnValues {
+    UncertainValue<FP> icu, tnt;
+    std::vector<std::pair<SimulationTime<FP>, SimulationTime<FP>>> holidays;
+    explicit NodeOwnValues(const Parameters<FP>& p)
+        : icu(p.template get<ICUCapacity<FP>>())
+        , tnt(p.template get<TestAndTraceCapacity<FP>>())
+        , holidays(p.template get<ContactPatterns<FP>>().get_school_holidays())
+    {
+    }
+    void put_back(Parameters<FP>& p) const
+    {
+        p.template get<ICUCapacity<FP>>()                           = icu;
+        p.template get<TestAndTraceCapacity<FP>>()                  = tnt;
+        p.template get<ContactPatterns<FP>>().get_school_holidays() = holidays;
+    }
+};
+
+// the sampled contact dampings act on the commuters as well: every damping of the shared contact patterns becomes a
+// damping of the edge's coefficient vectors it names, spread over the compartments by the age group weights
+// (parameter_space.h:241-248, damping_sampling.h:256-307)
+template <class FP, class Contacts>
+MobilityParameters<FP> damp_mobility(MobilityParameters<FP> edge, const Contacts& contacts)
+{
+    auto& members = edge.get_coefficients();
+    for (const auto& ds : contacts.get_dampings()) {
+        const auto& weights = ds.get_group_weights();
+        for (size_t member : ds.get_matrix_indices()) {
+            if (member < members.get_num_matrices()) {
+                const Eigen::Index len       = members[member].get_baseline().size();
+                const Eigen::Index per_group = len / weights.size();
+                Eigen::VectorX<FP> factor(len);
+                for (Eigen::Index j = 0; j < len; ++j) {
+                    factor[j] = ds.get_value().value() * weights[j / per_group];
+                }
+                members[member].add_damping(factor, ds.get_level(), ds.get_type(), ds.get_time());
+            }
+        }
+    }
+    return edge;
+}
+} // namespace detail
+
+// draw_sample(Graph<Model, MobilityParameters>&), parameter_space.h:207-251. The draw order is the reference's (it fixes
+// the random numbers every parameter gets): the infection parameters and the contact dampings once, on the first
+// node's model, then per node its demographics; every node ends up with the shared draw plus its own capacities and
+// holidays. Dynamic NPIs are not part of this backend.
 template <class FP>
 Graph<Model<FP>, MobilityParameters<FP>> draw_sample(Graph<Model<FP>, MobilityParameters<FP>>& graph)
 {
-    Graph<Model<FP>, MobilityParameters<FP>> sampled_graph;
-    auto& shared_params_model = graph.nodes()[0].property;
-    draw_sample_infection(shared_params_model);
-    auto& shared_contacts = shared_params_model.parameters.template get<ContactPatterns<FP>>();
-    shared_contacts.draw_sample_dampings();
-    // (DynamicNPIsInfectedSymptoms: not part of this backend)
-    for (auto& params_node : graph.nodes()) {
-        auto& node_model = params_node.property;
-        draw_sample_demographics(node_model);
-        auto local_icu_capacity = node_model.parameters.template get<ICUCapacity<FP>>();
-        auto local_tnt_capacity = node_model.parameters.template get<TestAndTraceCapacity<FP>>();
-        auto local_holidays     = node_model.parameters.template get<ContactPatterns<FP>>().get_school_holidays();
-        if (&node_model != &shared_params_model) {
-            node_model.parameters = shared_params_model.parameters;
+    auto& nodes = graph.nodes();
+    auto& lead  = nodes.front().property;
+    draw_sample_infection(lead);
+    lead.parameters.template get<ContactPatterns<FP>>().draw_sample_dampings();
+
+    Graph<Model<FP>, MobilityParameters<FP>> sampled;
+    for (size_t k = 0; k < nodes.size(); ++k) {
+        auto& model = nodes[k].property;
+        draw_sample_demographics(model);
+        const detail::NodeOwnValues<FP> own(model.parameters);
+        if (k != 0) {
+            model.parameters = lead.parameters;
         }
-        node_model.parameters.template get<ICUCapacity<FP>>()                           = local_icu_capacity;
-        node_model.parameters.template get<TestAndTraceCapacity<FP>>()                  = local_tnt_capacity;
-        node_model.parameters.template get<ContactPatterns<FP>>().get_school_holidays() = local_holidays;
-        node_model.parameters.template get<ContactPatterns<FP>>().make_matrix();
-        node_model.apply_constraints();
-        sampled_graph.add_node(params_node.id, node_model);
+        own.put_back(model.parameters);
+        model.parameters.template get<ContactPatterns<FP>>().make_matrix();
+        model.apply_constraints();
+        sampled.add_node(nodes[k].id, model);
     }
+    const auto& contacts = lead.parameters.template get<ContactPatterns<FP>>();
     for (auto& edge : graph.edges()) {
-        auto edge_params = edge.property;
-        auto& coeffs     = edge_params.get_coefficients();
-        for (auto& d : shared_contacts.get_dampings()) { // apply_dampings + make_mobility_damping_vector
-            for (size_t i : d.get_matrix_indices()) {
-                if (i >= coeffs.get_num_matrices()) {
-                    continue;
-                }
-                const Eigen::Index n = coeffs[i].get_baseline().size();
-                const Eigen::Index G = d.get_group_weights().size();
-                Eigen::VectorX<FP> v(n);
-                for (Eigen::Index j = 0; j < n; ++j) {
-                    v[j] = d.get_value().value() * d.get_group_weights()[j / (n / G)];
-                }
-                coeffs[i].add_damping(v, d.get_level(), d.get_type(), d.get_time());
-            }
-        }
-        sampled_graph.add_edge(edge.start_node_idx, edge.end_node_idx, edge_params);
+        sampled.add_edge(edge.start_node_idx, edge.end_node_idx, detail::damp_mobility<FP>(edge.property, contacts));
     }
-    return sampled_graph;
+    return sampled;
 }
 } // namespace osecir
 
@@ -138,7 +169,48 @@ void advance_batch(std::vector<SimT>& sims, double t_max)
     for (size_t r = 0; r < sims.size(); ++r) {
         dev.set_run(int(r), packed[r], num_psets, num_ctables);
     }
+    // MobilityEdge(coeffs, save_indices): get_mobility_results of every run's edges
+    std::vector<std::vector<size_t>> save;
+    for (auto& e : sims[0].get_graph().edges()) {
+        const auto& si = e.property.get_parameters().get_save_indices();
+        if (!si.empty() && save.empty()) {
+            save = si;
+        }
+        if (!save.empty() && si != save) {
+            throw std::runtime_error("ParameterStudy: all edges must share the saved_compartment_indices");
+        }
+    }
+    int mob_cap = 0;
+    if (!save.empty()) {
+        std::vector<int32_t> ptr(1, 0), idx;
+        for (auto& grp : save) {
+            for (auto i : grp) {
+                idx.push_back(int32_t(i));
+            }
+            ptr.push_back(int32_t(idx.size()));
+        }
+        mob_cap = int(std::ceil((t_max - t0) / dtg)) + 2;
+        cuda_check(mio_cuda_enable_mobility_results(dev.get(), int32_t(save.size()), ptr.data(), idx.data(), mob_cap));
+    }
     cuda_check(mio_cuda_advance(dev.get(), t_max));
+    if (!save.empty()) {
+        const size_t E = sims[0].get_graph().edges().size(), K1 = save.size() + 1, cap = size_t(mob_cap);
+        std::vector<int32_t> npts(sims.size() * E);
+        std::vector<double> times(cap), values(sims.size() * E * cap * K1);
+        cuda_check(mio_cuda_get_mobility_results(dev.get(), 0, int(sims.size()), npts.data(), times.data(),
+                                                 values.data()));
+        for (size_t r = 0; r < sims.size(); ++r) {
+            for (size_t e = 0; e < E; ++e) {
+                auto& ts = sims[r].get_graph().edges()[e].property.get_mobility_results();
+                for (int i = 0; i < npts[r * E + e]; ++i) {
+                    Eigen::VectorX<FP> v{Eigen::Index(K1)};
+                    const size_t off = ((r * E + e) * cap + size_t(i)) * K1;
+                    std::copy(values.begin() + off, values.begin() + off + K1, v.data());
+                    ts.add_time_point(times[size_t(i)], v);
+                }
+            }
+        }
+    }
     const size_t N = size_t(dev.N()), n = size_t(dev.n());
     const size_t nsim = sims.size(), ndays = size_t(days);
     std::vector<double> daily(nsim * N * ndays * n), state(nsim * N * n), day_state(N * n);

@@ -235,6 +235,19 @@ MIO_API int mio_cuda_get_trajectory(mio_handle* h, int32_t slot0, int32_t count,
 
 /* statistics: kernels launched by this handle so far; (run, step) pairs whose return phase needed the literal
  * in-order replay because of underflow fix-ups */
+/* MobilityEdge::get_mobility_results (cpp/memilio/mobility/metapopulation_mobility_instant.h:421-445, called at :599
+ * and :620): every edge is given the same saved_compartment_indices -- num_groups index groups, group_ptr[num_groups+1]
+ * into group_idx (reference element indices age*C + compartment). From then on every graph step appends one time point
+ * per edge that carries commuters: the sums of the mobile population over each index group and, last, its total. The
+ * per-edge traveler state this needs is materialised only for handles that ask for it (R*E*n doubles), and their return
+ * steps are replayed with the literal sequential edge loop. capacity = time points kept per edge; a second call with a
+ * larger capacity keeps what was recorded. */
+MIO_API int mio_cuda_enable_mobility_results(mio_handle* h, int32_t num_groups, const int32_t* group_ptr,
+                                             const int32_t* group_idx, int32_t capacity);
+/* npts[count][E] points recorded per edge, times[capacity] (the graph times of the steps, common to all edges),
+ * values[count][E][capacity][num_groups + 1] */
+MIO_API int mio_cuda_get_mobility_results(mio_handle* h, int32_t slot0, int32_t count, int32_t* npts, double* times,
+                                          double* values);
 MIO_API int mio_cuda_get_stats(mio_handle* h, int64_t* launches, int64_t* exact_replays);
 
 /* ---- ParameterStudy sampling (host C++, no device needed) --------------------------------------------------------

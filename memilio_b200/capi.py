@@ -28,7 +28,7 @@ EXPORTS = [
     "mio_study_sample_runs", "mio_study_distribute_runs", "mio_study_rng_raw", "mio_damping_cache_build",
     "mio_cuda_ensemble_create", "mio_cuda_ensemble_destroy", "mio_cuda_attach_ensemble", "mio_cuda_ensemble_info",
     "mio_cuda_ensemble_reduce", "mio_cuda_select_percentiles", "mio_cuda_reduce_host_columns",
-    "mio_cuda_ensemble_set_window",
+    "mio_cuda_ensemble_set_window", "mio_cuda_enable_mobility_results", "mio_cuda_get_mobility_results",
 ]
 KERNEL_CLASSES = ["integrate", "depart", "return", "return_exact", "record", "ensemble"]
 
@@ -148,6 +148,33 @@ class GraphSimulation:
         values = np.zeros((count, N, cap, n))
         _check(lib().mio_cuda_get_trajectory(self._h, slot0, count, cdefs.iptr(npts), cdefs.dptr(times),
                                              cdefs.dptr(values)))
+        return npts, times, values
+
+    def enable_mobility_results(self, save_groups, capacity: int):
+        """MobilityEdge(coeffs, save_indices) for every edge: record get_mobility_results()."""
+        ptr = np.zeros(len(save_groups) + 1, dtype=np.int32)
+        idx = []
+        for i, g in enumerate(save_groups):
+            idx += [int(x) for x in g]
+            ptr[i + 1] = len(idx)
+        idx = np.ascontiguousarray(idx if idx else [0], dtype=np.int32)
+        self._mob_K, self._mob_cap = len(save_groups), capacity
+        L = lib()
+        L.mio_cuda_enable_mobility_results.argtypes = [C.c_void_p, C.c_int32, cdefs.c_int32_p, cdefs.c_int32_p, C.c_int32]
+        _check(L.mio_cuda_enable_mobility_results(self._h, len(save_groups), cdefs.iptr(ptr), cdefs.iptr(idx), capacity))
+
+    def mobility_results(self, slot0=0, count=None):
+        """(npts[count][E], times[capacity], values[count][E][capacity][K+1])"""
+        count = self.max_runs - slot0 if count is None else count
+        E = self.p.num_edges
+        npts = np.zeros((count, E), dtype=np.int32)
+        times = np.zeros(self._mob_cap)
+        values = np.zeros((count, E, self._mob_cap, self._mob_K + 1))
+        L = lib()
+        L.mio_cuda_get_mobility_results.argtypes = [C.c_void_p, C.c_int32, C.c_int32, cdefs.c_int32_p, cdefs.c_double_p,
+                                                    cdefs.c_double_p]
+        _check(L.mio_cuda_get_mobility_results(self._h, slot0, count, cdefs.iptr(npts), cdefs.dptr(times),
+                                               cdefs.dptr(values)))
         return npts, times, values
 
     def stats(self):

@@ -105,6 +105,14 @@ struct mio_handle {
     bool aux_pending = false; // a departure happened and the next node phase has to write the return coefficients
     int* d_work = nullptr;        // [0] work item counter of the persistent node-phase kernel, [1] run list length
     int* d_run_list = nullptr;    // [R] runs flagged for the exact replay of a return step
+    // get_mobility_results (optional)
+    int mob_K = 0, mob_cap = 0, mob_npts = 0;
+    std::vector<int32_t> mob_gptr, mob_gidx;
+    std::vector<double> mob_times;
+    std::vector<unsigned char> edge_active;
+    int *d_mob_gptr = nullptr, *d_mob_gdev = nullptr, *d_ref_to_dev = nullptr;
+    unsigned char* d_edge_active = nullptr;
+    double *d_edge_m = nullptr, *d_mob_values = nullptr;
     // optional per-kernel-class device timing (CUDA events on the launching stream)
     bool profiling = false;
     struct Span {
@@ -293,7 +301,8 @@ void destroy(mio_handle* h)
                     h->d_run_block,  h->d_node_local,  h->d_node_ctl,   h->d_counters,
                     h->d_y[0],       h->d_y[1],        h->d_y[2],       h->d_y[3],      h->d_fac,
                     h->d_aux,        h->d_run_flags,   h->d_daily,      h->d_traj_npts, h->d_traj_times,
-                    h->d_traj_values, h->d_stats,      h->d_vacc_partial, h->d_vacc_full, h->d_work, h->d_run_list, h->d_w_edge};
+                    h->d_traj_values, h->d_stats,      h->d_vacc_partial, h->d_vacc_full, h->d_work, h->d_run_list, h->d_w_edge,
+                    h->d_mob_gptr,   h->d_mob_gdev,    h->d_ref_to_dev, h->d_edge_active, h->d_edge_m, h->d_mob_values};
     for (void* p : ptrs) {
         if (p) {
             cudaFree(p);
@@ -561,8 +570,14 @@ int mio_cuda_graph_create(const mio_graph_desc* d, int device, mio_handle** out)
         }
         // coefficient vectors in the device's lane order (identity for osecir)
         std::vector<double> coeff_dev((size_t)E * n);
+        h->edge_active.assign((size_t)E, 0);
         for (int e = 0; e < E; ++e) {
             to_device_layout(LAY, G, C_ref, d->edge_coeff + (size_t)e * n_ref, coeff_dev.data() + (size_t)e * n);
+            for (int j = 0; j < n_ref; ++j) {
+                if (d->edge_coeff[(size_t)e * n_ref + j] > 0.0) {
+                    h->edge_active[(size_t)e] = 1;
+                }
+            }
         }
         const double* edge_coeff = coeff_dev.data();
         // outgoing CSR = reference edge order; incoming CSR sorted by (dst, src)
@@ -900,6 +915,7 @@ int mio_cuda_reset(mio_handle* h)
     h->have_mobile = false;
     h->snap_idx = h->v0_idx = -1;
     h->days_recorded        = 0;
+    h->mob_npts             = 0;
     CUDA_TRY(cudaMemsetAsync(h->d_counters, 0, sizeof(int) * (size_t)h->max_runs * h->geo.N * 4, h->stream));
     if (h->d_run_flags) {
         CUDA_TRY(cudaMemsetAsync(h->d_run_flags, 0, sizeof(int) * (size_t)h->max_runs, h->stream));
@@ -989,6 +1005,14 @@ int mio_cuda_advance(mio_handle* h, double t_max)
             ea.list_count     = h->d_work + 1;
             ea.csr.w_edge     = h->d_w_edge;
             ea.num_runs       = R;
+            ea.edge_m         = h->d_edge_m;
+            MobilityResultArgs mra{};
+            bool mob_point = false; // this graph step moved commuters: one time point per edge
+            if (h->d_edge_m) {
+                mra = MobilityResultArgs{geo.n,          geo.n_ref,        geo.E,       h->mob_K,        h->d_mob_gptr,
+                                         h->d_mob_gdev,  h->d_ref_to_dev,  h->d_edge_active, h->d_edge_m, h->d_mob_values,
+                                         h->mob_cap,     h->mob_npts,      R};
+            }
             ea.dt             = dt;
             ea.t              = h->t;
             if (h->have_mobile && h->return_time <= h->t) {
@@ -1004,11 +1028,20 @@ int mio_cuda_advance(mio_handle* h, double t_max)
                     ScopedSpan sp(h, MIO_KC_RETURN);
                     CUDA_TRY(launch_return(ea, h->stream));
                 }
+                if (h->d_edge_m) {
+                    // the per-edge returning populations come out of the literal replay: every run is replayed
+                    CUDA_TRY(cudaMemsetAsync(h->d_run_flags, 1, sizeof(int) * (size_t)R, h->stream));
+                }
                 // runs that need the order dependent underflow fix-up are replayed literally (the kernel exits
                 // at once for unflagged runs and clears the flag, so no host round trip is needed)
                 {
                     ScopedSpan sp(h, MIO_KC_RETURN_EXACT);
                     CUDA_TRY(launch_return_exact(ea, h->stream));
+                }
+                if (h->d_edge_m && h->mob_npts < h->mob_cap) {
+                    CUDA_TRY(launch_mobility_results(mra, h->stream));
+                    ++h->launches;
+                    mob_point = true;
                 }
                 h->cur         = ret_idx;
                 h->have_mobile = false;
@@ -1031,6 +1064,12 @@ int mio_cuda_advance(mio_handle* h, double t_max)
                     ScopedSpan sp(h, MIO_KC_DEPART);
                     CUDA_TRY(launch_depart(ea, h->stream));
                 }
+                if (h->d_edge_m && h->mob_npts < h->mob_cap) {
+                    CUDA_TRY(launch_edge_mobile_depart(ea, h->stream));
+                    CUDA_TRY(launch_mobility_results(mra, h->stream));
+                    h->launches += 2;
+                    mob_point = true;
+                }
                 h->snap_idx    = h->cur;
                 h->v0_idx      = dep_idx;
                 h->cur         = dep_idx;
@@ -1040,6 +1079,10 @@ int mio_cuda_advance(mio_handle* h, double t_max)
                 h->return_time = h->t + dt;
             }
             h->toggle = !h->toggle;
+            if (mob_point) {
+                h->mob_times[(size_t)h->mob_npts] = h->t;
+                ++h->mob_npts;
+            }
         }
         // daily record: the value the reference's interpolate_simulation_result yields at integer days
         if (h->d_daily || h->ens) {
@@ -1177,6 +1220,97 @@ int mio_cuda_get_trajectory(mio_handle* h, int32_t slot0, int32_t count, int32_t
     CUDA_TRY(cudaMemcpy(npts, h->d_traj_npts + off, sizeof(int) * rows, cudaMemcpyDeviceToHost));
     CUDA_TRY(cudaMemcpy(times, h->d_traj_times + off * cap, sizeof(double) * rows * cap, cudaMemcpyDeviceToHost));
     CUDA_TRY(cudaMemcpy(values, h->d_traj_values + off * cap * n, sizeof(double) * rows * cap * n,
+                        cudaMemcpyDeviceToHost));
+    return MIO_OK;
+}
+
+int mio_cuda_enable_mobility_results(mio_handle* h, int32_t num_groups, const int32_t* group_ptr,
+                                     const int32_t* group_idx, int32_t capacity)
+{
+    if (!h || num_groups < 0 || capacity < 1 || (num_groups > 0 && (!group_ptr || !group_idx))) {
+        return fail(MIO_INVALID_VALUE, "invalid arguments");
+    }
+    const Geometry& geo = h->geo;
+    if (geo.E == 0) {
+        return fail(MIO_INVALID_VALUE, "graph has no edges");
+    }
+    const size_t R = (size_t)h->max_runs;
+    if (R * geo.E * geo.n * sizeof(double) > (size_t)8 << 30) {
+        return fail(MIO_OUT_OF_RANGE, "mobility results keep the traveler state of every edge of every run: too many "
+                                      "runs for this handle (use a handle with few runs)");
+    }
+    for (int g = 0; g < num_groups; ++g) {
+        for (int q = group_ptr[g]; q < group_ptr[g + 1]; ++q) {
+            if (group_idx[q] < 0 || group_idx[q] >= geo.n_ref) {
+                return fail(MIO_OUT_OF_RANGE, "saved compartment index out of range");
+            }
+        }
+    }
+    CUDA_TRY(cudaSetDevice(h->device));
+    CUDA_TRY(cudaStreamSynchronize(h->stream));
+    const int K1 = num_groups + 1;
+    if (h->d_edge_m && h->mob_K != num_groups) {
+        return fail(MIO_INVALID_VALUE, "mobility results are already enabled with other index groups");
+    }
+    if (!h->d_edge_m) {
+        h->mob_K = num_groups;
+        h->mob_gptr.assign(group_ptr, group_ptr + num_groups + 1);
+        h->mob_gidx.assign(group_idx, group_idx + (num_groups > 0 ? group_ptr[num_groups] : 0));
+        std::vector<int> gdev(h->mob_gidx.size()), r2d((size_t)geo.n_ref);
+        for (int j = 0; j < geo.n_ref; ++j) {
+            r2d[(size_t)j] = dev_index_of_ref(geo.LAY, geo.G, j / geo.C_ref, j % geo.C_ref);
+        }
+        for (size_t q = 0; q < gdev.size(); ++q) {
+            gdev[q] = r2d[(size_t)h->mob_gidx[q]];
+        }
+        CUDA_TRY(dev_alloc(&h->d_mob_gptr, h->mob_gptr.size()));
+        CUDA_TRY(cudaMemcpy(h->d_mob_gptr, h->mob_gptr.data(), sizeof(int) * h->mob_gptr.size(), cudaMemcpyHostToDevice));
+        CUDA_TRY(dev_alloc(&h->d_mob_gdev, std::max<size_t>(gdev.size(), 1)));
+        if (!gdev.empty()) {
+            CUDA_TRY(cudaMemcpy(h->d_mob_gdev, gdev.data(), sizeof(int) * gdev.size(), cudaMemcpyHostToDevice));
+        }
+        CUDA_TRY(dev_alloc(&h->d_ref_to_dev, r2d.size()));
+        CUDA_TRY(cudaMemcpy(h->d_ref_to_dev, r2d.data(), sizeof(int) * r2d.size(), cudaMemcpyHostToDevice));
+        CUDA_TRY(dev_alloc(&h->d_edge_active, h->edge_active.size()));
+        CUDA_TRY(cudaMemcpy(h->d_edge_active, h->edge_active.data(), h->edge_active.size(), cudaMemcpyHostToDevice));
+        CUDA_TRY(dev_alloc(&h->d_edge_m, R * geo.E * geo.n));
+        CUDA_TRY(cudaMemset(h->d_edge_m, 0, sizeof(double) * R * geo.E * geo.n));
+    }
+    if (capacity > h->mob_cap) {
+        double* nv = nullptr;
+        CUDA_TRY(dev_alloc(&nv, R * geo.E * (size_t)capacity * K1));
+        CUDA_TRY(cudaMemset(nv, 0, sizeof(double) * R * geo.E * (size_t)capacity * K1));
+        if (h->d_mob_values && h->mob_npts > 0) {
+            CUDA_TRY(cudaMemcpy2D(nv, sizeof(double) * (size_t)capacity * K1, h->d_mob_values,
+                                  sizeof(double) * (size_t)h->mob_cap * K1, sizeof(double) * (size_t)h->mob_npts * K1,
+                                  R * geo.E, cudaMemcpyDeviceToDevice));
+        }
+        cudaFree(h->d_mob_values);
+        h->d_mob_values = nv;
+        h->mob_cap      = capacity;
+        h->mob_times.resize((size_t)capacity, 0.0);
+    }
+    return MIO_OK;
+}
+
+int mio_cuda_get_mobility_results(mio_handle* h, int32_t slot0, int32_t count, int32_t* npts, double* times,
+                                  double* values)
+{
+    if (int rc = check_slots(h, slot0, count, npts)) {
+        return rc;
+    }
+    if (!h->d_mob_values || !times || !values) {
+        return fail(MIO_INVALID_VALUE, "mobility results are not enabled, or null output");
+    }
+    CUDA_TRY(cudaSetDevice(h->device));
+    const size_t E = (size_t)h->geo.E, K1 = (size_t)h->mob_K + 1, cap = (size_t)h->mob_cap;
+    for (int r = 0; r < count; ++r) {
+        for (size_t e = 0; e < E; ++e) {
+            npts[(size_t)r * E + e] = h->edge_active[e] ? h->mob_npts : 0;
+        }
+    }
+    std::copy(h->mob_times.begin(), h->mob_times.end(), times);
+    CUDA_TRY(cudaMemcpy(values, h->d_mob_values + (size_t)slot0 * E * cap * K1, sizeof(double) * (size_t)count * E * cap * K1,
                         cudaMemcpyDeviceToHost));
     return MIO_OK;
 }

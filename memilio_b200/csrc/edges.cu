@@ -1111,6 +1111,9 @@ __global__ void __launch_bounds__(32, FACT ? MIO_EXACT_MINBLOCKS_FACT : MIO_EXAC
                 yf[i] += m[i];
                 yt[i] -= m[i];
             }
+            if (a.edge_m != nullptr && act) { // the returning population of the edge (after the fix-up), :599
+                store10(a.edge_m + ((size_t)run * E + e) * geo.n + gl * NC, m);
+            }
             if (act) {
                 store10(a.y_out + rt * geo.n + gl * NC, yt);
                 if (fixes) {
@@ -1139,6 +1142,71 @@ __global__ void __launch_bounds__(32, FACT ? MIO_EXACT_MINBLOCKS_FACT : MIO_EXAC
     if (act) {
         store10(a.y_out + (rbase + cur.from) * geo.n + gl * NC, yf);
     }
+}
+
+// ---------------------------------------------------------------------------------------------------------------
+// get_mobility_results support (single simulations that ask for it; not on the ensemble path).
+// Departure: the mobile population of edge e is coeff_e * u_from (u = snapshot * (1 - damping) * mobility factor *
+// commuter nondetection * mask, see integrate.cu), instant.h:608-615.
+__global__ void edge_mobile_depart_kernel(int n, int N, int E, const int* __restrict__ edge_start,
+                                          const double* __restrict__ coeff, const double* __restrict__ u,
+                                          double* __restrict__ edge_m, size_t total)
+{
+    const size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (i < total) {
+        const size_t re  = i / n;
+        const int j      = (int)(i - re * n);
+        const size_t run = re / E;
+        const int e      = (int)(re - run * E);
+        edge_m[i]        = coeff[(size_t)e * n + j] * u[(run * N + edge_start[e]) * n + j];
+    }
+}
+
+cudaError_t launch_edge_mobile_depart(const EdgeArgs& a, cudaStream_t stream)
+{
+    const size_t total = (size_t)a.num_runs * a.geo.E * a.geo.n;
+    if (total > 0) {
+        edge_mobile_depart_kernel<<<(unsigned)((total + 255) / 256), 256, 0, stream>>>(
+            a.geo.n, a.geo.N, a.geo.E, a.csr.edge_start, a.csr.coeff, a.u, a.edge_m, total);
+    }
+    return cudaGetLastError();
+}
+
+// add_mobility_result_time_point, instant.h:421-445: per edge the sums over the saved index groups (in the order the
+// indices were given) and the total over all compartments (reference element order), one thread per (run, edge)
+__global__ void mobility_results_kernel(MobilityResultArgs a)
+{
+    const size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= (size_t)a.num_runs * a.E) {
+        return;
+    }
+    const int e = (int)(i % a.E);
+    if (!a.edge_active[e]) {
+        return;
+    }
+    const double* m = a.edge_m + i * a.n;
+    double* out     = a.values + (i * a.capacity + a.slot) * (a.K + 1);
+    for (int g = 0; g < a.K; ++g) {
+        double s = 0.0;
+        for (int q = a.group_ptr[g]; q < a.group_ptr[g + 1]; ++q) {
+            s += m[a.group_dev_idx[q]];
+        }
+        out[g] = s;
+    }
+    double tot = 0.0;
+    for (int j = 0; j < a.n_ref; ++j) {
+        tot += m[a.ref_to_dev[j]];
+    }
+    out[a.K] = tot;
+}
+
+cudaError_t launch_mobility_results(const MobilityResultArgs& a, cudaStream_t stream)
+{
+    const size_t total = (size_t)a.num_runs * a.E;
+    if (total > 0) {
+        mobility_results_kernel<<<(unsigned)((total + 127) / 128), 128, 0, stream>>>(a);
+    }
+    return cudaGetLastError();
 }
 
 __global__ void record_daily_kernel(int N, int n, const double* __restrict__ y, double* __restrict__ daily,

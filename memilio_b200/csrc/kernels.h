@@ -106,7 +106,24 @@ struct EdgeArgs {
     double t_dep;        // return only: departure time of the returning commuters
     double dt;           // dt of this graph step
     int num_runs;
+    double* edge_m;      // [R][E][n] or null: mobile population of every edge (MobilityEdge::m_mobile_population's last
+                         // value) written by the literal replay, for get_mobility_results
 };
+
+// MobilityEdge::add_mobility_result_time_point (metapopulation_mobility_instant.h:421-445) for all edges of all runs
+struct MobilityResultArgs {
+    int n, n_ref, E, K;        // device / reference state size, edges, index groups (saved_compartment_indices)
+    const int* group_ptr;      // [K+1]
+    const int* group_dev_idx;  // device index of every saved reference index, group after group
+    const int* ref_to_dev;     // [n_ref] device index of reference element j (the total is summed in reference order)
+    const unsigned char* edge_active; // [E] edge has a positive coefficient (edges without never carry commuters)
+    const double* edge_m;      // [R][E][n]
+    double* values;            // [R][E][capacity][K+1]
+    int capacity, slot, num_runs;
+};
+// edge_m[r][e] = coeff_e * u[r][from(e)]: the mobile population of every edge right after a departure
+cudaError_t launch_edge_mobile_depart(const EdgeArgs& a, cudaStream_t stream);
+cudaError_t launch_mobility_results(const MobilityResultArgs& a, cudaStream_t stream);
 
 cudaError_t launch_integrate(const IntegrateArgs& a, cudaStream_t stream);
 cudaError_t launch_depart(const EdgeArgs& a, cudaStream_t stream);

@@ -191,3 +191,37 @@ def test_error_behaviour():
     with pytest.raises(capi.MioCudaError) as e:
         capi.GraphSimulation(p)  # edges not in reference order
     assert e.value.code == 3
+
+
+@pytest.mark.parametrize("G,N", [(6, 24), (1, 2)])
+def test_mobility_results_match_oracle(G, N):
+    # MobilityEdge::get_mobility_results (instant.h:421-445): per edge and graph step the sums of the mobile population
+    # over the saved index groups and its total, departure and return (after the underflow fix-up) alike
+    if N == 2:
+        p = scenarios.example_ode_secir_graph(runs=2)
+        tmax = 30.0
+    else:
+        p = synthetic.county_problem(N=N, runs=3, G=G, max_out_degree=5, n_seeded=3, damping_day=3.0, perturb=0.1)
+        tmax = 8.0
+    save = [[a * 10 + flat.INS for a in range(G)] + [a * 10 + flat.INSC for a in range(G)],
+            [a * 10 + flat.ISY for a in range(G)] + [a * 10 + flat.ISYC for a in range(G)]]
+    steps = int(round(tmax / 0.5))
+    with capi.GraphSimulation(p) as sim:
+        sim.enable_mobility_results(save, steps + 2)
+        sim.advance(tmax / 2)
+        sim.enable_mobility_results(save, 2 * steps + 5)  # growing the capacity keeps what was recorded
+        sim.advance(tmax)
+        npts, times, values = sim.mobility_results()
+        state = sim.state()
+        cnt = sim.counters()
+    fixups = 0
+    for r in range(p.num_runs):
+        o_npts, o_times, o_values, o_state = oracle_lib.graph_simulate_mobility(p, r, tmax, save, cap=2 * steps + 5)
+        np.testing.assert_array_equal(npts[r], o_npts)
+        assert (o_npts == steps).all()
+        np.testing.assert_array_equal(times[:steps], o_times[0, :steps])
+        assert_close(values[r][:, :steps], o_values[:, :steps], rtol=1e-8, atol=1e-9, what=f"run {r} edge results")
+        assert_close(state[r], o_state, what="node states with every return step replayed literally")
+        fixups += int(cnt[r][:, 3].sum())
+    if G == 6:
+        assert fixups > 0  # returns with the order dependent fix-up were recorded
