@@ -332,7 +332,7 @@ def main():
         sim.set_runs(0, problem, 0, R)
 
     def reduce():
-        return ensemble.reduce_distributed(rec_t, R, rank, world)
+        return ensemble.reduce_distributed(rec_t, R, rank, world, rec=rec)
 
     def step_device(profile=False):
         fresh()

@@ -355,6 +355,24 @@ MIO_API void mio_cuda_ensemble_destroy(mio_ensemble* e);
 MIO_API int mio_cuda_attach_ensemble(mio_handle* h, mio_ensemble* e, int64_t run_offset);
 MIO_API int mio_cuda_ensemble_info(mio_ensemble* e, int64_t* num_columns, int64_t* stride, int64_t* num_runs,
                                    void** device_ptr);
+/* ---- multi-GPU: ParameterStudy::run's MPI part (cpp/memilio/compartments/parameter_studies.h:163-213) ---------------
+ * One process per GPU; rank r simulates the block distribute_runs gives it (:354-367) into its own ensemble record.
+ * mio_cuda_ensemble_reduce_sharded re-shards the records from runs to columns with one grouped NCCL send/receive
+ * exchange over NVLink, selects the exact order statistics and the mean of the rank's column block over the runs of
+ * all ranks, and gathers the rows on rank 0 like the reference gathers on its root (:190-212).
+ * The communicator: rank 0 calls mio_cuda_comm_get_unique_id and hands the 128 bytes to the other ranks by whatever
+ * means the application has (MPI_Bcast in the reference's setting); every rank then calls mio_cuda_comm_create.
+ * NCCL is bound at run time (libnccl.so.2). At most 8 ranks. */
+#define MIO_COMM_ID_BYTES 128
+typedef struct mio_comm mio_comm;
+MIO_API int mio_cuda_comm_get_unique_id(char* id /*[MIO_COMM_ID_BYTES]*/);
+MIO_API int mio_cuda_comm_create(int device, int rank, int world, const char* id, mio_comm** out);
+MIO_API void mio_cuda_comm_destroy(mio_comm* c);
+/* e: this rank's record holding num_runs_local runs (NULL and 0 for a rank without runs; num_columns is then taken
+ * from the argument). Outputs on rank 0 only: percentiles[num_p][num_columns], mean[num_columns] (either may be NULL);
+ * other ranks may pass NULL. Collective: every rank of the communicator must call it. */
+MIO_API int mio_cuda_ensemble_reduce_sharded(mio_ensemble* e, mio_comm* c, int64_t num_runs_local, int64_t num_columns,
+                                             int32_t num_p, const double* p, double* percentiles, double* mean);
 /* Day window of the record: the days [first_day, first_day + num_days) since t0 are recorded into the slots
  * [0, num_days), other days are skipped (default first_day = 0). A study whose full record does not fit device memory
  * (ODE-SECIRVVS, 12 500 runs x 1.1 M columns = 110 GB) keeps all its runs resident, advances them one window at a

@@ -9,7 +9,7 @@ import sys
 HERE = os.path.dirname(os.path.abspath(__file__))
 CSRC = os.path.join(HERE, "csrc")
 LIB = os.path.join(CSRC, "libmio_cuda.so")
-CU_SOURCES = ["integrate.cu", "edges.cu", "reduce.cu", "capi.cu", "peak.cu"]
+CU_SOURCES = ["integrate.cu", "edges.cu", "reduce.cu", "capi.cu", "peak.cu", "comm.cu"]
 CXX_SOURCES = ["study.cpp"]
 NVCC_FLAGS = ["-gencode", "arch=compute_100a,code=sm_100a", "-O3", "-lineinfo", "-std=c++17", "-Xcompiler",
               "-fPIC,-fvisibility=hidden,-O2", "-Xptxas", "-v", "--expt-relaxed-constexpr"]
@@ -50,7 +50,7 @@ def build(force: bool = False, verbose: bool = False, defines=(), out: str = LIB
         results = list(pool.map(compile_one, CU_SOURCES + CXX_SOURCES))
     objs = [o for o, _ in results]
     logs = [l for _, l in results]
-    cmd = [_nvcc(), "-shared", "-o", out] + objs + ["-gencode", "arch=compute_100a,code=sm_100a"]
+    cmd = [_nvcc(), "-shared", "-o", out] + objs + ["-gencode", "arch=compute_100a,code=sm_100a", "-ldl"]
     r = subprocess.run(cmd, capture_output=True, text=True)
     if r.returncode != 0:
         sys.stderr.write(r.stdout + r.stderr)

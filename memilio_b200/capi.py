@@ -28,7 +28,8 @@ EXPORTS = [
     "mio_study_sample_runs", "mio_study_distribute_runs", "mio_study_rng_raw", "mio_damping_cache_build",
     "mio_cuda_ensemble_create", "mio_cuda_ensemble_destroy", "mio_cuda_attach_ensemble", "mio_cuda_ensemble_info",
     "mio_cuda_ensemble_reduce", "mio_cuda_select_percentiles", "mio_cuda_reduce_host_columns",
-    "mio_cuda_ensemble_set_window", "mio_cuda_enable_mobility_results", "mio_cuda_get_mobility_results",
+    "mio_cuda_ensemble_set_window", "mio_cuda_comm_get_unique_id", "mio_cuda_comm_create", "mio_cuda_comm_destroy",
+    "mio_cuda_ensemble_reduce_sharded", "mio_cuda_enable_mobility_results", "mio_cuda_get_mobility_results",
 ]
 KERNEL_CLASSES = ["integrate", "depart", "return", "return_exact", "record", "ensemble"]
 

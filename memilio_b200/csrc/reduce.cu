@@ -374,7 +374,7 @@ cudaError_t launch_select(const SelectArgs& a, cudaStream_t stream)
     // columns that fit into shared memory (two CTAs per SM) are staged there: one pass over HBM
     const size_t hist_staged = sizeof(unsigned int) * 256 * SEL_MAX_P;
     const size_t staged      = hist_staged + sizeof(unsigned long long) * (size_t)a.total;
-    if (staged <= 110 * 1024) {
+    if (staged <= 200 * 1024) { // (two CTAs per SM up to 110 KB, one beyond)
         cudaFuncSetAttribute(select_percentiles_kernel<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)staged);
         select_percentiles_kernel<true><<<(unsigned)a.num_columns, SEL_THREADS, staged, stream>>>(a);
     }

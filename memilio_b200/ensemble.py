@@ -27,6 +27,12 @@ def _lib():
         L.mio_cuda_ensemble_info.argtypes = [C.c_void_p, cdefs.c_int64_p, cdefs.c_int64_p, cdefs.c_int64_p,
                                              C.POINTER(C.c_void_p)]
         L.mio_cuda_ensemble_set_window.argtypes = [C.c_void_p, C.c_int32]
+        L.mio_cuda_comm_get_unique_id.argtypes = [C.c_char_p]
+        L.mio_cuda_comm_create.argtypes = [C.c_int, C.c_int, C.c_int, C.c_char_p, C.POINTER(C.c_void_p)]
+        L.mio_cuda_comm_destroy.argtypes = [C.c_void_p]
+        L.mio_cuda_comm_destroy.restype = None
+        L.mio_cuda_ensemble_reduce_sharded.argtypes = [C.c_void_p, C.c_void_p, C.c_int64, C.c_int64, C.c_int32,
+                                                       cdefs.c_double_p, cdefs.c_double_p, cdefs.c_double_p]
         L.mio_cuda_ensemble_reduce.argtypes = [C.c_void_p, C.c_int32, cdefs.c_double_p, cdefs.c_double_p,
                                                cdefs.c_double_p]
         L.mio_cuda_select_percentiles.argtypes = [C.c_int, C.c_int32, C.POINTER(C.c_void_p), cdefs.c_int64_p,
@@ -108,6 +114,56 @@ class EnsembleRecord:
             pass
 
 
+# ---- sharded reduction in the C library (NCCL) -------------------------------------------------------------------
+COMM_ID_BYTES = 128
+_COMMS = {}
+
+
+class Comm:
+    """mio_comm: the library's own NCCL communicator (one rank per GPU). The 128-byte unique id of rank 0 reaches the
+    other ranks through torch.distributed here (the application's job: MPI_Bcast in the reference's setting)."""
+
+    def __init__(self, device: int, rank: int, world: int, group=None):
+        import torch
+        import torch.distributed as dist
+        buf = C.create_string_buffer(COMM_ID_BYTES)
+        if rank == 0:
+            _check(_lib().mio_cuda_comm_get_unique_id(buf))
+        t = torch.tensor(list(buf.raw), dtype=torch.uint8)
+        if dist.get_backend(group) == "nccl":
+            t = t.to(f"cuda:{device}")
+        dist.broadcast(t, src=0, group=group)
+        uid = bytes(t.cpu().tolist())
+        self._h = C.c_void_p()
+        _check(_lib().mio_cuda_comm_create(device, rank, world, uid, C.byref(self._h)))
+        self.device, self.rank, self.world = device, rank, world
+
+    def close(self):
+        if self._h:
+            _lib().mio_cuda_comm_destroy(self._h)
+            self._h = C.c_void_p()
+
+
+def get_comm(device: int, rank: int, world: int, group=None) -> Comm:
+    key = (device, rank, world)
+    if key not in _COMMS:
+        _COMMS[key] = Comm(device, rank, world, group)
+    return _COMMS[key]
+
+
+def reduce_sharded(rec: Optional["EnsembleRecord"], count_local: int, num_columns: int, comm: Comm,
+                   p: Sequence[float] = DEFAULT_PERCENTILES, mean: bool = True):
+    """mio_cuda_ensemble_reduce_sharded: exchange (NCCL), exact selection of this rank's column block over the runs of
+    all ranks, gather on rank 0. Returns (percentiles, mean) on rank 0, (None, None) elsewhere. Collective."""
+    pa = np.ascontiguousarray(p, dtype=np.float64)
+    root = comm.rank == 0
+    out = np.zeros((len(pa), num_columns)) if root else None
+    mn = np.zeros(num_columns) if (root and mean) else None
+    _check(_lib().mio_cuda_ensemble_reduce_sharded(rec._h if rec is not None else None, comm._h, count_local, num_columns,
+                                                   len(pa), cdefs.dptr(pa), cdefs.dptr(out), cdefs.dptr(mn)))
+    return (out, mn) if root else (None, None)
+
+
 # ---- sharded reduction -------------------------------------------------------------------------------------------
 def column_partition(num_columns: int, world: int) -> List[Tuple[int, int]]:
     """(first column, count) owned by each rank after the exchange (same rule as distribute_runs)."""
@@ -182,10 +238,18 @@ def gather_columns(local_cols, rank: int, world: int, num_columns: int, device, 
 
 
 def reduce_distributed(local, count_local: int, rank: int, world: int, p: Sequence[float] = DEFAULT_PERCENTILES,
-                       mean: bool = True, select: Optional[Callable] = None, group=None):
+                       mean: bool = True, select: Optional[Callable] = None, group=None, rec=None):
     """Sharded ensemble reduction: exchange, local exact selection, gather on rank 0.
-    `local` is this rank's record [num_columns][stride] (torch tensor). Returns (percentiles, mean) on rank 0."""
+    `local` is this rank's record [num_columns][stride] (torch tensor). Returns (percentiles, mean) on rank 0.
+    On GPUs (NCCL process group) the whole reduction runs in the C library (mio_cuda_ensemble_reduce_sharded, `rec` =
+    the record, or None on a rank without runs); the torch.distributed path below serves the CPU tests (gloo)."""
     ncol = int(local.shape[0])
+    if world > 1 and select is None and local.is_cuda:
+        import torch.distributed as dist
+        if dist.get_backend(group) == "nccl":
+            dev = local.device.index if local.device.index is not None else 0
+            return reduce_sharded(rec if count_local > 0 else None, count_local, ncol, get_comm(dev, rank, world, group),
+                                  p, mean)
     if world == 1:
         segs, counts = [local], [count_local]  # row length = stride, the first count_local entries are valid
     else:
@@ -225,7 +289,7 @@ def windowed_advance_reduce(sim, rec, local, count: int, t0: float, tmax: float,
             sim.advance(min(tmax, float(day0 + d1 - 1)))
         if timer:
             timer("reduce")
-        pct, mn = reduce_distributed(local, count, rank, world, p, mean)
+        pct, mn = reduce_distributed(local, count, rank, world, p, mean, rec=rec if sim is not None else None)
         if rank == 0:
             rows = pct if mn is None else np.concatenate([pct, mn[None, :]], axis=0)
             node_part = rows[:, :N * blk * El].reshape(k, N, blk, El)

@@ -456,7 +456,7 @@ class ParameterStudy:
         t_wait, t_adv = 0.0, time.perf_counter() - t_start
         self.last_h2d_bytes = h2d
         t2 = time.perf_counter()
-        pct, mn = ensemble.reduce_distributed(rec.as_torch(), count, rank, world, p, mean)
+        pct, mn = ensemble.reduce_distributed(rec.as_torch(), count, rank, world, p, mean, rec=rec)
         if trace:
             import sys
             print(f"[run_ensemble] waiting for sampling+upload {1e3 * t_wait:.1f} ms, advance {1e3 * t_adv:.1f} ms, "
