@@ -160,6 +160,26 @@ public:
     {
         return m_v.data();
     }
+    void setConstant(T v)
+    {
+        for (auto& x : m_v) {
+            x = v;
+        }
+    }
+    // m.diagonal().setConstant(v)
+    struct DiagonalView {
+        MatrixX& m;
+        void setConstant(T v)
+        {
+            for (Index i = 0; i < (m.m_r < m.m_c ? m.m_r : m.m_c); ++i) {
+                m(i, i) = v;
+            }
+        }
+    };
+    DiagonalView diagonal()
+    {
+        return DiagonalView{*this};
+    }
 
 private:
     Index m_r = 0, m_c = 0;

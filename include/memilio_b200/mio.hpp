@@ -882,4 +882,5 @@ using DefaultIntegratorCore = AdaptiveCoreT<MIO_INTEGRATOR_CK54>;  // compartmen
 #include "osecir.hpp"
 #include "graph.hpp"
 #include "study.hpp"
+#include "osecirvvs.hpp"
 #include "io.hpp"

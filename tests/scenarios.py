@@ -125,6 +125,38 @@ def vvs_golden_case():
                 vacc_full=vacc.copy(), csv=load_csv("ode-secirvvs-compare.csv"), t0=0.0, tmax=50.0, dt0=0.1, tol=1e-10)
 
 
+def example_ode_secirvvs():
+    """cpp/examples/ode_secirvvs.cpp:24-136: osecirvvs, 1 age group, tmax 30, cumulative vaccinations 10 per day."""
+    G = 1
+    y0 = np.zeros(flat.OSECIRVVS_NCOMP)
+    init = dict(V_EN=10, V_EII=11, V_EPI=12, V_INSN=13, V_INSNC=13, V_INSPI=14, V_INSPIC=14, V_INSII=15, V_INSIIC=15,
+                V_ISYN=5, V_ISYNC=5, V_ISYPI=6, V_ISYPIC=6, V_ISYII=7, V_ISYIIC=7, V_ISEVN=8, V_ISEVII=1, V_ISEVPI=2,
+                V_ICRN=3, V_ICRPI=4, V_ICRII=5, V_SII=6, V_SPI=7)
+    for k, v in init.items():
+        y0[getattr(flat, k)] = v
+    cur = 0.0
+    for c in range(flat.OSECIRVVS_NCOMP):  # set_difference_from_group_total, populations.h:194-205
+        cur = cur + y0[c]
+    cur -= y0[flat.V_SN]
+    y0[flat.V_SN] = 1000 - cur
+    pset = flat.osecirvvs_pset(G, Seasonality=0.2, TimeExposed=3.33, TimeInfectedNoSymptoms=1.87,
+                               TimeInfectedSymptoms=7, TimeInfectedSevere=6, TimeInfectedCritical=7,
+                               TransmissionProbabilityOnContact=0.15, RelativeTransmissionNoSymptoms=0.5,
+                               RiskOfInfectionFromSymptomatic=0.0, MaxRiskOfInfectionFromSymptomatic=0.4,
+                               RecoveredPerInfectedNoSymptoms=0.2, SeverePerInfectedSymptoms=0.1, CriticalPerSevere=0.1,
+                               DeathsPerCritical=0.1, ReducExposedPartialImmunity=0.8,
+                               ReducExposedImprovedImmunity=0.331, ReducInfectedSymptomsPartialImmunity=0.65,
+                               ReducInfectedSymptomsImprovedImmunity=0.243,
+                               ReducInfectedSevereCriticalDeadPartialImmunity=0.1,
+                               ReducInfectedSevereCriticalDeadImprovedImmunity=0.091, ReducTimeInfectedMild=0.9)
+    local = np.array([100.0, 0.0143])
+    flat.osecirvvs_apply_constraints(pset, G, local)
+    ct = flat.contact_table(G, [ContactLocation(np.full((1, 1), 5.0), None, [5.0], [np.full((1, 1), 0.3)])], 1, 2)
+    vacc = (10.0 * np.arange(31))[None, :].copy()
+    return dict(G=G, pset=pset, local=local, ct=ct, ct_max_loc=1, ct_max_pts=2, y0=y0, vacc_partial=vacc,
+                vacc_full=vacc.copy(), t0=0.0, tmax=30.0, dt0=0.1)
+
+
 def age_sum(values, G):
     return values.reshape(values.shape[0], G, 10).sum(axis=1) if G > 1 else values
 

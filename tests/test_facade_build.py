@@ -15,7 +15,8 @@ CXX = shutil.which("g++")
 
 
 @pytest.mark.skipif(CXX is None, reason="no host compiler")
-@pytest.mark.parametrize("example", ["ode_secir.cpp", "ode_secir_graph.cpp", "ode_secir_parameter_study_graph.cpp"])
+@pytest.mark.parametrize("example", ["ode_secir.cpp", "ode_secir_graph.cpp", "ode_secir_parameter_study_graph.cpp",
+                                     "ode_secirvvs.cpp"])
 def test_reference_example_compiles_unchanged(example):
     src = os.path.join(REF_EXAMPLES, example)
     if not os.path.exists(src):

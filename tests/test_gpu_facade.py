@@ -173,3 +173,20 @@ def test_reference_parameter_study_graph_example_runs():
         assert "Seeds: " in r.stdout
         for run in range(10):
             assert f"Run {run} done" in r.stdout
+
+
+def test_reference_ode_secirvvs_example_runs_and_matches_oracle():
+    # cpp/examples/ode_secirvvs.cpp through the osecirvvs facade (include/memilio_b200/osecirvvs.hpp): prints the last
+    # time point's 27 compartments; osecirvvs::Simulation (day chunks, vaccination) on the GPU vs the CPU oracle
+    import re
+    r = subprocess.run([_ref_binary("ode_secirvvs")], capture_output=True, text=True, timeout=300)
+    assert r.returncode == 0, r.stderr[-2000:]
+    vals = [float(x) for x in re.findall(r"compartment \d+: ([-0-9.eE+]+)", r.stdout)]
+    assert len(vals) == 27
+    s = scenarios.example_ode_secirvvs()
+    t_o, y_o, _, _ = oracle_lib.simulate_vvs(s["G"], s["pset"], s["local"], s["ct"], s["ct_max_loc"], s["ct_max_pts"],
+                                             s["y0"], s["t0"], s["tmax"], s["dt0"], vacc_partial=s["vacc_partial"],
+                                             vacc_full=s["vacc_full"])
+    assert abs(t_o[-1] - 30.0) < 1e-12
+    np.testing.assert_allclose(vals, y_o[-1], rtol=1e-8, atol=1e-9)
+    assert abs(sum(vals) - 1000.0) < 1e-8  # the population of the example is conserved
