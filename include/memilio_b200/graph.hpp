@@ -289,7 +289,28 @@ namespace detail
 
 // Flat image of one graph: descriptors of mio_cuda.h. Parameter sets and contact tables are deduplicated by value
 // (after draw_sample all nodes share one parameter set; contact tables differ only by school holidays).
+// what the packing needs to know about a node's simulation type: model kind, state size per age group, contact
+// patterns, and (osecirvvs) the node type and the cumulative vaccination arrays. Specialised next to the models.
+template <class Sim>
+struct SimTraits;
+template <class FP>
+struct SimTraits<osecir::Simulation<FP>> {
+    static constexpr int model_kind = MIO_MODEL_OSECIR;
+    static constexpr int sim_kind   = MIO_SIM_MODEL;
+    static constexpr int NC         = osecir::detail::NC;
+    static const ContactMatrixGroup<FP>& contacts(const osecir::Model<FP>& m)
+    {
+        return static_cast<const ContactMatrixGroup<FP>&>(m.parameters.template get<osecir::ContactPatterns<FP>>());
+    }
+    static void vaccinations(const osecir::Model<FP>&, std::vector<double>&, std::vector<double>&, int& days)
+    {
+        days = 0;
+    }
+};
+
 struct PackedGraph {
+    int model_kind = MIO_MODEL_OSECIR, sim_kind = MIO_SIM_MODEL, vacc_days = 0;
+    std::vector<double> vacc_partial, vacc_full; // [N][G][vacc_days]
     int G = 0, N = 0, E = 0, n = 0, ct_max_loc = 1, ct_max_pts = 1, mob_max_pts = 0;
     std::vector<int32_t> edge_start, edge_end, node_pset, node_ctable;
     std::vector<double> edge_coeff;
@@ -309,28 +330,30 @@ struct PackedGraph {
 template <class FP, class GraphT>
 PackedGraph pack_graph(const GraphT& g, int ct_max_pts_min = 1)
 {
-    using namespace osecir;
     PackedGraph p;
     if (g.nodes().empty()) {
         throw std::runtime_error("pack_graph: graph without nodes");
     }
+    using Sim    = std::decay_t<decltype(g.nodes()[0].property.get_simulation())>;
+    using Traits = SimTraits<Sim>;
     const auto& m0 = g.nodes()[0].property.get_simulation().get_model();
+    p.model_kind   = Traits::model_kind;
+    p.sim_kind     = Traits::sim_kind;
     p.G            = int(m0.parameters.get_num_groups().value);
     p.N            = int(g.nodes().size());
     p.E            = int(g.edges().size());
-    p.n            = p.G * osecir::detail::NC;
+    p.n            = p.G * Traits::NC;
     p.t0           = g.nodes()[0].property.get_result().get_last_time();
     p.integrator   = g.nodes()[0].property.get_simulation().get_integrator_core().desc();
     int L = 1, K = ct_max_pts_min;
     for (auto& nd : g.nodes()) {
-        const auto& cm = static_cast<const ContactMatrixGroup<FP>&>(
-            nd.property.get_simulation().get_model().parameters.template get<ContactPatterns<FP>>());
+        const auto& cm = Traits::contacts(nd.property.get_simulation().get_model());
         L = std::max(L, int(cm.get_num_matrices()));
         K = std::max(K, osecir::detail::num_change_points(cm));
     }
     p.ct_max_loc = L;
     p.ct_max_pts = K;
-    const size_t psz = size_t(mio_pset_size(MIO_MODEL_OSECIR, p.G));
+    const size_t psz = size_t(mio_pset_size(p.model_kind, p.G));
     for (auto& nd : g.nodes()) {
         const auto& sim   = nd.property.get_simulation();
         const auto& model = sim.get_model();
@@ -342,9 +365,7 @@ PackedGraph pack_graph(const GraphT& g, int ct_max_pts_min = 1)
         if (ip == p.psets.end()) {
             p.psets.push_back(std::move(ps));
         }
-        auto ct = osecir::detail::contact_table(
-            static_cast<const ContactMatrixGroup<FP>&>(model.parameters.template get<ContactPatterns<FP>>()), p.G, L,
-            K);
+        auto ct = osecir::detail::contact_table(Traits::contacts(model), p.G, L, K);
         auto ic = std::find(p.ctables.begin(), p.ctables.end(), ct);
         p.node_ctable.push_back(int32_t(ic - p.ctables.begin()));
         if (ic == p.ctables.end()) {
@@ -355,6 +376,12 @@ PackedGraph pack_graph(const GraphT& g, int ct_max_pts_min = 1)
         const auto& y = nd.property.get_result().get_last_value();
         p.y0.insert(p.y0.end(), y.data(), y.data() + p.n);
         p.dt0.push_back(sim.get_dt());
+        int days = 0;
+        Traits::vaccinations(model, p.vacc_partial, p.vacc_full, days);
+        if (&nd != &g.nodes()[0] && days != p.vacc_days) {
+            throw std::runtime_error("pack_graph: the nodes' vaccination arrays must cover the same days");
+        }
+        p.vacc_days = days;
     }
     // edges: baseline = sum of the group's members; dampings must be common to all edges (one table per run)
     bool have_mob = false;
@@ -419,8 +446,11 @@ public:
         , m_days(record_days)
     {
         mio_graph_desc d{};
-        d.model        = MIO_MODEL_OSECIR;
-        d.sim_kind     = MIO_SIM_MODEL;
+        d.model        = p.model_kind;
+        d.sim_kind     = p.sim_kind;
+        d.vacc_days    = p.vacc_days;
+        d.vacc_partial = p.vacc_days > 0 ? p.vacc_partial.data() : nullptr;
+        d.vacc_full    = p.vacc_days > 0 ? p.vacc_full.data() : nullptr;
         d.num_groups   = p.G;
         d.num_nodes    = p.N;
         d.num_edges    = p.E;

@@ -583,4 +583,31 @@ TimeSeries<FP> simulate(FP t0, FP tmax, FP dt, const Model<FP>& model,
 }
 
 } // namespace osecirvvs
+
+namespace detail
+{
+template <class FP, bool BASE>
+struct SimTraits<osecirvvs::SimulationT<FP, BASE>> {
+    static constexpr int model_kind = MIO_MODEL_OSECIRVVS;
+    static constexpr int sim_kind   = BASE ? MIO_SIM_BASE : MIO_SIM_MODEL;
+    static constexpr int NC         = osecirvvs::detail::NC;
+    static const ContactMatrixGroup<FP>& contacts(const osecirvvs::Model<FP>& m)
+    {
+        return static_cast<const ContactMatrixGroup<FP>&>(m.parameters.template get<osecirvvs::ContactPatterns<FP>>());
+    }
+    static void vaccinations(const osecirvvs::Model<FP>& m, std::vector<double>& partial, std::vector<double>& full,
+                             int& days)
+    {
+        const auto& vp = m.parameters.template get<osecirvvs::DailyPartialVaccinations<FP>>();
+        const auto& vf = m.parameters.template get<osecirvvs::DailyFullVaccinations<FP>>();
+        if (vp.num_days() != vf.num_days()) {
+            throw std::runtime_error("osecirvvs: DailyPartialVaccinations and DailyFullVaccinations must cover the "
+                                     "same days");
+        }
+        days = int(vp.num_days());
+        partial.insert(partial.end(), vp.array().begin(), vp.array().end());
+        full.insert(full.end(), vf.array().begin(), vf.array().end());
+    }
+};
+} // namespace detail
 } // namespace mio

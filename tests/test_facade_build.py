@@ -31,5 +31,5 @@ def test_repository_examples_build_and_link():
     build.build()
     r = subprocess.run(["make", "-s", "-C", os.path.join(ROOT, "examples")], capture_output=True, text=True)
     assert r.returncode == 0, r.stderr[-3000:]
-    for prog in ("secir_single", "graph_two_nodes", "parameter_study"):
+    for prog in ("secir_single", "graph_two_nodes", "parameter_study", "graph_vvs"):
         assert os.path.exists(os.path.join(ROOT, "examples", "_build", prog))

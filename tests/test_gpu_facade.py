@@ -190,3 +190,29 @@ def test_reference_ode_secirvvs_example_runs_and_matches_oracle():
     assert abs(t_o[-1] - 30.0) < 1e-12
     np.testing.assert_allclose(vals, y_o[-1], rtol=1e-8, atol=1e-9)
     assert abs(sum(vals) - 1000.0) < 1e-8  # the population of the example is conserved
+
+
+def test_vvs_graph_example_matches_oracle():
+    # examples/graph_vvs.cpp: three osecirvvs::Simulation nodes with commuters through the C++ facade (the node and
+    # edge types of BASELINE configs[4]) against the CPU oracle on the same flat inputs
+    out = run_example("graph_vvs")
+    got = np.array([[float(w) for w in ln.split()] for ln in out.strip().splitlines()])[:, 1:]
+    s = scenarios.example_ode_secirvvs()
+    N, n = 3, 27
+    y0 = np.tile(s["y0"], (N, 1))
+    for k in range(N):
+        y0[k, flat.V_EN] = 10.0 + 20.0 * k
+        cur = 0.0
+        for c in range(n):
+            cur = cur + y0[k, c]
+        cur -= y0[k, flat.V_SN]
+        y0[k, flat.V_SN] = 1000 - cur
+    es, ee = zip(*[(i, j) for i in range(N) for j in range(N) if i != j])
+    from memilio_b200.problem import GraphProblem
+    p = GraphProblem(model=flat.MODEL_OSECIRVVS, num_groups=1, num_nodes=N, edge_start=list(es), edge_end=list(ee),
+                     edge_coeff=np.full((len(es), n), 0.05), psets=s["pset"][None, None, :], ctables=s["ct"][None, None, :],
+                     node_local=np.tile(s["local"], (1, N, 1)), y0=y0[None], ct_max_loc=1, ct_max_pts=2,
+                     dt0=np.full((1, N), 0.1), t0=0.0, dt_graph=0.5, sim_kind=flat.SIM_MODEL,
+                     vacc_partial=np.tile(s["vacc_partial"], (N, 1, 1)), vacc_full=np.tile(s["vacc_full"], (N, 1, 1)))
+    ref = oracle_lib.graph_simulate(p, 0, 10.0)
+    np.testing.assert_allclose(got, ref["state"], rtol=1e-8, atol=1e-9)
