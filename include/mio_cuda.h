@@ -172,7 +172,9 @@ typedef struct {
     /* osecirvvs only: cumulative vaccinations DailyPartialVaccinations / DailyFullVaccinations
      * (ode_secirvvs/parameters.h:470-497), run-invariant, [N][G][vacc_days]; NULL / 0 for osecir */
     int32_t vacc_days;
-    int32_t reserved2;
+    int32_t flow_simulation; /* 1: the nodes are mio::FlowSimulation (compartments/flow_simulation.h:37-97): the cumulative
+                              * flows are integrated (error control on the flows), the populations derived from them;
+                              * osecir only. 0: mio::Simulation */
     const double* vacc_partial;
     const double* vacc_full;
 } mio_graph_desc;
@@ -232,6 +234,15 @@ MIO_API int mio_cuda_get_daily(mio_handle* h, int32_t slot0, int32_t count, int3
 /* recorded trajectories (traj_capacity>0): times[count][N][cap], values[count][N][cap][n], npts[count][N] */
 MIO_API int mio_cuda_get_trajectory(mio_handle* h, int32_t slot0, int32_t count, int32_t* npts, double* times,
                                     double* values);
+
+/* mio::FlowSimulation::get_flows() (cpp/memilio/compartments/flow_simulation.h:104-119) of graphs created with
+ * flow_simulation = 1: get_flows().get_last_value() of every node, out[count][N][G*15] (age-major, the 15 flows in the
+ * order of osecir's Flows type list, cpp/models/ode_secir/model.h:45-59) */
+MIO_API int mio_cuda_get_flows(mio_handle* h, int32_t slot0, int32_t count, double* out);
+/* ... and the whole flow series (needs traj_capacity > 0): values[count][N][traj_capacity][G*15]; the time points
+ * are those of mio_cuda_get_trajectory, whose values are the populations that follow from the flows
+ * (compute_population_results, cpp/memilio/compartments/flow_simulation_base.h:84-97) */
+MIO_API int mio_cuda_get_flow_trajectory(mio_handle* h, int32_t slot0, int32_t count, double* values);
 
 /* statistics: kernels launched by this handle so far; (run, step) pairs whose return phase needed the literal
  * in-order replay because of underflow fix-ups */

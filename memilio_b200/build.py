@@ -36,8 +36,16 @@ def build(force: bool = False, verbose: bool = False, defines=(), out: str = LIB
     os.makedirs(objdir, exist_ok=True)
     from concurrent.futures import ThreadPoolExecutor
 
+    headers = [os.path.join(CSRC, f) for f in os.listdir(CSRC) if f.endswith((".cuh", ".h"))]
+    headers.append(os.path.join(os.path.dirname(HERE), "include", "mio_cuda.h"))
+    hdr_time = max(os.path.getmtime(f) for f in headers)
+    incremental = not force and not defines and not os.environ.get("MIO_NVCC_EXTRA")
+
     def compile_one(src):
         obj = os.path.join(objdir, os.path.splitext(src)[0] + ".o")
+        if incremental and os.path.exists(obj) and os.path.getmtime(obj) > max(
+                hdr_time, os.path.getmtime(os.path.join(CSRC, src))):
+            return obj, None  # up to date (object newer than its source and every header)
         extra = os.environ.get("MIO_NVCC_EXTRA", "").split()  # tuning experiments only
         cmd = [_nvcc()] + NVCC_FLAGS + extra + ["-D" + d for d in defines] + ["-c", os.path.join(CSRC, src), "-o", obj]
         r = subprocess.run(cmd, capture_output=True, text=True)
@@ -49,7 +57,9 @@ def build(force: bool = False, verbose: bool = False, defines=(), out: str = LIB
     with ThreadPoolExecutor(max_workers=min(8, os.cpu_count() or 1)) as pool:
         results = list(pool.map(compile_one, CU_SOURCES + CXX_SOURCES))
     objs = [o for o, _ in results]
-    logs = [l for _, l in results]
+    logs = [l for _, l in results if l is not None]
+    if incremental and len(logs) < len(results):
+        logs.append("(objects not listed above were up to date; `--force` rebuilds everything)")
     cmd = [_nvcc(), "-shared", "-o", out] + objs + ["-gencode", "arch=compute_100a,code=sm_100a", "-ldl"]
     r = subprocess.run(cmd, capture_output=True, text=True)
     if r.returncode != 0:

@@ -30,6 +30,7 @@ EXPORTS = [
     "mio_cuda_ensemble_reduce", "mio_cuda_select_percentiles", "mio_cuda_reduce_host_columns",
     "mio_cuda_ensemble_set_window", "mio_cuda_comm_get_unique_id", "mio_cuda_comm_create", "mio_cuda_comm_destroy",
     "mio_cuda_ensemble_reduce_sharded", "mio_cuda_enable_mobility_results", "mio_cuda_get_mobility_results",
+    "mio_cuda_get_flows", "mio_cuda_get_flow_trajectory",
 ]
 KERNEL_CLASSES = ["integrate", "depart", "return", "return_exact", "record", "ensemble"]
 
@@ -150,6 +151,24 @@ class GraphSimulation:
         _check(lib().mio_cuda_get_trajectory(self._h, slot0, count, cdefs.iptr(npts), cdefs.dptr(times),
                                              cdefs.dptr(values)))
         return npts, times, values
+
+    def flows(self, slot0=0, count=None) -> np.ndarray:
+        """FlowSimulation::get_flows().get_last_value() of every node: [count][N][G*15]"""
+        count = self.max_runs - slot0 if count is None else count
+        out = np.zeros((count, self.p.num_nodes, self.p.num_groups * 15))
+        L = lib()
+        L.mio_cuda_get_flows.argtypes = [C.c_void_p, C.c_int32, C.c_int32, cdefs.c_double_p]
+        _check(L.mio_cuda_get_flows(self._h, slot0, count, cdefs.dptr(out)))
+        return out
+
+    def flow_trajectory(self, slot0=0, count=None) -> np.ndarray:
+        """FlowSimulation::get_flows() as a series: [count][N][cap][G*15] (time points: see trajectory())"""
+        count = self.max_runs - slot0 if count is None else count
+        out = np.zeros((count, self.p.num_nodes, self.traj_capacity, self.p.num_groups * 15))
+        L = lib()
+        L.mio_cuda_get_flow_trajectory.argtypes = [C.c_void_p, C.c_int32, C.c_int32, cdefs.c_double_p]
+        _check(L.mio_cuda_get_flow_trajectory(self._h, slot0, count, cdefs.dptr(out)))
+        return out
 
     def enable_mobility_results(self, save_groups, capacity: int):
         """MobilityEdge(coeffs, save_indices) for every edge: record get_mobility_results()."""

@@ -24,7 +24,7 @@ class GraphDesc(C.Structure):
                 ("edge_start", c_int32_p), ("edge_end", c_int32_p), ("edge_coeff", c_double_p),
                 ("node_pset", c_int32_p), ("node_ctable", c_int32_p),
                 ("integrator", IntegratorDesc), ("t0", C.c_double), ("dt_graph", C.c_double),
-                ("vacc_days", C.c_int32), ("reserved2", C.c_int32), ("vacc_partial", c_double_p),
+                ("vacc_days", C.c_int32), ("flow_simulation", C.c_int32), ("vacc_partial", c_double_p),
                 ("vacc_full", c_double_p)]
 
 

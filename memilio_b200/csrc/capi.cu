@@ -92,6 +92,8 @@ struct mio_handle {
     double* d_daily  = nullptr;
     int* d_traj_npts = nullptr;
     double *d_traj_times = nullptr, *d_traj_values = nullptr;
+    // mio::FlowSimulation nodes: cumulative flows [R][N][G][16] (15 per age group + padding), their time series
+    double *d_flows = nullptr, *d_traj_flows = nullptr;
     // simulation state (GraphSimulationBase::m_t and the edges' common toggle / stored mobile population)
     double t            = 0.0;
     bool toggle         = false; // MobilityEdge::m_return_mobile_population
@@ -302,7 +304,8 @@ void destroy(mio_handle* h)
                     h->d_y[0],       h->d_y[1],        h->d_y[2],       h->d_y[3],      h->d_fac,
                     h->d_aux,        h->d_run_flags,   h->d_daily,      h->d_traj_npts, h->d_traj_times,
                     h->d_traj_values, h->d_stats,      h->d_vacc_partial, h->d_vacc_full, h->d_work, h->d_run_list, h->d_w_edge,
-                    h->d_mob_gptr,   h->d_mob_gdev,    h->d_ref_to_dev, h->d_edge_active, h->d_edge_m, h->d_mob_values};
+                    h->d_mob_gptr,   h->d_mob_gdev,    h->d_ref_to_dev, h->d_edge_active, h->d_edge_m, h->d_mob_values,
+                    h->d_flows,      h->d_traj_flows};
     for (void* p : ptrs) {
         if (p) {
             cudaFree(p);
@@ -467,6 +470,9 @@ int mio_cuda_graph_create(const mio_graph_desc* d, int device, mio_handle** out)
     }
     if (d->num_edges > 0 && (!d->edge_start || !d->edge_end || !d->edge_coeff)) {
         return fail(MIO_INVALID_VALUE, "edge arrays missing");
+    }
+    if (d->flow_simulation && (d->model != MIO_MODEL_OSECIR || d->integrator.kind == MIO_INTEGRATOR_RKF45)) {
+        return fail(MIO_INVALID_VALUE, "FlowSimulation nodes: ODE-SECIR with the Cash-Karp controller or Euler only");
     }
     int ndev = 0;
     if (cudaGetDeviceCount(&ndev) != cudaSuccess || ndev == 0) {
@@ -743,6 +749,16 @@ int mio_cuda_graph_create(const mio_graph_desc* d, int device, mio_handle** out)
         H_TRY(dev_alloc(&h->d_traj_times, R * N * (size_t)d->traj_capacity));
         H_TRY(dev_alloc(&h->d_traj_values, R * N * (size_t)d->traj_capacity * n_ref));
     }
+    if (d->flow_simulation) {
+        H_TRY(dev_alloc(&h->d_flows, R * N * W * 16));
+        H_TRY(cudaMemset(h->d_flows, 0, sizeof(double) * R * N * W * 16));
+        if (d->traj_capacity > 0) {
+            // time point 0 of the flow series is zero (FlowModel::get_initial_flows, flow_model.h:146-149)
+            const size_t cnt = R * N * (size_t)d->traj_capacity * G * 15;
+            H_TRY(dev_alloc(&h->d_traj_flows, cnt));
+            H_TRY(cudaMemset(h->d_traj_flows, 0, sizeof(double) * cnt));
+        }
+    }
     H_TRY(cudaMemset(h->d_counters, 0, sizeof(int) * R * N * 4));
 #undef H_TRY
     // the descriptor's host pointers are not valid after this call
@@ -861,6 +877,10 @@ int mio_cuda_set_runs(mio_handle* h, int32_t slot0, int32_t count, const mio_run
     CUDA_TRY(cudaMemcpyAsync(h->d_node_ctl + s0 * N * 4, nctl.data(), sizeof(double) * nctl.size(),
                              cudaMemcpyHostToDevice, h->stream));
     CUDA_TRY(cudaMemsetAsync(h->d_counters + s0 * N * 4, 0, sizeof(int) * (size_t)count * N * 4, h->stream));
+    if (h->d_flows) {
+        const size_t per = (size_t)N * geo.W * 16;
+        CUDA_TRY(cudaMemsetAsync(h->d_flows + s0 * per, 0, sizeof(double) * per * count, h->stream));
+    }
     if (h->d_daily) {
         // day 0 = initial value (interpolate_simulation_result, analyze_result.h:228-231)
         std::vector<double> tmp; // strided copy: slot day 0 of each (run,node)
@@ -975,6 +995,8 @@ int mio_cuda_advance(mio_handle* h, double t_max)
         ia.traj       = TrajectoryBuffers{h->desc.traj_capacity, h->d_traj_npts, h->d_traj_times, h->d_traj_values};
         ia.num_runs   = R;
         ia.work_counter = h->d_work;
+        ia.flows        = h->d_flows;
+        ia.traj_flows   = h->d_traj_flows;
         // the node phase right after a departure also provides the return coefficients (see IntegrateArgs::aux_out)
         ia.aux_out      = (geo.E > 0 && h->have_mobile && h->aux_pending) ? h->d_aux : nullptr;
         h->aux_pending  = false;
@@ -1220,6 +1242,40 @@ int mio_cuda_get_trajectory(mio_handle* h, int32_t slot0, int32_t count, int32_t
     CUDA_TRY(cudaMemcpy(npts, h->d_traj_npts + off, sizeof(int) * rows, cudaMemcpyDeviceToHost));
     CUDA_TRY(cudaMemcpy(times, h->d_traj_times + off * cap, sizeof(double) * rows * cap, cudaMemcpyDeviceToHost));
     CUDA_TRY(cudaMemcpy(values, h->d_traj_values + off * cap * n, sizeof(double) * rows * cap * n,
+                        cudaMemcpyDeviceToHost));
+    return MIO_OK;
+}
+
+int mio_cuda_get_flows(mio_handle* h, int32_t slot0, int32_t count, double* out)
+{
+    if (int rc = check_slots(h, slot0, count, out)) {
+        return rc;
+    }
+    if (!h->d_flows) {
+        return fail(MIO_INVALID_VALUE, "graph was created without flow_simulation");
+    }
+    CUDA_TRY(cudaSetDevice(h->device));
+    const size_t lanes = (size_t)count * h->geo.N * h->geo.W;
+    std::vector<double> tmp(lanes * 16);
+    CUDA_TRY(cudaMemcpy(tmp.data(), h->d_flows + (size_t)slot0 * h->geo.N * h->geo.W * 16, sizeof(double) * tmp.size(),
+                        cudaMemcpyDeviceToHost));
+    for (size_t l = 0; l < lanes; ++l) {
+        std::copy(tmp.begin() + l * 16, tmp.begin() + l * 16 + 15, out + l * 15);
+    }
+    return MIO_OK;
+}
+
+int mio_cuda_get_flow_trajectory(mio_handle* h, int32_t slot0, int32_t count, double* values)
+{
+    if (int rc = check_slots(h, slot0, count, values)) {
+        return rc;
+    }
+    if (!h->d_traj_flows) {
+        return fail(MIO_INVALID_VALUE, "graph was created without flow_simulation and traj_capacity");
+    }
+    CUDA_TRY(cudaSetDevice(h->device));
+    const size_t per = (size_t)h->geo.N * (size_t)h->desc.traj_capacity * h->geo.G * 15;
+    CUDA_TRY(cudaMemcpy(values, h->d_traj_flows + (size_t)slot0 * per, sizeof(double) * per * count,
                         cudaMemcpyDeviceToHost));
     return MIO_OK;
 }

@@ -57,6 +57,8 @@ struct IntegrateArgs {
     TrajectoryBuffers traj;
     int num_runs;
     int* work_counter; // [1] device scratch: the persistent node-phase kernel hands out its work items through it
+    double* flows;      // [R][N][W][16] or null: the nodes are mio::FlowSimulation, cumulative flows (15 per lane + pad)
+    double* traj_flows; // [R][N][capacity][G*15] or null: the flow series (with the trajectory buffers)
     double* aux_out;   // [R][N][W][4] or null: the launch that follows a departure writes the return coefficients of
                        // every node as a destination (by-product of its first right-hand side)
 };

@@ -39,6 +39,7 @@ class GraphProblem:
     sim_kind: int = flat.SIM_MODEL
     vacc_partial: Optional[np.ndarray] = None  # osecirvvs: [N][G][days] cumulative DailyPartialVaccinations
     vacc_full: Optional[np.ndarray] = None  # osecirvvs: [N][G][days] cumulative DailyFullVaccinations
+    flow_simulation: int = 0  # 1: the nodes are mio::FlowSimulation (compartments/flow_simulation.h:37-97), osecir only
 
     def __post_init__(self):
         self.edge_start = np.ascontiguousarray(self.edge_start, dtype=np.int32)
@@ -115,6 +116,7 @@ class GraphProblem:
         d.integrator = self.integrator
         d.t0 = self.t0
         d.dt_graph = self.dt_graph
+        d.flow_simulation = self.flow_simulation
         if self.vacc_partial is not None:
             d.vacc_days = int(self.vacc_partial.shape[2])
             d.vacc_partial = cdefs.dptr(self.vacc_partial)

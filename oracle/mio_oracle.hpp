@@ -823,6 +823,21 @@ struct Model {
         std::fill(dydt.begin(), dydt.end(), 0.0);
         get_derivatives(pop, y, t, dydt);
     }
+    // FlowModel::get_derivatives(flows, dydt), flow_model.h:112-125, and get_initial_flows :146-149
+    int num_flows() const
+    {
+        return parameters.G * NF;
+    }
+    void derivatives_from_flows(const Vec& flows, Vec& dydt) const
+    {
+        std::fill(dydt.begin(), dydt.end(), 0.0);
+        for (int i = 0; i < parameters.G; ++i) {
+            for (int k = 0; k < NF; ++k) {
+                dydt[i * NC + FLOW_SRC[k]] -= flows[i * NF + k];
+                dydt[i * NC + FLOW_DST[k]] += flows[i * NF + k];
+            }
+        }
+    }
 
     // model.h:687-715 get_mobility_factors
     Vec get_mobility_factors(double /*t*/, const Vec& y) const
@@ -873,6 +888,10 @@ struct Simulation {
     SystemIntegrator integrator;
     TimeSeries result;
     double dt;
+    // mio::FlowSimulation (compartments/flow_simulation.h:37-97, flow_simulation_base.h:40-120) instead of
+    // mio::Simulation: the integrands are the cumulative flows, the populations are derived from them
+    bool flow_sim = false;
+    TimeSeries flow_result;
     Simulation(const M& m, double t0 = 0., double dt_ = 0.1)
         : model(m)
         , integrator(std::make_unique<CashKarp54Core>())
@@ -884,8 +903,52 @@ struct Simulation {
     {
         integrator.core = std::move(c);
     }
+    void make_flow_simulation()
+    {
+        flow_sim = true;
+        flow_result.add(result.times[0], Vec(size_t(model.num_flows()), 0.0)); // get_initial_flows: zero
+    }
+    Vec& advance_flows(double tmax)
+    {
+        // FlowSimulation::advance, flow_simulation.h:63-92
+        assert(flow_result.n() == result.n());
+        Vec pop(result.last().size()), diff(size_t(model.num_flows()));
+        const size_t base = result.n() - 1; // the last available time point of the population result
+        integrator.advance(
+            [&](const Vec& flows, double t, Vec& dflows_dt) {
+                for (size_t j = 0; j < diff.size(); ++j) {
+                    diff[j] = flows[j] - flow_result.values[base][j];
+                }
+                model.derivatives_from_flows(diff, pop); // note: overwrites values in pop
+                for (size_t j = 0; j < pop.size(); ++j) {
+                    pop[j] += result.values[base][j];
+                }
+                std::fill(dflows_dt.begin(), dflows_dt.end(), 0.0);
+                model.get_flows(pop, pop, t, dflows_dt);
+            },
+            tmax, dt, flow_result);
+        // compute_population_results, flow_simulation_base.h:84-97
+        const size_t last_tp = result.n() - 1;
+        for (size_t i = result.n(); i < flow_result.n(); ++i) {
+            for (size_t j = 0; j < diff.size(); ++j) {
+                diff[j] = flow_result.values[i][j] - flow_result.values[last_tp][j];
+            }
+            Vec v(result.values[last_tp].size());
+            model.derivatives_from_flows(diff, v);
+            for (size_t j = 0; j < v.size(); ++j) {
+                v[j] += result.values[last_tp][j];
+            }
+            result.add(flow_result.times[i], v);
+        }
+        return result.last();
+    }
     Vec& advance(double tmax)
     {
+        if constexpr (requires(const M& m) { m.num_flows(); }) {
+            if (flow_sim) {
+                return advance_flows(tmax);
+            }
+        }
         return integrator.advance(
             [this](const Vec& y, double t, Vec& dydt) {
                 model.eval_right_hand_side(y, y, t, dydt);

@@ -76,6 +76,20 @@ struct Model {
         std::fill(dydt.begin(), dydt.end(), 0.0);
         get_derivatives(pop, y, t, dydt);
     }
+    int num_flows() const
+    {
+        return G * NF;
+    }
+    void derivatives_from_flows(const Vec& flows, Vec& dydt) const
+    {
+        std::fill(dydt.begin(), dydt.end(), 0.0);
+        for (int i = 0; i < G; ++i) {
+            for (int k = 0; k < NF; ++k) {
+                dydt[i * NC + FLOW_SRC[k]] -= flows[i * NF + k];
+                dydt[i * NC + FLOW_DST[k]] += flows[i * NF + k];
+            }
+        }
+    }
     // no ADL overloads for this model: instant.h:513-518, :537-541
     Vec get_mobility_factors(double, const Vec& y) const
     {

@@ -238,6 +238,46 @@ int orc_simulate(int model, int G, const double* pset, const double* local, cons
     return n;
 }
 
+// mio::FlowSimulation<osecir::Model> for one node, advanced to tmaxs[0], tmaxs[1], ... in turn (one advance call
+// each, flow_simulation.h:63-92): out_f[npts][G*15] the cumulative flows at every time point, out_y the derived
+// populations (simulate_flows, flow_simulation.h:99-120, is the case of one advance call)
+int orc_simulate_flows_stepwise(int G, const double* pset, const double* local, const double* ct, int max_loc,
+                                int max_pts_ct, const double* y0, double t0, int num_t, const double* tmaxs, double dt,
+                                const mio_integrator_desc* integ, int max_pts, double* out_t, double* out_y,
+                                double* out_f, double* out_dt, int64_t* counters)
+{
+    auto m = osecir_from_flat(G, pset, local, ct, max_loc, max_pts_ct, y0);
+    Simulation<osecir::Model> sim(m, t0, dt);
+    sim.set_integrator_core(make_core(*integ));
+    sim.make_flow_simulation();
+    for (int k = 0; k < num_t; ++k) {
+        sim.advance(tmaxs[k]);
+    }
+    const int n = int(sim.result.n());
+    for (int k = 0; k < std::min(n, max_pts); ++k) {
+        out_t[k] = sim.result.times[k];
+        std::copy(sim.result.values[k].begin(), sim.result.values[k].end(), out_y + int64_t(k) * G * osecir::NC);
+        std::copy(sim.flow_result.values[k].begin(), sim.flow_result.values[k].end(),
+                  out_f + int64_t(k) * G * osecir::NF);
+    }
+    if (out_dt) {
+        *out_dt = sim.dt;
+    }
+    if (counters) {
+        counters[0] = sim.integrator.n_steps;
+        counters[1] = sim.integrator.core->n_rejected;
+        counters[2] = sim.integrator.core->n_forced;
+    }
+    return n;
+}
+int orc_simulate_flows(int G, const double* pset, const double* local, const double* ct, int max_loc, int max_pts_ct,
+                       const double* y0, double t0, double tmax, double dt, const mio_integrator_desc* integ,
+                       int max_pts, double* out_t, double* out_y, double* out_f, double* out_dt, int64_t* counters)
+{
+    return orc_simulate_flows_stepwise(G, pset, local, ct, max_loc, max_pts_ct, y0, t0, 1, &tmax, dt, integ, max_pts,
+                                       out_t, out_y, out_f, out_dt, counters);
+}
+
 // osecirvvs::Simulation (sim_kind = MIO_SIM_MODEL) or mio::Simulation<osecirvvs::Model> (MIO_SIM_BASE) for one node
 int orc_simulate_vvs(int sim_kind, int G, const double* pset, const double* local, const double* ct, int max_loc,
                      int max_pts_ct, const double* y0, int vacc_days, const double* vacc_partial,
@@ -288,6 +328,11 @@ static int graph_simulate_impl(const mio_graph_desc* desc, const mio_run_data* r
     for (int k = 0; k < N; ++k) {
         g.add_node(make_model(k), desc->t0, run->dt0 ? run->dt0[k] : 0.1);
         g.nodes.back().sim.set_integrator_core(make_core(desc->integrator));
+        if constexpr (requires(Simulation<M>& sm) { sm.make_flow_simulation(); }) {
+            if (desc->flow_simulation) {
+                g.nodes.back().sim.make_flow_simulation();
+            }
+        }
     }
     for (int e = 0; e < E; ++e) {
         Vec c(desc->edge_coeff + int64_t(e) * n, desc->edge_coeff + int64_t(e + 1) * n);
@@ -431,6 +476,21 @@ int orc_graph_simulate(const mio_graph_desc* desc, const mio_run_data* run, doub
 {
     return graph_simulate_dispatch(desc, run, t_max, out_state, out_dt, out_counters, out_halfsteps, max_halfsteps,
                                    [](auto&) {});
+}
+
+// orc_graph_simulate of a graph of FlowSimulation nodes (desc->flow_simulation = 1, osecir): also the cumulative flows
+// of every node at the end, out_flows[N][G*15] (FlowSimulation::get_flows().get_last_value())
+int orc_graph_simulate_flows(const mio_graph_desc* desc, const mio_run_data* run, double t_max, double* out_state,
+                             double* out_flows, int64_t* out_counters)
+{
+    return graph_simulate_dispatch(desc, run, t_max, out_state, nullptr, out_counters, nullptr, 0, [&](auto& g) {
+        for (size_t k = 0; k < g.nodes.size(); ++k) {
+            if constexpr (requires { g.nodes[k].sim.flow_result; }) {
+                const auto& f = g.nodes[k].sim.flow_result.last();
+                std::copy(f.begin(), f.end(), out_flows + k * f.size());
+            }
+        }
+    });
 }
 
 // orc_graph_simulate + interpolate_simulation_result(graph): out_daily[N][num_days][n] (the per-node time series of
@@ -839,7 +899,14 @@ int orc_study_run_block(const mio_study_desc* sd, const mio_graph_desc* gd, int6
 // The setup of TestGraphSimulation.consistencyFlowMobility (cpp/tests/test_graph_simulation.cpp:256-339): three
 // identical ODE-SEIR nodes, all six directed edges with coefficient 0.001 on every compartment, t0 = 0, tmax = 1,
 // dt = 0.001. Returns the number of time points of node 0's result; out_times[cap], out_values[cap][4].
+int orc_seir_graph_golden_ex(int flow_sim, int cap, double* out_times, double* out_values);
 int orc_seir_graph_golden(int cap, double* out_times, double* out_values)
+{
+    return orc_seir_graph_golden_ex(0, cap, out_times, out_values);
+}
+// flow_sim != 0: the nodes are mio::FlowSimulation (sim_flows of the reference test, the one the golden file was
+// written from, test_graph_simulation.cpp:307-311,328-338)
+int orc_seir_graph_golden_ex(int flow_sim, int cap, double* out_times, double* out_values)
 {
     oseir::Model model(1);
     const double total_population = 10000;
@@ -857,6 +924,9 @@ int orc_seir_graph_golden(int cap, double* out_times, double* out_values)
     GraphSim<oseir::Model> g(0.0, 0.001);
     for (int k = 0; k < 3; ++k) {
         g.add_node(model, 0.0);
+        if (flow_sim) {
+            g.nodes.back().sim.make_flow_simulation();
+        }
     }
     for (int i = 0; i < 3; ++i) {
         for (int j = 0; j < 3; ++j) {

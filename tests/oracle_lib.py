@@ -246,3 +246,46 @@ def sample_problem(ps, run0: int, count: int) -> GraphProblem:
                         ct_max_loc=g.num_locations, ct_max_pts=ps.ct_max_pts, mobtables=mob,
                         mob_max_pts=ps.mob_max_pts, integrator=ps.integrator, t0=ps.t0, dt_graph=ps.dt,
                         sim_kind=g.sim_kind, vacc_partial=g.vacc_partial, vacc_full=g.vacc_full)
+
+
+def simulate_flows(G, pset, local, ct, max_loc, max_pts, y0, t0, tmax, dt, integrator=None, capacity=4096):
+    """mio::simulate_flows (FlowSimulation<osecir::Model>) on the oracle.
+    Returns (times[npts], populations[npts][n], flows[npts][G*15], final dt, counters[3])."""
+    return simulate_flows_stepwise(G, pset, local, ct, max_loc, max_pts, y0, t0, [tmax], dt, integrator, capacity)
+
+
+def simulate_flows_stepwise(G, pset, local, ct, max_loc, max_pts, y0, t0, tmaxs, dt, integrator=None, capacity=4096):
+    """One FlowSimulation advanced to every entry of tmaxs in turn (one advance call each)."""
+    integ = integrator if integrator is not None else cdefs.integrator_desc()
+    args = [np.ascontiguousarray(a, dtype=np.float64) for a in (pset, local, ct, y0)]
+    tm = np.ascontiguousarray(tmaxs, dtype=np.float64)
+    ot = np.zeros(capacity)
+    oy = np.zeros((capacity, G * 10))
+    of = np.zeros((capacity, G * 15))
+    odt = np.zeros(1)
+    cnt = np.zeros(3, dtype=np.int64)
+    L = lib()
+    L.orc_simulate_flows_stepwise.restype = C.c_int
+    npts = L.orc_simulate_flows_stepwise(G, cdefs.dptr(args[0]), cdefs.dptr(args[1]), cdefs.dptr(args[2]), max_loc,
+                                         max_pts, cdefs.dptr(args[3]), C.c_double(t0), len(tm), cdefs.dptr(tm),
+                                         C.c_double(dt), C.byref(integ), capacity, cdefs.dptr(ot), cdefs.dptr(oy),
+                                         cdefs.dptr(of), cdefs.dptr(odt), cdefs.lptr(cnt))
+    assert 0 < npts <= capacity
+    return ot[:npts].copy(), oy[:npts].copy(), of[:npts].copy(), float(odt[0]), cnt
+
+
+def graph_simulate_flows(p: GraphProblem, run: int, t_max: float):
+    """GraphSimulation::advance of a graph of FlowSimulation nodes (p.flow_simulation): dict(state, flows, counters)."""
+    d = p.desc(max_runs=1)
+    d.flow_simulation = 1
+    rd = p.run_data(run, 1)
+    N, n, G = p.num_nodes, p.n, p.num_groups
+    state = np.zeros((N, n))
+    flows = np.zeros((N, G * 15))
+    cnt = np.zeros((N, 4), dtype=np.int64)
+    L = lib()
+    L.orc_graph_simulate_flows.restype = C.c_int
+    steps = L.orc_graph_simulate_flows(C.byref(d), C.byref(rd), C.c_double(t_max), cdefs.dptr(state), cdefs.dptr(flows),
+                                       cdefs.lptr(cnt))
+    assert steps >= 0
+    return dict(state=state, flows=flows, counters=cnt, steps=steps)

@@ -216,3 +216,19 @@ def covid_range(name, G=6):
         return np.full(G, r[0]), np.full(G, r[1])
     a = np.asarray(r)
     return a[:, 0].copy(), a[:, 1].copy()
+
+
+def damping_flow_case(damping=None):
+    """TestOdeSecir.testDamping (cpp/tests/test_odesecir.cpp:604-676) and cpp/examples/ode_secir_contact_changes.cpp:
+    one age group, 10 of 1000 InfectedSymptoms, contact frequency 10, transmission probability and risk of infection
+    from symptomatic 1, every other parameter at its default; optionally one damping of the contact matrix at t = 0."""
+    G = 1
+    y0 = np.zeros(10)
+    y0[flat.ISY] = 10.0
+    y0[flat.S] = 1000.0 - 10.0
+    pset = flat.osecir_pset(G, TransmissionProbabilityOnContact=1.0, RiskOfInfectionFromSymptomatic=1.0)
+    local = np.array([flat.DBL_MAX, flat.DBL_MAX])
+    base = np.full((1, 1), 10.0)
+    times, mats = ([], []) if damping is None else ([0.0], [np.full((1, 1), float(damping))])
+    ct = flat.contact_table(G, [ContactLocation(base, None, times, mats)], 1, 2)
+    return dict(G=G, pset=pset, local=local, ct=ct, ct_max_loc=1, ct_max_pts=2, y0=y0)

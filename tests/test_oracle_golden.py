@@ -48,7 +48,8 @@ def test_vvs_oracle_reproduces_reference_golden_csv():
     assert set(np.arange(1, 51)).issubset(set(np.round(t[np.abs(t - np.round(t)) < 1e-12]).astype(int)))
 
 
-def test_graph_mechanics_seir_golden():
+@pytest.mark.parametrize("flow_sim", [0, 1])
+def test_graph_mechanics_seir_golden(flow_sim):
     # TestGraphSimulation.consistencyFlowMobility (cpp/tests/test_graph_simulation.cpp:276-339): node 0 of a fully
     # connected 3-node ODE-SEIR graph, 1000 graph steps of dt 0.001 with commuter departure / return every other step,
     # against cpp/tests/data/graphsimulation-compare.csv at the reference's 1e-10. Pins the oracle's GraphSim,
@@ -63,8 +64,10 @@ def test_graph_mechanics_seir_golden():
     t = np.zeros(cap)
     v = np.zeros((cap, 4))
     L = oracle_lib.lib()
-    L.orc_seir_graph_golden.restype = C.c_int
-    n = L.orc_seir_graph_golden(cap, cdefs.dptr(t), cdefs.dptr(v))
+    # flow_sim = 1: the nodes are mio::FlowSimulation (the variant the golden file was written from, :307-338); the
+    # reference test requires both variants to agree with it: pins the oracle's FlowSimulation restatement as well
+    L.orc_seir_graph_golden_ex.restype = C.c_int
+    n = L.orc_seir_graph_golden_ex(flow_sim, cap, cdefs.dptr(t), cdefs.dptr(v))
     assert n == ref.shape[0] == 1001
     np.testing.assert_allclose(t[:n], ref[:, 0], rtol=0, atol=1e-10)
     np.testing.assert_allclose(v[:n], ref[:, 1:5], rtol=0, atol=1e-10)
