@@ -293,11 +293,12 @@ namespace detail
 // patterns, and (osecirvvs) the node type and the cumulative vaccination arrays. Specialised next to the models.
 template <class Sim>
 struct SimTraits;
-template <class FP>
-struct SimTraits<osecir::Simulation<FP>> {
+template <class FP, class BaseT>
+struct SimTraits<osecir::Simulation<FP, BaseT>> {
     static constexpr int model_kind = MIO_MODEL_OSECIR;
     static constexpr int sim_kind   = MIO_SIM_MODEL;
     static constexpr int NC         = osecir::detail::NC;
+    static constexpr bool flow_simulation = osecir::Simulation<FP, BaseT>::is_flow_simulation;
     static const ContactMatrixGroup<FP>& contacts(const osecir::Model<FP>& m)
     {
         return static_cast<const ContactMatrixGroup<FP>&>(m.parameters.template get<osecir::ContactPatterns<FP>>());
@@ -308,7 +309,17 @@ struct SimTraits<osecir::Simulation<FP>> {
     }
 };
 
+template <class FP>
+struct SimTraits<Simulation<FP, osecir::Model<FP>>> : SimTraits<osecir::Simulation<FP>> {
+};
+template <class FP>
+struct SimTraits<FlowSimulation<FP, osecir::Model<FP>>>
+    : SimTraits<osecir::Simulation<FP, FlowSimulation<FP, osecir::Model<FP>>>> {
+};
+
 struct PackedGraph {
+    int flow_simulation = 0;    // the nodes are FlowSimulations
+    std::vector<double> flows0; // [N][G*15] the flows they continue from
     int model_kind = MIO_MODEL_OSECIR, sim_kind = MIO_SIM_MODEL, vacc_days = 0;
     std::vector<double> vacc_partial, vacc_full; // [N][G][vacc_days]
     int G = 0, N = 0, E = 0, n = 0, ct_max_loc = 1, ct_max_pts = 1, mob_max_pts = 0;
@@ -339,6 +350,7 @@ PackedGraph pack_graph(const GraphT& g, int ct_max_pts_min = 1)
     const auto& m0 = g.nodes()[0].property.get_simulation().get_model();
     p.model_kind   = Traits::model_kind;
     p.sim_kind     = Traits::sim_kind;
+    p.flow_simulation = Traits::flow_simulation ? 1 : 0;
     p.G            = int(m0.parameters.get_num_groups().value);
     p.N            = int(g.nodes().size());
     p.E            = int(g.edges().size());
@@ -376,6 +388,10 @@ PackedGraph pack_graph(const GraphT& g, int ct_max_pts_min = 1)
         const auto& y = nd.property.get_result().get_last_value();
         p.y0.insert(p.y0.end(), y.data(), y.data() + p.n);
         p.dt0.push_back(sim.get_dt());
+        if constexpr (Traits::flow_simulation) {
+            const auto& f = sim.get_flows().get_last_value();
+            p.flows0.insert(p.flows0.end(), f.data(), f.data() + f.size());
+        }
         int days = 0;
         Traits::vaccinations(model, p.vacc_partial, p.vacc_full, days);
         if (&nd != &g.nodes()[0] && days != p.vacc_days) {
@@ -470,6 +486,7 @@ public:
         d.integrator   = p.integrator;
         d.t0           = p.t0;
         d.dt_graph     = dt_graph;
+        d.flow_simulation = p.flow_simulation;
         cuda_check(mio_cuda_graph_create(&d, device, &m_h));
     }
     DeviceGraph(const DeviceGraph&) = delete;
@@ -497,6 +514,9 @@ public:
         mio_run_data rd{ps.data(),       ct.data(),        p.node_local.data(), p.y0.data(),
                         p.dt0.data(),    p.mob_max_pts > 0 ? p.mobtable.data() : nullptr};
         cuda_check(mio_cuda_set_runs(m_h, slot, 1, &rd));
+        if (p.flow_simulation) {
+            cuda_check(mio_cuda_set_flows(m_h, slot, 1, p.flows0.data()));
+        }
     }
     int n() const
     {
@@ -583,6 +603,7 @@ public:
             cuda_check(mio_cuda_advance(m_dev->get(), m_t));
             cuda_check(mio_cuda_get_state(m_dev->get(), 0, 1, state.data()));
             append_time_point(m_t, state.data());
+            append_flow_time_point(m_t);
         }
         if (!m_save.empty()) {
             const size_t E = m_graph.edges().size(), K1 = m_save.size() + 1, cap = size_t(m_mob_cap);
@@ -633,6 +654,21 @@ public:
             Eigen::VectorX<FP> v(n);
             std::copy(state + k * n, state + (k + 1) * n, v.data());
             m_graph.nodes()[k].property.get_result().add_time_point(t, v);
+        }
+    }
+    // graphs of FlowSimulation nodes: the flows of every node at the end of the graph step
+    void append_flow_time_point(FP t)
+    {
+        using Sim = std::decay_t<decltype(m_graph.nodes()[0].property.get_simulation())>;
+        if constexpr (detail::SimTraits<Sim>::flow_simulation) {
+            const size_t nf = size_t(m_graph.nodes()[0].property.get_simulation().get_flows().get_num_elements());
+            std::vector<double> flows(m_graph.nodes().size() * nf);
+            cuda_check(mio_cuda_get_flows(m_dev->get(), 0, 1, flows.data()));
+            for (size_t k = 0; k < m_graph.nodes().size(); ++k) {
+                Eigen::VectorX<FP> v{Eigen::Index(nf)};
+                std::copy(flows.begin() + k * nf, flows.begin() + (k + 1) * nf, v.data());
+                m_graph.nodes()[k].property.get_simulation().get_flows().add_time_point(t, v);
+            }
         }
     }
     void set_t(FP t)

@@ -823,46 +823,54 @@ private:
 };
 
 // ---- integrator cores (math/integrator.h, adapt_rk.h, stepper_wrapper.h, euler.h): descriptors only ----------------
-class IntegratorCore
+// (class templates over FP like the reference's; the arithmetic on the device is double)
+template <class FP = ScalarType>
+class OdeIntegratorCore
 {
 public:
-    virtual ~IntegratorCore() = default;
+    virtual ~OdeIntegratorCore() = default;
     virtual mio_integrator_desc desc() const = 0;
+    virtual std::unique_ptr<OdeIntegratorCore<FP>> clone() const = 0;
 };
-class EulerIntegratorCore : public IntegratorCore
+using IntegratorCore = OdeIntegratorCore<ScalarType>;
+template <class FP = ScalarType>
+class EulerIntegratorCore : public OdeIntegratorCore<FP>
 {
 public:
     mio_integrator_desc desc() const override
     {
         return mio_integrator_desc{MIO_INTEGRATOR_EULER, 0, 0, 0, 0, 0};
     }
+    std::unique_ptr<OdeIntegratorCore<FP>> clone() const override
+    {
+        return std::make_unique<EulerIntegratorCore>(*this);
+    }
 };
-template <int KIND>
-class AdaptiveCoreT : public IntegratorCore
+template <class FP, int KIND>
+class AdaptiveCoreT : public OdeIntegratorCore<FP>
 {
 public:
-    AdaptiveCoreT(ScalarType abs_tol = 1e-10, ScalarType rel_tol = 1e-5,
-                  ScalarType dt_min = std::numeric_limits<ScalarType>::min(),
-                  ScalarType dt_max = std::numeric_limits<ScalarType>::max())
+    AdaptiveCoreT(FP abs_tol = 1e-10, FP rel_tol = 1e-5, FP dt_min = std::numeric_limits<ScalarType>::min(),
+                  FP dt_max = std::numeric_limits<ScalarType>::max())
         : m_abs(abs_tol)
         , m_rel(rel_tol)
         , m_dt_min(dt_min)
         , m_dt_max(dt_max)
     {
     }
-    void set_abs_tolerance(ScalarType v)
+    void set_abs_tolerance(FP v)
     {
         m_abs = v;
     }
-    void set_rel_tolerance(ScalarType v)
+    void set_rel_tolerance(FP v)
     {
         m_rel = v;
     }
-    void set_dt_min(ScalarType v)
+    void set_dt_min(FP v)
     {
         m_dt_min = v;
     }
-    void set_dt_max(ScalarType v)
+    void set_dt_max(FP v)
     {
         m_dt_max = v;
     }
@@ -870,12 +878,18 @@ public:
     {
         return mio_integrator_desc{KIND, 0, m_abs, m_rel, m_dt_min, m_dt_max};
     }
+    std::unique_ptr<OdeIntegratorCore<FP>> clone() const override
+    {
+        return std::make_unique<AdaptiveCoreT>(*this);
+    }
 
 private:
-    ScalarType m_abs, m_rel, m_dt_min, m_dt_max;
+    FP m_abs, m_rel, m_dt_min, m_dt_max;
 };
-using RKIntegratorCore      = AdaptiveCoreT<MIO_INTEGRATOR_RKF45>; // math/adapt_rk.h:145-310
-using DefaultIntegratorCore = AdaptiveCoreT<MIO_INTEGRATOR_CK54>;  // compartments/simulation.h:33-34 (boost CK54)
+template <class FP = ScalarType>
+using RKIntegratorCore = AdaptiveCoreT<FP, MIO_INTEGRATOR_RKF45>; // math/adapt_rk.h:145-310
+template <class FP = ScalarType>
+using DefaultIntegratorCore = AdaptiveCoreT<FP, MIO_INTEGRATOR_CK54>; // compartments/simulation.h:33-34 (boost CK54)
 
 } // namespace mio
 

@@ -407,6 +407,51 @@ public:
     {
         return populations.get_compartments();
     }
+    // FlowModel::get_flat_flow_index (compartments/flow_model.h:181-192): position of the flow Source -> Target of an
+    // age group in the flow vectors of a FlowSimulation; the flows of one age group are contiguous
+    template <InfectionState Source, InfectionState Target>
+    size_t get_flat_flow_index(AgeGroup age) const
+    {
+        constexpr int k = flow_position(Source, Target);
+        static_assert(k >= 0, "no such flow in the ODE-SECIR model");
+        return size_t(age) * size_t(num_flows_per_group) + size_t(k);
+    }
+    Eigen::VectorX<FP> get_initial_flows() const // flow_model.h:146-149
+    {
+        Eigen::VectorX<FP> f(Eigen::Index(size_t(parameters.get_num_groups().value) * num_flows_per_group));
+        for (Eigen::Index i = 0; i < f.size(); ++i) {
+            f[i] = 0;
+        }
+        return f;
+    }
+    static constexpr int num_flows_per_group = 15;
+    // the model's Flows type list (model.h:45-59) as (source, target) pairs, in its order
+    static constexpr int flow_position(InfectionState s, InfectionState t)
+    {
+        using I = InfectionState;
+        constexpr I list[num_flows_per_group][2] = {
+            {I::Susceptible, I::Exposed},
+            {I::Exposed, I::InfectedNoSymptoms},
+            {I::InfectedNoSymptoms, I::InfectedSymptoms},
+            {I::InfectedNoSymptoms, I::Recovered},
+            {I::InfectedNoSymptomsConfirmed, I::InfectedSymptomsConfirmed},
+            {I::InfectedNoSymptomsConfirmed, I::Recovered},
+            {I::InfectedSymptoms, I::InfectedSevere},
+            {I::InfectedSymptoms, I::Recovered},
+            {I::InfectedSymptomsConfirmed, I::InfectedSevere},
+            {I::InfectedSymptomsConfirmed, I::Recovered},
+            {I::InfectedSevere, I::InfectedCritical},
+            {I::InfectedSevere, I::Recovered},
+            {I::InfectedSevere, I::Dead},
+            {I::InfectedCritical, I::Dead},
+            {I::InfectedCritical, I::Recovered}};
+        for (int k = 0; k < num_flows_per_group; ++k) {
+            if (list[k][0] == s && list[k][1] == t) {
+                return k;
+            }
+        }
+        return -1;
+    }
     Populations populations;
     ParameterSet parameters;
 };
@@ -468,26 +513,42 @@ int num_change_points(const ContactMatrixGroup<FP>& cm)
 }
 } // namespace detail
 
+} // namespace osecir
+
+// mio::Simulation / mio::FlowSimulation (compartments/simulation.h:36-190, flow_simulation.h:37-97): defined for
+// osecir::Model below; as BaseT of osecir::Simulation they select what a node integrates
+template <class FP, class M>
+class Simulation;
+template <class FP, class M>
+class FlowSimulation;
+
+namespace osecir
+{
+
 // osecir::Simulation (model.h:258-367): one node. advance() runs the node on the GPU as a 1-node graph and appends
 // every accepted integrator step to the result, like SystemIntegrator::advance does (integrator.h:224).
-template <class FP = ScalarType>
+// BaseT = mio::FlowSimulation<FP, Model<FP>>: the integrands are the cumulative flows (flow_simulation.h:63-92), the
+// result is derived from them, get_flows() is their series.
+template <class FP = ScalarType, class BaseT = mio::Simulation<FP, osecir::Model<FP>>>
 class Simulation
 {
 public:
     using Model = osecir::Model<FP>;
+    static constexpr bool is_flow_simulation = std::is_same_v<BaseT, mio::FlowSimulation<FP, osecir::Model<FP>>>;
     Simulation(const Model& model, FP t0 = 0., FP dt = 0.1)
         : m_model(model)
         , m_t0(t0)
         , m_dt(dt)
         , m_result(t0, model.get_initial_values())
-        , m_core(std::make_shared<DefaultIntegratorCore>())
+        , m_flow_result(t0, model.get_initial_flows())
+        , m_core(std::make_shared<DefaultIntegratorCore<FP>>())
     {
     }
-    void set_integrator_core(std::unique_ptr<IntegratorCore>&& core)
+    void set_integrator_core(std::unique_ptr<OdeIntegratorCore<FP>>&& core)
     {
         m_core = std::move(core);
     }
-    const IntegratorCore& get_integrator_core() const
+    const OdeIntegratorCore<FP>& get_integrator_core() const
     {
         return *m_core;
     }
@@ -498,6 +559,17 @@ public:
     const TimeSeries<FP>& get_result() const
     {
         return m_result;
+    }
+    // FlowSimulation::get_flows, flow_simulation.h:104-119
+    TimeSeries<FP>& get_flows()
+    {
+        static_assert(is_flow_simulation, "get_flows() needs BaseT = mio::FlowSimulation");
+        return m_flow_result;
+    }
+    const TimeSeries<FP>& get_flows() const
+    {
+        static_assert(is_flow_simulation, "get_flows() needs BaseT = mio::FlowSimulation");
+        return m_flow_result;
     }
     const Model& get_model() const
     {
@@ -519,23 +591,25 @@ public:
     {
         const int G   = int(m_model.parameters.get_num_groups().value);
         const int n   = G * detail::NC;
+        const int nf  = G * Model::num_flows_per_group;
         const auto& cm = static_cast<const ContactMatrixGroup<FP>&>(
             m_model.parameters.template get<ContactPatterns<FP>>());
         const int L = int(cm.get_num_matrices()), K = std::max(1, detail::num_change_points(cm));
         mio_graph_desc d{};
-        d.model         = MIO_MODEL_OSECIR;
-        d.sim_kind      = MIO_SIM_MODEL;
-        d.num_groups    = G;
-        d.num_nodes     = 1;
-        d.num_psets     = 1;
-        d.num_ctables   = 1;
-        d.ct_max_loc    = L;
-        d.ct_max_pts    = K;
-        d.max_runs      = 1;
-        d.traj_capacity = 1 << 16;
-        d.integrator    = m_core->desc();
-        d.t0            = m_result.get_last_time();
-        d.dt_graph      = std::numeric_limits<double>::infinity();
+        d.model           = MIO_MODEL_OSECIR;
+        d.sim_kind        = MIO_SIM_MODEL;
+        d.num_groups      = G;
+        d.num_nodes       = 1;
+        d.num_psets       = 1;
+        d.num_ctables     = 1;
+        d.ct_max_loc      = L;
+        d.ct_max_pts      = K;
+        d.max_runs        = 1;
+        d.traj_capacity   = 1 << 16;
+        d.integrator      = m_core->desc();
+        d.t0              = m_result.get_last_time();
+        d.dt_graph        = std::numeric_limits<double>::infinity();
+        d.flow_simulation = is_flow_simulation ? 1 : 0;
         const size_t psz = size_t(mio_pset_size(MIO_MODEL_OSECIR, G));
         std::vector<double> pset(psz, 0.0), local(MIO_NODE_LOCAL);
         m_model.parameters.pack_values(pset.data(), local.data());
@@ -546,6 +620,10 @@ public:
         cuda_check(mio_cuda_graph_create(&d, 0, &h));
         try {
             cuda_check(mio_cuda_set_runs(h, 0, 1, &rd));
+            if constexpr (is_flow_simulation) {
+                // the integration continues from the last flow time point (error control acts on the flows)
+                cuda_check(mio_cuda_set_flows(h, 0, 1, m_flow_result.get_last_value().data()));
+            }
             cuda_check(mio_cuda_advance(h, tmax));
             int32_t npts = 0;
             const size_t cap = size_t(d.traj_capacity);
@@ -558,6 +636,15 @@ public:
                 Eigen::VectorX<FP> v(n);
                 std::copy(values.begin() + size_t(k) * n, values.begin() + size_t(k + 1) * n, v.data());
                 m_result.add_time_point(times[size_t(k)], v);
+            }
+            if constexpr (is_flow_simulation) {
+                std::vector<double> fv(cap * size_t(nf));
+                cuda_check(mio_cuda_get_flow_trajectory(h, 0, 1, fv.data()));
+                for (int k = 1; k < npts; ++k) {
+                    Eigen::VectorX<FP> v(nf);
+                    std::copy(fv.begin() + size_t(k) * nf, fv.begin() + size_t(k + 1) * nf, v.data());
+                    m_flow_result.add_time_point(times[size_t(k)], v);
+                }
             }
             cuda_check(mio_cuda_get_node_dt(h, 0, 1, &m_dt));
         }
@@ -572,22 +659,70 @@ public:
 private:
     Model m_model;
     FP m_t0, m_dt;
-    TimeSeries<FP> m_result;
-    std::shared_ptr<IntegratorCore> m_core;
+    TimeSeries<FP> m_result, m_flow_result;
+    std::shared_ptr<OdeIntegratorCore<FP>> m_core;
 };
 
-// osecir::simulate, model.h:383-411
-template <class FP = ScalarType>
-TimeSeries<FP> simulate(FP t0, FP tmax, FP dt, const Model<FP>& model,
-                        std::unique_ptr<IntegratorCore>&& integrator = nullptr)
+} // namespace osecir
+
+// the generic simulation types for the ODE-SECIR model (the reference's osecir::Simulation only adds the dynamic NPI
+// check to its base): mio::Simulation<FP, osecir::Model<FP>> and mio::FlowSimulation<FP, osecir::Model<FP>>
+template <class FP>
+class Simulation<FP, osecir::Model<FP>> : public osecir::Simulation<FP>
+{
+public:
+    using osecir::Simulation<FP>::Simulation;
+};
+template <class FP>
+class FlowSimulation<FP, osecir::Model<FP>>
+    : public osecir::Simulation<FP, FlowSimulation<FP, osecir::Model<FP>>>
+{
+public:
+    using osecir::Simulation<FP, FlowSimulation<FP, osecir::Model<FP>>>::Simulation;
+};
+
+// mio::simulate / mio::simulate_flows, compartments/simulation.h:223-236, flow_simulation.h:110-121
+template <class FP, class Model, class Sim = Simulation<FP, Model>>
+TimeSeries<FP> simulate(FP t0, FP tmax, FP dt, const Model& model,
+                        std::unique_ptr<OdeIntegratorCore<FP>>&& integrator_core = nullptr)
 {
     model.check_constraints();
-    Simulation<FP> sim(model, t0, dt);
-    if (integrator) {
-        sim.set_integrator_core(std::move(integrator));
+    Sim sim(model, t0, dt);
+    if (integrator_core) {
+        sim.set_integrator_core(std::move(integrator_core));
     }
     sim.advance(tmax);
     return sim.get_result();
+}
+template <class FP, class Model, class Sim = FlowSimulation<FP, Model>>
+std::vector<TimeSeries<FP>> simulate_flows(FP t0, FP tmax, FP dt, const Model& model,
+                                           std::unique_ptr<OdeIntegratorCore<FP>>&& integrator_core = nullptr)
+{
+    model.check_constraints();
+    Sim sim(model, t0, dt);
+    if (integrator_core) {
+        sim.set_integrator_core(std::move(integrator_core));
+    }
+    sim.advance(tmax);
+    return {sim.get_result(), sim.get_flows()};
+}
+
+namespace osecir
+{
+
+// osecir::simulate / osecir::simulate_flows, model.h:383-411
+template <class FP = ScalarType>
+TimeSeries<FP> simulate(FP t0, FP tmax, FP dt, const Model<FP>& model,
+                        std::unique_ptr<OdeIntegratorCore<FP>>&& integrator = nullptr)
+{
+    return mio::simulate<FP, Model<FP>, Simulation<FP>>(t0, tmax, dt, model, std::move(integrator));
+}
+template <class FP = ScalarType>
+std::vector<TimeSeries<FP>> simulate_flows(FP t0, FP tmax, FP dt, const Model<FP>& model,
+                                           std::unique_ptr<OdeIntegratorCore<FP>>&& integrator = nullptr)
+{
+    return mio::simulate_flows<FP, Model<FP>, Simulation<FP, mio::FlowSimulation<FP, Model<FP>>>>(
+        t0, tmax, dt, model, std::move(integrator));
 }
 
 // draw_sample_infection / draw_sample_demographics / draw_sample(Model&), parameter_space.h:125-205

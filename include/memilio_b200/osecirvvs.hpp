@@ -460,14 +460,14 @@ public:
         , m_t0(t0)
         , m_dt(dt)
         , m_result(t0, model.get_initial_values())
-        , m_core(std::make_shared<DefaultIntegratorCore>())
+        , m_core(std::make_shared<DefaultIntegratorCore<FP>>())
     {
     }
-    void set_integrator_core(std::unique_ptr<IntegratorCore>&& core)
+    void set_integrator_core(std::unique_ptr<OdeIntegratorCore<FP>>&& core)
     {
         m_core = std::move(core);
     }
-    const IntegratorCore& get_integrator_core() const
+    const OdeIntegratorCore<FP>& get_integrator_core() const
     {
         return *m_core;
     }
@@ -562,7 +562,7 @@ private:
     Model m_model;
     FP m_t0, m_dt;
     TimeSeries<FP> m_result;
-    std::shared_ptr<IntegratorCore> m_core;
+    std::shared_ptr<OdeIntegratorCore<FP>> m_core;
 };
 
 template <class FP = ScalarType>
@@ -571,7 +571,7 @@ using Simulation = SimulationT<FP, false>;
 // osecirvvs::simulate, model.h:792-818
 template <class FP = ScalarType>
 TimeSeries<FP> simulate(FP t0, FP tmax, FP dt, const Model<FP>& model,
-                        std::unique_ptr<IntegratorCore>&& integrator = nullptr)
+                        std::unique_ptr<OdeIntegratorCore<FP>>&& integrator = nullptr)
 {
     model.check_constraints();
     Simulation<FP> sim(model, t0, dt);
@@ -588,6 +588,7 @@ namespace detail
 {
 template <class FP, bool BASE>
 struct SimTraits<osecirvvs::SimulationT<FP, BASE>> {
+    static constexpr bool flow_simulation = false;
     static constexpr int model_kind = MIO_MODEL_OSECIRVVS;
     static constexpr int sim_kind   = BASE ? MIO_SIM_BASE : MIO_SIM_MODEL;
     static constexpr int NC         = osecirvvs::detail::NC;

@@ -239,6 +239,9 @@ MIO_API int mio_cuda_get_trajectory(mio_handle* h, int32_t slot0, int32_t count,
  * flow_simulation = 1: get_flows().get_last_value() of every node, out[count][N][G*15] (age-major, the 15 flows in the
  * order of osecir's Flows type list, cpp/models/ode_secir/model.h:45-59) */
 MIO_API int mio_cuda_get_flows(mio_handle* h, int32_t slot0, int32_t count, double* out);
+/* the flows a FlowSimulation continues from (mio_cuda_set_runs starts them at zero, FlowModel::get_initial_flows,
+ * cpp/memilio/compartments/flow_model.h:146-149): flows[count][N][G*15], to be called after mio_cuda_set_runs */
+MIO_API int mio_cuda_set_flows(mio_handle* h, int32_t slot0, int32_t count, const double* flows);
 /* ... and the whole flow series (needs traj_capacity > 0): values[count][N][traj_capacity][G*15]; the time points
  * are those of mio_cuda_get_trajectory, whose values are the populations that follow from the flows
  * (compute_population_results, cpp/memilio/compartments/flow_simulation_base.h:84-97) */

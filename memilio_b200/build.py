@@ -36,16 +36,26 @@ def build(force: bool = False, verbose: bool = False, defines=(), out: str = LIB
     os.makedirs(objdir, exist_ok=True)
     from concurrent.futures import ThreadPoolExecutor
 
-    headers = [os.path.join(CSRC, f) for f in os.listdir(CSRC) if f.endswith((".cuh", ".h"))]
-    headers.append(os.path.join(os.path.dirname(HERE), "include", "mio_cuda.h"))
-    hdr_time = max(os.path.getmtime(f) for f in headers)
     incremental = not force and not defines and not os.environ.get("MIO_NVCC_EXTRA")
+
+    def deps_time(src):
+        """newest mtime of a source and the local headers it includes (transitively)"""
+        import re
+        seen, todo = set(), [os.path.join(CSRC, src)]
+        while todo:
+            f = os.path.normpath(todo.pop())
+            if f in seen or not os.path.exists(f):
+                continue
+            seen.add(f)
+            with open(f) as fh:
+                for inc in re.findall(r'^\s*#include\s+"([^"]+)"', fh.read(), flags=re.M):
+                    todo.append(os.path.join(os.path.dirname(f), inc))
+        return max(os.path.getmtime(f) for f in seen)
 
     def compile_one(src):
         obj = os.path.join(objdir, os.path.splitext(src)[0] + ".o")
-        if incremental and os.path.exists(obj) and os.path.getmtime(obj) > max(
-                hdr_time, os.path.getmtime(os.path.join(CSRC, src))):
-            return obj, None  # up to date (object newer than its source and every header)
+        if incremental and os.path.exists(obj) and os.path.getmtime(obj) > deps_time(src):
+            return obj, None  # up to date (object newer than its source and the headers it includes)
         extra = os.environ.get("MIO_NVCC_EXTRA", "").split()  # tuning experiments only
         cmd = [_nvcc()] + NVCC_FLAGS + extra + ["-D" + d for d in defines] + ["-c", os.path.join(CSRC, src), "-o", obj]
         r = subprocess.run(cmd, capture_output=True, text=True)

@@ -1265,6 +1265,31 @@ int mio_cuda_get_flows(mio_handle* h, int32_t slot0, int32_t count, double* out)
     return MIO_OK;
 }
 
+int mio_cuda_set_flows(mio_handle* h, int32_t slot0, int32_t count, const double* flows)
+{
+    if (int rc = check_slots(h, slot0, count, flows)) {
+        return rc;
+    }
+    if (!h->d_flows) {
+        return fail(MIO_INVALID_VALUE, "graph was created without flow_simulation");
+    }
+    CUDA_TRY(cudaSetDevice(h->device));
+    const size_t lanes = (size_t)count * h->geo.N * h->geo.W;
+    std::vector<double> tmp(lanes * 16, 0.0);
+    for (size_t l = 0; l < lanes; ++l) {
+        std::copy(flows + l * 15, flows + l * 15 + 15, tmp.begin() + l * 16);
+    }
+    CUDA_TRY(cudaMemcpy(h->d_flows + (size_t)slot0 * h->geo.N * h->geo.W * 16, tmp.data(), sizeof(double) * tmp.size(),
+                        cudaMemcpyHostToDevice));
+    if (h->d_traj_flows) { // time point 0 of the flow series
+        const size_t cap = (size_t)h->desc.traj_capacity, nf = (size_t)h->geo.G * 15;
+        CUDA_TRY(cudaMemcpy2D(h->d_traj_flows + (size_t)slot0 * h->geo.N * cap * nf, sizeof(double) * cap * nf, flows,
+                              sizeof(double) * nf, sizeof(double) * nf, (size_t)count * h->geo.N,
+                              cudaMemcpyHostToDevice));
+    }
+    return MIO_OK;
+}
+
 int mio_cuda_get_flow_trajectory(mio_handle* h, int32_t slot0, int32_t count, double* values)
 {
     if (int rc = check_slots(h, slot0, count, values)) {

@@ -216,3 +216,61 @@ def test_vvs_graph_example_matches_oracle():
                      vacc_partial=np.tile(s["vacc_partial"], (N, 1, 1)), vacc_full=np.tile(s["vacc_full"], (N, 1, 1)))
     ref = oracle_lib.graph_simulate(p, 0, 10.0)
     np.testing.assert_allclose(got, ref["state"], rtol=1e-8, atol=1e-9)
+
+
+# ---- mio::FlowSimulation through the facade -------------------------------------------------------------
+def test_flows_example_single_node_matches_oracle():
+    out = run_example("flows", "single")
+    lines = out.strip().splitlines()
+    rows = np.array([[float(w) for w in ln.split()] for ln in lines if not ln.startswith("#")])
+    s = scenarios.golden_case("py_default_g3")
+    t_o, y_o, f_o, _, _ = oracle_lib.simulate_flows_stepwise(s["G"], s["pset"], s["local"], s["ct"], s["ct_max_loc"],
+                                                             s["ct_max_pts"], s["y0"], 0.0, [20.0, 50.0], s["dt0"],
+                                                             s["integrator"])
+    assert rows.shape == (len(t_o), 1 + 30 + 45)
+    np.testing.assert_allclose(rows[:, 0], t_o, rtol=1e-8, atol=1e-10)
+    np.testing.assert_allclose(rows[:, 1:31], y_o, rtol=1e-8, atol=1e-9)
+    np.testing.assert_allclose(rows[:, 31:], f_o, rtol=1e-8, atol=1e-9)
+    # mio::simulate_flows (one advance call) and Model::get_flat_flow_index
+    t1, y1, f1, _, _ = oracle_lib.simulate_flows(s["G"], s["pset"], s["local"], s["ct"], s["ct_max_loc"],
+                                                 s["ct_max_pts"], s["y0"], 0.0, 50.0, s["dt0"], s["integrator"])
+    last = [ln for ln in lines if ln.startswith("#")][0].split()[1:]
+    assert int(last[0]) == len(t1)
+    np.testing.assert_allclose([float(last[1]), float(last[2])], [y1[-1][0], f1[-1][0]], rtol=1e-8)
+
+
+def test_flows_example_graph_matches_oracle_every_half_day():
+    out = run_example("flows", "graph")
+    rows = np.array([[float(w) for w in ln.split()] for ln in out.strip().splitlines()])
+    p = scenarios.example_ode_secir_graph()
+    p.flow_simulation = 1
+    for k in range(2):
+        node = rows[rows[:, 1] == k]
+        assert node.shape == (21, 2 + 10 + 15)
+        np.testing.assert_array_equal(node[:, 0], np.arange(21) * 0.5)
+        np.testing.assert_array_equal(node[0, 12:], 0.0)
+    for step in (1, 2, 3, 10, 20):
+        ref = oracle_lib.graph_simulate_flows(p, 0, 0.5 * step)
+        for k in range(2):
+            node = rows[rows[:, 1] == k]
+            np.testing.assert_allclose(node[step, 2:12], ref["state"][k], rtol=1e-8, atol=1e-9)
+            np.testing.assert_allclose(node[step, 12:], ref["flows"][k], rtol=1e-8, atol=1e-9)
+
+
+def test_reference_contact_changes_example_runs():
+    # cpp/examples/ode_secir_contact_changes.cpp: mio::simulate_flows with an explicit Euler step of 0.1; prints the
+    # S->E flow of the first step without / with a damping of 0.5, 1 and -1 (the relations of TestOdeSecir.testDamping)
+    import re
+    r = subprocess.run([_ref_binary("ode_secir_contact_changes")], capture_output=True, text=True, timeout=300)
+    assert r.returncode == 0, r.stderr[-2000:]
+    vals = [float(m) for m in re.findall(r"first time step is: ([-+0-9.eE]+?)\.?\n", r.stdout)]
+    assert len(vals) == 4
+    a, b, c, d = vals
+    integ = scenarios.cdefs.integrator_desc(kind=flat.INTEGRATOR_EULER)
+    s = scenarios.damping_flow_case(None)
+    _, _, f_o, _, _ = oracle_lib.simulate_flows(1, s["pset"], s["local"], s["ct"], 1, 2, s["y0"], 0.0, 1.0, 0.1, integ)
+    np.testing.assert_allclose(a, f_o[1][0], rtol=1e-5)  # printed with six significant digits
+    np.testing.assert_allclose([b, c, d], [a / 2, 0.0, 2 * a], rtol=1e-5, atol=1e-12)
+    # four flow tables of 11 time points (t = 0 .. 1) and 15 flows were printed
+    tab = _table(r.stdout)
+    assert tab.shape == (44, 16)
