@@ -79,6 +79,9 @@ struct mio_handle {
         *d_out_ptr = nullptr, *d_out_dst = nullptr, *d_edge_start = nullptr, *d_edge_end = nullptr;
     double *d_coeff = nullptr, *d_w_in = nullptr, *d_w_out = nullptr, *d_s_out = nullptr, *d_umask = nullptr;
     double* d_w_edge = nullptr; // factorized graphs: [E][W] weight per (edge, lane) in reference edge order
+    double* d_xdamp = nullptr;
+    int *d_xslot = nullptr, *d_xsrc = nullptr; // schedule of the block-parallel literal replay (see EdgeArgs)
+    int xchunks = 0, xepp = 0;
     int factorized = 0;
     int num_mob = 0;
     int mob_comp[NC] = {0, 0, 0, 0, 0, 0, 0, 0, 0, 0};
@@ -305,7 +308,7 @@ void destroy(mio_handle* h)
                     h->d_aux,        h->d_run_flags,   h->d_daily,      h->d_traj_npts, h->d_traj_times,
                     h->d_traj_values, h->d_stats,      h->d_vacc_partial, h->d_vacc_full, h->d_work, h->d_run_list, h->d_w_edge,
                     h->d_mob_gptr,   h->d_mob_gdev,    h->d_ref_to_dev, h->d_edge_active, h->d_edge_m, h->d_mob_values,
-                    h->d_flows,      h->d_traj_flows};
+                    h->d_flows,      h->d_traj_flows,  h->d_xslot,      h->d_xsrc,        h->d_xdamp};
     for (void* p : ptrs) {
         if (p) {
             cudaFree(p);
@@ -713,6 +716,37 @@ int mio_cuda_graph_create(const mio_graph_desc* d, int device, mio_handle** out)
             H_TRY(up_d(&h->d_w_edge, w_age.data(), w_age.size()));
         }
         H_TRY(up_d(&h->d_s_out, s_out.data(), s_out.size()));
+        {
+            // chunks of the block-parallel literal replay: consecutive edges of one source, distinct destinations
+            const int epp = EXB_P1_WARPS * (32 / W);
+            std::vector<int> xslot, xsrc;
+            int e = 0;
+            while (e < E) {
+                const int src = d->edge_start[e];
+                std::vector<int> seen;
+                const size_t base = xslot.size();
+                xslot.resize(base + (size_t)epp * 2, -1);
+                int q = 0;
+                while (e < E && q < epp && d->edge_start[e] == src &&
+                       std::find(seen.begin(), seen.end(), d->edge_end[e]) == seen.end()) {
+                    xslot[base + 2 * q]     = e;
+                    xslot[base + 2 * q + 1] = d->edge_end[e];
+                    seen.push_back(d->edge_end[e]);
+                    ++q;
+                    ++e;
+                }
+                for (; q < epp; ++q) {
+                    xslot[base + 2 * q + 1] = 0;
+                }
+                const bool hazard = !xsrc.empty() && std::find(seen.begin(), seen.end(), xsrc[xsrc.size() - 2]) != seen.end();
+                xsrc.push_back(src);
+                xsrc.push_back((int)seen.size() | (hazard ? 1 << 16 : 0));
+            }
+            h->xchunks = (int)xsrc.size() / 2;
+            h->xepp    = epp;
+            H_TRY(up_i(&h->d_xslot, xslot));
+            H_TRY(up_i(&h->d_xsrc, xsrc));
+        }
         H_TRY(up_d(&h->d_umask, umask.data(), umask.size()));
     }
     // per-run state
@@ -733,6 +767,7 @@ int mio_cuda_graph_create(const mio_graph_desc* d, int device, mio_handle** out)
         H_TRY(dev_alloc(&h->d_vis, R * N * n));
         H_TRY(dev_alloc(&h->d_run_flags, R));
         H_TRY(dev_alloc(&h->d_run_list, R));
+        H_TRY(dev_alloc(&h->d_xdamp, R * n));
         H_TRY(cudaMemset(h->d_run_flags, 0, sizeof(int) * R));
         H_TRY(dev_alloc(&h->d_stats, (size_t)4));
         H_TRY(cudaMemset(h->d_stats, 0, sizeof(long long) * 4));
@@ -1026,6 +1061,11 @@ int mio_cuda_advance(mio_handle* h, double t_max)
             ea.run_list       = h->d_run_list;
             ea.list_count     = h->d_work + 1;
             ea.csr.w_edge     = h->d_w_edge;
+            ea.xslot          = h->d_xslot;
+            ea.xsrc           = h->d_xsrc;
+            ea.xchunks        = h->xchunks;
+            ea.xepp           = h->xepp;
+            ea.xdamp          = h->d_xdamp;
             ea.num_runs       = R;
             ea.edge_m         = h->d_edge_m;
             MobilityResultArgs mra{};

@@ -17,6 +17,10 @@
 #include "device_common.cuh"
 #include "kernels.h"
 
+#include <algorithm>
+#include <cstdlib>
+#include <cstring>
+
 namespace miocu
 {
 
@@ -838,17 +842,35 @@ __global__ void __launch_bounds__(RETURN_TMA_THREADS, MIO_RETURN_TMA_MINBLOCKS) 
 //                          edges share the source (edges are sorted by source).
 template <int THREADS>
 __global__ void __launch_bounds__(THREADS) collect_flagged_kernel(EdgeArgs a, int* __restrict__ run_list,
-                                                                   int* __restrict__ list_count)
+                                                                   int* __restrict__ list_count, int copy_state)
 {
     const int run = blockIdx.x;
     if (run >= a.num_runs || a.run_flags[run] == 0) {
         return;
     }
-    const size_t total = (size_t)a.geo.N * a.geo.n / 2; // n is even
+    // (the block-parallel replay reads the pre-return state itself)
+    const size_t total = copy_state ? (size_t)a.geo.N * a.geo.n / 2 : 0; // n is even
     const double2* src = reinterpret_cast<const double2*>(a.y_in + (size_t)run * a.geo.N * a.geo.n);
     double2* dst       = reinterpret_cast<double2*>(a.y_out + (size_t)run * a.geo.N * a.geo.n);
     for (size_t i = threadIdx.x; i < total; i += THREADS) {
         dst[i] = src[i];
+    }
+    if (!copy_state && a.xdamp != nullptr && a.geo.mob_max_pts > 0) {
+        // mobility damping of the run at the departure time for the block-parallel replay (mobility_damping_eval)
+        const double* mob = a.st.run_block + (size_t)run * a.geo.block_stride + a.geo.mob_off;
+        const int K       = (int)mob[0];
+        for (int j = threadIdx.x; j < a.geo.n && K > 0; j += THREADS) {
+            const double* times = mob + 1;
+            const double* D     = mob + 1 + a.geo.mob_max_pts + j;
+            int k               = 0;
+            while (k < K && !(a.t_dep < times[k])) {
+                ++k;
+            }
+            const double* Dl = k > 0 ? D + (size_t)(k - 1) * a.geo.n : nullptr;
+            const double* Dr = k < K ? D + (size_t)k * a.geo.n : Dl;
+            const double xr  = k < K ? times[k] : DBL_MAX;
+            a.xdamp[(size_t)run * a.geo.n + j] = smoother_cosine(a.t_dep, xr - 1.0, xr, Dl ? *Dl : 0.0, Dr ? *Dr : 0.0);
+        }
     }
     __syncthreads(); // every thread has read the flag
     if (threadIdx.x == 0) {
@@ -1145,6 +1167,344 @@ __global__ void __launch_bounds__(32, FACT ? MIO_EXACT_MINBLOCKS_FACT : MIO_EXAC
 }
 
 // ---------------------------------------------------------------------------------------------------------------
+// return_exact_blocks_kernel: the same literal replay, parallel over the edges of ONE source node.
+// The reference's edge order is grouped by source; inside a source's block every destination occurs once, and the
+// underflow test of an edge only reads the running state of its destination, so the edges of a block are independent
+// of each other; only the blocks are sequential. One CTA owns a flagged run, its running state Y[N][n] lives in
+// shared memory (N*n*8 bytes: 192 KB for 400 counties x 6 age groups); local memory must be avoided (the L1 left
+// beside the state is tiny: spills and indexed local arrays cost an L2 round trip each). A chunk is <= EPP edges of one source; in step s three groups of warps work side by side
+// on three chunks (ring of three chunk buffers B in shared memory), one barrier per step:
+//   R warps (one W-lane group per edge): chunk s+1 -- the returning population of every edge by the explicit Euler step
+//     of the destination (order independent; operands fetched two chunks ahead) -> B;
+//   T warps (one W-lane group per edge): chunk s -- in order: test against Y[dest], fix-up (-> B), Y[dest] -= m;
+//   S warps (one lane per state element): chunk s-1 -- Y[source] += m, edge after edge in edge order.
+// When the source of chunk s-1 is a destination of chunk s (flag in the schedule) the T warps wait for the S warps.
+// Every node's running state sees exactly the reference's sequence of operations (sources ascending, own block in edge
+// order), so the result is bit-identical to return_exact_kernel and to the oracle. LAY == 1 (ODE-SECIR) only.
+template <int G, bool FACT>
+struct ExbOps {
+    double c[FACT ? 1 : NC]; // coefficient vector of the edge for this lane (FACT: the weight)
+    double2 a0, a1;          // return coefficients of the destination (aux)
+    int e, to, from;         // e < 0: empty slot
+};
+
+template <int G, bool FACT>
+__global__ void __launch_bounds__(EXB_THREADS, 1)
+    return_exact_blocks_kernel(EdgeArgs a, const int* __restrict__ run_list, const int* __restrict__ list_count)
+{
+    constexpr int LAY = 1;
+    constexpr int W   = G;
+    constexpr int NPW = 32 / W;
+    constexpr int TW  = EXB_P1_WARPS;
+    constexpr int EPP = TW * NPW;
+    extern __shared__ __align__(16) double smem[];
+    const Geometry& geo = a.geo;
+    const int n         = geo.n;
+    double* const Y      = smem;                      // [N][n]
+    double* const B      = Y + (size_t)geo.N * n;     // [3][EPP][n] returning populations of three chunks
+    double* const damp_s = B + (size_t)3 * EPP * n;   // [W][NC]
+    double* const rate_s = damp_s + W * NC;           // [W][17] (odd stride: the lanes of a group hit distinct banks)
+    const int SS         = (n + W + 1) & ~1;          // (even: 16-byte loads)
+    double* const snap_s = rate_s + W * 18;           // [2][SS] snapshot at departure and mobility factors of the
+                                                      // source node of a chunk (staged by the S warps)
+    int* const bany      = reinterpret_cast<int*>(snap_s + 2 * SS); // [3][EPP] the edge carries commuters
+    const int count = *list_count;
+    const int warp  = threadIdx.x >> 5;
+    const bool is_t = warp < TW;
+    const bool is_r = !is_t && warp < 2 * TW;
+    const bool is_s = warp >= 2 * TW;
+    Group<G, LAY> g;
+    const int lane  = g.lane;
+    const int gl    = g.gl;
+    const int q     = (is_t ? warp : warp - TW) * NPW + lane / W; // T, R: the lane group's slot in a chunk
+    const bool lane_on = !is_s && !g.spare();
+    const int nchunks  = a.xchunks;
+    const size_t total2 = (size_t)geo.N * n / 2;
+    const size_t bstride = (size_t)EPP * n;
+    unsigned maskbits   = 0u;
+    if constexpr (FACT) {
+        for (int i = 0; i < NC; ++i) {
+            maskbits |= (a.csr.umask[gl * NC + i] != 0.0 ? 1u : 0u) << i;
+        }
+    }
+
+    for (int item = blockIdx.x; item < count; item += gridDim.x) {
+        const int run      = run_list[item];
+        const size_t rbase = (size_t)run * geo.N;
+        const double* blk  = a.st.run_block + (size_t)run * geo.block_stride;
+        const double* mob  = geo.mob_max_pts > 0 ? blk + geo.mob_off : nullptr;
+        const bool damped  = mob != nullptr && mob[0] > 0.0;
+        const bool one_pset = geo.num_psets == 1;
+        __syncthreads(); // the previous run's state has left shared memory
+        {
+            const double2* src = reinterpret_cast<const double2*>(a.y_in + rbase * n);
+            double2* dst       = reinterpret_cast<double2*>(Y);
+            for (size_t i = threadIdx.x; i < total2; i += EXB_THREADS) {
+                dst[i] = src[i];
+            }
+            if (threadIdx.x < W * NC) {
+                // mobility damping at the departure time, evaluated by collect_flagged_kernel (no call, and so no
+                // stack frame, in this kernel)
+                damp_s[threadIdx.x] = damped ? a.xdamp[(size_t)run * n + threadIdx.x] : 0.0;
+            }
+            if (threadIdx.x < W * 16) {
+                const int gi = threadIdx.x / 16, ri = threadIdx.x - gi * 16;
+                rate_s[gi * 17 + ri] = blk[PHDR + gi * AGE_REC + ri];
+            }
+        }
+        const double nd_run = nondetection_at(blk, a.t_dep); // one parameter set per run
+
+        // R: operands of (chunk, slot q) for this lane
+        auto load_ops = [&](int e, int to, int from, ExbOps<G, FACT>& d) {
+            d.e    = lane_on ? e : -1;
+            d.to   = to;
+            d.from = from;
+            if (d.e >= 0) {
+                if constexpr (FACT) {
+                    d.c[0] = __ldg(a.csr.w_edge + (size_t)e * W + gl);
+                }
+                else {
+                    const double2* cp = reinterpret_cast<const double2*>(a.csr.coeff + (size_t)e * n + gl * NC);
+#pragma unroll
+                    for (int i = 0; i < NC / 2; ++i) {
+                        const double2 v = __ldg(cp + i);
+                        d.c[2 * i]      = v.x;
+                        d.c[2 * i + 1]  = v.y;
+                    }
+                }
+                const double2* ax = reinterpret_cast<const double2*>(a.aux + ((rbase + to) * W + gl) * AUX);
+                d.a0              = ax[0];
+                d.a1              = ax[1];
+            }
+        };
+        // S: snapshot and mobility factors of the source of chunk c -> shared memory (two chunks ahead of the R warps)
+        auto stage_source = [&](int c) {
+            if (c < nchunks) {
+                const int from = __ldg(a.xsrc + 2 * c);
+                double* dst    = snap_s + (c & 1) * SS;
+                for (int j = threadIdx.x - 2 * TW * 32; j < n + W; j += EXB_P2_WARPS * 32) {
+                    dst[j] = j < n ? a.snap[(rbase + from) * n + j] : a.fac[(rbase + from) * W + (j - n)];
+                }
+            }
+        };
+        // R: the returning population of the lane's edge (instant.h:608-615 at departure, :460-471 the Euler step)
+        // -> chunk buffer
+        auto returning = [&](const ExbOps<G, FACT>& d, int buf, int c) {
+            bool pos = false;
+            double m[NC];
+            if (d.e >= 0) {
+                const double* srec = snap_s + (c & 1) * SS;
+                double sf[NC];
+                lds10(srec + gl * NC, sf);
+                const double ff = srec[n + gl];
+                LaneCoef c_t;
+                double nd = nd_run;
+                if (one_pset) {
+                    c_t.load(rate_s + gl * 17);
+                }
+                else {
+                    const int ps_t = a.st.node_pset ? a.st.node_pset[d.to] : 0;
+                    const int ps_f = a.st.node_pset ? a.st.node_pset[d.from] : 0;
+                    c_t.load(blk + ps_t * geo.pset_stride + PHDR + gl * AGE_REC);
+                    nd = nondetection_at(blk + ps_f * geo.pset_stride, a.t_dep);
+                }
+#pragma unroll
+                for (int i = 0; i < NC; ++i) {
+                    double c = FACT ? (((maskbits >> i) & 1u) ? d.c[0] : 0.0) : d.c[i];
+                    if (damped) {
+                        c = __dsub_rn(c, __dmul_rn(damp_s[gl * NC + i], c));
+                    }
+                    pos  = pos || (c > 0.0);
+                    m[i] = sf[i] * c;
+                }
+                m[cISy] *= ff;
+                if (nd != 1.0) {
+                    m[cISy] *= nd;
+                    m[cINS] *= nd;
+                }
+                euler_return<G, LAY>(g, c_t, d.a0.x, d.a0.y, d.a1.x, a.dt, m);
+            }
+            const bool any = g.any(pos); // the reference skips edges without a positive coefficient
+            if (lane_on) {
+                // a slot without commuters (empty, or no positive coefficient) holds -0.0: the S warps add every row
+                // of the buffer, and x + -0.0 == x for every x
+                if (!(d.e >= 0 && any)) {
+#pragma unroll
+                    for (int i = 0; i < NC; ++i) {
+                        m[i] = -0.0;
+                    }
+                }
+                store10(B + buf * bstride + (size_t)q * n + gl * NC, m);
+                if (gl == 0) {
+                    bany[buf * EPP + q] = (d.e >= 0 && any) ? 1 : 0;
+                }
+            }
+        };
+        auto slot_of = [&](int s, int& e, int& to, int& from) {
+            e = -1, to = 0, from = 0;
+            if (!is_s && s < nchunks) {
+                const int2 v = __ldg(reinterpret_cast<const int2*>(a.xslot) + (size_t)s * EPP + q);
+                e            = v.x;
+                to           = v.y;
+                from         = __ldg(a.xsrc + 2 * s);
+            }
+        };
+
+        ExbOps<G, FACT> near, far;
+        int e_n = -1, to_n = 0, from_n = 0; // R: slot of chunk s + 3; T: slot of chunk s + 1
+        int e_cur = -1, to_cur = 0;        // T: slot of chunk s
+        int from_prev = 0, from_next = 0;  // S: source of chunk s - 1 / s
+        if (is_r) {
+            int e0, t0, f0;
+            slot_of(0, e0, t0, f0);
+            load_ops(e0, t0, f0, far);
+            slot_of(1, e0, t0, f0);
+            load_ops(e0, t0, f0, near);
+            slot_of(2, e_n, to_n, from_n);
+        }
+        else if (is_t) {
+            int f0;
+            slot_of(0, e_cur, to_cur, f0);
+            if (!lane_on) {
+                e_cur = -1;
+            }
+            slot_of(1, e_n, to_n, f0);
+        }
+        else {
+            stage_source(0);
+            stage_source(1);
+            from_next = nchunks > 0 ? __ldg(a.xsrc) : 0;
+        }
+        __syncthreads(); // the state and the run constants are in shared memory
+        if (is_r) {
+            returning(far, 0, 0);
+        }
+        __syncthreads();
+        for (int s = 0; s <= nchunks; ++s) {
+            // chunk s - 1's source is a destination of chunk s: the T warps wait for the S warps
+            const bool hazard = s > 0 && s < nchunks && (__ldg(a.xsrc + 2 * s + 1) >> 16) != 0;
+            if (is_r) {
+                if (s + 1 < nchunks) {
+                    // fetch ahead: operands of chunk s + 3, slot of chunk s + 4
+                    int e_f, to_f, from_f;
+                    slot_of(s + 3, e_f, to_f, from_f);
+                    load_ops(e_n, to_n, from_n, far);
+                    e_n = e_f, to_n = to_f, from_n = from_f;
+                    returning(near, (s + 1) % 3, s + 1);
+                    near = far;
+                }
+            }
+            else if (is_t) {
+                if (hazard) {
+                    asm volatile("bar.sync 1, %0;" ::"r"((TW + EXB_P2_WARPS) * 32) : "memory");
+                }
+                if (s < nchunks) {
+                    // in order: underflow test against the destination's running state, fix-up (instant.h:579-596)
+                    const int buf = s % 3;
+                    int e_f, to_f, from_f;
+                    slot_of(s + 2, e_f, to_f, from_f);
+                    double* const mrec = B + buf * bstride + (size_t)q * n + gl * NC;
+                    double* const yrec = Y + (size_t)to_cur * n + gl * NC;
+                    const bool any_cur = e_cur >= 0 && bany[buf * EPP + q] != 0;
+                    int fixes = 0;
+                    double yt[NC], m[NC], rem[NC];
+                    bool neg_any = false;
+                    if (e_cur >= 0) {
+                        lds10(yrec, yt);
+                        lds10(mrec, m);
+#pragma unroll
+                        for (int i = 0; i < NC; ++i) {
+                            rem[i]  = yt[i] - m[i];
+                            neg_any = neg_any || (rem[i] < 0);
+                        }
+                    }
+                    if (__any_sync(0xffffffffu, neg_any)) {
+                        if (neg_any) {
+                            // the deficits go to the age group's biggest remainder (first maximum); that element is
+                            // kept in a scalar while the deficits are applied in compartment order
+                            int max_index = 0;
+                            double best = rem[0], mm = m[0];
+#pragma unroll
+                            for (int i = 1; i < NC; ++i) {
+                                if (rem[i] > best) {
+                                    best      = rem[i];
+                                    max_index = i;
+                                    mm        = m[i];
+                                }
+                            }
+#pragma unroll
+                            for (int j = 0; j < NC; ++j) {
+                                if (rem[j] < 0) {
+                                    mm -= rem[j];
+                                    if (j == max_index) {
+                                        mm += rem[j];
+                                    }
+                                    else {
+                                        m[j] += rem[j];
+                                    }
+                                    ++fixes;
+                                }
+                            }
+#pragma unroll
+                            for (int k = 0; k < NC; ++k) {
+                                if (k == max_index) {
+                                    m[k] = mm;
+                                }
+                            }
+                        }
+                    }
+                    if (any_cur) {
+#pragma unroll
+                        for (int i = 0; i < NC; ++i) {
+                            yt[i] -= m[i];
+                        }
+                        store10(yrec, yt);
+                        if (fixes) {
+                            store10(mrec, m);
+                            atomicAdd(a.st.counters + (rbase + to_cur) * 4 + 3, fixes);
+                        }
+                    }
+                    e_cur  = lane_on ? e_n : -1;
+                    to_cur = to_n;
+                    e_n = e_f, to_n = to_f;
+                }
+            }
+            else {
+                if (s >= 1) {
+                    // the commuters of chunk s - 1 come home: Y[source] += m, edge after edge (scalars, not arrays)
+                    const int from = from_prev;
+                    const double* bp = B + ((s - 1) % 3) * bstride;
+                    constexpr int NN = W * NC; // == n
+                    for (int comp = threadIdx.x - 2 * TW * 32; comp < NN; comp += EXB_P2_WARPS * 32) {
+                        double acc       = Y[(size_t)from * NN + comp];
+                        const double* mp = bp + comp;
+#pragma unroll 5
+                        for (int k = 0; k < EPP; ++k) {
+                            acc += mp[k * NN];
+                        }
+                        Y[(size_t)from * NN + comp] = acc;
+                    }
+                }
+                from_prev = from_next;
+                from_next = s + 1 < nchunks ? __ldg(a.xsrc + 2 * (s + 1)) : 0;
+                if (hazard) {
+                    asm volatile("bar.sync 1, %0;" ::"r"((TW + EXB_P2_WARPS) * 32) : "memory");
+                }
+                stage_source(s + 2);
+            }
+            __syncthreads();
+        }
+        {
+            const double2* src = reinterpret_cast<const double2*>(Y);
+            double2* dst       = reinterpret_cast<double2*>(a.y_out + rbase * n);
+            for (size_t i = threadIdx.x; i < total2; i += EXB_THREADS) {
+                dst[i] = src[i];
+            }
+        }
+    }
+}
+
+// ---------------------------------------------------------------------------------------------------------------
 // get_mobility_results support (single simulations that ask for it; not on the ensemble path).
 // Departure: the mobile population of edge e is coeff_e * u_from (u = snapshot * (1 - damping) * mobility factor *
 // commuter nondetection * mask, see integrate.cu), instant.h:608-615.
@@ -1223,6 +1583,30 @@ __global__ void record_daily_kernel(int N, int n, const double* __restrict__ y, 
     }
 }
 
+static int edge_sm_count()
+{
+    static int sms = 0;
+    if (sms == 0) {
+        int dev = 0;
+        cudaGetDevice(&dev);
+        cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev);
+    }
+    return sms;
+}
+// MIO_EXACT_REPLAY=blocks selects return_exact_blocks_kernel. The default is return_exact_kernel: measured on the
+// benchmark (10 000 runs x 400 counties, 38 124 replays per pass) the block-parallel kernel needs 165-220 ms per pass
+// against 143 ms -- one run per SM (its state fills the shared memory) leaves two or three warps per scheduler, and the
+// chain ordered-sum -> test of the next source's block (the source of a block is nearly always a destination of the
+// next one in a county graph) costs about 3000 cycles per source node at that occupancy; see DESIGN.md section 9.
+static bool exact_replay_blocks()
+{
+    static const bool blocks = [] {
+        const char* v = std::getenv("MIO_EXACT_REPLAY");
+        return v != nullptr && std::strcmp(v, "blocks") == 0;
+    }();
+    return blocks;
+}
+
 template <int G, int LAY>
 static cudaError_t launch_edges_g(const EdgeArgs& a, int which, cudaStream_t stream)
 {
@@ -1281,7 +1665,31 @@ static cudaError_t launch_edges_g(const EdgeArgs& a, int which, cudaStream_t str
     else {
         // a.run_list: [R] run indices, a.list_count: [1]
         cudaMemsetAsync(a.list_count, 0, sizeof(int), stream);
-        collect_flagged_kernel<256><<<(unsigned)a.num_runs, 256, 0, stream>>>(a, a.run_list, a.list_count);
+        // block-parallel replay when the run's state fits into shared memory (ODE-SECIR; not when the per-edge
+        // populations are recorded)
+        const size_t shmem_x = sizeof(double) * ((size_t)a.geo.N * a.geo.n + (size_t)3 * a.xepp * a.geo.n + W * NC + W * 18 + 2 * (a.geo.n + W + 1)) +
+                               sizeof(int) * (size_t)3 * a.xepp;
+        bool blocks = false;
+        if constexpr (LAY == 1) {
+            blocks = a.xslot != nullptr && a.edge_m == nullptr && shmem_x <= 227 * 1024 && exact_replay_blocks();
+        }
+        collect_flagged_kernel<256><<<(unsigned)a.num_runs, 256, 0, stream>>>(a, a.run_list, a.list_count, blocks ? 0 : 1);
+        if constexpr (LAY == 1) {
+            if (blocks) {
+                const unsigned ctas = (unsigned)std::min(a.num_runs, edge_sm_count() * (shmem_x <= 110 * 1024 ? 2 : 1));
+                if (a.csr.factorized && a.csr.w_edge != nullptr) {
+                    auto kern = return_exact_blocks_kernel<G, true>;
+                    cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)shmem_x);
+                    kern<<<ctas, EXB_THREADS, shmem_x, stream>>>(a, a.run_list, a.list_count);
+                }
+                else {
+                    auto kern = return_exact_blocks_kernel<G, false>;
+                    cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)shmem_x);
+                    kern<<<ctas, EXB_THREADS, shmem_x, stream>>>(a, a.run_list, a.list_count);
+                }
+                return cudaGetLastError();
+            }
+        }
         const unsigned warps = (unsigned)((a.num_runs + NPW - 1) / NPW);
         if (a.csr.factorized && a.csr.w_edge != nullptr) {
             return_exact_kernel<G, LAY, true><<<warps, 32, 0, stream>>>(a, a.run_list, a.list_count);

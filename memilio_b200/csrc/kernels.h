@@ -33,6 +33,14 @@ namespace miocu
 #endif
 constexpr int INTEGRATE_THREADS = MIO_INTEGRATE_THREADS;
 constexpr int EDGE_THREADS      = MIO_EDGE_THREADS;
+// return_exact_blocks_kernel: T warps (in-order test / fix-up of a chunk of edges), as many R warps (returning
+// populations of the next chunk), S warps (ordered sum into the source node)
+#ifndef MIO_EXB_P1_WARPS
+#define MIO_EXB_P1_WARPS 5
+#endif
+constexpr int EXB_P1_WARPS = MIO_EXB_P1_WARPS;
+constexpr int EXB_P2_WARPS = 2;
+constexpr int EXB_THREADS  = (2 * EXB_P1_WARPS + EXB_P2_WARPS) * 32;
 
 struct TrajectoryBuffers {
     int capacity;   // 0 = off
@@ -108,6 +116,13 @@ struct EdgeArgs {
     double t_dep;        // return only: departure time of the returning commuters
     double dt;           // dt of this graph step
     int num_runs;
+    // schedule of the block-parallel literal replay (return_exact_blocks_kernel), run-invariant: chunk s = up to xepp
+    // consecutive edges of ONE source node with distinct destinations; xslot[s][q] = {edge or -1, destination}
+    const int* xslot;    // [xchunks][xepp][2] or null
+    const int* xsrc;     // [xchunks][2] {source node, number of edges | hazard << 16} of a chunk; hazard: the source of
+                         // the previous chunk is a destination of this one
+    int xchunks, xepp;
+    double* xdamp;       // [R][n] scratch: mobility damping of a flagged run at the departure time
     double* edge_m;      // [R][E][n] or null: mobile population of every edge (MobilityEdge::m_mobile_population's last
                          // value) written by the literal replay, for get_mobility_results
 };

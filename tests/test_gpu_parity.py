@@ -225,3 +225,29 @@ def test_mobility_results_match_oracle(G, N):
         fixups += int(cnt[r][:, 3].sum())
     if G == 6:
         assert fixups > 0  # returns with the order dependent fix-up were recorded
+
+
+def test_block_parallel_exact_replay_matches_oracle():
+    # MIO_EXACT_REPLAY=blocks: the literal replay parallel over the edges of one source node
+    # (return_exact_blocks_kernel, not the default: see DESIGN.md section 9) is bit-identical in its fix-up decisions
+    import os
+    import subprocess
+    import sys
+    code = (
+        "import sys, numpy as np; sys.path.insert(0, 'tests'); import oracle_lib\n"
+        "from memilio_b200 import capi, synthetic\n"
+        "p = synthetic.county_problem(N=40, runs=5, G=6, max_out_degree=8, n_seeded=3, damping_day=5.0, perturb=0.1)\n"
+        "sim = capi.GraphSimulation(p); sim.advance(12.0); st = sim.state(); cnt = sim.counters(); s = sim.stats()\n"
+        "tot = 0\n"
+        "for r in range(5):\n"
+        "    ref = oracle_lib.graph_simulate(p, r, 12.0)\n"
+        "    np.testing.assert_allclose(st[r], ref['state'], rtol=1e-8, atol=1e-9)\n"
+        "    np.testing.assert_array_equal(cnt[r], ref['counters'])\n"
+        "    tot += int(ref['counters'][:, 3].sum())\n"
+        "assert tot > 0 and s['exact_replays'] > 0\n"
+        "print('ok', tot, s['exact_replays'])\n")
+    root = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+    r = subprocess.run([sys.executable, "-c", code], cwd=root, env=dict(os.environ, MIO_EXACT_REPLAY="blocks"),
+                       capture_output=True, text=True, timeout=600)
+    assert r.returncode == 0, r.stderr[-3000:]
+    assert r.stdout.startswith("ok")
