@@ -72,6 +72,8 @@ def parse():
                          "(0 = one record for all days; needed when runs x columns does not fit the device)")
     ap.add_argument("--model", default="osecir", choices=["osecir", "osecirvvs"],
                     help="osecir = BASELINE configs[3] (the default bench line); osecirvvs = configs[4]'s model on one GPU")
+    ap.add_argument("--flow-sim", action="store_true",
+                    help="the nodes are mio::FlowSimulation (SURVEY 8f-1): the cumulative flows are integrated (osecir)")
     ap.add_argument("--sim-kind", default="model", choices=["model", "base"],
                     help="osecirvvs node type: osecirvvs::Simulation (vaccination, ADL mobility hooks) or the plain "
                          "mio::Simulation the reference's graph benchmark instantiates")
@@ -147,6 +149,8 @@ def workload_config(args):
                         f"(BASELINE configs[3]): {args.runs} runs/GPU x {args.nodes} counties x {args.days:g} days",
             "runs_per_gpu": args.runs, "counties": args.nodes, "edges": None, "age_groups": 6, "days": args.days,
             "dt_graph": 0.5, "integrator": "cash_karp54 abs 1e-10 rel 1e-5", "parallelism": f"runs sharded x{args.gpus}",
+            "node_simulation": "mio::FlowSimulation (cumulative flows integrated, error control on the flows)"
+            if args.flow_sim else "osecir::Simulation",
             "l2_policy": "inputs larger than L2 (state 4 x %.2f GB per GPU)" % (args.runs * args.nodes * 480 / 1e9),
             "sampling": "osecir::draw_sample(graph) semantics, threefry2x32 seeds {1..6}, uniform ranges of set_covid_parameters",
             "outputs": "per-node daily p05/p25/p50/p75/p95 + mean of age-summed compartments and of the node-summed state"}
@@ -167,7 +171,8 @@ def cpu_baseline(args, sample_runs, workers, study_runs):
         out = os.path.join(tmp, f"w{r}.npz")
         outs.append(out)
         procs.append(subprocess.Popen(
-            [sys.executable, worker, "--model", args.model, "--sim-kind", args.sim_kind, "--nodes", str(args.nodes),
+            [sys.executable, worker, "--model", args.model, "--sim-kind", args.sim_kind, "--flow-sim", str(int(args.flow_sim)),
+             "--nodes", str(args.nodes),
              "--days", str(args.days), "--sample-runs", str(sample_runs), "--study-runs", str(study_runs),
              "--workers", str(workers), "--rank", str(r), "--out", out, "--start-file", start],
             stdout=subprocess.DEVNULL, env=dict(os.environ, OMP_NUM_THREADS="1")))
@@ -301,6 +306,7 @@ def main():
     else:
         graph = synthetic.covid_study_graph(N=N)
     ps = study.ParameterStudy(graph, 0.0, T, 0.5, world * R)
+    ps.flow_simulation = int(args.flow_sim)
     problem = ps.sample(run0, R)
     num_groups = graph.num_groups
     host_sampling_s = time.perf_counter() - t_s

@@ -333,7 +333,8 @@ class ParameterStudy:
                             ct_max_loc=g.num_locations, ct_max_pts=self.ct_max_pts,
                             node_ctable=node_ct if nct > 1 else None, mobtables=mob, mob_max_pts=self.mob_max_pts,
                             integrator=self.integrator, t0=self.t0, dt_graph=self.dt, sim_kind=g.sim_kind,
-                            vacc_partial=g.vacc_partial, vacc_full=g.vacc_full)
+                            vacc_partial=g.vacc_partial, vacc_full=g.vacc_full,
+                            flow_simulation=int(getattr(self, "flow_simulation", 0)))
 
     # -- run ----------------------------------------------------------------------------------------------------
     def run(self, process_result: Optional[Callable] = None, batch: int = 1024, device: int = 0, rank: int = 0,

@@ -17,20 +17,23 @@ sys.path.insert(0, ROOT)
 sys.path.insert(0, os.path.join(ROOT, "tests"))
 
 
-def build_study(model, nodes, days, sim_kind, total_runs):
+def build_study(model, nodes, days, sim_kind, total_runs, flow_sim=0):
     from memilio_b200 import flat, study, synthetic
     if model == "osecirvvs":
         graph = synthetic.vvs_study_graph(N=nodes, days=int(days) + 1,
                                           sim_kind=flat.SIM_MODEL if sim_kind == "model" else flat.SIM_BASE)
     else:
         graph = synthetic.covid_study_graph(N=nodes)
-    return study.ParameterStudy(graph, 0.0, float(days), 0.5, total_runs)
+    ps = study.ParameterStudy(graph, 0.0, float(days), 0.5, total_runs)
+    ps.flow_simulation = int(flow_sim)  # the nodes are mio::FlowSimulation (compartments/flow_simulation.h:37-97)
+    return ps
 
 
 def main():
     ap = argparse.ArgumentParser()
     ap.add_argument("--model", default="osecir")
     ap.add_argument("--sim-kind", default="model")
+    ap.add_argument("--flow-sim", type=int, default=0)
     ap.add_argument("--nodes", type=int, default=400)
     ap.add_argument("--days", type=float, default=100.0)
     ap.add_argument("--sample-runs", type=int, required=True, help="runs of the whole CPU sample (all workers)")
@@ -42,7 +45,7 @@ def main():
     a = ap.parse_args()
     import numpy as np
     import oracle_lib
-    ps = build_study(a.model, a.nodes, a.days, a.sim_kind, a.study_runs)
+    ps = build_study(a.model, a.nodes, a.days, a.sim_kind, a.study_runs, a.flow_sim)
     problem = oracle_lib.sample_problem(ps, 0, 1)  # graph topology and capacities for the oracle's descriptors
     # distribute_runs(sample_runs, workers, rank), parameter_studies.h:354-367
     base, rem = divmod(a.sample_runs, a.workers)

@@ -6,6 +6,7 @@
 #include "mio_oracle_vvs.hpp"
 #include "mio_oracle_analyze.hpp"
 #include "mio_oracle_seir.hpp"
+#include "mio_oracle_npis.hpp"
 #include "../include/mio_cuda.h"
 
 #include <cstring>
@@ -276,6 +277,171 @@ int orc_simulate_flows(int G, const double* pset, const double* local, const dou
 {
     return orc_simulate_flows_stepwise(G, pset, local, ct, max_loc, max_pts_ct, y0, t0, 1, &tmax, dt, integ, max_pts,
                                        out_t, out_y, out_f, out_dt, counters);
+}
+
+// ---- dynamic NPIs (mio_oracle_npis.hpp) ----------------------------------------------------------------------------
+// Flat description of DynamicNPIs<FP> (epidemiology/dynamic_npis.h:40-120): per threshold ONE list of DampingSamplings.
+struct orc_npi_desc {
+    int32_t num_thresholds;
+    const double* thresholds;  // [num_thresholds]
+    const int32_t* npi_ptr;    // [num_thresholds + 1] into the DampingSampling arrays
+    const double* npi_value;   // [total]
+    const int32_t* npi_level;  // [total]
+    const int32_t* npi_type;   // [total]
+    const int32_t* idx_ptr;    // [total + 1] into npi_matrix_idx
+    const int32_t* npi_matrix_idx;
+    const double* npi_weights; // [total][num_weights]
+    int32_t num_weights;
+    int32_t reserved;
+    double duration, delay, base, directive_begin, directive_end;
+};
+
+static DynamicNPIs npis_from_flat(const orc_npi_desc* d)
+{
+    DynamicNPIs n;
+    n.duration        = d->duration;
+    n.delay           = d->delay;
+    n.base            = d->base;
+    n.directive_begin = d->directive_begin;
+    n.directive_end   = d->directive_end;
+    for (int t = 0; t < d->num_thresholds; ++t) {
+        std::vector<DampingSamplingO> list;
+        for (int k = d->npi_ptr[t]; k < d->npi_ptr[t + 1]; ++k) {
+            DampingSamplingO ds;
+            ds.value = d->npi_value[k];
+            ds.level = d->npi_level[k];
+            ds.type  = d->npi_type[k];
+            ds.matrix_indices.assign(d->npi_matrix_idx + d->idx_ptr[k], d->npi_matrix_idx + d->idx_ptr[k + 1]);
+            ds.group_weights.assign(d->npi_weights + size_t(k) * d->num_weights,
+                                    d->npi_weights + size_t(k + 1) * d->num_weights);
+            list.push_back(ds);
+        }
+        n.set_threshold(d->thresholds[t], list);
+    }
+    return n;
+}
+
+// a group of column vector damping expressions (rows x 1) with constant-valued dampings given as lists
+static DampingExprGroup group_from_lists(int num_mats, int rows, const int32_t* counts, const double* times,
+                                         const int32_t* levels, const int32_t* types, const double* values)
+{
+    DampingExprGroup g;
+    int k = 0;
+    for (int m = 0; m < num_mats; ++m) {
+        g.m.emplace_back(Mat(rows, 1, 1.0));
+        for (int i = 0; i < counts[m]; ++i, ++k) {
+            g.m.back().dampings.add(Damping{times[k], levels[k], types[k], Mat(rows, 1, values[k])});
+        }
+    }
+    return g;
+}
+
+// implement_dynamic_npis (dynamic_npis.h:335-395) on a group of rows x 1 expressions, make_matrix = identity (the
+// make_mask of cpp/tests/test_dynamic_npis.cpp). Output per matrix: count, then (time, level, type, coefficients[rows]).
+int orc_npi_implement(int num_mats, int rows, const int32_t* counts, const double* times, const int32_t* levels,
+                      const int32_t* types, const double* values, int num_calls, const orc_npi_desc* calls,
+                      const double* begins, const double* ends, int32_t* out_counts, double* out_times,
+                      int32_t* out_levels, int32_t* out_types, double* out_coeffs, int capacity)
+{
+    auto g = group_from_lists(num_mats, rows, counts, times, levels, types, values);
+    for (int c = 0; c < num_calls; ++c) {
+        auto n = npis_from_flat(&calls[c]);
+        implement_dynamic_npis(g, n.thresholds.at(0).second, begins[c], ends[c], [rows](const Vec& w) {
+            Mat m(rows, 1);
+            for (int i = 0; i < rows; ++i) {
+                m(i, 0) = w[size_t(i)];
+            }
+            return m;
+        });
+    }
+    int k = 0;
+    for (int m = 0; m < num_mats; ++m) {
+        out_counts[m] = int32_t(g.m[size_t(m)].dampings.list.size());
+        for (auto& d : g.m[size_t(m)].dampings.list) {
+            if (k >= capacity) {
+                return -1;
+            }
+            out_times[k]  = d.time;
+            out_levels[k] = d.level;
+            out_types[k]  = d.type;
+            std::copy(d.m.a.begin(), d.m.a.end(), out_coeffs + size_t(k) * rows);
+            ++k;
+        }
+    }
+    return k;
+}
+
+// get_active_damping / get_damping_indices (dynamic_npis.h:270-306) on one 1 x 1 expression
+double orc_npi_active_damping(int count, const double* times, const int32_t* levels, const int32_t* types,
+                              const double* values, int lvl, int type, double t)
+{
+    int32_t c = count;
+    auto g    = group_from_lists(1, 1, &c, times, levels, types, values);
+    return get_active_damping(g.m[0], lvl, type, t)(0, 0);
+}
+int orc_npi_damping_indices(int count, const double* times, const int32_t* levels, const int32_t* types,
+                            const double* values, int lvl, int type, double begin, double end, int32_t* out)
+{
+    int32_t c = count;
+    auto g    = group_from_lists(1, 1, &c, times, levels, types, values);
+    auto idx  = get_damping_indices(g.m[0], lvl, type, begin, end);
+    for (size_t i = 0; i < idx.size(); ++i) {
+        out[i] = int32_t(idx[i]);
+    }
+    return int(idx.size());
+}
+
+// osecir::Simulation with DynamicNPIsInfectedSymptoms (model.h:289-367) for one node. The contact locations are
+// given by their baselines in `ct` (no change points there) plus the raw list of predefined dampings
+// (st_*: location, time, level, type, matrix [G*G]). frozen: the MockSimulation of the reference's tests.
+// Outputs: the trajectory like orc_simulate; the contact matrix at the query times q_t, out_cm[nq][G*G]; the number
+// of dampings of every location afterwards, out_ndamp[max_loc]; returns the number of time points.
+int orc_npi_simulate(int G, const double* pset, const double* local, const double* ct, int max_loc, int max_pts_ct,
+                     const double* y0, double t0, int num_t, const double* tmaxs, double dt,
+                     const mio_integrator_desc* integ, const orc_npi_desc* npi, int frozen, int num_static,
+                     const int32_t* st_loc, const double* st_time, const int32_t* st_level, const int32_t* st_type,
+                     const double* st_mat, int nq, const double* q_t, double* out_cm, int32_t* out_ndamp, int max_pts,
+                     double* out_t, double* out_y, int64_t* counters)
+{
+    auto m = osecir_from_flat(G, pset, local, ct, max_loc, max_pts_ct, y0);
+    auto& cp = m.parameters.ContactPatterns;
+    for (auto& e : cp.m) {
+        e.dampings.clear();
+    }
+    for (int k = 0; k < num_static; ++k) {
+        Mat dm(G, G);
+        std::copy(st_mat + size_t(k) * G * G, st_mat + size_t(k + 1) * G * G, dm.a.begin());
+        cp.m.at(size_t(st_loc[k])).dampings.add(Damping{st_time[k], st_level[k], st_type[k], dm});
+    }
+    osecir::NpiSimulation sim(m, npis_from_flat(npi), t0, dt);
+    sim.frozen = frozen != 0;
+    sim.sim.set_integrator_core(make_core(*integ));
+    for (int k = 0; k < num_t; ++k) {
+        sim.advance(tmaxs[k]);
+    }
+    const auto& cpo = sim.sim.model.parameters.ContactPatterns;
+    for (int k = 0; k < nq; ++k) {
+        for (int i = 0; i < G; ++i) {
+            for (int j = 0; j < G; ++j) {
+                out_cm[(size_t(k) * G + i) * G + j] = cpo.at(q_t[k], i, j);
+            }
+        }
+    }
+    for (size_t l = 0; l < cpo.m.size(); ++l) {
+        out_ndamp[l] = int32_t(cpo.m[l].dampings.list.size());
+    }
+    const int n = int(sim.sim.result.n());
+    for (int k = 0; k < std::min(n, max_pts); ++k) {
+        out_t[k] = sim.sim.result.times[k];
+        std::copy(sim.sim.result.values[k].begin(), sim.sim.result.values[k].end(), out_y + int64_t(k) * G * osecir::NC);
+    }
+    if (counters) {
+        counters[0] = sim.sim.integrator.n_steps;
+        counters[1] = sim.sim.integrator.core->n_rejected;
+        counters[2] = sim.sim.integrator.core->n_forced;
+        counters[3] = sim.num_implemented;
+    }
+    return n;
 }
 
 // osecirvvs::Simulation (sim_kind = MIO_SIM_MODEL) or mio::Simulation<osecirvvs::Model> (MIO_SIM_BASE) for one node

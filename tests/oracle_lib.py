@@ -245,7 +245,8 @@ def sample_problem(ps, run0: int, count: int) -> GraphProblem:
                         edge_coeff=g.edge_coeff, psets=psets, ctables=ctables, node_local=local, y0=y0,
                         ct_max_loc=g.num_locations, ct_max_pts=ps.ct_max_pts, mobtables=mob,
                         mob_max_pts=ps.mob_max_pts, integrator=ps.integrator, t0=ps.t0, dt_graph=ps.dt,
-                        sim_kind=g.sim_kind, vacc_partial=g.vacc_partial, vacc_full=g.vacc_full)
+                        sim_kind=g.sim_kind, vacc_partial=g.vacc_partial, vacc_full=g.vacc_full,
+                        flow_simulation=int(getattr(ps, "flow_simulation", 0)))
 
 
 def simulate_flows(G, pset, local, ct, max_loc, max_pts, y0, t0, tmax, dt, integrator=None, capacity=4096):
@@ -289,3 +290,125 @@ def graph_simulate_flows(p: GraphProblem, run: int, t_max: float):
                                        cdefs.lptr(cnt))
     assert steps >= 0
     return dict(state=state, flows=flows, counters=cnt, steps=steps)
+
+
+# ---- dynamic NPIs (oracle/mio_oracle_npis.hpp) -------------------------------------------------------------------------
+class NpiDesc(C.Structure):
+    _fields_ = [("num_thresholds", C.c_int32), ("thresholds", cdefs.c_double_p), ("npi_ptr", cdefs.c_int32_p),
+                ("npi_value", cdefs.c_double_p), ("npi_level", cdefs.c_int32_p), ("npi_type", cdefs.c_int32_p),
+                ("idx_ptr", cdefs.c_int32_p), ("npi_matrix_idx", cdefs.c_int32_p), ("npi_weights", cdefs.c_double_p),
+                ("num_weights", C.c_int32), ("reserved", C.c_int32), ("duration", C.c_double), ("delay", C.c_double),
+                ("base", C.c_double), ("directive_begin", C.c_double), ("directive_end", C.c_double)]
+
+
+def npi_desc(thresholds, duration=14.0, delay=0.0, base=1.0, directive_begin=None, directive_end=None):
+    """thresholds: list of (value, [dict(value, level, type, matrix_indices, group_weights), ...])"""
+    fi = np.finfo(np.float64)
+    keep = dict(th=np.array([t for t, _ in thresholds], dtype=np.float64), ptr=[0], val=[], lvl=[], typ=[], iptr=[0],
+                idx=[], w=[])
+    for _, lst in thresholds:
+        for s in lst:
+            keep["val"].append(s["value"])
+            keep["lvl"].append(s["level"])
+            keep["typ"].append(s["type"])
+            keep["idx"] += list(s["matrix_indices"])
+            keep["iptr"].append(len(keep["idx"]))
+            keep["w"].append(np.asarray(s["group_weights"], dtype=np.float64))
+        keep["ptr"].append(len(keep["val"]))
+    nw = len(keep["w"][0]) if keep["w"] else 1
+    arr = dict(th=keep["th"], ptr=np.array(keep["ptr"], np.int32), val=np.array(keep["val"] or [0.0], np.float64),
+               lvl=np.array(keep["lvl"] or [0], np.int32), typ=np.array(keep["typ"] or [0], np.int32),
+               iptr=np.array(keep["iptr"], np.int32), idx=np.array(keep["idx"] or [0], np.int32),
+               w=np.ascontiguousarray(np.stack(keep["w"]) if keep["w"] else np.zeros((1, 1))))
+    if len(arr["th"]) == 0:
+        arr["th"] = np.zeros(1)
+    d = NpiDesc(len(thresholds), cdefs.dptr(arr["th"]), cdefs.iptr(arr["ptr"]), cdefs.dptr(arr["val"]),
+                cdefs.iptr(arr["lvl"]), cdefs.iptr(arr["typ"]), cdefs.iptr(arr["iptr"]), cdefs.iptr(arr["idx"]),
+                cdefs.dptr(arr["w"]), nw, 0, duration, delay, base,
+                float(fi.min) if directive_begin is None else directive_begin,
+                float(fi.max) if directive_end is None else directive_end)
+    d._keep = arr
+    return d
+
+
+def _damping_lists(mats):
+    """mats: per matrix a list of (value, level, type, time)"""
+    counts = np.array([len(m) for m in mats], np.int32)
+    flatl = [d for m in mats for d in m]
+    times = np.array([d[3] for d in flatl] or [0.0], np.float64)
+    levels = np.array([d[1] for d in flatl] or [0], np.int32)
+    types = np.array([d[2] for d in flatl] or [0], np.int32)
+    values = np.array([d[0] for d in flatl] or [0.0], np.float64)
+    return counts, times, levels, types, values
+
+
+def npi_implement(mats, rows, calls, capacity=64):
+    """implement_dynamic_npis on a group of rows x 1 expressions with constant dampings; calls: list of
+    (npi sampling dict, begin, end). Returns per matrix a list of (time, level, type, coeffs[rows])."""
+    counts, times, levels, types, values = _damping_lists(mats)
+    dl = [npi_desc([(0.0, [c[0]])]) for c in calls]  # (kept alive: the array below holds plain copies of the structs)
+    descs = (NpiDesc * len(calls))(*dl)
+    begins = np.array([c[1] for c in calls], np.float64)
+    ends = np.array([c[2] for c in calls], np.float64)
+    oc = np.zeros(len(mats), np.int32)
+    ot = np.zeros(capacity)
+    ol = np.zeros(capacity, np.int32)
+    oy = np.zeros(capacity, np.int32)
+    ov = np.zeros((capacity, rows))
+    L = lib()
+    n = L.orc_npi_implement(len(mats), rows, cdefs.iptr(counts), cdefs.dptr(times), cdefs.iptr(levels),
+                            cdefs.iptr(types), cdefs.dptr(values), len(calls), descs, cdefs.dptr(begins),
+                            cdefs.dptr(ends), cdefs.iptr(oc), cdefs.dptr(ot), cdefs.iptr(ol), cdefs.iptr(oy),
+                            cdefs.dptr(ov), capacity)
+    assert n >= 0
+    out, k = [], 0
+    for m in range(len(mats)):
+        out.append([(ot[k + i], int(ol[k + i]), int(oy[k + i]), ov[k + i].copy()) for i in range(oc[m])])
+        k += oc[m]
+    return out
+
+
+def npi_active_damping(dampings, lvl, typ, t):
+    counts, times, levels, types, values = _damping_lists([dampings])
+    L = lib()
+    L.orc_npi_active_damping.restype = C.c_double
+    return L.orc_npi_active_damping(int(counts[0]), cdefs.dptr(times), cdefs.iptr(levels), cdefs.iptr(types),
+                                    cdefs.dptr(values), lvl, typ, C.c_double(t))
+
+
+def npi_damping_indices(dampings, lvl, typ, begin, end):
+    counts, times, levels, types, values = _damping_lists([dampings])
+    out = np.zeros(max(1, len(dampings)), np.int32)
+    n = lib().orc_npi_damping_indices(int(counts[0]), cdefs.dptr(times), cdefs.iptr(levels), cdefs.iptr(types),
+                                      cdefs.dptr(values), lvl, typ, C.c_double(begin), C.c_double(end), cdefs.iptr(out))
+    return [int(x) for x in out[:n]]
+
+
+def npi_simulate(G, pset, local, ct, max_loc, max_pts, y0, t0, tmaxs, dt, npi, integrator=None, frozen=False,
+                 static=(), query=(), capacity=8192):
+    """osecir::Simulation with DynamicNPIsInfectedSymptoms on the oracle. static: predefined dampings as
+    (location, time, level, type, matrix[G][G]). Returns dict(t, y, contact[nq][G][G], num_dampings[max_loc],
+    counters[4] = accepted, rejected, forced, NPIs implemented)."""
+    integ = integrator if integrator is not None else cdefs.integrator_desc()
+    args = [np.ascontiguousarray(a, dtype=np.float64) for a in (pset, local, ct, y0)]
+    tm = np.ascontiguousarray(tmaxs, dtype=np.float64)
+    sl = np.array([s[0] for s in static] or [0], np.int32)
+    stt = np.array([s[1] for s in static] or [0.0], np.float64)
+    slv = np.array([s[2] for s in static] or [0], np.int32)
+    sty = np.array([s[3] for s in static] or [0], np.int32)
+    sm = np.ascontiguousarray(np.stack([np.asarray(s[4], dtype=np.float64).reshape(G, G) for s in static])
+                              if static else np.zeros((1, G, G)))
+    q = np.ascontiguousarray(query if len(query) else [0.0], dtype=np.float64)
+    ocm = np.zeros((len(q), G, G))
+    ond = np.zeros(max_loc, np.int32)
+    ot = np.zeros(capacity)
+    oy = np.zeros((capacity, G * 10))
+    cnt = np.zeros(4, dtype=np.int64)
+    L = lib()
+    n = L.orc_npi_simulate(G, cdefs.dptr(args[0]), cdefs.dptr(args[1]), cdefs.dptr(args[2]), max_loc, max_pts,
+                           cdefs.dptr(args[3]), C.c_double(t0), len(tm), cdefs.dptr(tm), C.c_double(dt),
+                           C.byref(integ), C.byref(npi), int(frozen), len(static), cdefs.iptr(sl), cdefs.dptr(stt),
+                           cdefs.iptr(slv), cdefs.iptr(sty), cdefs.dptr(sm), len(query), cdefs.dptr(q),
+                           cdefs.dptr(ocm), cdefs.iptr(ond), capacity, cdefs.dptr(ot), cdefs.dptr(oy), cdefs.lptr(cnt))
+    assert 0 < n <= capacity
+    return dict(t=ot[:n].copy(), y=oy[:n].copy(), contact=ocm[:len(query)], num_dampings=ond, counters=cnt)
