@@ -160,6 +160,18 @@ public:
     {
         return m_v.data();
     }
+    T* data()
+    {
+        return m_v.data();
+    }
+    Index size() const
+    {
+        return m_r * m_c;
+    }
+    bool operator==(const MatrixX& o) const
+    {
+        return m_r == o.m_r && m_c == o.m_c && m_v == o.m_v;
+    }
     void setConstant(T v)
     {
         for (auto& x : m_v) {

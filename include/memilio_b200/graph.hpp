@@ -299,6 +299,21 @@ struct SimTraits<osecir::Simulation<FP, BaseT>> {
     static constexpr int sim_kind   = MIO_SIM_MODEL;
     static constexpr int NC         = osecir::detail::NC;
     static constexpr bool flow_simulation = osecir::Simulation<FP, BaseT>::is_flow_simulation;
+    static bool has_dynamic_npis(const osecir::Model<FP>& m)
+    {
+        return !m.parameters.template get<osecir::DynamicNPIsInfectedSymptoms<FP>>().get_thresholds().empty();
+    }
+    // the dynamic NPI decision of a node before a graph step that starts at t (see osecir::Simulation)
+    static bool check_dynamic_npis(osecir::Simulation<FP, BaseT>& sim, FP t, FP t_step_end)
+    {
+        const bool changed = sim.check_dynamic_npis(t);
+        const FP npi_end   = sim.get_dynamic_npi_end();
+        if (t < npi_end && npi_end < t_step_end - 1e-10) {
+            throw std::runtime_error("GraphSimulation: a dynamic NPI ends inside a graph step (the node would be "
+                                     "integrated in two chunks); align duration and delay with the graph's dt");
+        }
+        return changed;
+    }
     static const ContactMatrixGroup<FP>& contacts(const osecir::Model<FP>& m)
     {
         return static_cast<const ContactMatrixGroup<FP>&>(m.parameters.template get<osecir::ContactPatterns<FP>>());
@@ -318,6 +333,7 @@ struct SimTraits<FlowSimulation<FP, osecir::Model<FP>>>
 };
 
 struct PackedGraph {
+    bool dynamic_npis = false;  // nodes carry dynamic NPIs: one contact table per node, room for added change points
     int flow_simulation = 0;    // the nodes are FlowSimulations
     std::vector<double> flows0; // [N][G*15] the flows they continue from
     int model_kind = MIO_MODEL_OSECIR, sim_kind = MIO_SIM_MODEL, vacc_days = 0;
@@ -359,6 +375,12 @@ PackedGraph pack_graph(const GraphT& g, int ct_max_pts_min = 1)
     p.integrator   = g.nodes()[0].property.get_simulation().get_integrator_core().desc();
     int L = 1, K = ct_max_pts_min;
     for (auto& nd : g.nodes()) {
+        p.dynamic_npis = p.dynamic_npis || Traits::has_dynamic_npis(nd.property.get_simulation().get_model());
+    }
+    if (p.dynamic_npis) {
+        K = std::max(K, 24);
+    }
+    for (auto& nd : g.nodes()) {
         const auto& cm = Traits::contacts(nd.property.get_simulation().get_model());
         L = std::max(L, int(cm.get_num_matrices()));
         K = std::max(K, osecir::detail::num_change_points(cm));
@@ -378,7 +400,7 @@ PackedGraph pack_graph(const GraphT& g, int ct_max_pts_min = 1)
             p.psets.push_back(std::move(ps));
         }
         auto ct = osecir::detail::contact_table(Traits::contacts(model), p.G, L, K);
-        auto ic = std::find(p.ctables.begin(), p.ctables.end(), ct);
+        auto ic = p.dynamic_npis ? p.ctables.end() : std::find(p.ctables.begin(), p.ctables.end(), ct);
         p.node_ctable.push_back(int32_t(ic - p.ctables.begin()));
         if (ic == p.ctables.end()) {
             p.ctables.push_back(std::move(ct));
@@ -559,6 +581,7 @@ public:
             auto p = detail::pack_graph<FP>(m_graph);
             m_dev  = std::make_shared<detail::DeviceGraph>(p, m_dt, 1, int(p.psets.size()), int(p.ctables.size()), 0);
             m_dev->set_run(0, p, int(p.psets.size()), int(p.ctables.size()));
+            m_ct_shape = {p.ct_max_loc, p.ct_max_pts, int(p.ctables.size())};
             // MobilityEdge(coeffs, save_indices): the backend records one set of index groups for all edges
             for (auto& e : m_graph.edges()) {
                 const auto& si = e.property.get_parameters().get_save_indices();
@@ -599,6 +622,7 @@ public:
             if (m_t + dt > t_max) {
                 dt = t_max - m_t;
             }
+            update_dynamic_npis(m_t, m_t + dt);
             m_t += dt;
             cuda_check(mio_cuda_advance(m_dev->get(), m_t));
             cuda_check(mio_cuda_get_state(m_dev->get(), 0, 1, state.data()));
@@ -656,6 +680,38 @@ public:
             m_graph.nodes()[k].property.get_result().add_time_point(t, v);
         }
     }
+    // dynamic NPIs of the nodes (ode_secir/model.h:299-353): every node takes its decision before the graph step; the
+    // contact tables of nodes whose contact patterns changed are replaced on the device
+    void update_dynamic_npis(FP t, FP t_step_end)
+    {
+        using Sim    = std::decay_t<decltype(m_graph.nodes()[0].property.get_simulation())>;
+        using Traits = detail::SimTraits<Sim>;
+        bool any = false, changed = false;
+        for (auto& nd : m_graph.nodes()) {
+            any = any || Traits::has_dynamic_npis(nd.property.get_simulation().get_model());
+        }
+        if (!any) {
+            return;
+        }
+        if (m_dt > 1.0) {
+            throw std::runtime_error("GraphSimulation: dynamic NPIs need a graph step of at most one day");
+        }
+        for (auto& nd : m_graph.nodes()) {
+            changed = Traits::check_dynamic_npis(nd.property.get_simulation(), t, t_step_end) || changed;
+        }
+        if (changed) {
+            auto p = detail::pack_graph<FP>(m_graph);
+            if (m_ct_shape != std::array<int, 3>{p.ct_max_loc, p.ct_max_pts, int(p.ctables.size())}) {
+                throw std::runtime_error("GraphSimulation: the dynamic NPIs added more contact change points than the "
+                                         "device tables hold");
+            }
+            std::vector<double> ct;
+            for (auto& tbl : p.ctables) {
+                ct.insert(ct.end(), tbl.begin(), tbl.end());
+            }
+            cuda_check(mio_cuda_set_contact_tables(m_dev->get(), 0, 1, ct.data()));
+        }
+    }
     // graphs of FlowSimulation nodes: the flows of every node at the end of the graph step
     void append_flow_time_point(FP t)
     {
@@ -686,6 +742,7 @@ private:
     std::shared_ptr<detail::DeviceGraph> m_dev;
     std::vector<std::vector<size_t>> m_save; // saved_compartment_indices common to the edges
     int m_mob_cap = 0, m_mob_seen = 0;
+    std::array<int, 3> m_ct_shape{0, 0, 0}; // contact table shape of the device handle (locations, points, tables)
 };
 
 // make_mobility_sim, metapopulation_mobility_instant.h:656-678

@@ -557,6 +557,23 @@ public:
         Eigen::MatrixX<FP> m;
         int level, type;
         FP time;
+        // the reference's accessors (epidemiology/damping.h:60-120)
+        const Eigen::MatrixX<FP>& get_coeffs() const
+        {
+            return m;
+        }
+        DampingLevel get_level() const
+        {
+            return DampingLevel(level);
+        }
+        DampingType get_type() const
+        {
+            return DampingType(type);
+        }
+        SimulationTime<FP> get_time() const
+        {
+            return SimulationTime<FP>(time);
+        }
     };
     ContactMatrix() = default;
     explicit ContactMatrix(const Eigen::MatrixX<FP>& baseline)
@@ -597,13 +614,65 @@ public:
     {
         add_damping(m, DampingLevel(0), DampingType(0), t);
     }
+    // the list is kept sorted by (time, type, level); a damping with the same key replaces the old one
+    // (Dampings::add_, epidemiology/damping.h:606-617)
     void add_damping(const Eigen::MatrixX<FP>& m, DampingLevel l, DampingType ty, SimulationTime<FP> t)
     {
-        m_dampings.push_back(RawDamping{m, l.value, ty.value, t.get()});
+        RawDamping d{m, l.value, ty.value, t.get()};
+        auto before = [](const RawDamping& a, const RawDamping& b) {
+            return std::make_tuple(a.time, a.type, a.level) < std::make_tuple(b.time, b.type, b.level);
+        };
+        auto pos = std::lower_bound(m_dampings.begin(), m_dampings.end(), d, before);
+        if (pos != m_dampings.end() && !before(d, *pos)) {
+            *pos = d;
+        }
+        else {
+            m_dampings.insert(pos, d);
+        }
+    }
+    void remove_damping(size_t i)
+    {
+        m_dampings.erase(m_dampings.begin() + std::ptrdiff_t(i));
     }
     void clear_dampings()
     {
         m_dampings.clear();
+    }
+    // contact_matrix.h:190-194, damping.h:381-396: baseline - D(t) (baseline - minimum), D(t) from the cache of
+    // accumulated dampings (built by the library) with the cosine ramp over the day before a change point
+    Eigen::MatrixX<FP> get_matrix_at(SimulationTime<FP> t) const
+    {
+        const Eigen::Index R = m_baseline.rows(), C = m_baseline.cols();
+        const size_t K = m_dampings.size(), RC = size_t(R) * size_t(C);
+        std::vector<double> times(K), mats(K * RC), ot(std::max<size_t>(K, 1)), om(std::max<size_t>(K, 1) * RC);
+        std::vector<int32_t> levels(K), types(K);
+        for (size_t k = 0; k < K; ++k) {
+            times[k]  = m_dampings[k].time;
+            levels[k] = m_dampings[k].level;
+            types[k]  = m_dampings[k].type;
+            std::copy(m_dampings[k].m.data(), m_dampings[k].m.data() + RC, mats.begin() + std::ptrdiff_t(k * RC));
+        }
+        int32_t nout = 0;
+        cuda_check(mio_damping_cache_build(int32_t(R), int32_t(C), int32_t(K), times.data(), levels.data(), types.data(),
+                                           mats.data(), &nout, ot.data(), om.data()));
+        int ub = 0; // first change point after t
+        while (ub < nout && !(t.get() < ot[size_t(ub)])) {
+            ++ub;
+        }
+        Eigen::MatrixX<FP> out(R, C);
+        const double pi = 3.141592653589793238462643383279502884;
+        for (size_t j = 0; j < RC; ++j) {
+            const double left = ub > 0 ? om[size_t(ub - 1) * RC + j] : 0.0;
+            double d          = left;
+            if (ub < nout) { // smoother_cosine over [change point - 1, change point], math/smoother.h:32-55
+                const double xr = ot[size_t(ub)], xl = xr - 1.0, right = om[size_t(ub) * RC + j];
+                if (t.get() > xl) {
+                    d = 0.5 * (left - right) * std::cos(pi / (xr - xl) * (t.get() - xl)) + 0.5 * (left + right);
+                }
+            }
+            out.data()[j] = m_baseline.data()[j] - d * (m_baseline.data()[j] - m_minimum.data()[j]);
+        }
+        return out;
     }
     const std::vector<RawDamping>& get_dampings() const
     {
@@ -641,6 +710,26 @@ public:
         for (auto& m : m_matrices) {
             m.clear_dampings();
         }
+    }
+    // contact_matrix.h:392-400: sum over the members
+    Eigen::MatrixX<FP> get_matrix_at(SimulationTime<FP> t) const
+    {
+        Eigen::MatrixX<FP> sum = m_matrices.at(0).get_matrix_at(t);
+        for (size_t l = 1; l < m_matrices.size(); ++l) {
+            const Eigen::MatrixX<FP> ml = m_matrices[l].get_matrix_at(t);
+            for (Eigen::Index j = 0; j < sum.size(); ++j) {
+                sum.data()[j] = sum.data()[j] + ml.data()[j];
+            }
+        }
+        return sum;
+    }
+    auto begin()
+    {
+        return m_matrices.begin();
+    }
+    auto end()
+    {
+        return m_matrices.end();
     }
 
 private:
@@ -893,6 +982,7 @@ using DefaultIntegratorCore = AdaptiveCoreT<FP, MIO_INTEGRATOR_CK54>; // compart
 
 } // namespace mio
 
+#include "npis.hpp"
 #include "osecir.hpp"
 #include "graph.hpp"
 #include "study.hpp"

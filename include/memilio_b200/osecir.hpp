@@ -35,6 +35,11 @@ public:
     {
         return m_v[get_flat_index(i)];
     }
+    // populations.h:108-112: the entry of index i in a flat vector of compartment values
+    FP get_from(const Eigen::VectorX<FP>& y, Index i) const
+    {
+        return y[Eigen::Index(get_flat_index(i))];
+    }
     size_t numel() const
     {
         return m_v.size();
@@ -193,6 +198,16 @@ struct ContactPatterns {
     }
 };
 
+// DynamicNPIsInfectedSymptoms, parameters.h:395-410: NPIs that follow the relative number of symptomatic infections
+template <class FP = ScalarType>
+struct DynamicNPIsInfectedSymptoms {
+    using Type = DynamicNPIs<FP>;
+    static Type get_default(AgeGroup)
+    {
+        return Type();
+    }
+};
+
 template <class FP = ScalarType>
 class Parameters
 {
@@ -208,7 +223,7 @@ class Parameters
                    Slot<RelativeTransmissionNoSymptoms<FP>>, Slot<RecoveredPerInfectedNoSymptoms<FP>>,
                    Slot<RiskOfInfectionFromSymptomatic<FP>>, Slot<MaxRiskOfInfectionFromSymptomatic<FP>>,
                    Slot<SeverePerInfectedSymptoms<FP>>, Slot<CriticalPerSevere<FP>>, Slot<DeathsPerSevere<FP>>,
-                   Slot<DeathsPerCritical<FP>>>;
+                   Slot<DeathsPerCritical<FP>>, Slot<DynamicNPIsInfectedSymptoms<FP>>>;
 
 public:
     explicit Parameters(AgeGroup num_groups)
@@ -587,7 +602,72 @@ public:
     {
         return m_dt;
     }
+    // Simulation::advance (model.h:289-367): without dynamic NPIs one integration to tmax; with them chunks of at most
+    // a day (ending at the NPI's end), the threshold is looked at before every chunk
     Eigen::VectorX<FP> advance(FP tmax)
+    {
+        if (m_model.parameters.template get<DynamicNPIsInfectedSymptoms<FP>>().get_thresholds().empty()) {
+            return advance_chunk(tmax);
+        }
+        FP t = m_result.get_last_time();
+        while (t < tmax) {
+            check_dynamic_npis(t);
+            FP dt_eff = std::min<FP>(1.0, tmax - t);
+            if (t < m_npi_end) {
+                dt_eff = std::min<FP>(dt_eff, m_npi_end - t);
+            }
+            advance_chunk(t + dt_eff);
+            t = t + dt_eff;
+        }
+        return m_result.get_last_value();
+    }
+    // The decision taken before a chunk that starts at t (model.h:303-353): is the biggest exceeded threshold stronger
+    // than the NPI in force, or has that one expired? Then its dampings enter the contact patterns from t + delay
+    // (no delay at t <= 0 and for a renewal at expiry) for `duration` days, inside the directive window; the damping
+    // times are one day later than the NPI times so that the smoothing ramp lies in the future. Returns whether the
+    // contact patterns changed.
+    bool check_dynamic_npis(FP t)
+    {
+        auto& npis = m_model.parameters.template get<DynamicNPIsInfectedSymptoms<FP>>();
+        if (npis.get_thresholds().empty()) {
+            return false;
+        }
+        const FP window_begin = npis.get_directive_begin().get(), window_end = npis.get_directive_end().get();
+        auto at_least = [](FP a, FP b) { // floating_point_greater_equal(a, b, 1e-10)
+            return !(a - b < -(1e-10 + std::numeric_limits<FP>::min() * std::max(std::abs(a), std::abs(b))));
+        };
+        if (!at_least(t, window_begin) || !(t < window_end)) {
+            return false;
+        }
+        const FP level = get_infections_relative(*this, t, m_result.get_last_value()) * npis.get_base_value();
+        auto hit       = npis.get_max_exceeded_threshold(level);
+        const bool expired = at_least(t, m_npi_end);
+        if (hit == npis.get_thresholds().end() || !(hit->first > m_npi_threshold || expired)) {
+            return false;
+        }
+        const bool renewal = expired && !(hit->first > m_npi_threshold);
+        const FP delay     = (renewal || !(t > 0)) ? FP(0) : npis.get_implementation_delay().get();
+        const FP start     = t + delay;
+        if (!(start < window_end)) {
+            return false;
+        }
+        const FP end    = std::min<FP>(window_end, start + npis.get_duration().get());
+        m_npi_threshold = hit->first;
+        m_npi_end       = end;
+        const FP damp_from = (!renewal && start > 0) ? start + 1 : start;
+        implement_dynamic_npis<FP>(m_model.parameters.template get<ContactPatterns<FP>>().get_cont_freq_mat(),
+                                   hit->second, SimulationTime<FP>(damp_from), SimulationTime<FP>(end + 1),
+                                   [](const Eigen::VectorX<FP>& g) {
+                                       return make_contact_damping_matrix<FP>(g);
+                                   });
+        return true;
+    }
+    // end of the dynamic NPI in force (a chunk must not step over it, model.h:355-361)
+    FP get_dynamic_npi_end() const
+    {
+        return m_npi_end;
+    }
+    Eigen::VectorX<FP> advance_chunk(FP tmax)
     {
         const int G   = int(m_model.parameters.get_num_groups().value);
         const int n   = G * detail::NC;
@@ -661,7 +741,20 @@ private:
     FP m_t0, m_dt;
     TimeSeries<FP> m_result, m_flow_result;
     std::shared_ptr<OdeIntegratorCore<FP>> m_core;
+    FP m_npi_threshold = -std::numeric_limits<FP>::max(); // threshold and end of the dynamic NPI in force
+    FP m_npi_end       = 0;
 };
+
+// get_infections_relative, model.h:413-423: symptomatic infections relative to the model's total population
+template <class FP, class BaseT>
+FP get_infections_relative(const Simulation<FP, BaseT>& sim, FP /*t*/, const Eigen::VectorX<FP>& y)
+{
+    FP sum_inf = 0;
+    for (auto i = AgeGroup(0); i < sim.get_model().parameters.get_num_groups(); i++) {
+        sum_inf += sim.get_model().populations.get_from(y, {i, InfectionState::InfectedSymptoms});
+    }
+    return sum_inf / sim.get_model().populations.get_total();
+}
 
 } // namespace osecir
 

@@ -589,6 +589,14 @@ namespace detail
 template <class FP, bool BASE>
 struct SimTraits<osecirvvs::SimulationT<FP, BASE>> {
     static constexpr bool flow_simulation = false;
+    static bool has_dynamic_npis(const osecirvvs::Model<FP>&) // (not part of this backend for ODE-SECIRVVS)
+    {
+        return false;
+    }
+    static bool check_dynamic_npis(osecirvvs::SimulationT<FP, BASE>&, FP, FP)
+    {
+        return false;
+    }
     static constexpr int model_kind = MIO_MODEL_OSECIRVVS;
     static constexpr int sim_kind   = BASE ? MIO_SIM_BASE : MIO_SIM_MODEL;
     static constexpr int NC         = osecirvvs::detail::NC;

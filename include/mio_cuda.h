@@ -242,6 +242,11 @@ MIO_API int mio_cuda_get_flows(mio_handle* h, int32_t slot0, int32_t count, doub
 /* the flows a FlowSimulation continues from (mio_cuda_set_runs starts them at zero, FlowModel::get_initial_flows,
  * cpp/memilio/compartments/flow_model.h:146-149): flows[count][N][G*15], to be called after mio_cuda_set_runs */
 MIO_API int mio_cuda_set_flows(mio_handle* h, int32_t slot0, int32_t count, const double* flows);
+/* Dynamic NPIs (cpp/models/ode_secir/model.h:299-353, cpp/memilio/epidemiology/dynamic_npis.h:335-395) change the
+ * contact patterns of a node while the simulation runs: the host evaluates the thresholds between graph steps (the
+ * C++ facade does, osecir::Simulation / GraphSimulation) and replaces the contact tables of the run,
+ * ctables[count][num_ctables][mio_ctable_size] as in mio_run_data. The simulation continues where it is. */
+MIO_API int mio_cuda_set_contact_tables(mio_handle* h, int32_t slot0, int32_t count, const double* ctables);
 /* ... and the whole flow series (needs traj_capacity > 0): values[count][N][traj_capacity][G*15]; the time points
  * are those of mio_cuda_get_trajectory, whose values are the populations that follow from the flows
  * (compute_population_results, cpp/memilio/compartments/flow_simulation_base.h:84-97) */

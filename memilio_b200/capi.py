@@ -30,7 +30,7 @@ EXPORTS = [
     "mio_cuda_ensemble_reduce", "mio_cuda_select_percentiles", "mio_cuda_reduce_host_columns",
     "mio_cuda_ensemble_set_window", "mio_cuda_comm_get_unique_id", "mio_cuda_comm_create", "mio_cuda_comm_destroy",
     "mio_cuda_ensemble_reduce_sharded", "mio_cuda_enable_mobility_results", "mio_cuda_get_mobility_results",
-    "mio_cuda_get_flows", "mio_cuda_get_flow_trajectory", "mio_cuda_set_flows",
+    "mio_cuda_get_flows", "mio_cuda_get_flow_trajectory", "mio_cuda_set_flows", "mio_cuda_set_contact_tables",
 ]
 KERNEL_CLASSES = ["integrate", "depart", "return", "return_exact", "record", "ensemble"]
 

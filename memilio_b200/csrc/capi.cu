@@ -1305,6 +1305,37 @@ int mio_cuda_get_flows(mio_handle* h, int32_t slot0, int32_t count, double* out)
     return MIO_OK;
 }
 
+// Replace the contact tables of resident runs (dynamic NPIs change a node's contact patterns during the simulation,
+// cpp/models/ode_secir/model.h:299-353): ctables[count][num_ctables][ctable_size], the layout of mio_cuda_set_runs.
+int mio_cuda_set_contact_tables(mio_handle* h, int32_t slot0, int32_t count, const double* ctables)
+{
+    if (int rc = check_slots(h, slot0, count, ctables)) {
+        return rc;
+    }
+    CUDA_TRY(cudaSetDevice(h->device));
+    const Geometry& geo = h->geo;
+    const size_t csz    = (size_t)geo.ctable_stride, nct = (size_t)geo.num_ctables;
+    for (size_t r = 0; r < (size_t)count; ++r) {
+        for (size_t c = 0; c < nct; ++c) {
+            const double* ct = ctables + (r * nct + c) * csz;
+            const int L      = (int)ct[0];
+            if (L < 1 || L > geo.ct_max_loc) {
+                return fail(MIO_INVALID_VALUE, "contact table: number of locations out of range");
+            }
+            for (int l = 0; l < L; ++l) {
+                if (ct[1 + l] < 0 || ct[1 + l] > geo.ct_max_pts) {
+                    return fail(MIO_INVALID_VALUE, "contact table: number of change points out of range");
+                }
+            }
+        }
+    }
+    CUDA_TRY(cudaMemcpy2DAsync(h->d_run_block + (size_t)slot0 * geo.block_stride + geo.ct_off,
+                               sizeof(double) * geo.block_stride, ctables, sizeof(double) * nct * csz,
+                               sizeof(double) * nct * csz, (size_t)count, cudaMemcpyHostToDevice, h->stream));
+    CUDA_TRY(cudaStreamSynchronize(h->stream));
+    return MIO_OK;
+}
+
 int mio_cuda_set_flows(mio_handle* h, int32_t slot0, int32_t count, const double* flows)
 {
     if (int rc = check_slots(h, slot0, count, flows)) {

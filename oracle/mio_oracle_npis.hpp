@@ -194,20 +194,16 @@ inline double get_infections_relative(const Model& model, const Vec& y)
     return sum_inf / total;
 }
 
-// osecir::Simulation with DynamicNPIsInfectedSymptoms (model.h:289-367). `frozen`: the base advance appends the last
-// value unchanged (the MockSimulation of cpp/tests/test_dynamic_npis.cpp).
-struct NpiSimulation {
-    orc::Simulation<Model> sim;
+// The dynamic NPI part of osecir::Simulation (model.h:289-367: DynamicNPIsInfectedSymptoms, m_dynamic_npi) around a
+// node's base simulation. `frozen`: the base advance appends the last value unchanged (the MockSimulation of
+// cpp/tests/test_dynamic_npis.cpp).
+struct NpiController {
     DynamicNPIs npis;
     std::pair<double, double> dynamic_npi = {-std::numeric_limits<double>::max(), 0.0};
     bool frozen                           = false;
     int num_implemented                   = 0;
-    NpiSimulation(const Model& m, const DynamicNPIs& n, double t0 = 0., double dt = 0.1)
-        : sim(m, t0, dt)
-        , npis(n)
-    {
-    }
-    void base_advance(double tmax)
+
+    void base_advance(orc::Simulation<Model>& sim, double tmax) const
     {
         if (frozen) {
             const Vec v = sim.result.last();
@@ -217,10 +213,10 @@ struct NpiSimulation {
             sim.advance(tmax);
         }
     }
-    Vec& advance(double tmax)
+    Vec& advance(orc::Simulation<Model>& sim, double tmax)
     {
         if (npis.thresholds.empty()) {
-            base_advance(tmax);
+            base_advance(sim, tmax);
             return sim.result.last();
         }
         auto& contact_patterns = sim.model.parameters.ContactPatterns;
@@ -262,10 +258,24 @@ struct NpiSimulation {
             if (t < npi_end) {
                 dt_eff = std::min(dt_eff, npi_end - t);
             }
-            base_advance(t + dt_eff);
+            base_advance(sim, t + dt_eff);
             t = t + dt_eff;
         }
         return sim.result.last();
+    }
+};
+
+struct NpiSimulation {
+    orc::Simulation<Model> sim;
+    NpiController ctl;
+    NpiSimulation(const Model& m, const DynamicNPIs& n, double t0 = 0., double dt = 0.1)
+        : sim(m, t0, dt)
+    {
+        ctl.npis = n;
+    }
+    Vec& advance(double tmax)
+    {
+        return ctl.advance(sim, tmax);
     }
 };
 

@@ -414,7 +414,7 @@ int orc_npi_simulate(int G, const double* pset, const double* local, const doubl
         cp.m.at(size_t(st_loc[k])).dampings.add(Damping{st_time[k], st_level[k], st_type[k], dm});
     }
     osecir::NpiSimulation sim(m, npis_from_flat(npi), t0, dt);
-    sim.frozen = frozen != 0;
+    sim.ctl.frozen = frozen != 0;
     sim.sim.set_integrator_core(make_core(*integ));
     for (int k = 0; k < num_t; ++k) {
         sim.advance(tmaxs[k]);
@@ -439,7 +439,7 @@ int orc_npi_simulate(int G, const double* pset, const double* local, const doubl
         counters[0] = sim.sim.integrator.n_steps;
         counters[1] = sim.sim.integrator.core->n_rejected;
         counters[2] = sim.sim.integrator.core->n_forced;
-        counters[3] = sim.num_implemented;
+        counters[3] = sim.ctl.num_implemented;
     }
     return n;
 }
@@ -486,7 +486,8 @@ static int graph_simulate_impl(const mio_graph_desc* desc, const mio_run_data* r
                                double* out_dt, int64_t* out_counters, double* out_halfsteps, int max_halfsteps,
                                int ncomp, MakeModel&& make_model,
                                const std::function<void(GraphSim<M>&)>& on_done = nullptr,
-                               const std::vector<std::vector<size_t>>& save_indices = {})
+                               const std::vector<std::vector<size_t>>& save_indices = {},
+                               const std::function<void(int, SimulationNode<M>&, double, double)>& node_advance = nullptr)
 {
     const int G = desc->num_groups, N = desc->num_nodes, E = desc->num_edges;
     const int n = G * ncomp;
@@ -525,8 +526,13 @@ static int graph_simulate_impl(const mio_graph_desc* desc, const mio_run_data* r
         if (g.t + dts > t_max) {
             dts = t_max - g.t;
         }
-        for (auto& nd : g.nodes) {
-            nd.advance(g.t, dts);
+        for (int k = 0; k < N; ++k) {
+            if (node_advance) { // (nodes whose simulation type overrides advance, e.g. dynamic NPIs)
+                node_advance(k, g.nodes[size_t(k)], g.t, dts);
+            }
+            else {
+                g.nodes[size_t(k)].advance(g.t, dts);
+            }
         }
         g.t += dts;
         for (auto& e : g.edges) {
@@ -642,6 +648,59 @@ int orc_graph_simulate(const mio_graph_desc* desc, const mio_run_data* run, doub
 {
     return graph_simulate_dispatch(desc, run, t_max, out_state, out_dt, out_counters, out_halfsteps, max_halfsteps,
                                    [](auto&) {});
+}
+
+// orc_graph_simulate (ODE-SECIR) with DynamicNPIsInfectedSymptoms on the nodes: node_npis[N] (num_thresholds = 0: none).
+// The nodes' contact tables must come without change points (the dampings live in the lists the NPIs edit).
+// out_cm[N][nq][G*G]: the nodes' contact matrices at the query times afterwards.
+int orc_npi_graph_simulate(const mio_graph_desc* desc, const mio_run_data* run, const orc_npi_desc* node_npis,
+                           double t_max, double* out_state, double* out_halfsteps, int max_halfsteps, int nq,
+                           const double* q_t, double* out_cm, int32_t* out_implemented)
+{
+    if (desc->model != MIO_MODEL_OSECIR) {
+        return -1;
+    }
+    const int G = desc->num_groups, N = desc->num_nodes;
+    const int64_t psz = pset_size(desc->model, G);
+    const int64_t csz = ctable_size(G, desc->ct_max_loc, desc->ct_max_pts);
+    const int n       = G * osecir::NC;
+    std::vector<osecir::NpiController> ctl(size_t(N), osecir::NpiController{});
+    for (int k = 0; k < N; ++k) {
+        ctl[size_t(k)].npis = npis_from_flat(&node_npis[k]);
+    }
+    return graph_simulate_impl<osecir::Model>(
+        desc, run, t_max, out_state, nullptr, nullptr, out_halfsteps, max_halfsteps, osecir::NC,
+        [&](int k) {
+            auto m = osecir_from_flat(G, run->psets + (desc->node_pset ? desc->node_pset[k] : 0) * psz,
+                                      run->node_local + int64_t(k) * MIO_NODE_LOCAL,
+                                      run->ctables + (desc->node_ctable ? desc->node_ctable[k] : 0) * csz,
+                                      desc->ct_max_loc, desc->ct_max_pts, run->y0 + int64_t(k) * n);
+            for (auto& e : m.parameters.ContactPatterns.m) {
+                e.dampings.clear();
+            }
+            return m;
+        },
+        [&](GraphSim<osecir::Model>& g) {
+            for (int k = 0; k < N; ++k) {
+                const auto& cp = g.nodes[size_t(k)].sim.model.parameters.ContactPatterns;
+                for (int q = 0; q < nq; ++q) {
+                    for (int i = 0; i < G; ++i) {
+                        for (int j = 0; j < G; ++j) {
+                            out_cm[((size_t(k) * nq + q) * G + i) * G + j] = cp.at(q_t[q], i, j);
+                        }
+                    }
+                }
+                if (out_implemented) {
+                    out_implemented[k] = ctl[size_t(k)].num_implemented;
+                }
+            }
+        },
+        {},
+        [&](int k, SimulationNode<osecir::Model>& nd, double t, double dts) {
+            // SimulationNode::advance (instant.h:83-90) with osecir::Simulation::advance as the node's advance
+            ctl[size_t(k)].advance(nd.sim, t + dts);
+            nd.last_state = nd.sim.result.last();
+        });
 }
 
 // orc_graph_simulate of a graph of FlowSimulation nodes (desc->flow_simulation = 1, osecir): also the cumulative flows

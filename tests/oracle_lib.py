@@ -412,3 +412,22 @@ def npi_simulate(G, pset, local, ct, max_loc, max_pts, y0, t0, tmaxs, dt, npi, i
                            cdefs.dptr(ocm), cdefs.iptr(ond), capacity, cdefs.dptr(ot), cdefs.dptr(oy), cdefs.lptr(cnt))
     assert 0 < n <= capacity
     return dict(t=ot[:n].copy(), y=oy[:n].copy(), contact=ocm[:len(query)], num_dampings=ond, counters=cnt)
+
+
+def npi_graph_simulate(p: GraphProblem, run: int, t_max: float, node_npis, halfsteps: int = 0, query=()):
+    """orc_graph_simulate with dynamic NPIs on the nodes; node_npis: one npi_desc per node. Returns dict(state,
+    halfsteps[halfsteps][N][n], contact[N][nq][G][G], implemented[N])."""
+    d = p.desc(max_runs=1)
+    rd = p.run_data(run, 1)
+    N, n, G = p.num_nodes, p.n, p.num_groups
+    descs = (NpiDesc * N)(*node_npis)
+    state = np.zeros((N, n))
+    hs = np.zeros((max(halfsteps, 1), N, n))
+    q = np.ascontiguousarray(query if len(query) else [0.0], dtype=np.float64)
+    cm = np.zeros((N, len(q), G, G))
+    impl = np.zeros(N, np.int32)
+    steps = lib().orc_npi_graph_simulate(C.byref(d), C.byref(rd), descs, C.c_double(t_max), cdefs.dptr(state),
+                                         cdefs.dptr(hs), halfsteps, len(query), cdefs.dptr(q), cdefs.dptr(cm),
+                                         cdefs.iptr(impl))
+    assert steps >= 0
+    return dict(state=state, halfsteps=hs[:halfsteps], contact=cm[:, :len(query)], implemented=impl, steps=steps)

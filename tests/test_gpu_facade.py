@@ -274,3 +274,56 @@ def test_reference_contact_changes_example_runs():
     # four flow tables of 11 time points (t = 0 .. 1) and 15 flows were printed
     tab = _table(r.stdout)
     assert tab.shape == (44, 16)
+
+
+# ---- dynamic NPIs through the facade: decisions on the host, integration chunks on the GPU -------------
+def _npi(threshold, value, duration):
+    return oracle_lib.npi_desc([(threshold, [dict(value=value, level=0, type=0, matrix_indices=[0],
+                                                  group_weights=np.ones(1))])], duration=duration, base=50000.0)
+
+
+def test_dynamic_npis_example_single_node_matches_oracle():
+    out = run_example("dynamic_npis", "single")
+    lines = out.strip().splitlines()
+    rows = np.array([[float(w) for w in ln.split()] for ln in lines if not ln.startswith("#")])
+    cm = np.array([float(ln.split()[1]) for ln in lines if ln.startswith("#")])
+    s = scenarios.damping_flow_case(None)  # 10 of 1000 ... overwritten below: 10 of 100, default rates
+    y0 = np.zeros(10)
+    y0[flat.ISY] = 10.0
+    y0[flat.S] = 90.0
+    pset = flat.osecir_pset(1)
+    ref = oracle_lib.npi_simulate(1, pset, s["local"], s["ct"], 1, 2, y0, 0.0, [12.0], 0.1, _npi(1000.0, 0.8, 4.5),
+                                  query=np.arange(14.0))
+    assert ref["counters"][3] >= 2  # the NPI was implemented and renewed
+    assert rows.shape == (len(ref["t"]), 11)
+    np.testing.assert_allclose(rows[:, 0], ref["t"], rtol=1e-8, atol=1e-10)
+    np.testing.assert_allclose(rows[:, 1:], ref["y"], rtol=1e-8, atol=1e-9)
+    np.testing.assert_allclose(cm, ref["contact"][:, 0, 0], rtol=1e-12, atol=1e-12)
+    assert cm.min() == 2.0  # contacts reduced by 0.8 while the NPI is in force (renewed over the whole period)
+
+
+def test_dynamic_npis_example_graph_matches_oracle():
+    out = run_example("dynamic_npis", "graph")
+    lines = out.strip().splitlines()
+    rows = np.array([[float(w) for w in ln.split()] for ln in lines if not ln.startswith("#")])
+    cm = np.array([[float(w) for w in ln.split()[1:]] for ln in lines if ln.startswith("#")])
+    p = scenarios.example_ode_secir_graph()
+    # the example's variant: no predefined damping, other initial values in the first node, the NPI there
+    base = np.full((1, 1), 10.0)
+    ct = flat.contact_table(1, [flat.ContactLocation(base, None, [], [])], 1, 2)
+    p.ctables[0, 0] = ct
+    p.ctables[0, 1] = ct
+    p.y0[0, 0] = 0.0
+    p.y0[0, 0, flat.S] = 9900.0
+    p.y0[0, 0, flat.E] = 100.0
+    p.y0[0, 0, flat.ISY] = 50.0
+    none = oracle_lib.npi_desc([], base=50000.0)
+    ref = oracle_lib.npi_graph_simulate(p, 0, 10.0, [_npi(200.0, 0.6, 4.0), none], halfsteps=20, query=np.arange(12.0))
+    assert ref["implemented"][0] >= 2 and ref["implemented"][1] == 0
+    for k in range(2):
+        node = rows[rows[:, 1] == k]
+        assert node.shape == (21, 12)
+        np.testing.assert_array_equal(node[:, 0], np.arange(21) * 0.5)
+        np.testing.assert_allclose(node[1:, 2:], ref["halfsteps"][:, k], rtol=1e-8, atol=1e-9)
+        np.testing.assert_allclose(cm[cm[:, 0] == k][:, 1], ref["contact"][k, :, 0, 0], rtol=1e-12, atol=1e-12)
+    assert cm[cm[:, 0] == 0][:, 1].min() < 4.01 and np.all(cm[cm[:, 0] == 1][:, 1] == 10.0)
