@@ -196,10 +196,22 @@ public:
     {
         return m_saved_compartment_indices;
     }
+    // dynamic NPIs on the mobility coefficients (metapopulation_mobility_instant.h:225-245, :549-566). The device keeps
+    // one mobility damping table per run, so edges that adapt their coefficients individually are refused by
+    // GraphSimulation::advance (loudly) rather than ignored.
+    const DynamicNPIs<FP>& get_dynamic_npis_infected() const
+    {
+        return m_dynamic_npis;
+    }
+    void set_dynamic_npis_infected(const DynamicNPIs<FP>& v)
+    {
+        m_dynamic_npis = v;
+    }
 
 private:
     MobilityCoefficientGroup<FP> m_coefficients;
     std::vector<std::vector<size_t>> m_saved_compartment_indices;
+    DynamicNPIs<FP> m_dynamic_npis;
 };
 
 // MobilityEdge, metapopulation_mobility_instant.h:270-420: parameters only; apply_mobility runs in csrc/edges.cu
@@ -687,6 +699,12 @@ public:
         using Sim    = std::decay_t<decltype(m_graph.nodes()[0].property.get_simulation())>;
         using Traits = detail::SimTraits<Sim>;
         bool any = false, changed = false;
+        for (auto& e : m_graph.edges()) {
+            if (!e.property.get_parameters().get_dynamic_npis_infected().get_thresholds().empty()) {
+                throw std::runtime_error("GraphSimulation: dynamic NPIs on mobility edges are not supported by this "
+                                         "backend (one mobility damping table per run)");
+            }
+        }
         for (auto& nd : m_graph.nodes()) {
             any = any || Traits::has_dynamic_npis(nd.property.get_simulation().get_model());
         }

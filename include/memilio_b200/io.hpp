@@ -1,9 +1,11 @@
-// io.hpp -- the few IO entry points the Graph-ODE examples call (cpp/memilio/io/io.h:49-59,354, io/result_io.h:135-215,
-// utils/base_dir.h). The reference writes HDF5; no HDF5 library exists in this build, so save_results / save_edges
-// write the same tables (percentile directories p05..p95, Results / Results_sum per run) as plain CSV. The percentile
-// and mean reductions run on the device (mio_cuda_reduce_host_columns). The HDF5 container is SURVEY 8f-3 ("next").
+// io.hpp -- the few IO entry points the Graph-ODE examples call (cpp/memilio/io/io.h:49-59,354, io/result_io.h:44-215,
+// utils/base_dir.h). save_result writes the reference's HDF5 layout (one group per region id with the datasets Time,
+// Group1..GroupG, Total; io/result_io.cpp:33-100) through the library-free writer of h5lite.hpp;
+// save_results / save_edges produce the reference's files (results_run<i>.h5, results_run<i>_sum.h5, pXX/Results.h5,
+// pXX/Results_sum.h5). The percentile and mean reductions run on the device (mio_cuda_reduce_host_columns).
 #pragma once
 
+#include "h5lite.hpp"
 #include "study.hpp"
 
 #include <filesystem>
@@ -136,6 +138,44 @@ inline IOResult<void> write_csv(const std::vector<TimeSeries<ScalarType>>& nodes
 }
 } // namespace detail
 
+// save_result, io/result_io.h:44, io/result_io.cpp:33-100: per region id a group with "Time" [T], "Group<k>" [T][C] for
+// every age group and "Total" [T][C] (their sum, accumulated in group order)
+inline IOResult<void> save_result(const std::vector<TimeSeries<ScalarType>>& results, const std::vector<int>& ids,
+                                  int num_groups, const std::string& filename)
+{
+    std::vector<h5lite::Group> groups;
+    for (size_t r = 0; r < results.size(); ++r) {
+        const auto& ts  = results[r];
+        const size_t T  = size_t(ts.get_num_time_points());
+        const size_t C  = size_t(ts.get_num_elements()) / size_t(num_groups);
+        h5lite::Group g;
+        g.name = std::to_string(r < ids.size() ? ids[r] : int(r));
+        h5lite::Dataset time{"Time", {T}, {}};
+        for (size_t t = 0; t < T; ++t) {
+            time.values.push_back(ts.get_time(Eigen::Index(t)));
+        }
+        g.datasets.push_back(std::move(time));
+        h5lite::Dataset total{"Total", {T, C}, std::vector<double>(T * C, 0.0)};
+        for (int k = 0; k < num_groups; ++k) {
+            h5lite::Dataset grp{"Group" + std::to_string(k + 1), {T, C}, std::vector<double>(T * C, 0.0)};
+            for (size_t t = 0; t < T; ++t) {
+                for (size_t c = 0; c < C; ++c) {
+                    const double v        = ts[Eigen::Index(t)][Eigen::Index(size_t(k) * C + c)];
+                    grp.values[t * C + c] = v;
+                    total.values[t * C + c] += v;
+                }
+            }
+            g.datasets.push_back(std::move(grp));
+        }
+        g.datasets.push_back(std::move(total));
+        groups.push_back(std::move(g));
+    }
+    if (!h5lite::write_file(filename, groups)) {
+        return failure(StatusCode::FileNotFound, "Failed to open the file " + filename);
+    }
+    return success();
+}
+
 // save_results, io/result_io.h:135-202: per-run results (optional) and the p05/p25/p50/p75/p95 percentiles of the
 // per-node results and of the node-summed results
 template <class Model>
@@ -144,14 +184,14 @@ IOResult<void> save_results(const std::vector<std::vector<TimeSeries<ScalarType>
                             const std::filesystem::path& result_dir, bool save_single_runs = true,
                             bool save_percentiles = true)
 {
-    (void)ensemble_params;
     auto ensemble_result_sum = sum_nodes(ensemble_results);
+    const int num_groups     = int(size_t(ensemble_params.at(0).at(0).parameters.get_num_groups()));
     if (save_single_runs) {
         for (size_t i = 0; i < ensemble_results.size(); ++i) {
-            auto r1 = detail::write_csv(ensemble_result_sum[i], {0},
-                                        result_dir / ("results_run" + std::to_string(i) + "_sum.csv"));
-            auto r2 = detail::write_csv(ensemble_results[i], county_ids,
-                                        result_dir / ("results_run" + std::to_string(i) + ".csv"));
+            auto r1 = save_result(ensemble_result_sum[i], {0}, num_groups,
+                                  (result_dir / ("results_run" + std::to_string(i) + "_sum.h5")).string());
+            auto r2 = save_result(ensemble_results[i], county_ids, num_groups,
+                                  (result_dir / ("results_run" + std::to_string(i) + ".h5")).string());
             if (!r1 || !r2) {
                 return !r1 ? r1 : r2;
             }
@@ -162,8 +202,10 @@ IOResult<void> save_results(const std::vector<std::vector<TimeSeries<ScalarType>
                                                           {"p75", 0.75}, {"p95", 0.95}};
         for (auto& [name, p] : ps) {
             auto dir = create_directories_or_exit(result_dir / name);
-            auto r1  = detail::write_csv(ensemble_percentile(ensemble_result_sum, p), {0}, dir / "Results_sum.csv");
-            auto r2  = detail::write_csv(ensemble_percentile(ensemble_results, p), county_ids, dir / "Results.csv");
+            auto r1  = save_result(ensemble_percentile(ensemble_result_sum, p), {0}, num_groups,
+                                   (dir / "Results_sum.h5").string());
+            auto r2  = save_result(ensemble_percentile(ensemble_results, p), county_ids, num_groups,
+                                   (dir / "Results.h5").string());
             if (!r1 || !r2) {
                 return !r1 ? r1 : r2;
             }

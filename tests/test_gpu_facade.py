@@ -173,6 +173,20 @@ def test_reference_parameter_study_graph_example_runs():
         assert "Seeds: " in r.stdout
         for run in range(10):
             assert f"Run {run} done" in r.stdout
+        # save_results wrote the reference's HDF5 files (io/result_io.h:135-202; tests/h5lite.py reads them)
+        import h5lite
+        out = os.path.join(tmp, "example_results", "ode_secir_parameter_study_graph")
+        res = {q: h5lite.read_result(os.path.join(out, q, "Results.h5")) for q in ("p05", "p50", "p95")}
+        assert sorted(res["p50"]) == [1001, 1002, 1003]
+        g = res["p50"][1001]
+        assert sorted(g) == ["Group%d" % k for k in range(1, 7)] + ["Time", "Total"]
+        np.testing.assert_array_equal(g["Time"], np.arange(g["Time"].shape[0], dtype=float))
+        assert g["Total"].shape == (g["Time"].shape[0], 10)
+        np.testing.assert_allclose(sum(g["Group%d" % k] for k in range(1, 7)), g["Total"], rtol=1e-13)
+        assert np.all(res["p05"][1001]["Total"] <= res["p50"][1001]["Total"] + 1e-9)
+        assert np.all(res["p50"][1001]["Total"] <= res["p95"][1001]["Total"] + 1e-9)
+        total = h5lite.read_result(os.path.join(out, "p50", "Results_sum.h5"))
+        assert list(total) == [0] and total[0]["Total"].shape == g["Total"].shape
 
 
 def test_reference_ode_secirvvs_example_runs_and_matches_oracle():
