@@ -333,7 +333,10 @@ __global__ void __launch_bounds__(EDGE_THREADS, MIO_DEPART_MINBLOCKS) depart_ker
 #endif
 constexpr int DEPART_SMEM_THREADS = MIO_DEPART_SMEM_THREADS;
 
-template <int G, int LAY, int M>
+// NR runs per CTA (1 or 2): the edge list and the weights are the same for every run, so a CTA that stages the
+// emigration vectors of two consecutive runs fetches them once for both (the load/store unit, not HBM, limits this
+// kernel; half of its wavefronts were these run-invariant global loads).
+template <int G, int LAY, int M, int NR>
 __global__ void __launch_bounds__(DEPART_SMEM_THREADS, MIO_DEPART_SMEM_MINBLOCKS) depart_smem_kernel(EdgeArgs a)
 {
     extern __shared__ __align__(16) double smem[];
@@ -342,17 +345,20 @@ __global__ void __launch_bounds__(DEPART_SMEM_THREADS, MIO_DEPART_SMEM_MINBLOCKS
     constexpr int W     = G * LAY;
     constexpr int NPW   = 32 / W;
     constexpr int WARPS = DEPART_SMEM_THREADS / 32;
-    const int run       = blockIdx.x;
-    if (run >= a.num_runs) {
+    const int run0      = blockIdx.x * NR;
+    if (run0 >= a.num_runs) {
         return;
     }
-    stage_run_block(smem, a.st.run_block + (size_t)run * geo.block_stride, geo.block_stride * 8, &mbar);
-    double* us = smem + geo.block_stride;
+    const int nr = min(NR, a.num_runs - run0); // runs of this CTA (the blocks and vectors of consecutive runs are
+                                               // contiguous in global memory)
+    stage_run_block(smem, a.st.run_block + (size_t)run0 * geo.block_stride, nr * geo.block_stride * 8, &mbar);
+    double* us = smem + NR * geo.block_stride;
+    const int run_recs = geo.N * W; // (node, lane) records of one run
     {
         // one (node, age) record per thread and iteration: only its M mobile compartments are read (M loads in
         // flight per thread, no register shuffling of the other compartments)
-        const double* ug = a.u + (size_t)run * geo.N * geo.n;
-        const int total  = geo.N * W;
+        const double* ug = a.u + (size_t)run0 * geo.N * geo.n;
+        const int total  = nr * run_recs;
         int comp[M];
 #pragma unroll
         for (int m = 0; m < M; ++m) {
@@ -376,7 +382,9 @@ __global__ void __launch_bounds__(DEPART_SMEM_THREADS, MIO_DEPART_SMEM_MINBLOCKS
     __shared__ int cm_ok;
     if (threadIdx.x < 32) {
         double lo = 1.0, hi = 0.0;
-        if (geo.num_ctables == 1 && !a.aux_by_node_phase) { // only the right-hand side of the node update needs it
+        // only the right-hand side of the node update needs it (NR == 1: with NR > 1 the node phase provides the
+        // return coefficients, see the launch)
+        if (NR == 1 && geo.num_ctables == 1 && !a.aux_by_node_phase) {
             warp_contact_matrix<G>(smem + geo.ct_off, geo.ct_max_loc, geo.ct_max_pts, a.t, cm_s, lo, hi);
         }
         if (threadIdx.x == 0) {
@@ -386,21 +394,22 @@ __global__ void __launch_bounds__(DEPART_SMEM_THREADS, MIO_DEPART_SMEM_MINBLOCKS
     __syncthreads();
     const double* cm = cm_ok ? cm_s : nullptr;
     EdgeLane<G, LAY> L;
-    L.run            = run;
     const int warp   = threadIdx.x >> 5;
     const int passes = (geo.N + NPW * WARPS - 1) / (NPW * WARPS);
     for (int pass = 0; pass < passes; ++pass) {
-        const int item = (pass * WARPS + warp) * NPW + L.g.lane / W;
-        L.valid        = !L.g.spare() && item < geo.N;
-        L.node         = L.valid ? a.csr.order_in[item] : 0;
-        L.rn           = (size_t)run * geo.N + L.node;
-        const int gl   = L.g.gl;
-        const int beg   = L.valid ? a.csr.in_ptr[L.node] : 0;
-        const int cnt   = L.valid ? a.csr.in_ptr[L.node + 1] - beg : 0;
-        double v[M];
+        const int item   = (pass * WARPS + warp) * NPW + L.g.lane / W;
+        const bool valid = !L.g.spare() && item < geo.N;
+        L.node           = valid ? a.csr.order_in[item] : 0;
+        const int gl     = L.g.gl;
+        const int beg    = valid ? a.csr.in_ptr[L.node] : 0;
+        const int cnt    = valid ? a.csr.in_ptr[L.node + 1] - beg : 0;
+        double v[NR][M];
 #pragma unroll
-        for (int m = 0; m < M; ++m) {
-            v[m] = 0.0;
+        for (int r = 0; r < NR; ++r) {
+#pragma unroll
+            for (int m = 0; m < M; ++m) {
+                v[r][m] = 0.0;
+            }
         }
         // the edge list and weights come from global memory (L2): the batch of BATCH edges after the current one is
         // fetched before the current batch's shared-memory reads and FMAs (software pipeline), so that the index ->
@@ -437,28 +446,37 @@ __global__ void __launch_bounds__(DEPART_SMEM_THREADS, MIO_DEPART_SMEM_MINBLOCKS
                 if (w[j] != 0.0) {
                     const double* p = us + (src[j] * W + gl) * M;
 #pragma unroll
-                    for (int m = 0; m < M; ++m) {
-                        v[m] += w[j] * p[m];
+                    for (int r = 0; r < NR; ++r) {
+#pragma unroll
+                        for (int m = 0; m < M; ++m) {
+                            v[r][m] += w[j] * p[r * run_recs * M + m];
+                        }
                     }
                 }
             }
         }
-        double V[NC];
 #pragma unroll
-        for (int i = 0; i < NC; ++i) {
-            V[i] = 0.0;
-        }
+        for (int r = 0; r < NR; ++r) {
+            double V[NC];
 #pragma unroll
-        for (int m = 0; m < M; ++m) {
-            const int c = a.csr.mob_comp[m];
+            for (int i = 0; i < NC; ++i) {
+                V[i] = 0.0;
+            }
 #pragma unroll
-            for (int i = 0; i < NC; ++i) { // register arrays: select instead of a dynamic index
-                if (i == c) {
-                    V[i] += v[m];
+            for (int m = 0; m < M; ++m) {
+                const int c = a.csr.mob_comp[m];
+#pragma unroll
+                for (int i = 0; i < NC; ++i) { // register arrays: select instead of a dynamic index
+                    if (i == c) {
+                        V[i] += v[r][m];
+                    }
                 }
             }
+            L.run   = run0 + r;
+            L.valid = valid && r < nr;
+            L.rn    = (size_t)(r < nr ? run0 + r : run0) * geo.N + L.node;
+            depart_node_update<G, LAY>(a, geo, L, smem + r * geo.block_stride, V, cm);
         }
-        depart_node_update<G, LAY>(a, geo, L, smem, V, cm);
     }
 }
 
@@ -1628,14 +1646,25 @@ static cudaError_t launch_edges_g(const EdgeArgs& a, int which, cudaStream_t str
         const int M          = a.csr.num_mob <= 5 ? 5 : NC;
         const size_t shmem_u = shmem + sizeof(double) * (size_t)a.geo.N * W * M;
         if (a.csr.factorized && a.csr.num_mob > 0 && shmem_u <= 110 * 1024) {
-            // two CTAs per SM keep both the FP64 tail and the shared-memory gather busy
-            if (M == 5) {
-                auto kern = depart_smem_kernel<G, LAY, 5>;
+            // one CTA of 512 threads per SM; two runs per CTA when the node phase provides the return coefficients and
+            // both runs' vectors fit the shared memory (MIO_DEPART_RUNS=1 keeps one run per CTA, for comparisons)
+            static const bool one_run = [] {
+                const char* v = std::getenv("MIO_DEPART_RUNS");
+                return v != nullptr && std::atoi(v) == 1;
+            }();
+            const bool two = M == 5 && a.aux_by_node_phase && 2 * shmem_u <= 227 * 1024 && !one_run;
+            if (two) {
+                auto kern = depart_smem_kernel<G, LAY, 5, 2>;
+                cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)(2 * shmem_u));
+                kern<<<(unsigned)((a.num_runs + 1) / 2), DEPART_SMEM_THREADS, 2 * shmem_u, stream>>>(a);
+            }
+            else if (M == 5) {
+                auto kern = depart_smem_kernel<G, LAY, 5, 1>;
                 cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)shmem_u);
                 kern<<<(unsigned)a.num_runs, DEPART_SMEM_THREADS, shmem_u, stream>>>(a);
             }
             else {
-                auto kern = depart_smem_kernel<G, LAY, NC>;
+                auto kern = depart_smem_kernel<G, LAY, NC, 1>;
                 cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)shmem_u);
                 kern<<<(unsigned)a.num_runs, DEPART_SMEM_THREADS, shmem_u, stream>>>(a);
             }
