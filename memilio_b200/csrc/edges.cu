@@ -1646,11 +1646,12 @@ static cudaError_t launch_edges_g(const EdgeArgs& a, int which, cudaStream_t str
         const int M          = a.csr.num_mob <= 5 ? 5 : NC;
         const size_t shmem_u = shmem + sizeof(double) * (size_t)a.geo.N * W * M;
         if (a.csr.factorized && a.csr.num_mob > 0 && shmem_u <= 110 * 1024) {
-            // one CTA of 512 threads per SM; two runs per CTA when the node phase provides the return coefficients and
-            // both runs' vectors fit the shared memory (MIO_DEPART_RUNS=1 keeps one run per CTA, for comparisons)
+            // one CTA of 512 threads per SM, one run per CTA. MIO_DEPART_RUNS=2: two runs per CTA (the run-invariant
+            // edge list / weight loads are shared) -- measured slower (148 vs 131 ms per 30 days: 272 B of spills at
+            // 128 registers and half as many CTAs to balance), kept for comparisons only
             static const bool one_run = [] {
                 const char* v = std::getenv("MIO_DEPART_RUNS");
-                return v != nullptr && std::atoi(v) == 1;
+                return !(v != nullptr && std::atoi(v) == 2);
             }();
             const bool two = M == 5 && a.aux_by_node_phase && 2 * shmem_u <= 227 * 1024 && !one_run;
             if (two) {
