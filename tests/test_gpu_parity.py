@@ -94,9 +94,8 @@ def test_county_graph_ensemble_matches_oracle(G, N):
         ref = oracle_lib.graph_simulate(p, r, tmax, halfsteps=24)
         assert_close(state[r], ref["state"], what=f"run {r} final state")
         np.testing.assert_array_equal(cnt[r][:, :3], ref["counters"][:, :3])
-        # fix-ups are applied (and counted) by the literal replay of flagged steps
-        assert abs(int(cnt[r][:, 3].sum()) - int(ref["counters"][:, 3].sum())) <= max(
-            2, 0.02 * ref["counters"][:, 3].sum())
+        # fix-ups are applied (and counted) by the literal replay of flagged steps: per node, equal to the oracle's
+        np.testing.assert_array_equal(cnt[r][:, 3], ref["counters"][:, 3])
         assert_close(dts[r], ref["dt"], rtol=1e-7, what="node dt")
         # daily record = state after the edge phase at integer days (what interpolate_simulation_result returns)
         np.testing.assert_array_equal(daily[r][:, 0], p.y0[r])
@@ -177,7 +176,7 @@ def test_full_size_county_graph_single_run():
     assert_close(state, ref["state"], what="config 3 final state")
     mism = int((cnt[:, :3] != ref["counters"][:, :3]).any(axis=1).sum())
     assert mism == 0, f"{mism} nodes with different accepted/rejected/forced step counts"
-    assert abs(int(cnt[:, 3].sum()) - int(ref["counters"][:, 3].sum())) <= 0.02 * ref["counters"][:, 3].sum()
+    np.testing.assert_array_equal(cnt[:, 3], ref["counters"][:, 3])  # underflow fix-ups per node
 
 
 def test_error_behaviour():

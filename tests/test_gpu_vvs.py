@@ -120,8 +120,7 @@ def test_vvs_graph_variants_match_oracle(name):
         assert_close(state[r], ref["state"], rtol=1e-6 if name == "rkf45" else 1e-8, what=f"{name} run {r}")
         np.testing.assert_array_equal(cnt[r][:, :3], ref["counters"][:, :3])
         fix += int(ref["counters"][:, 3].sum())
-        assert abs(int(cnt[r][:, 3].sum()) - int(ref["counters"][:, 3].sum())) <= max(
-            2, 0.02 * ref["counters"][:, 3].sum())
+        np.testing.assert_array_equal(cnt[r][:, 3], ref["counters"][:, 3])  # underflow fix-ups per node
     print(name, "underflow fix-ups", fix, "replays", st["exact_replays"])
 
 
