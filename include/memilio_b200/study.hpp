@@ -128,6 +128,18 @@ void advance_batch(std::vector<SimT>& sims, double t_max)
     for (auto& s : sims) {
         packed.push_back(pack_graph<FP>(s.get_graph()));
         ct_pts = std::max(ct_pts, packed.back().ct_max_pts);
+        if (packed.back().dynamic_npis) {
+            // the threshold decisions are taken between graph steps by GraphSimulation::advance (one run); a batch
+            // is advanced in one call, so the NPIs would be silently ignored
+            throw std::runtime_error("ParameterStudy: nodes with dynamic NPIs are not supported in batched runs by "
+                                     "this backend (advance the simulations one by one with GraphSimulation::advance)");
+        }
+        for (auto& e : s.get_graph().edges()) {
+            if (!e.property.get_parameters().get_dynamic_npis_infected().get_thresholds().empty()) {
+                throw std::runtime_error("ParameterStudy: dynamic NPIs on mobility edges are not supported by this "
+                                         "backend");
+            }
+        }
     }
     int num_psets = 1, num_ctables = 1, mob_pts = 0;
     for (size_t r = 0; r < sims.size(); ++r) {
