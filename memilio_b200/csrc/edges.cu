@@ -207,7 +207,9 @@ __device__ __forceinline__ void gather_visitors(const EdgeArgs& a, const Geometr
 // Then the return coefficients of k as a destination (lambda_i, ICU adjusted rates) from v0 = y_out at time t.
 // Everything of the departure after the visitor gather: test_commuters bookkeeping, the in-place node update, and the
 // return coefficients of the node as a destination.
-template <int G, int LAY>
+// NODE_AUX: the node phase that follows provides the return coefficients (a.aux_by_node_phase, known at compile time:
+// the right-hand side below is then not part of the kernel at all, which halves its registers)
+template <int G, int LAY, bool NODE_AUX = false>
 __device__ __forceinline__ void depart_node_update(const EdgeArgs& a, const Geometry& geo, const EdgeLane<G, LAY>& L,
                                                    const double* smem, const double (&V)[NC],
                                                    const double* cm = nullptr)
@@ -250,7 +252,7 @@ __device__ __forceinline__ void depart_node_update(const EdgeArgs& a, const Geom
     // return coefficients of this node as destination: get_flows with pop = v0 (ode_secir/model.h:90-153,
     // ode_secirvvs/model.h:199-264). The node phase that follows evaluates exactly this right-hand side (same state,
     // same time) as its first stage and writes them then (aux_by_node_phase).
-    if (!a.aux_by_node_phase) {
+    if constexpr (!NODE_AUX) if (!a.aux_by_node_phase) {
         NodeRhs<G, LAY> rhs;
         rhs.age_rec = pset + PHDR + g.gl * AGE_REC;
         rhs.c.load(rhs.age_rec);
@@ -331,13 +333,20 @@ __global__ void __launch_bounds__(EDGE_THREADS, MIO_DEPART_MINBLOCKS) depart_ker
 #ifndef MIO_DEPART_SMEM_MINBLOCKS
 #define MIO_DEPART_SMEM_MINBLOCKS 1
 #endif
+#ifndef MIO_DEPART_BATCH
+#define MIO_DEPART_BATCH 8
+#endif
+#ifndef MIO_DEPART_SMEM_MINBLOCKS_AUX /* CTAs per SM of the variant without the right-hand side (NODE_AUX) */
+#define MIO_DEPART_SMEM_MINBLOCKS_AUX 1
+#endif
 constexpr int DEPART_SMEM_THREADS = MIO_DEPART_SMEM_THREADS;
 
 // NR runs per CTA (1 or 2): the edge list and the weights are the same for every run, so a CTA that stages the
 // emigration vectors of two consecutive runs fetches them once for both (the load/store unit, not HBM, limits this
 // kernel; half of its wavefronts were these run-invariant global loads).
-template <int G, int LAY, int M, int NR>
-__global__ void __launch_bounds__(DEPART_SMEM_THREADS, MIO_DEPART_SMEM_MINBLOCKS) depart_smem_kernel(EdgeArgs a)
+template <int G, int LAY, int M, int NR, bool NODE_AUX>
+__global__ void __launch_bounds__(DEPART_SMEM_THREADS, NODE_AUX ? MIO_DEPART_SMEM_MINBLOCKS_AUX : MIO_DEPART_SMEM_MINBLOCKS)
+    depart_smem_kernel(EdgeArgs a)
 {
     extern __shared__ __align__(16) double smem[];
     __shared__ __align__(8) uint64_t mbar;
@@ -384,7 +393,7 @@ __global__ void __launch_bounds__(DEPART_SMEM_THREADS, MIO_DEPART_SMEM_MINBLOCKS
         double lo = 1.0, hi = 0.0;
         // only the right-hand side of the node update needs it (NR == 1: with NR > 1 the node phase provides the
         // return coefficients, see the launch)
-        if (NR == 1 && geo.num_ctables == 1 && !a.aux_by_node_phase) {
+        if (NR == 1 && !NODE_AUX && geo.num_ctables == 1 && !a.aux_by_node_phase) {
             warp_contact_matrix<G>(smem + geo.ct_off, geo.ct_max_loc, geo.ct_max_pts, a.t, cm_s, lo, hi);
         }
         if (threadIdx.x == 0) {
@@ -414,7 +423,7 @@ __global__ void __launch_bounds__(DEPART_SMEM_THREADS, MIO_DEPART_SMEM_MINBLOCKS
         // the edge list and weights come from global memory (L2): the batch of BATCH edges after the current one is
         // fetched before the current batch's shared-memory reads and FMAs (software pipeline), so that the index ->
         // value dependency is not exposed once per batch
-        constexpr int BATCH = 8;
+        constexpr int BATCH = MIO_DEPART_BATCH;
         const int mx        = warp_max(cnt);
         int src[BATCH], src_n[BATCH];
         double w[BATCH], w_n[BATCH];
@@ -475,7 +484,7 @@ __global__ void __launch_bounds__(DEPART_SMEM_THREADS, MIO_DEPART_SMEM_MINBLOCKS
             L.run   = run0 + r;
             L.valid = valid && r < nr;
             L.rn    = (size_t)(r < nr ? run0 + r : run0) * geo.N + L.node;
-            depart_node_update<G, LAY>(a, geo, L, smem + r * geo.block_stride, V, cm);
+            depart_node_update<G, LAY, NODE_AUX>(a, geo, L, smem + r * geo.block_stride, V, cm);
         }
     }
 }
@@ -1655,17 +1664,22 @@ static cudaError_t launch_edges_g(const EdgeArgs& a, int which, cudaStream_t str
             }();
             const bool two = M == 5 && a.aux_by_node_phase && 2 * shmem_u <= 227 * 1024 && !one_run;
             if (two) {
-                auto kern = depart_smem_kernel<G, LAY, 5, 2>;
+                auto kern = depart_smem_kernel<G, LAY, 5, 2, true>;
                 cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)(2 * shmem_u));
                 kern<<<(unsigned)((a.num_runs + 1) / 2), DEPART_SMEM_THREADS, 2 * shmem_u, stream>>>(a);
             }
+            else if (M == 5 && a.aux_by_node_phase) {
+                auto kern = depart_smem_kernel<G, LAY, 5, 1, true>;
+                cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)shmem_u);
+                kern<<<(unsigned)a.num_runs, DEPART_SMEM_THREADS, shmem_u, stream>>>(a);
+            }
             else if (M == 5) {
-                auto kern = depart_smem_kernel<G, LAY, 5, 1>;
+                auto kern = depart_smem_kernel<G, LAY, 5, 1, false>;
                 cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)shmem_u);
                 kern<<<(unsigned)a.num_runs, DEPART_SMEM_THREADS, shmem_u, stream>>>(a);
             }
             else {
-                auto kern = depart_smem_kernel<G, LAY, NC, 1>;
+                auto kern = depart_smem_kernel<G, LAY, NC, 1, false>;
                 cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)shmem_u);
                 kern<<<(unsigned)a.num_runs, DEPART_SMEM_THREADS, shmem_u, stream>>>(a);
             }
