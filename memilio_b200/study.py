@@ -388,6 +388,11 @@ class ParameterStudy:
             p = ensemble.DEFAULT_PERCENTILES
         if mode is None:
             mode = ensemble.ENS_AGE_SUM
+        if world > 1:
+            # several ranks share the host: every rank samples with its share of the cores instead of all of them
+            import os
+            if "MIO_SAMPLE_THREADS" not in os.environ:
+                os.environ["MIO_SAMPLE_THREADS"] = str(max(2, (os.cpu_count() or 2) // world))
         if day_block is not None:
             return self._run_ensemble_windows(p, mean, device, rank, world, mode, pinned, int(day_block))
         run0, count = distribute_runs(self.num_runs, world, rank)
@@ -409,15 +414,12 @@ class ParameterStudy:
         bounds = [(i * count // nb, (i + 1) * count // nb) for i in range(nb)]
         if world > 1 and nb >= 2 and count >= 1000:
             # several ranks share the host's cores: sampling is 3-4 times slower per rank and the first batch's sampling
-            # is not hidden behind any GPU work, so a small batch goes first (10 %, the rest in equal parts); every rank
-            # samples with its share of the cores instead of all of them
+            # is not hidden behind any GPU work, so a small batch goes first (10 %, the rest in equal parts)
             first = count // 10
             rest = count - first
             bounds = [(0, first)] + [(first + i * rest // nb, first + (i + 1) * rest // nb) for i in range(nb)]
             nb += 1
-            import os
-            if "MIO_SAMPLE_THREADS" not in os.environ:
-                os.environ["MIO_SAMPLE_THREADS"] = str(max(2, (os.cpu_count() or 2) // world))
+
         bmax = max(b - a for a, b in bounds)
         key = (count, bmax, days, mode, device, pinned)
         cache = getattr(self, "_ens", None)
