@@ -1369,7 +1369,7 @@ __global__ void __launch_bounds__(EXB_THREADS, 1)
         };
         auto slot_of = [&](int s, int& e, int& to, int& from) {
             e = -1, to = 0, from = 0;
-            if (!is_s && s < nchunks) {
+            if (lane_on && s < nchunks) { // (spare lanes have no slot)
                 const int2 v = __ldg(reinterpret_cast<const int2*>(a.xslot) + (size_t)s * EPP + q);
                 e            = v.x;
                 to           = v.y;
