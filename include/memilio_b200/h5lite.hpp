@@ -13,6 +13,8 @@
 #include <cstdint>
 #include <cstring>
 #include <fstream>
+#include <iterator>
+#include <stdexcept>
 #include <string>
 #include <utility>
 #include <vector>
@@ -262,6 +264,164 @@ private:
         put<uint64_t>(root.heap);
         std::copy(m_buf.begin(), m_buf.end(), saved.begin());
         m_buf.swap(saved);
+    }
+};
+
+// Reader for the same subset of the format (what tests/h5lite.py does in Python): the files of save_result written by
+// this writer or by libhdf5 (superblock 0, symbol table groups, version 1 object headers incl. continuation blocks,
+// contiguous little-endian doubles). Throws std::runtime_error on anything else.
+class Reader
+{
+public:
+    explicit Reader(const std::string& filename)
+    {
+        std::ifstream in(filename, std::ios::binary);
+        if (!in) {
+            throw std::runtime_error("h5lite: cannot open " + filename);
+        }
+        m_b.assign(std::istreambuf_iterator<char>(in), std::istreambuf_iterator<char>());
+        const unsigned char sig[] = {0x89, 'H', 'D', 'F', '\r', '\n', 0x1a, '\n'};
+        require(m_b.size() >= 96 && std::memcmp(m_b.data(), sig, 8) == 0, "not an HDF5 file");
+        require(m_b[8] == 0 && m_b[13] == 8 && m_b[14] == 8, "superblock version 0 with 8-byte offsets expected");
+        m_root = symbol_entry(56);
+    }
+    // names of the members of a group (root: empty path) in name order, with their symbol table entries
+    struct Member {
+        std::string name;
+        uint64_t header;
+        uint32_t cache;
+        uint64_t btree, heap;
+    };
+    std::vector<Member> list(const Member* group = nullptr) const
+    {
+        const Member& g = group ? *group : m_root;
+        uint64_t btree = g.btree, heap = g.heap;
+        if (g.cache != 1) {
+            bool found = false;
+            for (auto& m : messages(g.header)) {
+                if (m.type == 0x11) {
+                    btree = get<uint64_t>(m.at);
+                    heap  = get<uint64_t>(m.at + 8);
+                    found = true;
+                }
+            }
+            require(found, "not a group");
+        }
+        std::vector<Member> out;
+        walk(btree, heap, out);
+        return out;
+    }
+    // a dataset of doubles: shape and values (row major)
+    Dataset dataset(const Member& m) const
+    {
+        Dataset d;
+        d.name = m.name;
+        bool type_ok = false, have_layout = false;
+        uint64_t addr = 0, size = 0;
+        for (auto& msg : messages(m.header)) {
+            if (msg.type == 0x01) {
+                const int ver = m_b.at(msg.at), rank = m_b.at(msg.at + 1);
+                const uint64_t off = msg.at + (ver == 1 ? 8 : 4);
+                for (int i = 0; i < rank; ++i) {
+                    d.shape.push_back(get<uint64_t>(off + 8 * uint64_t(i)));
+                }
+            }
+            else if (msg.type == 0x03) {
+                type_ok = (m_b.at(msg.at) & 0x0f) == 1 && get<uint32_t>(msg.at + 4) == 8 && (m_b.at(msg.at + 1) & 1) == 0;
+            }
+            else if (msg.type == 0x08) {
+                require(m_b.at(msg.at) == 3 && m_b.at(msg.at + 1) == 1, "contiguous layout (version 3) expected");
+                addr        = get<uint64_t>(msg.at + 2);
+                size        = get<uint64_t>(msg.at + 10);
+                have_layout = true;
+            }
+        }
+        require(type_ok && have_layout && !d.shape.empty(), "dataset of little-endian doubles expected");
+        uint64_t n = 1;
+        for (uint64_t k : d.shape) {
+            n *= k;
+        }
+        require(size == 8 * n && addr + size <= m_b.size(), "dataset size mismatch");
+        d.values.resize(size_t(n));
+        std::memcpy(d.values.data(), m_b.data() + addr, size_t(size));
+        return d;
+    }
+
+private:
+    struct Message {
+        uint16_t type;
+        uint64_t at; // offset of the message body
+        uint16_t size;
+    };
+    std::vector<unsigned char> m_b;
+    Member m_root;
+
+    static void require(bool ok, const char* what)
+    {
+        if (!ok) {
+            throw std::runtime_error(std::string("h5lite: ") + what);
+        }
+    }
+    template <class T>
+    T get(uint64_t at) const
+    {
+        require(at + sizeof(T) <= m_b.size(), "truncated file");
+        T v;
+        std::memcpy(&v, m_b.data() + at, sizeof(T));
+        return v;
+    }
+    Member symbol_entry(uint64_t at) const
+    {
+        Member m;
+        m.header = get<uint64_t>(at + 8);
+        m.cache  = get<uint32_t>(at + 16);
+        m.btree  = m.cache == 1 ? get<uint64_t>(at + 24) : 0;
+        m.heap   = m.cache == 1 ? get<uint64_t>(at + 32) : 0;
+        m.name   = std::to_string(get<uint64_t>(at)); // placeholder: the heap offset, replaced by walk()
+        return m;
+    }
+    std::vector<Message> messages(uint64_t header) const
+    {
+        require(m_b.at(header) == 1, "object header version 1 expected");
+        const uint16_t count = get<uint16_t>(header + 2);
+        std::vector<std::pair<uint64_t, uint64_t>> blocks{{header + 16, get<uint32_t>(header + 8)}};
+        std::vector<Message> out;
+        for (size_t b = 0; b < blocks.size() && out.size() < count; ++b) {
+            uint64_t at = blocks[b].first, left = blocks[b].second;
+            while (left >= 8 && out.size() < count) {
+                const Message m{get<uint16_t>(at), at + 8, get<uint16_t>(at + 2)};
+                out.push_back(m);
+                if (m.type == 0x10) {
+                    blocks.emplace_back(get<uint64_t>(m.at), get<uint64_t>(m.at + 8));
+                }
+                at += 8 + m.size;
+                left -= std::min<uint64_t>(left, 8 + uint64_t(m.size));
+            }
+        }
+        return out;
+    }
+    void walk(uint64_t node, uint64_t heap, std::vector<Member>& out) const
+    {
+        require(std::memcmp(m_b.data() + node, "TREE", 4) == 0 && m_b.at(node + 4) == 0, "group B-tree node expected");
+        const int level     = m_b.at(node + 5);
+        const uint16_t used = get<uint16_t>(node + 6);
+        require(std::memcmp(m_b.data() + heap, "HEAP", 4) == 0, "local heap expected");
+        const uint64_t names = get<uint64_t>(heap + 24);
+        for (uint16_t i = 0; i < used; ++i) {
+            const uint64_t child = get<uint64_t>(node + 24 + 8 + 16 * uint64_t(i));
+            if (level > 0) {
+                walk(child, heap, out);
+                continue;
+            }
+            require(std::memcmp(m_b.data() + child, "SNOD", 4) == 0, "symbol table node expected");
+            const uint16_t n = get<uint16_t>(child + 6);
+            for (uint16_t k = 0; k < n; ++k) {
+                Member m = symbol_entry(child + 8 + 40 * uint64_t(k));
+                const uint64_t s = names + get<uint64_t>(child + 8 + 40 * uint64_t(k));
+                m.name = std::string(reinterpret_cast<const char*>(m_b.data() + s));
+                out.push_back(std::move(m));
+            }
+        }
     }
 };
 

@@ -176,6 +176,136 @@ inline IOResult<void> save_result(const std::vector<TimeSeries<ScalarType>>& res
     return success();
 }
 
+// SimulationResult / read_result, io/result_io.h:47-110, io/result_io.cpp:110-230: the groups' series (all age groups
+// side by side) and the totals of every region of a result file, regions in ascending id order
+class SimulationResult
+{
+public:
+    SimulationResult(const TimeSeries<ScalarType>& groups, const TimeSeries<ScalarType>& totals)
+        : m_groups(groups)
+        , m_totals(totals)
+    {
+    }
+    const TimeSeries<ScalarType>& get_groups() const
+    {
+        return m_groups;
+    }
+    const TimeSeries<ScalarType>& get_totals() const
+    {
+        return m_totals;
+    }
+
+private:
+    TimeSeries<ScalarType> m_groups, m_totals;
+};
+
+inline IOResult<std::vector<SimulationResult>> read_result(const std::string& filename)
+{
+    try {
+        h5lite::Reader file(filename);
+        auto regions = file.list();
+        std::sort(regions.begin(), regions.end(), [](const auto& a, const auto& b) {
+            return std::stoi(a.name) < std::stoi(b.name);
+        });
+        std::vector<SimulationResult> out;
+        for (auto& region : regions) {
+            std::vector<h5lite::Dataset> groups;
+            h5lite::Dataset time, total;
+            for (auto& m : file.list(&region)) {
+                if (m.name == "Time") {
+                    time = file.dataset(m);
+                }
+                else if (m.name == "Total") {
+                    total = file.dataset(m);
+                }
+            }
+            for (int k = 1;; ++k) { // Group1, Group2, ... in numerical order
+                bool found = false;
+                for (auto& m : file.list(&region)) {
+                    if (m.name == "Group" + std::to_string(k)) {
+                        groups.push_back(file.dataset(m));
+                        found = true;
+                    }
+                }
+                if (!found) {
+                    break;
+                }
+            }
+            if (time.shape.size() != 1 || total.shape.size() != 2 || total.shape[0] != time.shape[0]) {
+                return failure(StatusCode::InvalidFileFormat, "Number of time points does not match.");
+            }
+            const size_t T = size_t(time.shape[0]), C = size_t(total.shape[1]);
+            TimeSeries<ScalarType> gs{Eigen::Index(C * groups.size())}, ts{Eigen::Index(C)};
+            for (size_t t = 0; t < T; ++t) {
+                Eigen::VectorX<ScalarType> gv{Eigen::Index(C * groups.size())}, tv{Eigen::Index(C)};
+                for (size_t k = 0; k < groups.size(); ++k) {
+                    if (groups[k].shape != total.shape) {
+                        return failure(StatusCode::InvalidFileFormat, "Number of infection states does not match.");
+                    }
+                    for (size_t c = 0; c < C; ++c) {
+                        gv[Eigen::Index(k * C + c)] = groups[k].values[t * C + c];
+                    }
+                }
+                for (size_t c = 0; c < C; ++c) {
+                    tv[Eigen::Index(c)] = total.values[t * C + c];
+                }
+                gs.add_time_point(time.values[t], gv);
+                ts.add_time_point(time.values[t], tv);
+            }
+            out.emplace_back(gs, ts);
+        }
+        return out;
+    }
+    catch (const std::exception& e) {
+        return failure(StatusCode::InvalidFileFormat, e.what());
+    }
+}
+
+// save_edges of one run, io/mobility_io.cpp:206-306: one group per start node with "Time", "End<target id>" for every
+// edge of that node and "Total" (their sum in edge order); the edges of a start node are consecutive
+inline IOResult<void> save_edges(const std::vector<TimeSeries<ScalarType>>& results,
+                                 const std::vector<std::pair<int, int>>& ids, const std::string& filename)
+{
+    std::vector<h5lite::Group> groups;
+    size_t e = 0;
+    while (e < results.size()) {
+        const auto& first = results[e];
+        const size_t T    = size_t(first.get_num_time_points());
+        if (T == 0) {
+            return failure(StatusCode::InvalidValue, "No time points in the TimeSeries for Edge combination " +
+                                                         std::to_string(ids[e].first) + " -> " +
+                                                         std::to_string(ids[e].second));
+        }
+        const size_t C = size_t(first.get_num_elements());
+        h5lite::Group g;
+        g.name = std::to_string(ids[e].first);
+        h5lite::Dataset time{"Time", {T}, {}};
+        for (size_t t = 0; t < T; ++t) {
+            time.values.push_back(first.get_time(Eigen::Index(t)));
+        }
+        g.datasets.push_back(std::move(time));
+        h5lite::Dataset total{"Total", {T, C}, std::vector<double>(T * C, 0.0)};
+        const int start = ids[e].first;
+        for (; e < results.size() && ids[e].first == start; ++e) {
+            h5lite::Dataset d{"End" + std::to_string(ids[e].second), {T, C}, std::vector<double>(T * C, 0.0)};
+            const auto& r = results[e];
+            for (size_t t = 0; t < std::min(T, size_t(r.get_num_time_points())); ++t) {
+                for (size_t c = 0; c < C; ++c) {
+                    d.values[t * C + c] = r[Eigen::Index(t)][Eigen::Index(c)];
+                    total.values[t * C + c] += d.values[t * C + c];
+                }
+            }
+            g.datasets.push_back(std::move(d));
+        }
+        g.datasets.push_back(std::move(total));
+        groups.push_back(std::move(g));
+    }
+    if (!h5lite::write_file(filename, groups)) {
+        return failure(StatusCode::FileNotFound, "Failed to open the HDF5 file: " + filename);
+    }
+    return success();
+}
+
 // save_results, io/result_io.h:135-202: per-run results (optional) and the p05/p25/p50/p75/p95 percentiles of the
 // per-node results and of the node-summed results
 template <class Model>
@@ -214,21 +344,27 @@ IOResult<void> save_results(const std::vector<std::vector<TimeSeries<ScalarType>
     return success();
 }
 
-// save_edges, io/result_io.h:204-260 (mobility results per edge; empty series are written as header-only tables)
+// save_edges of an ensemble, io/mobility_io.cpp:162-204: Edges_run<i>.h5 per run and pXX/Edges.h5 for the percentiles
 inline IOResult<void> save_edges(const std::vector<std::vector<TimeSeries<ScalarType>>>& ensemble_edges,
                                  const std::vector<std::pair<int, int>>& pairs_edges,
                                  const std::filesystem::path& result_dir, bool save_single_runs = true,
                                  bool save_percentiles = true)
 {
-    (void)save_percentiles;
     if (save_single_runs) {
         for (size_t i = 0; i < ensemble_edges.size(); ++i) {
-            std::vector<int> ids;
-            for (auto& pr : pairs_edges) {
-                ids.push_back(pr.first * 100000 + pr.second);
+            auto r = save_edges(ensemble_edges[i], pairs_edges,
+                                (result_dir / ("Edges_run" + std::to_string(i) + ".h5")).string());
+            if (!r) {
+                return r;
             }
-            auto r = detail::write_csv(ensemble_edges[i], ids,
-                                       result_dir / ("Edges_run" + std::to_string(i) + ".csv"));
+        }
+    }
+    if (save_percentiles) {
+        const std::pair<const char*, ScalarType> ps[] = {{"p05", 0.05}, {"p25", 0.25}, {"p50", 0.5},
+                                                          {"p75", 0.75}, {"p95", 0.95}};
+        for (auto& [name, p] : ps) {
+            auto dir = create_directories_or_exit(result_dir / name);
+            auto r   = save_edges(ensemble_percentile(ensemble_edges, p), pairs_edges, (dir / "Edges.h5").string());
             if (!r) {
                 return r;
             }

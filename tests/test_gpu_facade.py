@@ -187,6 +187,14 @@ def test_reference_parameter_study_graph_example_runs():
         assert np.all(res["p50"][1001]["Total"] <= res["p95"][1001]["Total"] + 1e-9)
         total = h5lite.read_result(os.path.join(out, "p50", "Results_sum.h5"))
         assert list(total) == [0] and total[0]["Total"].shape == g["Total"].shape
+        # save_edges (io/mobility_io.cpp:162-306): per start node the mobility results of its edges, "End<target>"
+        edges = h5lite.read_result(os.path.join(out, "p50", "Edges.h5"))
+        assert sorted(edges) == [1001, 1002, 1003]
+        for start, g_e in edges.items():
+            ends = [k for k in g_e if k.startswith("End")]
+            assert ends and "Time" in g_e and "Total" in g_e and ("End%d" % start) not in ends
+            np.testing.assert_allclose(sum(g_e[k] for k in ends), g_e["Total"], rtol=1e-13)
+        assert edges[1001]["Total"].shape[1] == 3 and edges[1001]["Total"].max() > 0  # two index groups + total
 
 
 def test_reference_ode_secirvvs_example_runs_and_matches_oracle():

@@ -43,7 +43,33 @@ int main(int argc, char** argv)
         many.push_back(series(1000 + k));
         ids.push_back(1000 + k);
     }
-    return mio::save_result(many, ids, G, std::string(argv[1]) + "/many.h5") ? 0 : 2;
+    if (!mio::save_result(many, ids, G, std::string(argv[1]) + "/many.h5")) {
+        return 2;
+    }
+    // mio::read_result (io/result_io.cpp:110-230): our own file and the one the reference wrote with libhdf5
+    auto back = mio::read_result(std::string(argv[1]) + "/three.h5");
+    if (!back || back.value().size() != 3) {
+        return 3;
+    }
+    const auto& r5 = back.value()[0]; // regions come back in ascending id order: 5, 1001, 1002
+    if (r5.get_groups().get_num_time_points() != 5 || r5.get_groups().get_num_elements() != G * C ||
+        r5.get_groups()[2][4] != 5 + 0.25 * 2 + 10.0 * 4 || r5.get_totals()[4][1] != 2 * (5 + 0.25 * 4) + 10.0 * (1 + 4) ||
+        r5.get_totals().get_time(3) != 1.5) {
+        return 4;
+    }
+    auto ref = mio::read_result(argv[2]);
+    if (!ref || ref.value().size() != 1) {
+        return 5;
+    }
+    const auto& rr = ref.value()[0];
+    std::printf("ref %td %td %td %.17g %.17g\n", rr.get_groups().get_num_time_points(), rr.get_groups().get_num_elements(),
+                rr.get_totals().get_num_elements(), rr.get_totals()[0][0], rr.get_groups()[30][80]);
+    // save_edges (io/mobility_io.cpp:206-306): two start nodes, three edges
+    std::vector<mio::TimeSeries<double>> edges{series(1), series(2), series(3)};
+    if (!mio::save_edges(edges, {{1001, 1002}, {1001, 1003}, {1002, 1001}}, std::string(argv[1]) + "/edges.h5")) {
+        return 6;
+    }
+    return mio::read_result(std::string(argv[1]) + "/missing.h5") ? 7 : 0; // a missing file is an error, not a crash
 }
 '''
 
@@ -73,7 +99,18 @@ def test_facade_save_result_round_trip_and_structure(tmp_path):
     csrc = os.path.dirname(lib)
     subprocess.run(["g++", "-O1", "-std=c++20", "-I" + os.path.join(ROOT, "include"), str(src), "-o", str(exe),
                     "-L" + csrc, "-lmio_cuda", "-Wl,-rpath," + csrc], check=True)
-    subprocess.run([str(exe), str(tmp_path)], check=True)
+    r = subprocess.run([str(exe), str(tmp_path), GOLDEN], capture_output=True, text=True)
+    assert r.returncode == 0, (r.returncode, r.stdout, r.stderr)
+    # the facade's reader on the file libhdf5 wrote agrees with tests/h5lite.py
+    gold = h5lite.read_result(GOLDEN)[0]
+    w = r.stdout.split()
+    assert w[0] == "ref" and [int(x) for x in w[1:4]] == [31, 81, 27]
+    assert float(w[4]) == gold["Total"][0][0] and float(w[5]) == gold["Group3"][30][26]
+    edges = h5lite.read_result(str(tmp_path / "edges.h5"))
+    assert sorted(edges) == [1001, 1002]
+    assert sorted(edges[1001]) == ["End1002", "End1003", "Time", "Total"] and sorted(edges[1002]) == ["End1001", "Time", "Total"]
+    np.testing.assert_array_equal(edges[1001]["End1003"], _expected(2))
+    np.testing.assert_array_equal(edges[1001]["Total"], _expected(1) + _expected(2))
     r = h5lite.read_result(str(tmp_path / "three.h5"))
     assert sorted(r) == [5, 1001, 1002]
     for id_, g in r.items():
