@@ -2,6 +2,7 @@
 //   "single": one node, 10 of 100 symptomatic, contact frequency 10; above 1000 per 50 000 symptomatic infections the
 //             contacts are reduced by 0.8 for 4.5 days (renewed while the threshold stays exceeded); 12 days.
 //             Prints "t y0..y9" for every time point, then "# c(t)" lines: the contact matrix entry at t = 0..13.
+//   "predefined": the same with predefined dampings on the contact matrix (same slot as the NPI and another one).
 //   "graph":  the two nodes of graph_two_nodes with such an NPI (duration 4 days) in the first node; 10 days; prints
 //             "t node y0..y9" after every graph step and "# node c(t)" lines.
 #include "memilio_b200/mio.hpp"
@@ -22,13 +23,20 @@ static mio::DynamicNPIs<double> make_npis(double threshold, double value, double
     return npis;
 }
 
-static int single()
+static int single(bool with_predefined)
 {
     Model<double> model(1);
     model.populations[{mio::AgeGroup(0), InfectionState::InfectedSymptoms}] = 10;
     model.populations.set_difference_from_total({mio::AgeGroup(0), InfectionState::Susceptible}, 100);
     mio::ContactMatrixGroup<double>& cm = model.parameters.get<ContactPatterns<double>>();
     cm[0] = mio::ContactMatrix<double>(Eigen::MatrixX<double>::Constant(1, 1, 10.0));
+    if (with_predefined) {
+        // predefined dampings of the NPI's (level, type) slot inside and after the NPI window, and one of another slot:
+        // implement_dynamic_npis has to raise, keep and restore them
+        cm[0].add_damping(0.5, mio::DampingLevel(0), mio::DampingType(0), mio::SimulationTime<double>(3.0));
+        cm[0].add_damping(0.9, mio::DampingLevel(0), mio::DampingType(0), mio::SimulationTime<double>(8.0));
+        cm[0].add_damping(0.3, mio::DampingLevel(1), mio::DampingType(1), mio::SimulationTime<double>(6.0));
+    }
     model.parameters.get<DynamicNPIsInfectedSymptoms<double>>() = make_npis(1000.0, 0.8, 4.5);
     Simulation<double> sim(model, 0.0, 0.1);
     sim.advance(12.0);
@@ -111,5 +119,8 @@ int main(int argc, char** argv)
     if (argc > 1 && std::strcmp(argv[1], "graph") == 0) {
         return graph();
     }
-    return single();
+    if (argc > 1 && std::strcmp(argv[1], "predefined") == 0) {
+        return single(true);
+    }
+    return single(false);
 }

@@ -324,6 +324,27 @@ def test_dynamic_npis_example_single_node_matches_oracle():
     assert cm.min() == 2.0  # contacts reduced by 0.8 while the NPI is in force (renewed over the whole period)
 
 
+def test_dynamic_npis_with_predefined_dampings_match_oracle():
+    # predefined dampings in the NPI's slot (raised inside the window, restored after it) and in another slot
+    out = run_example("dynamic_npis", "predefined")
+    lines = out.strip().splitlines()
+    rows = np.array([[float(w) for w in ln.split()] for ln in lines if not ln.startswith("#")])
+    cm = np.array([float(ln.split()[1]) for ln in lines if ln.startswith("#")])
+    s = scenarios.damping_flow_case(None)
+    y0 = np.zeros(10)
+    y0[flat.ISY] = 10.0
+    y0[flat.S] = 90.0
+    one = np.ones((1, 1))
+    static = [(0, 3.0, 0, 0, 0.5 * one), (0, 8.0, 0, 0, 0.9 * one), (0, 6.0, 1, 1, 0.3 * one)]
+    ref = oracle_lib.npi_simulate(1, flat.osecir_pset(1), s["local"], s["ct"], 1, 2, y0, 0.0, [12.0], 0.1,
+                                  _npi(1000.0, 0.8, 4.5), static=static, query=np.arange(14.0))
+    assert rows.shape == (len(ref["t"]), 11)
+    np.testing.assert_allclose(rows[:, 0], ref["t"], rtol=1e-8, atol=1e-10)
+    np.testing.assert_allclose(rows[:, 1:], ref["y"], rtol=1e-8, atol=1e-9)
+    np.testing.assert_allclose(cm, ref["contact"][:, 0, 0], rtol=1e-12, atol=1e-12)
+    assert len(set(np.round(cm, 9))) >= 3  # several damping levels over the period
+
+
 def test_dynamic_npis_example_graph_matches_oracle():
     out = run_example("dynamic_npis", "graph")
     lines = out.strip().splitlines()
