@@ -3,7 +3,7 @@
 //             contacts are reduced by 0.8 for 4.5 days (renewed while the threshold stays exceeded); 12 days.
 //             Prints "t y0..y9" for every time point, then "# c(t)" lines: the contact matrix entry at t = 0..13.
 //   "predefined": the same with predefined dampings on the contact matrix (same slot as the NPI and another one).
-//   "graph":  the two nodes of graph_two_nodes with such an NPI (duration 4 days) in the first node; 10 days; prints
+//   "graph":  the two nodes of graph_two_nodes with such NPIs (thresholds crossed during the run); 10 days; prints
 //             "t node y0..y9" after every graph step and "# node c(t)" lines.
 #include "memilio_b200/mio.hpp"
 
@@ -83,8 +83,10 @@ static int graph()
     first.populations[{mio::AgeGroup(0), InfectionState::Susceptible}]      = 9900;
     first.populations[{mio::AgeGroup(0), InfectionState::Exposed}]          = 100;
     first.populations[{mio::AgeGroup(0), InfectionState::InfectedSymptoms}] = 50;
-    // 50 symptomatic of 10 050 are 249 per 50 000: the threshold of 200 is exceeded from the start in the first node
-    first.parameters.get<DynamicNPIsInfectedSymptoms<double>>() = make_npis(200.0, 0.6, 4.0);
+    // 50 symptomatic of 10 050 are 249 per 50 000: the threshold of 400 is crossed after some days in the first node,
+    // the second node (threshold 100) follows once the commuters have carried the infection over
+    first.parameters.get<DynamicNPIsInfectedSymptoms<double>>()  = make_npis(400.0, 0.6, 4.0);
+    second.parameters.get<DynamicNPIsInfectedSymptoms<double>>() = make_npis(100.0, 0.5, 3.0);
 
     mio::Graph<mio::SimulationNode<double, Sim>, mio::MobilityEdge<double>> g;
     g.add_node(1, first, 0.0);

@@ -360,13 +360,16 @@ def test_dynamic_npis_example_graph_matches_oracle():
     p.y0[0, 0, flat.S] = 9900.0
     p.y0[0, 0, flat.E] = 100.0
     p.y0[0, 0, flat.ISY] = 50.0
-    none = oracle_lib.npi_desc([], base=50000.0)
-    ref = oracle_lib.npi_graph_simulate(p, 0, 10.0, [_npi(200.0, 0.6, 4.0), none], halfsteps=20, query=np.arange(12.0))
-    assert ref["implemented"][0] >= 2 and ref["implemented"][1] == 0
+    npi1 = oracle_lib.npi_desc([(100.0, [dict(value=0.5, level=0, type=0, matrix_indices=[0],
+                                              group_weights=np.ones(1))])], duration=3.0, base=50000.0)
+    ref = oracle_lib.npi_graph_simulate(p, 0, 10.0, [_npi(400.0, 0.6, 4.0), npi1], halfsteps=20, query=np.arange(12.0))
+    # both thresholds are crossed DURING the run (the decisions depend on the evolving node states and the commuters)
+    assert ref["implemented"][0] >= 1 and ref["implemented"][1] >= 1
+    assert ref["contact"][0, 0, 0, 0] == 10.0 and ref["contact"][1, 8, 0, 0] == 10.0
     for k in range(2):
         node = rows[rows[:, 1] == k]
         assert node.shape == (21, 12)
         np.testing.assert_array_equal(node[:, 0], np.arange(21) * 0.5)
         np.testing.assert_allclose(node[1:, 2:], ref["halfsteps"][:, k], rtol=1e-8, atol=1e-9)
         np.testing.assert_allclose(cm[cm[:, 0] == k][:, 1], ref["contact"][k, :, 0, 0], rtol=1e-12, atol=1e-12)
-    assert cm[cm[:, 0] == 0][:, 1].min() < 4.01 and np.all(cm[cm[:, 0] == 1][:, 1] == 10.0)
+    assert cm[cm[:, 0] == 0][:, 1].min() < 4.01 and cm[cm[:, 0] == 1][:, 1].min() < 5.01
