@@ -412,7 +412,8 @@ class ParameterStudy:
             return out
         nb = max(1, min(num_batches, count))
         bounds = [(i * count // nb, (i + 1) * count // nb) for i in range(nb)]
-        if world > 1 and nb >= 2 and count >= 1000:
+        import os as _os
+        if (world > 1 or _os.environ.get("MIO_E2E_RAMP") == "1") and nb >= 2 and count >= 1000:
             # several ranks share the host's cores: sampling is 3-4 times slower per rank and the first batch's sampling
             # is not hidden behind any GPU work, so a small batch goes first (10 %, the rest in equal parts)
             first = count // 10
